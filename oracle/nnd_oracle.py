@@ -1,0 +1,230 @@
+"""ctypes front-end of the CPU oracle (oracle/nnd_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; nothing under pynndescent_b200/ does.
+
+`OracleNNDescent` replays the reference constructor's host logic
+(/root/reference/pynndescent/pynndescent_.py:976-1269) on top of the C restatement so
+that every intermediate (leaf_array, heap after init, candidates, ...) can be dumped and
+fed to the CUDA stages.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+METRIC_IDS = {"sqeuclidean": 0, "euclidean": 0, "l2": 0, "cosine": 1, "dot": 2, "correlation": 3}
+ANGULAR_METRICS = ("cosine", "dot", "correlation", "dice", "jaccard", "hellinger", "hamming")
+INT32_MIN = np.iinfo(np.int32).min + 1
+INT32_MAX = np.iinfo(np.int32).max - 1
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libnnd_oracle.so")
+    src = os.path.join(_HERE, "nnd_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc"})
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    L.orc_tau_rand_int.argtypes = [_i64p]; L.orc_tau_rand_int.restype = C.c_int32
+    L.orc_tau_rand.argtypes = [_i64p]; L.orc_tau_rand.restype = C.c_float
+    L.orc_det_log2.argtypes = [C.c_double]; L.orc_det_log2.restype = C.c_double
+    L.orc_dist.argtypes = [C.c_int, _f32p, _f32p, C.c_int]; L.orc_dist.restype = C.c_float
+    L.orc_checked_flagged_heap_push.argtypes = [_f32p, _i32p, _u8p, C.c_int, C.c_float, C.c_int32, C.c_uint8]
+    L.orc_checked_flagged_heap_push.restype = C.c_int
+    L.orc_checked_heap_push.argtypes = [_f32p, _i32p, C.c_int, C.c_float, C.c_int32]
+    L.orc_checked_heap_push.restype = C.c_int
+    L.orc_simple_heap_push.argtypes = [_f32p, _i32p, C.c_int, C.c_float, C.c_int32]
+    L.orc_simple_heap_push.restype = C.c_int
+    L.orc_deheap_sort.argtypes = [_i32p, _f32p, C.c_int64, C.c_int]
+    L.orc_new_build_candidates.argtypes = [_i32p, _u8p, C.c_int64, C.c_int, C.c_int, _i64p, C.c_int, _i32p, _i32p]
+    L.orc_process_candidates.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i32p,
+                                         _i32p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+    L.orc_process_candidates.restype = C.c_int64
+    L.orc_generate_updates.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _i32p, C.c_int, _f32p, C.c_int64,
+                                       C.c_int64, _i32p, _i32p, _f32p, C.c_int64]
+    L.orc_generate_updates.restype = C.c_int64
+    L.orc_init_rp_tree.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i32p, C.c_int64,
+                                   C.c_int]
+    L.orc_init_random.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i64p]
+    L.orc_make_forest.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_make_forest.restype = C.c_void_p
+    L.orc_forest_free.argtypes = [C.c_void_p]
+    L.orc_forest_leaf_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    L.orc_forest_leaf_array.argtypes = [C.c_void_p, C.c_int, _i32p]
+    L.orc_forest_tree_nodes.argtypes = [C.c_void_p, C.c_int]; L.orc_forest_tree_nodes.restype = C.c_int64
+    L.orc_forest_tree_arrays.argtypes = [C.c_void_p, C.c_int, _i32p, _i32p, _f32p, _f32p, _i32p]
+    L.orc_nn_descent_internal.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, C.c_int,
+                                          _i64p, C.c_int, C.c_int, C.c_double, C.c_int64, _i64p]
+    L.orc_nn_descent_internal.restype = C.c_int
+    L.orc_num_threads.restype = C.c_int
+    L.orc_set_num_threads.argtypes = [C.c_int]
+    _LIB = L
+    return L
+
+
+# ----------------------------------------------------------------- thin helpers
+def tau_rand_int(state):
+    return int(lib().orc_tau_rand_int(state))
+
+
+def tau_rand(state):
+    return float(lib().orc_tau_rand(state))
+
+
+def dist(metric, x, y):
+    x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+    return float(lib().orc_dist(METRIC_IDS[metric], x, y, x.shape[0]))
+
+
+def make_heap(n, k):
+    return (np.full((n, k), -1, np.int32), np.full((n, k), np.inf, np.float32), np.zeros((n, k), np.uint8))
+
+
+def make_forest(X, n_neighbors, n_trees, leaf_size, random_state, angular=False, max_depth=200, scheme="dfs"):
+    """rp_trees.py:2815-2922 make_forest + rptree_leaf_array -> (leaf_array, rng_states)."""
+    if leaf_size is None:
+        leaf_size = max(60, min(256, 5 * int(n_neighbors)))
+    rng_states = random_state.randint(INT32_MIN, INT32_MAX, size=(n_trees, 3)).astype(np.int64)
+    return forest_leaf_array(X, rng_states, leaf_size, angular, max_depth, scheme), rng_states
+
+
+def forest_leaf_array(X, rng_states, leaf_size, angular=False, max_depth=200, scheme="dfs"):
+    L = lib()
+    n_trees = rng_states.shape[0]
+    if n_trees == 0:
+        return np.array([[-1]], np.int32)
+    f = L.orc_make_forest(X, X.shape[0], X.shape[1], int(angular), np.ascontiguousarray(rng_states), n_trees,
+                          int(leaf_size), int(max_depth), 0 if scheme == "dfs" else 1)
+    nl = C.c_int64(); ml = C.c_int()
+    L.orc_forest_leaf_dims(f, int(leaf_size), C.byref(nl), C.byref(ml))
+    out = np.empty((nl.value, ml.value), np.int32)
+    L.orc_forest_leaf_array(f, ml.value, out)
+    L.orc_forest_free(f)
+    return out
+
+
+def init_rp_tree(X, metric, heap, leaf_array):
+    la = np.ascontiguousarray(leaf_array, np.int32)
+    lib().orc_init_rp_tree(X, X.shape[0], X.shape[1], METRIC_IDS[metric], heap[0], heap[1], heap[2], heap[0].shape[1],
+                           la, la.shape[0], la.shape[1])
+
+
+def init_random(X, metric, heap, rng_state):
+    lib().orc_init_random(X, X.shape[0], X.shape[1], METRIC_IDS[metric], heap[0], heap[1], heap[2], heap[0].shape[1],
+                          rng_state)
+
+
+def new_build_candidates(heap, max_candidates, rng_state, n_threads):
+    n, k = heap[0].shape
+    newc = np.empty((n, max_candidates), np.int32); oldc = np.empty((n, max_candidates), np.int32)
+    lib().orc_new_build_candidates(heap[0], heap[2], n, k, max_candidates, rng_state, n_threads, newc, oldc)
+    return newc, oldc
+
+
+def generate_updates(X, metric, newc, oldc, thr, r0=0, r1=None):
+    n, c = newc.shape
+    r1 = n if r1 is None else r1
+    cap = (r1 - r0) * (c * (c + 1) // 2 + c * c) + 16
+    p = np.empty(cap, np.int32); q = np.empty(cap, np.int32); d = np.empty(cap, np.float32)
+    m = lib().orc_generate_updates(X, n, X.shape[1], METRIC_IDS[metric], newc, oldc, c,
+                                   np.ascontiguousarray(thr, np.float32), r0, r1, p, q, d, cap)
+    return p[:m].copy(), q[:m].copy(), d[:m].copy()
+
+
+def process_candidates(X, metric, heap, newc, oldc, n_threads, block_size=16384):
+    n, k = heap[0].shape
+    em = C.c_int64()
+    c = lib().orc_process_candidates(X, n, X.shape[1], METRIC_IDS[metric], heap[0], heap[1], heap[2], k, newc, oldc,
+                                     newc.shape[1], block_size, n_threads, C.byref(em))
+    return int(c), int(em.value)
+
+
+def deheap_sort(ind, dist_):
+    lib().orc_deheap_sort(ind, dist_, ind.shape[0], ind.shape[1])
+    return ind, dist_
+
+
+def correction(metric, d):
+    """distances.py:2170-2188 fast_distance_alternatives[...]['correction'] (f64 output for the
+    pow-based cosine/dot correction, as the reference's numba.vectorize gives)."""
+    if metric in ("euclidean", "l2"):
+        return np.sqrt(d)
+    if metric in ("cosine", "dot"):
+        return 1.0 - np.power(2.0, -d.astype(np.float64))
+    return d.copy()
+
+
+class OracleNNDescent:
+    """Replays NNDescent.__init__ (pynndescent_.py:976-1269) over the C oracle.
+
+    n_threads is the numba thread count being emulated (it only matters inside
+    new_build_candidates, utils.py:259-263).  `forest` = "dfs" (reference rng order) or
+    "level" (node-hash rng, the GPU forest's scheme).  Intermediates are kept on `self`.
+    """
+
+    def __init__(self, data, metric="euclidean", n_neighbors=30, n_trees=None, leaf_size=None, random_state=None,
+                 max_candidates=None, n_iters=None, delta=0.001, tree_init=True, max_rptree_depth=200, n_threads=8,
+                 forest="dfs", leaf_array=None, keep_stages=False, block_size=16384):
+        from sklearn.utils import check_random_state
+        data = np.ascontiguousarray(data, np.float32)
+        n = data.shape[0]
+        if n_trees is None:
+            n_trees = max(3, min(12, int(round(2.0 * np.log10(n)))))
+        if n_iters is None:
+            n_iters = max(5, int(round(np.log2(n))))
+        self.metric = metric
+        self.n_neighbors = n_neighbors
+        rs = check_random_state(random_state)
+        if metric == "dot":
+            from sklearn.preprocessing import normalize  # pynndescent_.py:1101-1103
+            data = normalize(data, norm="l2", copy=True)
+        self._raw_data = data
+        self.rng_state = rs.randint(INT32_MIN, INT32_MAX, 3).astype(np.int64)
+        self.search_rng_state = rs.randint(INT32_MIN, INT32_MAX, 3).astype(np.int64)
+        angular = metric in ANGULAR_METRICS
+        if leaf_array is not None:
+            self.leaf_array = np.ascontiguousarray(leaf_array, np.int32)
+        elif tree_init and n_trees > 0:
+            self.leaf_array, self.tree_rng_states = make_forest(data, n_neighbors, n_trees, leaf_size, rs, angular,
+                                                                max_rptree_depth, forest)
+        else:
+            self.leaf_array = np.array([[-1]], np.int32)
+        C_ = min(60, n_neighbors) if max_candidates is None else max_candidates
+        self.max_candidates = C_
+        heap = make_heap(n, n_neighbors)
+        if tree_init:
+            init_rp_tree(data, metric, heap, self.leaf_array)
+        if keep_stages:
+            self.heap_after_leaf = tuple(a.copy() for a in heap)
+        init_random(data, metric, heap, self.rng_state)
+        if keep_stages:
+            self.heap_after_init = tuple(a.copy() for a in heap)
+            self.rng_state_after_init = self.rng_state.copy()
+        self.c_hist = np.zeros(n_iters, np.int64)
+        self.n_iters_run = lib().orc_nn_descent_internal(data, n, data.shape[1], METRIC_IDS[metric], heap[0], heap[1],
+                                                         heap[2], n_neighbors, C_, self.rng_state, n_threads, n_iters,
+                                                         delta, block_size, self.c_hist)
+        if keep_stages:
+            self.heap_final = tuple(a.copy() for a in heap)
+        deheap_sort(heap[0], heap[1])
+        self._neighbor_graph = (heap[0], heap[1])
+
+    @property
+    def neighbor_graph(self):
+        return self._neighbor_graph[0].copy(), correction(self.metric, self._neighbor_graph[1])

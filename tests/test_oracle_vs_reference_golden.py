@@ -1,0 +1,105 @@
+"""Pins the CPU oracle (oracle/nnd_oracle.c) to vectors produced by the REAL reference
+(tests/golden/make_golden.py, numba T=8).  CPU-only; runs in the `-m "not gpu"` suite."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+
+
+def test_tau_rand_kat(oracle):
+    g = load_golden("kat")
+    for n in "abc":
+        s = g[f"tau_{n}_state0"].copy()
+        ints = np.array([oracle.tau_rand_int(s) for _ in range(64)], np.int32)
+        assert np.array_equal(ints, g[f"tau_{n}_ints"])
+        assert np.array_equal(s, g[f"tau_{n}_state1"])
+        s = g[f"tau_{n}_state0"].copy()
+        fl = np.array([oracle.tau_rand(s) for _ in range(64)], np.float32)
+        assert np.array_equal(fl, g[f"tau_{n}_floats"])
+    # SURVEY 8a literal values
+    s = np.array([-5, 123456789, -987654321], np.int64)
+    assert [oracle.tau_rand_int(s) for _ in range(5)] == [-1530850136, 1419355108, -424356903, 1332770144, 572193240]
+    assert s.tolist() == [-100400832, 3507296892, -4142669084]
+
+
+@pytest.mark.parametrize("name,k", [("h5", 5), ("h15", 15), ("h30", 30)])
+def test_heap_push_kat(oracle, name, k):
+    g = load_golden("kat")
+    L = oracle.lib()
+    pri = np.full(k, np.inf, np.float32); ind = np.full(k, -1, np.int32); flg = np.zeros(k, np.uint8)
+    d, q, f = g[f"{name}_d"], g[f"{name}_q"], g[f"{name}_f"]
+    ret = [L.orc_checked_flagged_heap_push(pri, ind, flg, k, float(d[i]), int(q[i]), int(f[i])) for i in range(len(d))]
+    assert np.array_equal(np.array(ret, np.int32), g[f"{name}_ret"])
+    assert np.array_equal(pri, g[f"{name}_pri"]) and np.array_equal(ind, g[f"{name}_ind"])
+    assert np.array_equal(flg, g[f"{name}_flg"])
+    si, sd = oracle.deheap_sort(ind.copy()[None, :], pri.copy()[None, :])
+    assert np.array_equal(si[0], g[f"{name}_sorted_ind"]) and np.array_equal(sd[0], g[f"{name}_sorted_pri"])
+    pri2 = np.full(k, np.inf, np.float32); ind2 = np.full(k, -1, np.int32)
+    ret2 = [L.orc_simple_heap_push(pri2, ind2, k, float(d[i]), int(q[i])) for i in range(len(d))]
+    assert np.array_equal(np.array(ret2, np.int32), g[f"{name}_simple_ret"])
+    assert np.array_equal(pri2, g[f"{name}_simple_pri"]) and np.array_equal(ind2, g[f"{name}_simple_ind"])
+
+
+def test_heap_push_survey_literal(oracle):
+    L = oracle.lib()
+    pri = np.full(5, np.inf, np.float32); ind = np.full(5, -1, np.int32); flg = np.zeros(5, np.uint8)
+    seq = [(0.5, 7), (0.3, 2), (0.9, 4), (0.3, 9), (0.1, 7), (0.2, 1), (0.05, 3), (0.3, 2), (0.25, 8), (0.9, 11)]
+    ret = [L.orc_checked_flagged_heap_push(pri, ind, flg, 5, d, n, 1) for d, n in seq]
+    assert ret == [1, 1, 1, 1, 0, 1, 1, 0, 1, 0]
+    assert ind.tolist() == [2, 8, 9, 1, 3]
+    si, _ = oracle.deheap_sort(ind[None, :].copy(), pri[None, :].copy())
+    assert si[0].tolist() == [3, 1, 8, 9, 2]
+
+
+@pytest.mark.parametrize("metric", ["sqeuclidean", "cosine", "dot", "correlation"])
+def test_distance_kat(oracle, metric):
+    """Distances agree with the reference within 1e-5 relative (the reference's own low bits
+    depend on LLVM's fastmath vectorisation; the oracle has ONE defined order)."""
+    g = load_golden("kat")
+    A = g["dist_A"]
+    D = np.array([[oracle.dist(metric, A[i], A[j]) for j in range(24)] for i in range(24)], np.float32)
+    R = g[f"dist_{metric}"]
+    big = R > 1e30  # FLOAT32_MAX sentinel (non-positive similarity / zero vector)
+    assert np.array_equal(big, D > 1e30)
+    np.testing.assert_allclose(D[~big], R[~big], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_end_to_end_matches_reference(oracle, name):
+    """Full build replay: leaf_array, heaps after each init stage, candidates, per-iteration
+    accepted-push counts and the final graph are IDENTICAL to the reference's (indices exact,
+    distances rtol 1e-5)."""
+    G = load_golden(name)
+    metric = GOLDEN_CASES[name]
+    o = oracle.OracleNNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_threads=int(G["T"]),
+                               keep_stages=True)
+    assert np.array_equal(o.leaf_array, G["leaf_array"])
+    assert np.array_equal(o.heap_after_leaf[0], G["leaf_heap_idx"])
+    assert np.array_equal(o.heap_after_leaf[2], G["leaf_heap_flag"])
+    assert np.array_equal(o.heap_after_init[0], G["init_heap_idx"])
+    assert np.array_equal(o.rng_state_after_init, G["rng_state1"])
+    assert np.array_equal(o.c_hist[: o.n_iters_run], G["c_hist"])
+    assert np.array_equal(o.heap_final[0], G["final_heap_idx"])
+    gi, gd = o.neighbor_graph
+    assert np.array_equal(gi, G["graph_idx"])
+    np.testing.assert_allclose(gd, G["graph_dist"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cfg1_euclid_1k16", "latent_cosine_2k24"])
+def test_stage_candidates_and_join(oracle, name):
+    """Stage-injected: reference heap -> oracle candidates == reference candidates (T=8);
+    reference candidates -> oracle process_candidates == reference heap after the iteration."""
+    G = load_golden(name)
+    metric = GOLDEN_CASES[name]
+    data = G["X"]
+    heap = (G["init_heap_idx"].copy(), G["init_heap_dist"].copy(), G["init_heap_flag"].copy())
+    newc, oldc = oracle.new_build_candidates(heap, min(60, int(G["k"])), G["rng_state1"].copy(), int(G["T"]))
+    assert np.array_equal(newc, G["it0_new"]) and np.array_equal(oldc, G["it0_old"])
+    assert np.array_equal(heap[2], G["it0_flag_after_cand"])
+    c, _ = oracle.process_candidates(data, metric, heap, newc, oldc, int(G["T"]))
+    assert c == int(G["c_hist"][0])
+    assert np.array_equal(heap[0], G["it0_heap_idx"]) and np.array_equal(heap[2], G["it0_heap_flag"])
+    # block-size / thread-count invariance of generate+apply (SURVEY hard part 5)
+    heap2 = (G["init_heap_idx"].copy(), G["init_heap_dist"].copy(), G["it0_flag_after_cand"].copy())
+    c2, _ = oracle.process_candidates(data, metric, heap2, newc, oldc, 3, block_size=10 ** 9)
+    assert c2 == c and np.array_equal(heap2[0], heap[0]) and np.array_equal(heap2[1], heap[1])
