@@ -1,0 +1,159 @@
+/*
+ * nnd_b200.h -- C-ABI of libnnd_b200.so: the B200 (sm_100a) NN-descent kNN-graph hot path.
+ *
+ * This is the drop-in boundary for lmcinnes/pynndescent's numba seams:
+ *   seam 1  make_forest + rptree_leaf_array      pynndescent/pynndescent_.py:1118-1130
+ *   seam 2  nn_descent(...) -> (indices, dists)   pynndescent/pynndescent_.py:1247-1260 (def :324-366)
+ *   seam 3  _search_function / _deheap_function    pynndescent/pynndescent_.py:2336-2361   (next round)
+ *
+ * Conventions: extern "C"; every call returns 0 on success or a negative NND_ERR_* code and
+ * the text is available from nnd_last_error(); no exceptions cross the boundary.  All array
+ * arguments are DEVICE pointers unless the name ends in _host.  The caller owns every buffer
+ * (the Python host takes them from torch.Tensor.data_ptr()); scratch comes from an explicit
+ * workspace whose size is queried first -- the library never allocates device memory behind
+ * the caller's back except the small per-context constant tables made in nnd_create().
+ * `stream` is a cudaStream_t passed as void*.  A context is bound to one device and is not
+ * thread-safe.
+ *
+ * Parity contract: given the same inputs, every stage reproduces the
+ * reference's result bit-for-bit (indices, flags, heap layout, accepted-push count `c`) for a
+ * declared emulated numba thread count T; distances follow one defined summation order and
+ * agree with the reference's fastmath numbers to <= 1e-5 relative.
+ */
+#ifndef NND_B200_H
+#define NND_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NND_API __attribute__((visibility("default")))
+#else
+#define NND_API
+#endif
+
+#define NND_OK 0
+#define NND_ERR_INVALID (-1)     /* bad argument                                     */
+#define NND_ERR_CUDA (-2)        /* a CUDA runtime call failed                        */
+#define NND_ERR_WORKSPACE (-3)   /* workspace too small                               */
+#define NND_ERR_UNSUPPORTED (-4) /* metric / shape not implemented on the GPU path    */
+#define NND_ERR_OVERFLOW (-5)    /* an internal list would overflow (never silent)    */
+
+/* distances.py:2103-2188 names -> ids ("fast alternatives" are what the path computes in;
+ * the correction back to the true distance happens in nnd_deheap_sort).                 */
+#define NND_METRIC_SQEUCLIDEAN 0 /* distances.py:63-91   (euclidean / l2 / sqeuclidean) */
+#define NND_METRIC_ALT_COSINE 1  /* distances.py:583-630 (cosine)                       */
+#define NND_METRIC_ALT_DOT 2     /* distances.py:665-701 (dot; data pre-normalised)     */
+#define NND_METRIC_CORRELATION 3 /* distances.py:1283-1320                              */
+
+#define NND_CORRECT_NONE 0
+#define NND_CORRECT_SQRT 1   /* distances.py:2171       np.sqrt                         */
+#define NND_CORRECT_ALTCOS 2 /* distances.py:704-711    1 - 2^-d                        */
+
+typedef struct nnd_ctx nnd_ctx;
+
+NND_API const char *nnd_last_error(void);
+NND_API int nnd_version(void);
+
+/* context: device-resident jump-ahead tables for the Tausworthe rng (utils.py:17-57) */
+NND_API int nnd_create(nnd_ctx **out, int device);
+NND_API int nnd_destroy(nnd_ctx *ctx);
+
+/* ---- problem description shared by all stage calls ---------------------------------- */
+typedef struct {
+    const float *X; /* [N, ld] row-major, ld % 4 == 0, columns d..ld-1 zero, 16 B aligned */
+    int64_t N;
+    int32_t d, ld;
+    int32_t metric;  /* NND_METRIC_*                                                      */
+    const void *aux; /* from nnd_metric_prepare: cosine f32 norm2[N]; correlation f64 (mu,nrm2)[N] */
+    int32_t k;       /* n_neighbors                                                        */
+    int32_t *heap_idx;  /* [N,k]  utils.py:130-158 make_heap layout                        */
+    float *heap_dist;   /* [N,k]                                                           */
+    uint8_t *heap_flag; /* [N,k]                                                           */
+} nnd_problem;
+
+/* bytes of `aux` for (metric, N) */
+NND_API int nnd_metric_aux_bytes(int32_t metric, int64_t N, size_t *bytes);
+/* fills aux (per-point squared norms / means) in the canonical summation order */
+NND_API int nnd_metric_prepare(nnd_ctx *ctx, const float *X, int64_t N, int32_t d, int32_t ld, int32_t metric, void *aux,
+                       void *stream);
+/* utils.py:130-158 make_heap: idx=-1, dist=+inf, flag=0 */
+NND_API int nnd_make_heap(nnd_ctx *ctx, int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int64_t N, int32_t k,
+                  void *stream);
+
+/* ---- seam 1: RP forest (rp_trees.py:2815-2922) --------------------------------------- */
+/* Level-synchronous forest with the reference's split rule and stable partition; node
+ * randomness = hash(tree seed, level, node ordinal).  Output is the
+ * leaf set in CSR form: leaf_points[n_trees*N] (tree-major, leaves contiguous, DFS left-to-
+ * right order, ascending point id inside a leaf) and leaf_offsets[n_leaves+1].            */
+NND_API int nnd_forest_workspace_bytes(int64_t N, int32_t d, int32_t n_trees, size_t *bytes);
+NND_API int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t d, int32_t ld, int32_t angular,
+                     const int64_t *tree_rng_states_host /* [n_trees*3] rp_trees.py:2850-2852 */, int32_t n_trees,
+                     int32_t leaf_size, int32_t max_depth, int32_t *leaf_points /* [n_trees*N] */,
+                     int64_t *leaf_offsets /* [n_trees*N+1] capacity */, int64_t *n_leaves_host,
+                     int32_t *max_leaf_host, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- seam 2: NN-descent stages (pynndescent_.py:324-366) ------------------------------ */
+/* workspace for leaf init / descent iterations.  push_capacity = max half-updates one
+ * routing round may hold (rows are processed in blocks sized so this is never exceeded).  */
+NND_API int nnd_descent_workspace_bytes(int64_t N, int32_t k, int32_t C, int32_t T, int64_t push_capacity, size_t *bytes);
+
+/* pynndescent_.py:116-185 init_rp_tree (+ :73-113 generate_leaf_updates) from CSR leaves.
+ * n_updates_host (optional) receives the number of half-updates routed.                   */
+NND_API int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets,
+                  const int64_t *leaf_offsets_host, int64_t n_leaves, int32_t max_leaf, int64_t push_capacity,
+                  void *ws, size_t ws_bytes, int64_t *n_pushes_host, void *stream);
+
+/* pynndescent_.py:188-203 init_random; rng_state_host[3] is advanced exactly as the reference
+ * advances it.                                                                             */
+NND_API int nnd_init_random(nnd_ctx *ctx, const nnd_problem *P, int64_t *rng_state_host, void *ws, size_t ws_bytes,
+                    void *stream);
+
+/* utils.py:221-320 new_build_candidates, emulating T numba threads (stream n = rng_state+n,
+ * vertex ranges of N//T+1).  Outputs new_cand/old_cand int32[N,C] with the reference's heap
+ * layout; clears heap_flag of sampled new entries.                                          */
+NND_API int nnd_cand_workspace_bytes(int64_t N, int32_t k, int32_t C, int32_t T, size_t *bytes);
+/* tables_valid != 0: the T priority tables at the head of `ws` were filled by an earlier call with
+ * the same (rng_state, T, N, k) and `ws` was not touched since (the streams never advance).     */
+NND_API int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T,
+                         int32_t tables_valid, int32_t *new_cand, int32_t *old_cand, void *ws, size_t ws_bytes,
+                         void *stream);
+
+/* pynndescent_.py:217-263 process_candidates == utils.py:536-658 generate_graph_update_array
+ * + utils.py:661-733 apply_graph_update_array over all rows.  c_host = accepted pushes.
+ * stats_host (optional, int64[4]): gathered rows, evaluated pairs, routed half-updates, blocks */
+NND_API int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand,
+                           const int32_t *old_cand, int64_t push_capacity, void *ws, size_t ws_bytes,
+                           int64_t *c_host, int64_t *stats_host, void *stream);
+
+/* utils.py:189-218 deheap_sort (in place, exact tie order) fused with the distance
+ * correction of neighbor_graph (pynndescent_.py:2145-2158): out_dist may alias heap_dist.  */
+NND_API int nnd_deheap_sort(nnd_ctx *ctx, int32_t *idx, float *dist, int64_t N, int32_t k, int32_t correction,
+                    float *out_dist, void *stream);
+
+/* the whole of nn_descent_internal (pynndescent_.py:266-320): iterate build_candidates +
+ * process_candidates until c <= delta*k*N or n_iters.  c_hist_host[n_iters] optional.      */
+NND_API int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T,
+                int32_t n_iters, double delta, int64_t push_capacity, void *ws, size_t ws_bytes,
+                int32_t *iters_run_host, int64_t *c_hist_host, int64_t *stats_host, void *stream);
+
+/* ---- small exported primitives (unit tests / known-answer vectors) -------------------- */
+/* utils.py:17-57: out[i] = i-th tau_rand_int (as_float=0) or tau_rand (as_float=1) of the
+ * stream starting at state_host, i in [start, start+count), via GF(2) jump-ahead.          */
+NND_API int nnd_rng_stream(nnd_ctx *ctx, const int64_t *state_host, int64_t start, int64_t count, int32_t as_float,
+                   void *out, void *stream);
+/* state after `n` draws (host-side jump-ahead) */
+NND_API int nnd_rng_advance_host(nnd_ctx *ctx, int64_t *state_host, int64_t n);
+/* pair distances in the canonical order: out[i] = dist(X[a[i]], X[b[i]]) */
+NND_API int nnd_pair_distances(nnd_ctx *ctx, const nnd_problem *P, const int32_t *a, const int32_t *b, int64_t n, float *out,
+                       void *stream);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+NND_API int64_t nnd_launch_count(nnd_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NND_B200_H */

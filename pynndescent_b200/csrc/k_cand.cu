@@ -1,0 +1,256 @@
+// k_cand.cu -- new_build_candidates (utils.py:221-320) for T emulated numba threads.
+//
+// Reference: thread n owns vertex range R_n=[n*B,(n+1)*B), B=N//T+1, uses stream rng_state+n,
+// scans ALL edges (i,j) in heap-layout order and draws ONE priority per edge that touches R_n
+// (utils.py:266-306); the edge is pushed into cand[flag][i] (if i in R_n) and cand[flag][idx]
+// (if idx in R_n) with checked_heap_push.  Then flags of entries present in new_cand[i] are
+// cleared (utils.py:311-318).
+//
+// GPU formulation (bit-exact):
+//   k_cand_count : per row, #valid edges and #edges pointing into each R_n; in-degree histogram
+//   scan         : prefix sums -> the draw index of every (edge, stream) pair is a closed form
+//   k_cand_fill  : priority = table[n][draw index] (tables = the T streams, generated once by
+//                  GF(2) jump-ahead); forward priorities stored per edge, reverse edges routed
+//                  to their target vertex (counting sort by target)
+//   k_cand_select: one warp per vertex sorts its reverse edges by scan position, merges them with
+//                  its forward edges and replays checked_heap_push in scan order; clears flags
+#include "nnd_common.cuh"
+
+struct CandWs {
+    uint32_t *cnt;      // [(T+1)*N] per-stream per-row counts; last block = valid counts
+    uint32_t *pre;      // [(T+1)*N + 1] exclusive scan of cnt
+    uint32_t *indeg;    // [N+1]
+    uint32_t *revoff;   // [N+2] padded-segment offsets
+    uint32_t *cursor;   // [N]
+    unsigned long long *rev;  // [2*N*k + pad]  (key<<32 | prio bits), key = (i*k+j)*2 + isnew
+    float *fprio;       // [N*k]
+    float *table;       // [T * table_len]
+    uint32_t *scan_tmp;
+    int64_t table_len;
+};
+
+static int64_t cand_table_len(int64_t N, int k) { return N * (int64_t)k; }
+
+static int carve_cand_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, int T, CandWs *W, size_t *need) {
+    WsAlloc A(ws, ws_bytes);
+    (void)C;
+    int64_t Nb = N > 16 ? N : 16;
+    W->cnt = A.get<uint32_t>((size_t)(T + 1) * Nb);
+    W->pre = A.get<uint32_t>((size_t)(T + 1) * Nb + 2);
+    W->indeg = A.get<uint32_t>(Nb + 1);
+    W->revoff = A.get<uint32_t>(Nb + 2);
+    W->cursor = A.get<uint32_t>(Nb + 1);
+    W->rev = A.get<unsigned long long>((size_t)2 * Nb * k + NND_SEG_SMEM);
+    W->fprio = A.get<float>((size_t)Nb * k);
+    W->table_len = cand_table_len(Nb, k);
+    W->table = A.get<float>((size_t)T * W->table_len);
+    W->scan_tmp = A.get<uint32_t>(nnd_scan_tmp_elems((int64_t)(T + 1) * Nb + 2));
+    if (need) *need = A.off;
+    return A.ok ? NND_OK : NND_ERR_WORKSPACE;
+}
+extern "C" int nnd_cand_workspace_bytes(int64_t N, int32_t k, int32_t C, int32_t T, size_t *bytes) {
+    NND_CHECK(bytes && N > 0 && k > 0 && C > 0 && T > 0, NND_ERR_INVALID, "nnd_cand_workspace_bytes: bad args");
+    *bytes = nnd_cand_ws_bytes(N, k, C, T);
+    return NND_OK;
+}
+size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T) {
+    CandWs W; size_t need = 0;
+    carve_cand_ws(nullptr, 0, N, k, C, T, &W, &need);
+    return need + 1024;
+}
+
+__global__ void k_cand_count(const int32_t *ind, int k, int64_t N, int T, int64_t B, uint32_t *cnt, uint32_t *indeg) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t valid = 0;
+    for (int n = 0; n < T; ++n) {
+        int64_t bs = (int64_t)n * B, be = bs + B;
+        uint32_t c = 0;
+        for (int j = 0; j < k; ++j) { int32_t x = ind[i * k + j]; c += (x >= bs && x < be && x >= 0); }
+        cnt[(size_t)n * N + i] = c;
+    }
+    for (int j = 0; j < k; ++j) {
+        int32_t x = ind[i * k + j];
+        if (x >= 0) { ++valid; atomicAdd(&indeg[x], 1u); }
+    }
+    cnt[(size_t)T * N + i] = valid;
+}
+
+// draw index of edge (i, j) in stream n: number of earlier edges (scan order) touching R_n
+__device__ __forceinline__ uint32_t draw_index(const uint32_t *pre, int64_t N, int T, int64_t B, int n, int64_t i,
+                                               uint32_t within_valid, uint32_t within_n) {
+    const uint32_t *PR = pre + (size_t)n * N;  // prefix of "#edges into R_n" per row (relative to PR[0] base)
+    const uint32_t *PV = pre + (size_t)T * N;  // prefix of valid counts
+    const uint32_t baseR = PR[0], baseV = PV[0];
+    int64_t s = (int64_t)n * B, e = s + B < N ? s + B : N;
+    // PR[x]-baseR = sum over rows < x ; index N is not addressable inside the block, handle via next block's base
+    auto prR = [&](int64_t x) -> uint32_t { return (x < N ? PR[x] : pre[(size_t)(n + 1) * N]) - baseR; };
+    auto prV = [&](int64_t x) -> uint32_t { return (x < N ? PV[x] : pre[(size_t)(T + 1) * N]) - baseV; };
+    if (i < s) return prR(i) + within_n;
+    if (i < e) return prR(s) + (prV(i) - prV(s)) + within_valid;
+    return prR(s) + (prV(e) - prV(s)) + (prR(i) - prR(e)) + within_n;
+}
+
+__global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int64_t N, int T, int64_t B,
+                            const uint32_t *pre, const float *table, int64_t table_len, const uint32_t *revoff,
+                            uint32_t *cursor, unsigned long long *rev, float *fprio) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int ni = (int)(i / B);
+    uint32_t wv = 0;  // valid edges before j in this row
+    for (int j = 0; j < k; ++j) {
+        int32_t x = ind[i * k + j];
+        if (x < 0) { fprio[i * k + j] = 0.f; continue; }
+        const int nx = (int)(x / B);
+        uint32_t df = draw_index(pre, N, T, B, ni, i, wv, 0);
+        float pf = table[(size_t)ni * table_len + df];
+        fprio[i * k + j] = pf;
+        float pr = pf;
+        if (nx != ni) {
+            uint32_t wn = 0;  // earlier edges of this row pointing into R_nx
+            int64_t bs = (int64_t)nx * B, be = bs + B;
+            for (int jj = 0; jj < j; ++jj) { int32_t y = ind[i * k + jj]; wn += (y >= bs && y < be); }
+            uint32_t dr = draw_index(pre, N, T, B, nx, i, 0, wn);
+            pr = table[(size_t)nx * table_len + dr];
+        }
+        uint32_t slot = atomicAdd(&cursor[x], 1u);
+        unsigned long long key = ((unsigned long long)(i * k + j) << 1) | (unsigned long long)(flags[i * k + j] != 0);
+        rev[(size_t)revoff[x] + slot] = (key << 32) | (unsigned long long)__float_as_uint(pr);
+        ++wv;
+    }
+}
+
+#define SEL_WARPS 8
+__global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
+                                                                const uint32_t *indeg, const uint32_t *revoff,
+                                                                unsigned long long *rev, const float *fprio,
+                                                                int32_t *newc, int32_t *oldc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t v = (int64_t)blockIdx.x * SEL_WARPS + warp;
+    if (v >= N) return;
+    unsigned long long *buf = (unsigned long long *)smem_raw + (size_t)warp * NND_SEG_SMEM;
+    const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
+    unsigned char *hp = smem_raw + (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)warp * hstride;
+    float *npri = (float *)hp, *opri = npri + C;
+    int32_t *nind = (int32_t *)(opri + C), *oind = nind + C;
+    for (int c = lane; c < C; c += 32) { npri[c] = CUDART_INF_F; opri[c] = CUDART_INF_F; nind[c] = -1; oind[c] = -1; }
+    const uint32_t nrev = indeg[v];
+    unsigned long long *seg = rev + revoff[v];
+    unsigned long long *sorted;
+    if (nrev <= NND_SEG_SMEM) {
+        int p2 = (int)next_pow2_u32(nrev);
+        for (int j = lane; j < p2; j += 32) buf[j] = (j < (int)nrev) ? seg[j] : ~0ULL;
+        __syncwarp();
+        if (nrev > 1) warp_bitonic_sort_u64(buf, p2, lane);
+        sorted = buf;
+    } else {
+        uint32_t cap = padded_seg(nrev);
+        for (uint32_t j = nrev + lane; j < cap; j += 32) seg[j] = ~0ULL;
+        __syncwarp();
+        warp_bitonic_sort_u64(seg, (int)cap, lane);
+        sorted = seg;
+    }
+    __syncwarp();
+    // two-pointer merge of forward edges (v*k+j, ascending j) and sorted reverse edges
+    int jf = 0; uint32_t jr = 0;
+    const unsigned long long fbase = (unsigned long long)v * k;
+    for (;;) {
+        while (jf < k && ind[v * k + jf] < 0) ++jf;
+        bool hasf = jf < k, hasr = jr < nrev;
+        if (!hasf && !hasr) break;
+        unsigned long long rkey = hasr ? (sorted[jr] >> 33) : ~0ULL;  // scan position of the reverse edge
+        bool take_f = hasf && (!hasr || fbase + jf <= rkey);
+        float pr; int32_t cand; bool isnew;
+        if (take_f) {
+            pr = fprio[v * k + jf]; cand = ind[v * k + jf]; isnew = flags[v * k + jf] != 0; ++jf;
+        } else {
+            unsigned long long r = sorted[jr]; ++jr;
+            pr = __uint_as_float((uint32_t)(r & 0xFFFFFFFFULL));
+            isnew = (r >> 32) & 1ULL;
+            cand = (int32_t)((r >> 33) / (unsigned long long)k);
+        }
+        if (isnew) warp_heap_push(npri, nind, nullptr, C, pr, cand, 0, lane);
+        else warp_heap_push(opri, oind, nullptr, C, pr, cand, 0, lane);
+    }
+    __syncwarp();
+    // utils.py:311-318: clear the flag of every neighbour that was sampled into new_cand[v]
+    for (int j = lane; j < k; j += 32) {
+        int32_t x = ind[v * k + j];
+        bool found = false;
+        for (int c = 0; c < C; ++c) found |= (nind[c] == x);
+        if (found) flags[v * k + j] = 0;
+    }
+    for (int c = lane; c < C; c += 32) { newc[v * C + c] = nind[c]; oldc[v * C + c] = oind[c]; }
+}
+
+__global__ void k_rng_table(const uint64_t *jump, long long s0, long long s1, long long s2, int64_t start, int64_t count,
+                            int as_float, void *out, int chunk) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = t * chunk;
+    if (b >= count) return;
+    long long s[3] = {s0, s1, s2};
+    tau_jump(s, (unsigned long long)(start + b), jump);
+    int64_t e = b + chunk < count ? b + chunk : count;
+    for (int64_t i = b; i < e; ++i) {
+        int32_t r = tau_step(s);
+        if (as_float) ((float *)out)[i] = tau_to_float(r);
+        else ((int32_t *)out)[i] = r;
+    }
+}
+
+int nnd_rng_table_launch(nnd_ctx *ctx, const int64_t *state, int64_t start, int64_t count, int as_float, void *out,
+                         cudaStream_t st) {
+    if (count <= 0) return NND_OK;
+    const int chunk = 256;
+    int64_t nthreads = cdiv(count, chunk);
+    k_rng_table<<<(unsigned)cdiv(nthreads, 128), 128, 0, st>>>(ctx->d_jump, state[0], state[1], state[2], start, count,
+                                                              as_float, out, chunk);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+extern "C" int nnd_rng_stream(nnd_ctx *ctx, const int64_t *state_host, int64_t start, int64_t count, int32_t as_float,
+                              void *out, void *stream) {
+    NND_CHECK(ctx && state_host && out && start >= 0 && count >= 0, NND_ERR_INVALID, "nnd_rng_stream: bad args");
+    return nnd_rng_table_launch(ctx, state_host, start, count, as_float, out, (cudaStream_t)stream);
+}
+
+extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host,
+                                    int32_t T, int32_t tables_valid, int32_t *new_cand, int32_t *old_cand, void *ws,
+                                    size_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && rng_state_host && new_cand && old_cand, NND_ERR_INVALID, "nnd_build_candidates: bad args");
+    NND_CHECK(T >= 1 && T <= 256 && C >= 1 && C <= 256, NND_ERR_INVALID, "nnd_build_candidates: T=%d C=%d out of range", T, C);
+    const int64_t N = P->N; const int k = P->k;
+    NND_CHECK((double)N * k * 2 < 4.0e9, NND_ERR_UNSUPPORTED, "N*k too large for 32-bit edge keys");
+    CandWs W;
+    NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_build_candidates: workspace too small");
+    const int64_t B = N / T + 1;
+    // the T priority streams: constant across iterations (utils.py:262 copies rng_state, never advances it)
+    if (!tables_valid) {
+        for (int n = 0; n < T; ++n) {
+            int64_t s[3] = {rng_state_host[0] + n, rng_state_host[1] + n, rng_state_host[2] + n};
+            NND_TRY(nnd_rng_table_launch(ctx, s, 0, W.table_len, 1, W.table + (size_t)n * W.table_len, st));
+        }
+    }
+    NND_CUDA(cudaMemsetAsync(W.indeg, 0, sizeof(uint32_t) * (N + 1), st));
+    NND_CUDA(cudaMemsetAsync(W.cursor, 0, sizeof(uint32_t) * (N + 1), st));
+    k_cand_count<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, k, N, T, B, W.cnt, W.indeg); NND_LAUNCH(ctx);
+    NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
+    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
+    k_cand_fill<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.pre, W.table, W.table_len,
+                                                       W.revoff, W.cursor, W.rev, W.fprio);
+    NND_LAUNCH(ctx);
+    const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
+    size_t smem = (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)SEL_WARPS * hstride;
+    NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
+    NND_CUDA(cudaFuncSetAttribute(k_cand_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cand_select<<<(unsigned)cdiv(N, SEL_WARPS), SEL_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
+                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}

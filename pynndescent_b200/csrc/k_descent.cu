@@ -1,0 +1,584 @@
+// k_descent.cu -- the NN-descent inner loop on sm_100a:
+//   k_join    : all-pairs distances inside a leaf (init_rp_tree) or a candidate row (local join),
+//               rows staged in shared memory by the bulk-copy (TMA) engine, 4x4 register tiles
+//   k_scatter : counting-sort routing of half-updates to their target heap rows
+//   k_apply   : one warp per heap row replays the pushes in the reference's canonical order
+//
+// Reference semantics (file:line under /root/reference/pynndescent):
+//   generate_leaf_updates        pynndescent_.py:73-113   (strict '<' filter, pairs i<j)
+//   generate_graph_update_array  utils.py:536-658         ('<=' filter, new x new (k>=j) then new x old)
+//   apply_graph_update_array     utils.py:661-733         (push (d,q)->row p then (d,p)->row q, in emission order)
+//   checked_flagged_heap_push    utils.py:471-533
+//
+// Exactness: a half-update (row t <- other o, dist dd) is emitted iff dd < thr[t] where thr is a
+// snapshot of the heap roots.  The reference emits iff dd <= max(thr_p,thr_q) and then the push
+// re-checks dd < root(now) <= thr, so every half-update dropped here would have been rejected,
+// and the survivors are replayed per row in ascending emission sequence => identical heaps,
+// identical flags, identical accepted-push count.
+#include <type_traits>
+#include <vector>
+
+#include "nnd_common.cuh"
+
+#define TILE 4
+#define DK 128  // d-chunk staged per pass (floats)
+#define SD (DK + 4)  // padded smem row stride: consecutive rows shift by 4 banks
+
+struct JoinParams {
+    const float *X; int64_t N; int d, ld; int metric; const void *aux;
+    const float *thr;
+    int mode;  // 0 local join, 1 leaf
+    const int32_t *newc, *oldc; int C; int64_t unit_begin, unit_end;
+    const int32_t *leaf_points; const int64_t *leaf_offsets;
+    int m_max, slot_stride;
+    int32_t *out_tgt, *out_oth; float *out_d; uint32_t *out_pos; unsigned long long *out_seq;
+    uint32_t *tgt_count;
+    unsigned long long *cursor; unsigned long long capacity;
+    unsigned long long *stats;  // [0] rows gathered [1] pairs evaluated
+    int *overflow;
+};
+
+static size_t join_smem_bytes(int m_max, int metric) {
+    size_t b = 16;                       // mbarrier
+    b += (size_t)m_max * 4 * 2;          // ids, thr
+    if (metric == NND_METRIC_ALT_COSINE) b += (size_t)m_max * 4;
+    if (metric == NND_METRIC_CORRELATION) b += (size_t)m_max * 16;
+    b = (b + 15) & ~size_t(15);
+    b += (size_t)m_max * SD * 4;
+    return b;
+}
+
+template <int METRIC, int TPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = (uint64_t *)smem_raw;
+    int32_t *ids = (int32_t *)(smem_raw + 16);
+    float *thr_s = (float *)(ids + P.m_max);
+    unsigned char *cur = (unsigned char *)(thr_s + P.m_max);
+    float *n2_s = nullptr; double *mu_s = nullptr;
+    if (METRIC == NND_METRIC_ALT_COSINE) { n2_s = (float *)cur; cur += (size_t)P.m_max * 4; }
+    if (METRIC == NND_METRIC_CORRELATION) {
+        cur = (unsigned char *)(((uintptr_t)cur + 7) & ~uintptr_t(7));
+        mu_s = (double *)cur; cur += (size_t)P.m_max * 16;
+    }
+    float *rows = (float *)(((uintptr_t)cur + 15) & ~uintptr_t(15));
+    __shared__ int s_nn, s_m;
+
+    const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
+    const int64_t unit = P.unit_begin + blockIdx.x;
+    if (unit >= P.unit_end) return;
+
+    // ---- member list (order-preserving compaction of the -1 holes; warp 0) ----
+    if (tid < 32) {
+        int cnt = 0;
+        if (P.mode == 0) {
+            for (int part = 0; part < 2; ++part) {
+                const int32_t *src = (part == 0 ? P.newc : P.oldc) + unit * P.C;
+                for (int b0 = 0; b0 < P.C; b0 += 32) {
+                    int j = b0 + lane;
+                    int32_t v = (j < P.C) ? src[j] : -1;
+                    unsigned mk = __ballot_sync(0xffffffffu, v >= 0);
+                    if (v >= 0) ids[cnt + __popc(mk & ((1u << lane) - 1))] = v;
+                    cnt += __popc(mk);
+                }
+                if (part == 0 && lane == 0) s_nn = cnt;
+            }
+        } else {
+            int64_t o0 = P.leaf_offsets[unit], o1 = P.leaf_offsets[unit + 1];
+            cnt = (int)(o1 - o0);
+            for (int j = lane; j < cnt; j += 32) ids[j] = P.leaf_points[o0 + j];
+            if (lane == 0) s_nn = cnt;
+        }
+        if (lane == 0) { s_m = cnt; mbar_init(bar, 1); mbar_fence_init(); }
+    }
+    __syncthreads();
+    const int nn = s_nn, m = s_m;
+    if (nn == 0 || (P.mode == 1 && m < 2)) return;
+    for (int j = tid; j < m; j += nthr) {
+        int32_t id = ids[j];
+        thr_s[j] = P.thr[id];
+        if (METRIC == NND_METRIC_ALT_COSINE) n2_s[j] = ((const float *)P.aux)[id];
+        if (METRIC == NND_METRIC_CORRELATION) {
+            mu_s[2 * j] = ((const double *)P.aux)[2 * (int64_t)id];
+            mu_s[2 * j + 1] = ((const double *)P.aux)[2 * (int64_t)id + 1];
+        }
+    }
+    if (tid == 0 && P.stats) {
+        atomicAdd(&P.stats[0], (unsigned long long)m);
+        unsigned long long np = (P.mode == 0) ? ((unsigned long long)nn * (nn + 1) / 2 + (unsigned long long)nn * (m - nn))
+                                              : ((unsigned long long)m * (m - 1) / 2);
+        atomicAdd(&P.stats[1], np);
+    }
+
+    // ---- my tiles: (ta,tb) with tb >= ta over ceil(nn/4) x ceil(m/4) ----
+    const int ntr = (nn + TILE - 1) / TILE, ntc = (m + TILE - 1) / TILE;
+    const int ntiles = ntr * ntc - ntr * (ntr - 1) / 2;
+    int my_ta[TPT], my_tb[TPT];
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+        int t = tid + i * nthr;
+        my_ta[i] = -1; my_tb[i] = 0;
+        if (t < ntiles) {
+            int ta = 0;
+            while (t >= ntc - ta) { t -= ntc - ta; ++ta; }
+            my_ta[i] = ta; my_tb[i] = ta + t;
+        }
+    }
+
+    typedef typename std::conditional<METRIC == NND_METRIC_CORRELATION, double, float>::type acc_t;
+    acc_t acc[TPT][TILE * TILE];
+#pragma unroll
+    for (int i = 0; i < TPT; ++i)
+#pragma unroll
+        for (int p = 0; p < TILE * TILE; ++p) acc[i][p] = (acc_t)0;
+
+    // ---- d-chunks: bulk-copy rows -> smem, then register-tiled sequential accumulation ----
+    uint32_t phase = 0;
+    for (int c0 = 0; c0 < P.ld; c0 += DK) {
+        const int len = min(DK, P.ld - c0);
+        if (tid < 32) {
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)m * (uint32_t)len * 4u);
+            __syncwarp();
+            for (int r = lane; r < m; r += 32)
+                bulk_g2s(rows + (size_t)r * SD, P.X + (int64_t)ids[r] * P.ld + c0, (uint32_t)len * 4u, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            if (my_ta[i] < 0) continue;
+            const float *ra[TILE], *rb[TILE];
+            acc_t ma[TILE], mb[TILE];
+#pragma unroll
+            for (int u = 0; u < TILE; ++u) {
+                int ia = min(my_ta[i] * TILE + u, nn - 1), ib = min(my_tb[i] * TILE + u, m - 1);
+                ra[u] = rows + (size_t)ia * SD; rb[u] = rows + (size_t)ib * SD;
+                if (METRIC == NND_METRIC_CORRELATION) { ma[u] = (acc_t)mu_s[2 * ia]; mb[u] = (acc_t)mu_s[2 * ib]; }
+                else { ma[u] = 0; mb[u] = 0; }
+            }
+            for (int e = 0; e < len; e += 4) {
+                float4 va[TILE], vb[TILE];
+#pragma unroll
+                for (int u = 0; u < TILE; ++u) {
+                    va[u] = *(const float4 *)(ra[u] + e);
+                    vb[u] = *(const float4 *)(rb[u] + e);
+                }
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+#pragma unroll
+                    for (int u = 0; u < TILE; ++u) {
+                        float xa = (w == 0) ? va[u].x : (w == 1) ? va[u].y : (w == 2) ? va[u].z : va[u].w;
+#pragma unroll
+                        for (int v = 0; v < TILE; ++v) {
+                            float xb = (w == 0) ? vb[v].x : (w == 1) ? vb[v].y : (w == 2) ? vb[v].z : vb[v].w;
+                            if (METRIC == NND_METRIC_SQEUCLIDEAN) {
+                                float df = __fsub_rn(xa, xb);
+                                acc[i][u * TILE + v] = __fmaf_rn(df, df, (float)acc[i][u * TILE + v]);
+                            } else if (METRIC == NND_METRIC_CORRELATION) {
+                                if (c0 + e + w < P.d) {
+                                    double sx = __dadd_rn((double)xa, -(double)ma[u]);
+                                    double sy = __dadd_rn((double)xb, -(double)mb[v]);
+                                    acc[i][u * TILE + v] = __fma_rn(sx, sy, (double)acc[i][u * TILE + v]);
+                                }
+                            } else {
+                                acc[i][u * TILE + v] = __fmaf_rn(xa, xb, (float)acc[i][u * TILE + v]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone done with this chunk before it is overwritten
+    }
+
+    // ---- finalise, filter, count pushes ----
+    float dd[TPT][TILE * TILE];
+    uint32_t pm[TPT];
+    int npush = 0;
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+        pm[i] = 0;
+        if (my_ta[i] < 0) continue;
+#pragma unroll
+        for (int u = 0; u < TILE; ++u)
+#pragma unroll
+            for (int v = 0; v < TILE; ++v) {
+                int a = my_ta[i] * TILE + u, b = my_tb[i] * TILE + v;
+                bool valid = (a < nn) && (b < m) && ((b > a) || (b == a && P.mode == 0));
+                float r = 0.0f;
+                if (valid) {
+                    if (METRIC == NND_METRIC_SQEUCLIDEAN) r = (float)acc[i][u * TILE + v];
+                    else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine((float)acc[i][u * TILE + v], n2_s[a], n2_s[b]);
+                    else if (METRIC == NND_METRIC_ALT_DOT) r = finish_alt_dot((float)acc[i][u * TILE + v]);
+                    else r = finish_correlation((double)acc[i][u * TILE + v], mu_s[2 * a + 1], mu_s[2 * b + 1]);
+                    if (r < thr_s[a]) pm[i] |= 1u << (2 * (u * TILE + v));
+                    if (b != a && r < thr_s[b]) pm[i] |= 2u << (2 * (u * TILE + v));
+                }
+                dd[i][u * TILE + v] = r;
+            }
+        npush += __popc(pm[i]);
+    }
+    // warp-aggregated slot allocation in the global push list
+    int incl = npush;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (total > 0) {
+        if (lane == 31) base = atomicAdd(P.cursor, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+    }
+    if (npush > 0) {
+        unsigned long long w = base + (unsigned long long)(incl - npush);
+        if (base + (unsigned long long)total > P.capacity) { *P.overflow = 1; return; }
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            uint32_t mk = pm[i];
+            while (mk) {
+                int bit = __ffs(mk) - 1;
+                mk &= mk - 1;
+                int pr = bit >> 1, side = bit & 1;
+                int a = my_ta[i] * TILE + pr / TILE, b = my_tb[i] * TILE + pr % TILE;
+                int32_t pa = ids[a], pb = ids[b];
+                int32_t tgt = side ? pb : pa, oth = side ? pa : pb;
+                // dd[i][pr] with a compile-time-unrollable select (keeps dd in registers)
+                float r = 0.0f;
+#pragma unroll
+                for (int s = 0; s < TILE * TILE; ++s) if (s == pr) r = dd[i][s];
+                P.out_tgt[w] = tgt; P.out_oth[w] = oth; P.out_d[w] = r;
+                P.out_pos[w] = atomicAdd(&P.tgt_count[tgt], 1u);
+                P.out_seq[w] = ((unsigned long long)unit << 20) |
+                               ((unsigned long long)(a * P.slot_stride + b) << 1) | (unsigned long long)side;
+                ++w;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ routing
+__global__ void k_snapshot_thr(const float *heap_dist, int k, float *thr, int64_t N) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) thr[i] = heap_dist[i * k];
+}
+
+__global__ void k_scatter(const int32_t *tgt, const int32_t *oth, const float *dd, const uint32_t *pos,
+                          const unsigned long long *seq, unsigned long long n, const uint32_t *off, Rec16 *rec) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rec16 r; r.key = seq[i]; r.oth = oth[i]; r.d = dd[i];
+    rec[(size_t)off[tgt[i]] + pos[i]] = r;
+}
+
+// ------------------------------------------------------------------ apply
+#define APPLY_WARPS 8
+__global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag,
+                                                            int k, int64_t N, const uint32_t *cnt, const uint32_t *off,
+                                                            Rec16 *rec, unsigned long long *c_total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * APPLY_WARPS + warp;
+    if (row >= N) return;
+    const uint32_t n = cnt[row];
+    if (n == 0) return;
+    Rec16 *buf = (Rec16 *)smem_raw + (size_t)warp * NND_SEG_SMEM;
+    unsigned char *hp = smem_raw + (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)warp * (((size_t)k * 9 + 15) & ~size_t(15));
+    float *pri = (float *)hp; int32_t *ind = (int32_t *)(pri + k); uint8_t *flg = (uint8_t *)(ind + k);
+    for (int j = lane; j < k; j += 32) {
+        pri[j] = heap_dist[row * k + j]; ind[j] = heap_idx[row * k + j]; flg[j] = heap_flag[row * k + j];
+    }
+    __syncwarp();
+    const float root0 = pri[0];
+    Rec16 *seg = rec + off[row];
+    Rec16 *sorted; int ns;
+    if (n <= NND_SEG_SMEM) {
+        // keep only pushes that can possibly be accepted (root only decreases), compact into smem
+        int kept = 0;
+        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+            uint32_t j = b0 + lane;
+            Rec16 r; r.key = ~0ULL; r.oth = -1; r.d = 0.f;
+            bool keep = false;
+            if (j < n) { r = seg[j]; keep = r.d < root0; }
+            unsigned mk = __ballot_sync(0xffffffffu, keep);
+            if (keep) buf[kept + __popc(mk & ((1u << lane) - 1))] = r;
+            kept += __popc(mk);
+        }
+        if (kept == 0) return;
+        int p2 = (int)next_pow2_u32((uint32_t)kept);
+        for (int j = kept + lane; j < p2; j += 32) { buf[j].key = ~0ULL; buf[j].oth = -1; buf[j].d = CUDART_INF_F; }
+        __syncwarp();
+        if (kept > 1) warp_bitonic_sort_rec(buf, p2, lane);
+        sorted = buf; ns = kept;
+    } else {
+        uint32_t cap = padded_seg(n);
+        for (uint32_t j = n + lane; j < cap; j += 32) { seg[j].key = ~0ULL; seg[j].oth = -1; seg[j].d = CUDART_INF_F; }
+        __syncwarp();
+        warp_bitonic_sort_rec(seg, (int)cap, lane);
+        sorted = seg; ns = (int)n;
+    }
+    int c = 0;
+    for (int s = 0; s < ns; ++s) {
+        Rec16 r = sorted[s];
+        c += warp_heap_push(pri, ind, flg, k, r.d, r.oth, (uint8_t)1, lane);
+    }
+    if (c > 0) {
+        for (int j = lane; j < k; j += 32) {
+            heap_dist[row * k + j] = pri[j]; heap_idx[row * k + j] = ind[j]; heap_flag[row * k + j] = flg[j];
+        }
+        if (lane == 0) atomicAdd(c_total, (unsigned long long)c);
+    }
+}
+
+// ------------------------------------------------------------------ per-row worst-case push bound (for blocking)
+__global__ void k_row_bound(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *bound) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int nn = 0, no = 0;
+    for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
+    bound[i] = (uint32_t)(nn * (nn + 1) + 2 * nn * no);  // 2 half-updates per pair (self pairs: 1, bounded by 2)
+}
+__global__ void k_leaf_bound(const int64_t *leaf_offsets, int64_t n_leaves, uint32_t *bound) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves) return;
+    uint32_t m = (uint32_t)(leaf_offsets[i + 1] - leaf_offsets[i]);
+    bound[i] = m * (m - (m > 0));
+}
+
+// ------------------------------------------------------------------ host orchestration
+struct DescentWs {
+    float *thr; uint32_t *cnt, *off, *bound, *bound_scan, *scan_tmp;
+    int32_t *l_tgt, *l_oth; float *l_d; uint32_t *l_pos; unsigned long long *l_seq;
+    Rec16 *rec;
+    unsigned long long *dev_scalars;  // [0] cursor [1] c_total [2..3] stats [4] overflow(int)
+    // candidate-build scratch lives behind these (k_cand.cu)
+    char *cand_base; size_t cand_bytes;
+    int32_t *newc, *oldc;
+};
+
+size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T);
+
+static int carve_descent_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, int T, int64_t cap, DescentWs *W,
+                            size_t *need) {
+    WsAlloc A(ws, ws_bytes);
+    int64_t Nb = N > 16 ? N : 16;
+    W->thr = A.get<float>(Nb);
+    W->cnt = A.get<uint32_t>(Nb + 1);
+    W->off = A.get<uint32_t>(Nb + 2);
+    W->bound = A.get<uint32_t>(Nb + 1);
+    W->bound_scan = A.get<uint32_t>(Nb + 2);
+    W->scan_tmp = A.get<uint32_t>(nnd_scan_tmp_elems(Nb + 2));
+    W->l_tgt = A.get<int32_t>(cap); W->l_oth = A.get<int32_t>(cap); W->l_d = A.get<float>(cap);
+    W->l_pos = A.get<uint32_t>(cap); W->l_seq = A.get<unsigned long long>(cap);
+    W->rec = A.get<Rec16>((size_t)cap * 2 + NND_SEG_SMEM);
+    W->dev_scalars = A.get<unsigned long long>(16);
+    W->cand_bytes = nnd_cand_ws_bytes(N, k, C, T);
+    W->cand_base = A.get<char>(W->cand_bytes);
+    W->newc = A.get<int32_t>((size_t)Nb * C); W->oldc = A.get<int32_t>((size_t)Nb * C);
+    if (need) *need = A.off;
+    return A.ok ? NND_OK : NND_ERR_WORKSPACE;
+}
+
+extern "C" int nnd_descent_workspace_bytes(int64_t N, int32_t k, int32_t C, int32_t T, int64_t push_capacity,
+                                           size_t *bytes) {
+    NND_CHECK(bytes && N > 0 && k > 0 && push_capacity > 0, NND_ERR_INVALID, "nnd_descent_workspace_bytes: bad args");
+    DescentWs W; size_t need = 0;
+    carve_descent_ws(nullptr, 0, N, k, C, T, push_capacity, &W, &need);
+    *bytes = need + 4096;
+    return NND_OK;
+}
+
+template <int METRIC>
+static int launch_join_m(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaStream_t st) {
+    // worst-case tile count for this launch decides (TPT, threads)
+    int nn_max = (P.mode == 0) ? P.C : P.m_max;
+    int ntr = (nn_max + TILE - 1) / TILE, ntc = (P.m_max + TILE - 1) / TILE;
+    int ntiles = ntr * ntc - ntr * (ntr - 1) / 2;
+    size_t smem = join_smem_bytes(P.m_max, METRIC);
+    NND_CHECK(smem <= 220 * 1024, NND_ERR_UNSUPPORTED, "join: %d members need %zu B of shared memory", P.m_max, smem);
+    int tpt = (METRIC == NND_METRIC_CORRELATION) ? 1 : (ntiles <= 512 ? 1 : (ntiles <= 2048 ? 2 : 4));
+    int threads = (int)(cdiv(cdiv(ntiles, tpt), 32) * 32);
+    NND_CHECK(threads <= 1024, NND_ERR_UNSUPPORTED, "join: %d tiles exceed one CTA (members=%d)", ntiles, P.m_max);
+    if (threads < 32) threads = 32;
+    dim3 grid((unsigned)n_units);
+#define LJ(T_, M_)                                                                                       \
+    do {                                                                                                 \
+        NND_CUDA(cudaFuncSetAttribute(k_join<METRIC, T_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_join<METRIC, T_, M_><<<grid, threads, smem, st>>>(P);                                          \
+    } while (0)
+    if (tpt == 1) { if (threads <= 128) LJ(1, 128); else LJ(1, 512); }
+    else if (tpt == 2) { if (threads <= 512) LJ(2, 512); else LJ(2, 1024); }
+    else LJ(4, 1024);
+#undef LJ
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+static int launch_join(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaStream_t st) {
+    NND_CHECK(n_units < (1LL << 31), NND_ERR_INVALID, "join: too many units in one launch");
+    switch (P.metric) {
+    case NND_METRIC_SQEUCLIDEAN: return launch_join_m<NND_METRIC_SQEUCLIDEAN>(ctx, P, n_units, st);
+    case NND_METRIC_ALT_COSINE: return launch_join_m<NND_METRIC_ALT_COSINE>(ctx, P, n_units, st);
+    case NND_METRIC_ALT_DOT: return launch_join_m<NND_METRIC_ALT_DOT>(ctx, P, n_units, st);
+    case NND_METRIC_CORRELATION: return launch_join_m<NND_METRIC_CORRELATION>(ctx, P, n_units, st);
+    }
+    nnd_set_error("join: unknown metric %d", P.metric);
+    return NND_ERR_UNSUPPORTED;
+}
+
+// one routing round: join over units [u0,u1) -> scan -> scatter -> apply.  Returns pushes routed.
+static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_t u0, int64_t u1, DescentWs &W,
+                       int64_t cap, unsigned long long *n_pushed, cudaStream_t st) {
+    const int64_t N = P->N;
+    k_snapshot_thr<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_dist, P->k, W.thr, N); NND_LAUNCH(ctx);
+    NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (N + 1), st));
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long), st));  // cursor
+    J.thr = W.thr; J.unit_begin = u0; J.unit_end = u1;
+    J.out_tgt = W.l_tgt; J.out_oth = W.l_oth; J.out_d = W.l_d; J.out_pos = W.l_pos; J.out_seq = W.l_seq;
+    J.tgt_count = W.cnt; J.cursor = W.dev_scalars; J.capacity = (unsigned long long)cap;
+    J.stats = W.dev_scalars + 2; J.overflow = (int *)(W.dev_scalars + 4);
+    NND_TRY(launch_join(ctx, J, u1 - u0, st));
+    unsigned long long h[5];
+    NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    NND_CHECK(((int *)&h[4])[0] == 0, NND_ERR_OVERFLOW, "push list overflow (capacity %lld)", (long long)cap);
+    *n_pushed = h[0];
+    if (h[0] == 0) return NND_OK;
+    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, N, W.scan_tmp, st));  // offsets of power-of-two padded segments
+    k_scatter<<<(unsigned)cdiv((int64_t)h[0], 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_pos, W.l_seq, h[0], W.off, W.rec);
+    NND_LAUNCH(ctx);
+    size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
+    NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "apply: k=%d too large", P->k);
+    NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
+                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+// choose unit blocks so that the worst-case pushes of a block fit in `cap`:
+// bound_scan (exclusive prefix of per-unit bounds, copied to host) -> greedy cut points.
+static int plan_blocks(nnd_ctx *ctx, const uint32_t *d_bound, int64_t n_units, DescentWs &W, int64_t cap,
+                       std::vector<int64_t> &cuts, cudaStream_t st) {
+    // coarse: sum bounds per group of G units on the device-side scan, read group prefix on host
+    const int64_t G = 1024;
+    int64_t ng = cdiv(n_units, G);
+    std::vector<uint32_t> hb;  // per-unit bounds are small (<= ~65k); group sums computed on host from the scan
+    // exclusive scan may wrap 32 bits for huge inputs; do it per group on the host from raw bounds instead
+    hb.resize((size_t)n_units);
+    NND_CUDA(cudaMemcpyAsync(hb.data(), d_bound, sizeof(uint32_t) * n_units, cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    (void)W; (void)ctx; (void)ng;
+    cuts.clear(); cuts.push_back(0);
+    int64_t accb = 0;
+    for (int64_t g0 = 0; g0 < n_units; g0 += G) {
+        int64_t g1 = g0 + G < n_units ? g0 + G : n_units, s = 0;
+        for (int64_t i = g0; i < g1; ++i) s += hb[(size_t)i];
+        NND_CHECK(s <= cap, NND_ERR_OVERFLOW, "push_capacity %lld too small for %lld units (need %lld)", (long long)cap,
+                  (long long)G, (long long)s);
+        if (accb + s > cap) { cuts.push_back(g0); accb = 0; }
+        accb += s;
+    }
+    cuts.push_back(n_units);
+    return NND_OK;
+}
+
+extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets,
+                             const int64_t *leaf_offsets_host, int64_t n_leaves, int32_t max_leaf, int64_t push_capacity,
+                             void *ws, size_t ws_bytes, int64_t *n_pushes_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && leaf_points && leaf_offsets && n_leaves >= 0, NND_ERR_INVALID, "nnd_leaf_init: bad args");
+    NND_CHECK(max_leaf <= 512, NND_ERR_UNSUPPORTED, "leaf size %d > 512 not supported", max_leaf);
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, 1, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_leaf_init: workspace too small");
+    if (n_pushes_host) *n_pushes_host = 0;
+    if (n_leaves == 0) return NND_OK;
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long) * 16, st));
+    // block plan from leaf sizes (host copy of the offsets if given, else read back)
+    std::vector<int64_t> offs((size_t)n_leaves + 1);
+    if (leaf_offsets_host) memcpy(offs.data(), leaf_offsets_host, sizeof(int64_t) * (n_leaves + 1));
+    else {
+        NND_CUDA(cudaMemcpyAsync(offs.data(), leaf_offsets, sizeof(int64_t) * (n_leaves + 1), cudaMemcpyDeviceToHost, st));
+        NND_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<int64_t> cuts; cuts.push_back(0);
+    int64_t accb = 0;
+    for (int64_t i = 0; i < n_leaves; ++i) {
+        int64_t m = offs[i + 1] - offs[i], b = m * (m - 1);
+        NND_CHECK(m <= max_leaf, NND_ERR_INVALID, "leaf %lld has %lld > max_leaf points", (long long)i, (long long)m);
+        NND_CHECK(b <= push_capacity, NND_ERR_OVERFLOW, "push_capacity too small for one leaf");
+        if (accb + b > push_capacity) { cuts.push_back(i); accb = 0; }
+        accb += b;
+    }
+    cuts.push_back(n_leaves);
+    JoinParams J; memset(&J, 0, sizeof(J));
+    J.X = P->X; J.N = P->N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
+    J.mode = 1; J.leaf_points = leaf_points; J.leaf_offsets = leaf_offsets; J.C = 0;
+    J.m_max = max_leaf < 4 ? 4 : max_leaf; J.slot_stride = J.m_max;
+    unsigned long long total = 0;
+    for (size_t b = 0; b + 1 < cuts.size(); ++b) {
+        unsigned long long np = 0;
+        if (cuts[b] < cuts[b + 1]) NND_TRY(route_round(ctx, P, J, cuts[b], cuts[b + 1], W, push_capacity, &np, st));
+        total += np;
+    }
+    if (n_pushes_host) *n_pushes_host = (int64_t)total;
+    return NND_OK;
+}
+
+extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand,
+                                      const int32_t *old_cand, int64_t push_capacity, void *ws, size_t ws_bytes,
+                                      int64_t *c_host, int64_t *stats_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && new_cand && old_cand && C > 0 && C <= 128, NND_ERR_INVALID, "nnd_process_candidates: bad args");
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_process_candidates: workspace too small");
+    const int64_t N = P->N;
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long) * 16, st));
+    k_row_bound<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.bound); NND_LAUNCH(ctx);
+    std::vector<int64_t> cuts;
+    NND_TRY(plan_blocks(ctx, W.bound, N, W, push_capacity, cuts, st));
+    JoinParams J; memset(&J, 0, sizeof(J));
+    J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
+    J.mode = 0; J.newc = new_cand; J.oldc = old_cand; J.C = C; J.m_max = 2 * C < 4 ? 4 : 2 * C; J.slot_stride = 2 * C;
+    unsigned long long total = 0; int64_t blocks = 0;
+    for (size_t b = 0; b + 1 < cuts.size(); ++b) {
+        unsigned long long np = 0;
+        if (cuts[b] < cuts[b + 1]) { NND_TRY(route_round(ctx, P, J, cuts[b], cuts[b + 1], W, push_capacity, &np, st)); ++blocks; }
+        total += np;
+    }
+    unsigned long long h[5];
+    NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    if (c_host) *c_host = (int64_t)h[1];
+    if (stats_host) { stats_host[0] = (int64_t)h[2]; stats_host[1] = (int64_t)h[3]; stats_host[2] = (int64_t)total; stats_host[3] = blocks; }
+    return NND_OK;
+}
+
+// pynndescent_.py:266-320 nn_descent_internal
+extern "C" int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T,
+                           int32_t n_iters, double delta, int64_t push_capacity, void *ws, size_t ws_bytes,
+                           int32_t *iters_run_host, int64_t *c_hist_host, int64_t *stats_host, void *stream) {
+    NND_CHECK(ctx && P && rng_state_host && ws, NND_ERR_INVALID, "nnd_descent: bad args");
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, T, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_descent: workspace too small");
+    int it = 0;
+    int64_t tot[4] = {0, 0, 0, 0};
+    for (it = 0; it < n_iters; ++it) {
+        NND_TRY(nnd_build_candidates(ctx, P, C, rng_state_host, T, it > 0, W.newc, W.oldc, W.cand_base, W.cand_bytes, stream));
+        int64_t c = 0, stt[4];
+        // process_candidates re-carves the same workspace: identical layout, so the candidate
+        // arrays and rng tables carved above stay where they are
+        NND_TRY(nnd_process_candidates(ctx, P, C, W.newc, W.oldc, push_capacity, ws, ws_bytes, &c, stt, stream));
+        for (int q = 0; q < 4; ++q) tot[q] += stt[q];
+        if (c_hist_host) c_hist_host[it] = c;
+        if ((double)c <= delta * (double)P->k * (double)P->N) { ++it; break; }
+    }
+    if (iters_run_host) *iters_run_host = it;
+    if (stats_host) for (int q = 0; q < 4; ++q) stats_host[q] = tot[q];
+    return NND_OK;
+}

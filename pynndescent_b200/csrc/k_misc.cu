@@ -1,0 +1,364 @@
+// k_misc.cu -- context, error text, rng jump tables, scans, heap init / init_random / deheap_sort,
+// per-point metric auxiliaries and the nn_descent_internal driver loop.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "nnd_common.cuh"
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void nnd_set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *nnd_last_error(void) { return g_err; }
+extern "C" int nnd_version(void) { return 100; }
+extern "C" int64_t nnd_launch_count(nnd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------ context + GF(2) jump tables
+static void build_jump_tables(uint64_t *J) {
+    // column b of M_c = f_c(e_b); f_c is GF(2)-linear on the 64-bit word (utils.py:30-38: masks,
+    // shifts, xor and an arithmetic >> which only copies bits)
+    for (int c = 0; c < 3; ++c) {
+        uint64_t *M0 = J + ((size_t)c * NND_JUMP_POW) * 64;
+        for (int b = 0; b < 64; ++b) {
+            long long s[3] = {0, 0, 0};
+            s[c] = (long long)(1ULL << b);
+            tau_step(s);
+            M0[b] = (uint64_t)s[c];
+        }
+        for (int j = 1; j < NND_JUMP_POW; ++j) {
+            const uint64_t *A = J + ((size_t)c * NND_JUMP_POW + (j - 1)) * 64;
+            uint64_t *Bm = J + ((size_t)c * NND_JUMP_POW + j) * 64;
+            for (int b = 0; b < 64; ++b) {
+                uint64_t x = A[b], r = 0;
+                for (int t = 0; t < 64; ++t)
+                    if ((x >> t) & 1ULL) r ^= A[t];
+                Bm[b] = r;
+            }
+        }
+    }
+}
+
+extern "C" int nnd_create(nnd_ctx **out, int device) {
+    NND_CHECK(out, NND_ERR_INVALID, "nnd_create: null out");
+    NND_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NND_CUDA(cudaGetDeviceProperties(&prop, device));
+    NND_CHECK(prop.major >= 10, NND_ERR_UNSUPPORTED, "libnnd_b200 needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor);
+    nnd_ctx *c = new nnd_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount; c->launches = 0;
+    size_t n = (size_t)3 * NND_JUMP_POW * 64;
+    c->h_jump = (uint64_t *)malloc(n * 8);
+    build_jump_tables(c->h_jump);
+    NND_CUDA(cudaMalloc(&c->d_jump, n * 8));
+    NND_CUDA(cudaMemcpy(c->d_jump, c->h_jump, n * 8, cudaMemcpyHostToDevice));
+    *out = c;
+    return NND_OK;
+}
+extern "C" int nnd_destroy(nnd_ctx *ctx) {
+    if (!ctx) return NND_OK;
+    cudaFree(ctx->d_jump);
+    free(ctx->h_jump);
+    delete ctx;
+    return NND_OK;
+}
+extern "C" int nnd_rng_advance_host(nnd_ctx *ctx, int64_t *state_host, int64_t n) {
+    NND_CHECK(ctx && state_host && n >= 0, NND_ERR_INVALID, "nnd_rng_advance_host: bad args");
+    long long s[3] = {state_host[0], state_host[1], state_host[2]};
+    tau_jump(s, (unsigned long long)n, ctx->h_jump);
+    state_host[0] = s[0]; state_host[1] = s[1]; state_host[2] = s[2];
+    return NND_OK;
+}
+
+// ------------------------------------------------------------------ exclusive scan (u32), 3 kernels
+#define SCAN_T 1024
+#define SCAN_I 4
+#define SCAN_B (SCAN_T * SCAN_I)
+size_t nnd_scan_tmp_elems(int64_t n) { return (size_t)cdiv(n, SCAN_B) + 64; }
+
+template <int TF>
+__device__ __forceinline__ uint32_t scan_load(const uint32_t *in, int64_t i, int64_t n) {
+    if (i >= n) return 0;
+    uint32_t v = in[i];
+    return TF ? padded_seg(v) : v;
+}
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t ws[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = ws[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        ws[lane] = wi - w;
+        if (lane == 31 && total) *total = wi;
+    }
+    __syncthreads();
+    uint32_t r = ws[warp] + incl - v;
+    __syncthreads();
+    return r;
+}
+template <int TF>
+__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const uint32_t *in, int64_t n, uint32_t *bsum) {
+    __shared__ uint32_t tot;
+    int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_I;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) s += scan_load<TF>(in, base + i, n);
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_bsums(uint32_t *bsum, int64_t nb) {
+    __shared__ uint32_t tot;
+    uint32_t carry = 0;
+    for (int64_t b0 = 0; b0 < nb; b0 += SCAN_T) {
+        int64_t i = b0 + threadIdx.x;
+        uint32_t v = i < nb ? bsum[i] : 0;
+        uint32_t e = block_exclusive_scan(v, &tot);
+        if (i < nb) bsum[i] = carry + e;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bsum[nb] = carry;
+}
+template <int TF>
+__global__ void __launch_bounds__(SCAN_T) k_scan_final(const uint32_t *in, uint32_t *out, int64_t n, const uint32_t *bsum,
+                                                        int64_t nb) {
+    int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_I;
+    uint32_t v[SCAN_I], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) { v[i] = scan_load<TF>(in, base + i, n); s += v[i]; }
+    uint32_t e = block_exclusive_scan(s, nullptr) + bsum[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_I; ++i) { if (base + i < n) out[base + i] = e; e += v[i]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = bsum[nb];
+}
+template <int TF>
+static int scan_impl(nnd_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n, uint32_t *tmp, cudaStream_t st) {
+    if (n <= 0) { NND_CUDA(cudaMemsetAsync(out, 0, sizeof(uint32_t), st)); return NND_OK; }
+    int64_t nb = cdiv(n, SCAN_B);
+    k_scan_reduce<TF><<<(unsigned)nb, SCAN_T, 0, st>>>(in, n, tmp); NND_LAUNCH(ctx);
+    k_scan_bsums<<<1, SCAN_T, 0, st>>>(tmp, nb); NND_LAUNCH(ctx);
+    k_scan_final<TF><<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, n, tmp, nb); NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+int nnd_exclusive_scan_u32(nnd_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n, uint32_t *tmp, cudaStream_t st) {
+    return scan_impl<0>(ctx, in, out, n, tmp, st);
+}
+int nnd_exclusive_scan_u32_padded(nnd_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n, uint32_t *tmp, cudaStream_t st) {
+    return scan_impl<1>(ctx, in, out, n, tmp, st);
+}
+
+// ------------------------------------------------------------------ heap init, metric aux
+__global__ void k_make_heap(int32_t *idx, float *dist, uint8_t *flag, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { idx[i] = -1; dist[i] = CUDART_INF_F; flag[i] = 0; }
+}
+extern "C" int nnd_make_heap(nnd_ctx *ctx, int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int64_t N, int32_t k,
+                             void *stream) {
+    NND_CHECK(ctx && heap_idx && heap_dist && heap_flag && N > 0 && k > 0, NND_ERR_INVALID, "nnd_make_heap: bad args");
+    k_make_heap<<<(unsigned)cdiv(N * k, 256), 256, 0, (cudaStream_t)stream>>>(heap_idx, heap_dist, heap_flag, N * k);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+extern "C" int nnd_metric_aux_bytes(int32_t metric, int64_t N, size_t *bytes) {
+    NND_CHECK(bytes && N > 0, NND_ERR_INVALID, "nnd_metric_aux_bytes: bad args");
+    switch (metric) {
+    case NND_METRIC_SQEUCLIDEAN: case NND_METRIC_ALT_DOT: *bytes = 16; return NND_OK;
+    case NND_METRIC_ALT_COSINE: *bytes = (size_t)N * 4 + 16; return NND_OK;
+    case NND_METRIC_CORRELATION: *bytes = (size_t)N * 16 + 16; return NND_OK;
+    }
+    nnd_set_error("unknown metric id %d", metric);
+    return NND_ERR_UNSUPPORTED;
+}
+__global__ void k_metric_prepare(const float *X, int64_t N, int d, int ld, int metric, void *aux) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float *x = X + i * ld;
+    if (metric == NND_METRIC_ALT_COSINE) {
+        float acc = 0.0f;
+        for (int e = 0; e < d; ++e) acc = __fmaf_rn(x[e], x[e], acc);
+        ((float *)aux)[i] = acc;
+    } else if (metric == NND_METRIC_CORRELATION) {
+        double s = 0.0;
+        for (int e = 0; e < d; ++e) s = __dadd_rn(s, (double)x[e]);
+        double mu = __ddiv_rn(s, (double)d), nn = 0.0;
+        for (int e = 0; e < d; ++e) { double sx = __dadd_rn((double)x[e], -mu); nn = __fma_rn(sx, sx, nn); }
+        ((double *)aux)[2 * i] = mu; ((double *)aux)[2 * i + 1] = nn;
+    }
+}
+extern "C" int nnd_metric_prepare(nnd_ctx *ctx, const float *X, int64_t N, int32_t d, int32_t ld, int32_t metric, void *aux,
+                                  void *stream) {
+    NND_CHECK(ctx && X && N > 0 && d > 0 && ld >= d, NND_ERR_INVALID, "nnd_metric_prepare: bad args");
+    NND_CHECK(metric >= 0 && metric <= 3, NND_ERR_UNSUPPORTED, "metric id %d not supported on the GPU path", metric);
+    if (metric == NND_METRIC_SQEUCLIDEAN || metric == NND_METRIC_ALT_DOT) return NND_OK;
+    NND_CHECK(aux, NND_ERR_INVALID, "nnd_metric_prepare: aux is null");
+    k_metric_prepare<<<(unsigned)cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(X, N, d, ld, metric, aux);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+__global__ void k_pair_distances(const float *X, int d, int ld, int metric, const void *aux, const int32_t *a,
+                                 const int32_t *b, int64_t n, float *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = pair_distance_seq(X + (int64_t)a[i] * ld, X + (int64_t)b[i] * ld, d, metric, aux, a[i], b[i]);
+}
+extern "C" int nnd_pair_distances(nnd_ctx *ctx, const nnd_problem *P, const int32_t *a, const int32_t *b, int64_t n,
+                                  float *out, void *stream) {
+    NND_CHECK(ctx && P && a && b && out && n >= 0, NND_ERR_INVALID, "nnd_pair_distances: bad args");
+    if (n == 0) return NND_OK;
+    k_pair_distances<<<(unsigned)cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(P->X, P->d, P->ld, P->metric, P->aux, a, b, n, out);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+// ------------------------------------------------------------------ init_random (pynndescent_.py:188-203)
+__global__ void k_ir_need(const int32_t *idx, int k, int64_t N, uint32_t *need) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t nd = 0;
+    if (idx[i * k] < 0) {
+        int filled = 0;
+        for (int j = 0; j < k; ++j) filled += idx[i * k + j] >= 0;
+        nd = (uint32_t)(k - filled);
+    }
+    need[i] = nd;
+}
+#define IR_WARPS 4
+__global__ void __launch_bounds__(IR_WARPS * 32) k_init_random(const float *X, int64_t N, int d, int ld, int metric,
+                                                               const void *aux, int32_t *heap_idx, float *heap_dist,
+                                                               uint8_t *heap_flag, int k, const uint32_t *need,
+                                                               const uint32_t *need_off, const int32_t *draws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * IR_WARPS + warp;
+    if (row >= N) return;
+    const uint32_t nd = need[row];
+    if (nd == 0) return;
+    const size_t stride = ((size_t)k * 9 + 15) & ~size_t(15);
+    unsigned char *hp = smem_raw + (size_t)warp * stride;
+    float *pri = (float *)hp; int32_t *ind = (int32_t *)(pri + k); uint8_t *flg = (uint8_t *)(ind + k);
+    for (int j = lane; j < k; j += 32) { pri[j] = heap_dist[row * k + j]; ind[j] = heap_idx[row * k + j]; flg[j] = heap_flag[row * k + j]; }
+    __syncwarp();
+    const int32_t *dr = draws + need_off[row];
+    for (uint32_t b0 = 0; b0 < nd; b0 += 32) {
+        uint32_t t = b0 + lane;
+        int32_t cand = -1; float dd = 0.f;
+        if (t < nd) {
+            int32_t r = dr[t];
+            long long a = (r == (int32_t)0x80000000) ? (long long)r : (long long)(r < 0 ? -r : r);  // np.abs on int32 wraps
+            long long mm = a % N; if (mm < 0) mm += N;
+            cand = (int32_t)mm;
+            dd = pair_distance_seq(X + (int64_t)cand * ld, X + row * ld, d, metric, aux, cand, row);
+        }
+        uint32_t cntb = min(32u, nd - b0);
+        for (uint32_t s = 0; s < cntb; ++s) {
+            int32_t c = __shfl_sync(0xffffffffu, cand, (int)s);
+            float dv = __shfl_sync(0xffffffffu, dd, (int)s);
+            warp_heap_push(pri, ind, flg, k, dv, c, (uint8_t)1, lane);
+        }
+    }
+    for (int j = lane; j < k; j += 32) { heap_dist[row * k + j] = pri[j]; heap_idx[row * k + j] = ind[j]; heap_flag[row * k + j] = flg[j]; }
+}
+int nnd_rng_table_launch(nnd_ctx *ctx, const int64_t *state, int64_t start, int64_t count, int as_float, void *out,
+                         cudaStream_t st);
+
+extern "C" int nnd_init_random(nnd_ctx *ctx, const nnd_problem *P, int64_t *rng_state_host, void *ws, size_t ws_bytes,
+                               void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && rng_state_host && ws, NND_ERR_INVALID, "nnd_init_random: bad args");
+    const int64_t N = P->N; const int k = P->k;
+    WsAlloc A(ws, ws_bytes);
+    uint32_t *need = A.get<uint32_t>(N + 1), *off = A.get<uint32_t>(N + 2);
+    uint32_t *tmp = A.get<uint32_t>(nnd_scan_tmp_elems(N + 2));
+    NND_CHECK(A.ok, NND_ERR_WORKSPACE, "nnd_init_random: workspace too small");
+    k_ir_need<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_idx, k, N, need); NND_LAUNCH(ctx);
+    NND_TRY(nnd_exclusive_scan_u32(ctx, need, off, N, tmp, st));
+    uint32_t total = 0;
+    NND_CUDA(cudaMemcpyAsync(&total, off + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    if (total == 0) return NND_OK;
+    int32_t *draws = A.get<int32_t>(total);
+    NND_CHECK(A.ok, NND_ERR_WORKSPACE, "nnd_init_random: workspace too small for %u draws", total);
+    NND_TRY(nnd_rng_table_launch(ctx, rng_state_host, 0, total, 0, draws, st));
+    const size_t stride = ((size_t)k * 9 + 15) & ~size_t(15);
+    size_t smem = IR_WARPS * stride;
+    NND_CUDA(cudaFuncSetAttribute(k_init_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_init_random<<<(unsigned)cdiv(N, IR_WARPS), IR_WARPS * 32, smem, st>>>(P->X, N, P->d, P->ld, P->metric, P->aux, P->heap_idx,
+                                                                           P->heap_dist, P->heap_flag, k, need, off, draws);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return nnd_rng_advance_host(ctx, rng_state_host, (int64_t)total);
+}
+
+// ------------------------------------------------------------------ deheap_sort (utils.py:189-218) + correction
+__device__ __forceinline__ void siftdown_col(float *h1, int32_t *h2, int stride, int size, int elt) {
+    while (elt * 2 + 1 < size) {
+        int l = elt * 2 + 1, r = l + 1, swap = elt;
+        if (h1[swap * stride] < h1[l * stride]) swap = l;
+        if (r < size && h1[swap * stride] < h1[r * stride]) swap = r;
+        if (swap == elt) break;
+        float tf = h1[elt * stride]; h1[elt * stride] = h1[swap * stride]; h1[swap * stride] = tf;
+        int32_t ti = h2[elt * stride]; h2[elt * stride] = h2[swap * stride]; h2[swap * stride] = ti;
+        elt = swap;
+    }
+}
+__global__ void k_deheap_sort(int32_t *idx, float *dist, int64_t N, int k, int correction, float *out_dist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    float *sd = (float *)smem_raw;            // [k][T]
+    int32_t *si = (int32_t *)(sd + (size_t)k * T);
+    const int64_t row0 = (int64_t)blockIdx.x * T;
+    // coalesced load of T rows, transposed into smem
+    const int64_t nrows = min((int64_t)T, N - row0);
+    for (int64_t e = threadIdx.x; e < nrows * k; e += T) {
+        int r = (int)(e / k), j = (int)(e % k);
+        sd[(size_t)j * T + r] = dist[row0 * k + e];
+        si[(size_t)j * T + r] = idx[row0 * k + e];
+    }
+    __syncthreads();
+    if (threadIdx.x < nrows) {
+        float *h1 = sd + threadIdx.x; int32_t *h2 = si + threadIdx.x;
+        for (int j = k - 1; j > 0; --j) {
+            float tf = h1[0]; h1[0] = h1[(size_t)j * T]; h1[(size_t)j * T] = tf;
+            int32_t ti = h2[0]; h2[0] = h2[(size_t)j * T]; h2[(size_t)j * T] = ti;
+            siftdown_col(h1, h2, T, j, 0);
+        }
+    }
+    __syncthreads();
+    for (int64_t e = threadIdx.x; e < nrows * k; e += T) {
+        int r = (int)(e / k), j = (int)(e % k);
+        float v = sd[(size_t)j * T + r];
+        idx[row0 * k + e] = si[(size_t)j * T + r];
+        if (out_dist != dist) dist[row0 * k + e] = v;
+        out_dist[row0 * k + e] = (correction == NND_CORRECT_SQRT) ? __fsqrt_rn(v) : v;
+    }
+}
+extern "C" int nnd_deheap_sort(nnd_ctx *ctx, int32_t *idx, float *dist, int64_t N, int32_t k, int32_t correction,
+                               float *out_dist, void *stream) {
+    NND_CHECK(ctx && idx && dist && out_dist && N > 0 && k > 0, NND_ERR_INVALID, "nnd_deheap_sort: bad args");
+    NND_CHECK(correction == NND_CORRECT_NONE || correction == NND_CORRECT_SQRT, NND_ERR_UNSUPPORTED,
+              "deheap_sort: correction %d is applied on the host (float64 result, distances.py:704-711)", correction);
+    int T = 128;
+    while (T > 32 && (size_t)T * k * 8 > 96 * 1024) T >>= 1;
+    size_t smem = (size_t)T * k * 8;
+    NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "deheap_sort: k=%d too large", k);
+    NND_CUDA(cudaFuncSetAttribute(k_deheap_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_deheap_sort<<<(unsigned)cdiv(N, T), T, smem, (cudaStream_t)stream>>>(idx, dist, N, k, correction, out_dist);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}

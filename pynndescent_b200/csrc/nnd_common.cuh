@@ -1,0 +1,286 @@
+// nnd_common.cuh -- shared device/host helpers of libnnd_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nnd_b200.h"
+
+// ------------------------------------------------------------------ errors / context
+void nnd_set_error(const char *fmt, ...);
+
+#define NND_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            nnd_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return NND_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+#define NND_CHECK(cond, code, ...)  \
+    do {                            \
+        if (!(cond)) {              \
+            nnd_set_error(__VA_ARGS__); \
+            return (code);          \
+        }                           \
+    } while (0)
+#define NND_TRY(call)              \
+    do {                           \
+        int _r = (call);           \
+        if (_r != NND_OK) return _r; \
+    } while (0)
+
+struct nnd_ctx {
+    int device;
+    int sm_count;
+    int64_t launches;
+    uint64_t *d_jump;  // [3][NND_JUMP_POW][64] column-major GF(2) matrices M^(2^j)
+    uint64_t *h_jump;
+};
+#define NND_JUMP_POW 44
+#define NND_LAUNCH(ctx) ((ctx)->launches++)
+
+// bump allocator over the caller's workspace
+struct WsAlloc {
+    char *base;
+    size_t cap, off;
+    bool ok;
+    __host__ WsAlloc(void *p, size_t c) : base((char *)p), cap(c), off(0), ok(true) {}
+    template <typename T>
+    __host__ T *get(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        if (base == nullptr) { off += bytes; return nullptr; }  // sizing pass
+        if (off + bytes > cap) { ok = false; off += bytes; return nullptr; }
+        T *r = (T *)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------ canonical math
+// deterministic log2 in double: only + - * / fma, so CPU oracle and GPU agree bit-for-bit
+__device__ __forceinline__ double det_log2(double x) {
+    long long u = __double_as_longlong(x);
+    int e = (int)((u >> 52) & 0x7FF) - 1023;
+    u = (u & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL;
+    double m = __longlong_as_double(u);
+    if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e += 1; }
+    double t = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0));
+    double t2 = __dmul_rn(t, t);
+    double p = 1.0 / 27.0;
+    p = __fma_rn(p, t2, 1.0 / 25.0);
+    p = __fma_rn(p, t2, 1.0 / 23.0);
+    p = __fma_rn(p, t2, 1.0 / 21.0);
+    p = __fma_rn(p, t2, 1.0 / 19.0);
+    p = __fma_rn(p, t2, 1.0 / 17.0);
+    p = __fma_rn(p, t2, 1.0 / 15.0);
+    p = __fma_rn(p, t2, 1.0 / 13.0);
+    p = __fma_rn(p, t2, 1.0 / 11.0);
+    p = __fma_rn(p, t2, 1.0 / 9.0);
+    p = __fma_rn(p, t2, 1.0 / 7.0);
+    p = __fma_rn(p, t2, 1.0 / 5.0);
+    p = __fma_rn(p, t2, 1.0 / 3.0);
+    p = __fma_rn(p, t2, 1.0);
+    double ln_m = __dmul_rn(__dmul_rn(2.0, t), p);
+    return __fma_rn(ln_m, 1.4426950408889634, (double)e);
+}
+
+#define NND_FLT_MAX 3.402823466e+38f
+
+// distances.py:583-630 tail of alternative_cosine given dot and the two squared norms
+__device__ __forceinline__ float finish_alt_cosine(float dot, float nx, float ny) {
+    if (nx == 0.0f && ny == 0.0f) return 0.0f;
+    if (nx == 0.0f || ny == 0.0f) return NND_FLT_MAX;
+    if (dot <= 0.0f) return NND_FLT_MAX;
+    float r = __fdiv_rn(__fsqrt_rn(__fmul_rn(nx, ny)), dot);
+    return (float)det_log2((double)r);
+}
+// distances.py:665-701 tail of alternative_dot
+__device__ __forceinline__ float finish_alt_dot(float dot) {
+    if (dot <= 0.0f) return NND_FLT_MAX;
+    return (float)(-det_log2((double)dot));
+}
+// distances.py:1283-1320 tail of correlation given the centred dot and squared norms (f64)
+__device__ __forceinline__ float finish_correlation(double dp, double nx, double ny) {
+    if (nx == 0.0 && ny == 0.0) return 0.0f;
+    if (dp == 0.0) return 1.0f;
+    return (float)__dadd_rn(1.0, -__ddiv_rn(dp, __dsqrt_rn(__dmul_rn(nx, ny))));
+}
+
+// one whole pair distance by ONE thread straight from global memory (canonical sequential
+// chain).  Used by the low-volume paths (init_random, tests); the join kernel has its own
+// shared-memory tiled loop with the same per-pair operation order.
+__device__ __forceinline__ float pair_distance_seq(const float *__restrict__ x, const float *__restrict__ y, int d,
+                                                   int metric, const void *aux, int64_t ix, int64_t iy) {
+    if (metric == NND_METRIC_SQEUCLIDEAN) {
+        float acc = 0.0f;
+        for (int e = 0; e < d; ++e) { float df = __fsub_rn(x[e], y[e]); acc = __fmaf_rn(df, df, acc); }
+        return acc;
+    } else if (metric == NND_METRIC_ALT_COSINE || metric == NND_METRIC_ALT_DOT) {
+        float acc = 0.0f;
+        for (int e = 0; e < d; ++e) acc = __fmaf_rn(x[e], y[e], acc);
+        if (metric == NND_METRIC_ALT_DOT) return finish_alt_dot(acc);
+        const float *n2 = (const float *)aux;
+        return finish_alt_cosine(acc, n2[ix], n2[iy]);
+    } else {
+        const double *mu = (const double *)aux;
+        double mx = mu[2 * ix], my = mu[2 * iy], dp = 0.0;
+        for (int e = 0; e < d; ++e) {
+            double sx = __dadd_rn((double)x[e], -mx), sy = __dadd_rn((double)y[e], -my);
+            dp = __fma_rn(sx, sy, dp);
+        }
+        return finish_correlation(dp, mu[2 * ix + 1], mu[2 * iy + 1]);
+    }
+}
+
+// ------------------------------------------------------------------ Tausworthe rng
+// utils.py:17-40; int64 state words, arithmetic >>, not confined to 32 bits
+__host__ __device__ __forceinline__ int32_t tau_step(long long *s) {
+    s[0] = (long long)((((unsigned long long)(s[0] & 4294967294LL) << 12) & 0xFFFFFFFFULL)) ^
+           ((long long)((((unsigned long long)s[0] << 13) & 0xFFFFFFFFULL) ^ (unsigned long long)s[0]) >> 19);
+    s[1] = (long long)((((unsigned long long)(s[1] & 4294967288LL) << 4) & 0xFFFFFFFFULL)) ^
+           ((long long)((((unsigned long long)s[1] << 2) & 0xFFFFFFFFULL) ^ (unsigned long long)s[1]) >> 25);
+    s[2] = (long long)((((unsigned long long)(s[2] & 4294967280LL) << 17) & 0xFFFFFFFFULL)) ^
+           ((long long)((((unsigned long long)s[2] << 3) & 0xFFFFFFFFULL) ^ (unsigned long long)s[2]) >> 11);
+    return (int32_t)(uint32_t)((unsigned long long)(s[0] ^ s[1] ^ s[2]) & 0xFFFFFFFFULL);
+}
+// utils.py:43-57 tau_rand
+__host__ __device__ __forceinline__ float tau_to_float(int32_t r) {
+    double v = (double)r / 2147483647.0;
+    return (float)(v < 0 ? -v : v);
+}
+// x <- M^(2^j) x for every set bit j of n ; jump = [3][NND_JUMP_POW][64]
+__host__ __device__ inline void tau_jump(long long *s, unsigned long long n, const uint64_t *jump) {
+    for (int j = 0; n != 0 && j < NND_JUMP_POW; ++j, n >>= 1) {
+        if (!(n & 1)) continue;
+        for (int c = 0; c < 3; ++c) {
+            const uint64_t *M = jump + ((size_t)c * NND_JUMP_POW + j) * 64;
+            unsigned long long x = (unsigned long long)s[c], r = 0;
+            for (int b = 0; b < 64; ++b)
+                if ((x >> b) & 1ULL) r ^= M[b];
+            s[c] = (long long)r;
+        }
+    }
+}
+
+// 64-bit mixer used for the level-forest node randomness (oracle: mix64/node_key)
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// ------------------------------------------------------------------ heap push (smem rows)
+// utils.py:471-533 checked_flagged_heap_push executed by a whole warp on a row held in
+// shared memory: duplicate test is lane-parallel, the sift-down is done by lane 0.
+// Returns 1 if the push modified the row (uniform across the warp).
+__device__ __forceinline__ int warp_heap_push(float *pri, int32_t *ind, uint8_t *flg, int size, float p, int32_t n,
+                                              uint8_t f, int lane) {
+    if (p >= pri[0]) return 0;
+    bool dup = false;
+    for (int i = lane; i < size; i += 32) dup |= (ind[i] == n);
+    if (__any_sync(0xffffffffu, dup)) return 0;
+    if (lane == 0) {
+        int i = 0, i_swap;
+        for (;;) {
+            int ic1 = 2 * i + 1, ic2 = ic1 + 1;
+            if (ic1 >= size) break;
+            else if (ic2 >= size) { if (pri[ic1] > p) i_swap = ic1; else break; }
+            else if (pri[ic1] >= pri[ic2]) { if (p < pri[ic1]) i_swap = ic1; else break; }
+            else { if (p < pri[ic2]) i_swap = ic2; else break; }
+            pri[i] = pri[i_swap]; ind[i] = ind[i_swap];
+            if (flg) flg[i] = flg[i_swap];
+            i = i_swap;
+        }
+        pri[i] = p; ind[i] = n;
+        if (flg) flg[i] = f;
+    }
+    __syncwarp();
+    return 1;
+}
+
+// ------------------------------------------------------------------ warp bitonic sort (u64)
+// n must be a power of two; works on shared or global memory; ascending.
+__device__ __forceinline__ void warp_bitonic_sort_u64(unsigned long long *a, int n, int lane) {
+    for (int k2 = 2; k2 <= n; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                int l = i ^ j;
+                if (l > i) {
+                    unsigned long long x = a[i], y = a[l];
+                    bool up = ((i & k2) == 0);
+                    if ((x > y) == up) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+// same, sorting 16-byte records by their first 8 bytes (key), payload carried along
+struct __align__(16) Rec16 { unsigned long long key; int32_t oth; float d; };
+__device__ __forceinline__ void warp_bitonic_sort_rec(Rec16 *a, int n, int lane) {
+    for (int k2 = 2; k2 <= n; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                int l = i ^ j;
+                if (l > i) {
+                    Rec16 x = a[i], y = a[l];
+                    bool up = ((i & k2) == 0);
+                    if ((x.key > y.key) == up) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+__host__ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t v) {
+    if (v <= 1) return 1;
+    v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+    return v + 1;
+}
+// segments longer than this are padded to a power of two so they can be sorted in place
+#define NND_SEG_SMEM 128
+__host__ __device__ __forceinline__ uint32_t padded_seg(uint32_t n) { return n <= NND_SEG_SMEM ? n : next_pow2_u32(n); }
+
+// ------------------------------------------------------------------ PTX: mbarrier + bulk copy (TMA engine, 1-D)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// cp.async.bulk global -> shared::cta, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ host-visible kernels' launch helpers
+int nnd_exclusive_scan_u32(nnd_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n, uint32_t *block_tmp,
+                           cudaStream_t st);  // out has n+1 entries (out[n] = total)
+int nnd_exclusive_scan_u32_padded(nnd_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n, uint32_t *block_tmp,
+                                  cudaStream_t st);  // scans padded_seg(in[i])
+size_t nnd_scan_tmp_elems(int64_t n);
+int nnd_rng_table_launch(nnd_ctx *ctx, const int64_t *state, int64_t start, int64_t count, int as_float, void *out,
+                         cudaStream_t st);
+size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T);

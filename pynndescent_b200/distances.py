@@ -1,0 +1,52 @@
+"""Named-metric plugin surface (mirror of /root/reference/pynndescent/distances.py:2103-2188).
+
+Same string keys as the reference's `named_distances`; each supported key maps to the C enum of
+the kernel that computes its "fast alternative" plus the correction applied at the API edge
+(`fast_distance_alternatives`, distances.py:2170-2188).  Names the reference knows but the
+sm_100a path does not implement raise NotImplementedError -- never a CPU fallback; unknown names
+raise the reference's ValueError (pynndescent_.py:1292).
+"""
+import numpy as np
+
+NND_METRIC_SQEUCLIDEAN, NND_METRIC_ALT_COSINE, NND_METRIC_ALT_DOT, NND_METRIC_CORRELATION = 0, 1, 2, 3
+NND_CORRECT_NONE, NND_CORRECT_SQRT = 0, 1
+
+
+def correct_alternative_cosine(d):
+    """distances.py:704-711: 1 - 2^-d (float64 result like the reference's numba.vectorize)."""
+    return 1.0 - np.power(2.0, -np.asarray(d).astype(np.float64))
+
+
+# name -> (kernel metric id, device-side correction, host-side correction or None, angular trees)
+gpu_distances = {
+    "euclidean": (NND_METRIC_SQEUCLIDEAN, NND_CORRECT_SQRT, None, False),
+    "l2": (NND_METRIC_SQEUCLIDEAN, NND_CORRECT_SQRT, None, False),
+    "sqeuclidean": (NND_METRIC_SQEUCLIDEAN, NND_CORRECT_NONE, None, False),
+    "cosine": (NND_METRIC_ALT_COSINE, NND_CORRECT_NONE, correct_alternative_cosine, True),
+    "dot": (NND_METRIC_ALT_DOT, NND_CORRECT_NONE, correct_alternative_cosine, True),
+    "correlation": (NND_METRIC_CORRELATION, NND_CORRECT_NONE, None, True),
+}
+
+# every key of the reference's named_distances (distances.py:2103-2162)
+named_distances = (
+    "euclidean", "l2", "sqeuclidean", "manhattan", "taxicab", "l1", "chebyshev", "linfinity", "linfty", "linf",
+    "minkowski", "seuclidean", "standardised_euclidean", "wminkowski", "weighted_minkowski", "mahalanobis",
+    "canberra", "cosine", "dot", "inner_product", "correlation", "haversine", "braycurtis", "spearmanr", "tsss",
+    "true_angular", "hellinger", "kantorovich", "wasserstein", "wasserstein_1d", "wasserstein-1d", "kantorovich-1d",
+    "kantorovich_1d", "circular_kantorovich", "circular_wasserstein", "sinkhorn", "jensen-shannon", "jensen_shannon",
+    "symmetric-kl", "symmetric_kl", "symmetric_kullback_liebler", "hamming", "jaccard", "dice", "matching",
+    "kulsinski", "rogerstanimoto", "russellrao", "sokalsneath", "sokalmichener", "yule", "bit_hamming", "bit_jaccard",
+)
+
+
+def resolve(metric):
+    """pynndescent_.py:1271-1292 _set_distance_func resolution order, GPU edition."""
+    if callable(metric):
+        raise NotImplementedError("callable (numba) metrics cannot run on the sm_100a path; "
+                                  "use one of: " + ", ".join(sorted(gpu_distances)))
+    if metric in gpu_distances:
+        return gpu_distances[metric]
+    if metric in named_distances or (isinstance(metric, str) and metric.startswith("proxy_")):
+        raise NotImplementedError(f"metric {metric!r} is not implemented on the sm_100a path (no CPU fallback); "
+                                  "supported: " + ", ".join(sorted(gpu_distances)))
+    raise ValueError("Metric is neither callable, nor a recognised string")

@@ -1,0 +1,215 @@
+"""Stage-level driver over the C-ABI (include/nnd_b200.h).
+
+PyTorch is used ONLY as the device-array container (torch.empty / data_ptr / streams); every
+computation is a kernel of libnnd_b200.so.  The stage methods map 1:1 onto the numba functions
+of the reference so that tests can inject the reference's intermediates at any seam:
+
+    forest()             rp_trees.py:2815-2922    make_forest + rptree_leaf_array
+    leaf_init()          pynndescent_.py:116-185  init_rp_tree
+    init_random()        pynndescent_.py:188-203
+    build_candidates()   utils.py:221-320         new_build_candidates
+    process_candidates() pynndescent_.py:217-263
+    descent()            pynndescent_.py:266-320  nn_descent_internal
+    deheap_sort()        utils.py:189-218
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import Problem, check, lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, data, metric_id, n_neighbors, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pynndescent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        self._ctx = C.c_void_p()
+        check(lib.nnd_create(C.byref(self._ctx), self.device.index or 0))
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        self.N, self.d = data.shape
+        self.ld = (self.d + 3) // 4 * 4
+        self.k = int(n_neighbors)
+        self.metric_id = int(metric_id)
+        self.stream = torch.cuda.current_stream(self.device)
+        if isinstance(data, np.ndarray):
+            host = torch.from_numpy(data)
+        self.X = torch.zeros((self.N, self.ld), dtype=torch.float32, device=self.device)
+        self.X[:, : self.d].copy_(host.pin_memory() if self.N * self.d > (1 << 22) else host, non_blocking=False)
+        nb = C.c_size_t()
+        check(lib.nnd_metric_aux_bytes(self.metric_id, self.N, C.byref(nb)))
+        self.aux = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        check(lib.nnd_metric_prepare(self._ctx, _ptr(self.X), self.N, self.d, self.ld, self.metric_id, _ptr(self.aux),
+                                     self._st()))
+        self.heap_idx = torch.empty((self.N, self.k), dtype=torch.int32, device=self.device)
+        self.heap_dist = torch.empty((self.N, self.k), dtype=torch.float32, device=self.device)
+        self.heap_flag = torch.empty((self.N, self.k), dtype=torch.uint8, device=self.device)
+        self._ws = None
+        self._ws_key = None
+        self.make_heap()
+
+    # ------------------------------------------------------------------ plumbing
+    def _st(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def close(self):
+        if self._ctx:
+            lib.nnd_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def problem(self):
+        return Problem(self.X.data_ptr(), self.N, self.d, self.ld, self.metric_id, self.aux.data_ptr(), self.k,
+                       self.heap_idx.data_ptr(), self.heap_dist.data_ptr(), self.heap_flag.data_ptr())
+
+    def default_push_capacity(self):
+        return int(min(1 << 28, max(1 << 23, 256 * self.N)))
+
+    def workspace(self, C_, T, cap):
+        """One growing scratch buffer shared by all stages (layouts share a common prefix)."""
+        nb = C.c_size_t()
+        check(lib.nnd_descent_workspace_bytes(self.N, self.k, C_, T, cap, C.byref(nb)))
+        if self._ws is None or self._ws.numel() < nb.value:
+            self._ws = None
+            self._ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def launch_count(self):
+        return int(lib.nnd_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ stages
+    def make_heap(self):
+        check(lib.nnd_make_heap(self._ctx, _ptr(self.heap_idx), _ptr(self.heap_dist), _ptr(self.heap_flag), self.N,
+                                self.k, self._st()))
+
+    def set_heap(self, idx, dist, flag):
+        self.heap_idx.copy_(torch.from_numpy(np.ascontiguousarray(idx, np.int32)))
+        self.heap_dist.copy_(torch.from_numpy(np.ascontiguousarray(dist, np.float32)))
+        self.heap_flag.copy_(torch.from_numpy(np.ascontiguousarray(flag, np.uint8)))
+
+    def get_heap(self):
+        torch.cuda.synchronize(self.device)
+        return self.heap_idx.cpu().numpy(), self.heap_dist.cpu().numpy(), self.heap_flag.cpu().numpy()
+
+    def forest(self, tree_rng_states, leaf_size, angular, max_depth=200):
+        """-> (leaf_points int32[n_trees*N] device, leaf_offsets int64[n_leaves+1] device, n_leaves, max_leaf)"""
+        states = np.ascontiguousarray(tree_rng_states, np.int64).reshape(-1, 3)
+        n_trees = states.shape[0]
+        nb = C.c_size_t()
+        check(lib.nnd_forest_workspace_bytes(self.N, self.d, n_trees, C.byref(nb)))
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        leaf_points = torch.empty(n_trees * self.N, dtype=torch.int32, device=self.device)
+        leaf_offsets = torch.empty(n_trees * self.N + 1, dtype=torch.int64, device=self.device)
+        n_leaves = C.c_int64(); max_leaf = C.c_int32()
+        check(lib.nnd_forest_build(self._ctx, _ptr(self.X), self.N, self.d, self.ld, int(bool(angular)),
+                                   states.ctypes.data_as(C.POINTER(C.c_int64)), n_trees, int(leaf_size), int(max_depth),
+                                   _ptr(leaf_points), _ptr(leaf_offsets), C.byref(n_leaves), C.byref(max_leaf), _ptr(ws),
+                                   nb.value, self._st()))
+        del ws
+        return leaf_points, leaf_offsets[: n_leaves.value + 1], int(n_leaves.value), int(max_leaf.value)
+
+    def leaf_init(self, leaf_points, leaf_offsets, n_leaves, max_leaf, push_capacity=None):
+        cap = push_capacity or self.default_push_capacity()
+        ws = self.workspace(1, 1, cap)
+        npush = C.c_int64()
+        check(lib.nnd_leaf_init(self._ctx, C.byref(self.problem()), _ptr(leaf_points), _ptr(leaf_offsets), None,
+                                int(n_leaves), int(max_leaf), cap, _ptr(ws), ws.numel(), C.byref(npush), self._st()))
+        return int(npush.value)
+
+    def leaf_init_from_array(self, leaf_array, push_capacity=None):
+        """Reference-format leaves (rp_trees.py:2918 padded int32[n_leaves,max_leaf], -1 padded)."""
+        la = np.ascontiguousarray(leaf_array, np.int32)
+        if la.size == 0 or (la.shape == (1, 1) and la[0, 0] < 0):
+            return 0
+        sizes = (la >= 0).sum(1).astype(np.int64)
+        # leaves are left-packed (generate_leaf_updates stops at the first -1)
+        first_neg = np.where((la < 0).any(1), (la < 0).argmax(1), la.shape[1])
+        sizes = first_neg.astype(np.int64)
+        offs = np.zeros(la.shape[0] + 1, np.int64)
+        np.cumsum(sizes, out=offs[1:])
+        pts = np.concatenate([la[i, : sizes[i]] for i in range(la.shape[0])]) if la.shape[0] < 4096 else \
+            la[np.arange(la.shape[1])[None, :] < sizes[:, None]]
+        lp = torch.from_numpy(np.ascontiguousarray(pts, np.int32)).to(self.device)
+        lo = torch.from_numpy(offs).to(self.device)
+        return self.leaf_init(lp, lo, la.shape[0], max(int(sizes.max()), 1), push_capacity)
+
+    def init_random(self, rng_state):
+        """rng_state: np.int64[3], advanced in place like the reference does."""
+        ws = self._ws if self._ws is not None else self.workspace(1, 1, self.default_push_capacity())
+        st = (C.c_int64 * 3)(*[int(v) for v in rng_state])
+        check(lib.nnd_init_random(self._ctx, C.byref(self.problem()), st, _ptr(ws), ws.numel(), self._st()))
+        rng_state[:] = np.array(list(st), np.int64)
+
+    def build_candidates(self, max_candidates, rng_state, n_threads, tables_valid=False):
+        nb = C.c_size_t()
+        check(lib.nnd_cand_workspace_bytes(self.N, self.k, max_candidates, n_threads, C.byref(nb)))
+        key = ("cand", max_candidates, n_threads)
+        if getattr(self, "_cws_key", None) != key:
+            self._cws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            self._cws_key = key
+            tables_valid = False
+        newc = torch.empty((self.N, max_candidates), dtype=torch.int32, device=self.device)
+        oldc = torch.empty((self.N, max_candidates), dtype=torch.int32, device=self.device)
+        st = (C.c_int64 * 3)(*[int(v) for v in rng_state])
+        check(lib.nnd_build_candidates(self._ctx, C.byref(self.problem()), int(max_candidates), st, int(n_threads),
+                                       int(bool(tables_valid)), _ptr(newc), _ptr(oldc), _ptr(self._cws), nb.value,
+                                       self._st()))
+        return newc, oldc
+
+    def process_candidates(self, newc, oldc, push_capacity=None):
+        cap = push_capacity or self.default_push_capacity()
+        C_ = newc.shape[1]
+        ws = self.workspace(C_, 1, cap)
+        c = C.c_int64(); stats = (C.c_int64 * 4)()
+        check(lib.nnd_process_candidates(self._ctx, C.byref(self.problem()), C_, _ptr(newc), _ptr(oldc), cap, _ptr(ws),
+                                         ws.numel(), C.byref(c), stats, self._st()))
+        return int(c.value), [int(v) for v in stats]
+
+    def descent(self, max_candidates, rng_state, n_threads, n_iters, delta, push_capacity=None):
+        cap = push_capacity or self.default_push_capacity()
+        ws = self.workspace(max_candidates, n_threads, cap)
+        st = (C.c_int64 * 3)(*[int(v) for v in rng_state])
+        iters = C.c_int32(); chist = (C.c_int64 * max(n_iters, 1))(); stats = (C.c_int64 * 4)()
+        check(lib.nnd_descent(self._ctx, C.byref(self.problem()), int(max_candidates), st, int(n_threads), int(n_iters),
+                              float(delta), cap, _ptr(ws), ws.numel(), C.byref(iters), chist, stats, self._st()))
+        return int(iters.value), [int(chist[i]) for i in range(iters.value)], [int(v) for v in stats]
+
+    def deheap_sort(self, correction):
+        out = torch.empty_like(self.heap_dist)
+        check(lib.nnd_deheap_sort(self._ctx, _ptr(self.heap_idx), _ptr(self.heap_dist), self.N, self.k, int(correction),
+                                  _ptr(out), self._st()))
+        return self.heap_idx, out
+
+    # ------------------------------------------------------------------ small primitives
+    def rng_stream(self, state, start, count, as_float):
+        out = torch.empty(count, dtype=torch.float32 if as_float else torch.int32, device=self.device)
+        st = (C.c_int64 * 3)(*[int(v) for v in state])
+        check(lib.nnd_rng_stream(self._ctx, st, int(start), int(count), int(bool(as_float)), _ptr(out), self._st()))
+        torch.cuda.synchronize(self.device)
+        return out.cpu().numpy()
+
+    def rng_advance(self, state, n):
+        st = (C.c_int64 * 3)(*[int(v) for v in state])
+        check(lib.nnd_rng_advance_host(self._ctx, st, int(n)))
+        return np.array(list(st), np.int64)
+
+    def pair_distances(self, a, b):
+        ta = torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(self.device)
+        tb = torch.from_numpy(np.ascontiguousarray(b, np.int32)).to(self.device)
+        out = torch.empty(ta.numel(), dtype=torch.float32, device=self.device)
+        check(lib.nnd_pair_distances(self._ctx, C.byref(self.problem()), _ptr(ta), _ptr(tb), ta.numel(), _ptr(out),
+                                     self._st()))
+        torch.cuda.synchronize(self.device)
+        return out.cpu().numpy()

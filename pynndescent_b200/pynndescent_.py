@@ -1,0 +1,144 @@
+"""NNDescent -- host-side mirror of the reference's index object for the build path.
+
+Same constructor keywords, same `.neighbor_graph` contract as
+/root/reference/pynndescent/pynndescent_.py:792-1304, 2145-2158; the three numba seams
+(make_forest, nn_descent, deheap_sort + correction) are replaced by libnnd_b200.so kernels.
+
+Determinism contract: for a given (data, random_state) the result is a pure function of the
+emulated numba thread count T (`n_jobs`, default 8 -- the reference's own result depends on its
+thread count in exactly the same way, utils.py:259-263) and of nothing else: not of the GPU
+count, block sizes or kernel scheduling.
+"""
+import time
+from warnings import warn
+
+import numpy as np
+
+from . import distances as pynnd_dist
+from .engine import Engine
+
+INT32_MIN = np.iinfo(np.int32).min + 1
+INT32_MAX = np.iinfo(np.int32).max - 1
+DEFAULT_EMULATED_THREADS = 8
+
+
+def ts():
+    return time.ctime(time.time())
+
+
+class NNDescent:
+    """Approximate k-nearest-neighbour graph construction by NN-descent on one B200.
+
+    Parameters mirror pynndescent.NNDescent (pynndescent_.py:976-1007).  Extras (optional):
+    ``device`` (torch device string) and ``push_capacity`` (scratch sizing).  Keywords that select
+    code outside the accelerated hot path (sparse input, callable metrics, quantisation, ...)
+    raise NotImplementedError instead of silently running on the CPU.
+    """
+
+    def __init__(self, data, metric="euclidean", metric_kwds=None, bit_metric=False, n_neighbors=30, n_trees=None,
+                 angular_trees=False, leaf_size=None, pruning_degree_multiplier=1.5, diversify_prob=1.0,
+                 diversify_method="standard", degree_prune_aggressiveness=1.0, n_search_trees=1,
+                 search_tree_leaf_size=None, max_search_tree_depth=None, quantization=None, tree_init=True,
+                 init_graph=None, init_dist=None, random_state=None, low_memory=True, max_candidates=None,
+                 max_rptree_depth=200, n_iters=None, delta=0.001, n_jobs=None, compressed=False,
+                 parallel_batch_queries=False, verbose=False, device=None, push_capacity=None, leaf_array=None):
+        from sklearn.utils import check_random_state, check_array
+        from scipy.sparse import issparse
+
+        if issparse(data):
+            raise NotImplementedError("sparse input is outside the sm_100a hot path (SURVEY.md 2 #13)")
+        if metric_kwds:
+            raise NotImplementedError("metric_kwds are not supported by the GPU metrics")
+        if quantization is not None or bit_metric:
+            raise NotImplementedError("quantized / bit metrics are outside the sm_100a hot path")
+        if init_graph is not None or init_dist is not None:
+            raise NotImplementedError("init_graph warm start is a 'next' row (SURVEY.md 8f-4)")
+        if n_trees is None:
+            n_trees = max(3, min(12, int(round(2.0 * np.log10(data.shape[0])))))      # pynndescent_.py:1009-1010
+        if n_iters is None:
+            n_iters = max(5, int(round(np.log2(data.shape[0]))))                     # pynndescent_.py:1011-1012
+        self.n_trees = n_trees
+        self.n_neighbors = n_neighbors
+        self.metric = metric
+        self.metric_kwds = metric_kwds
+        self.leaf_size = leaf_size
+        self.max_candidates = max_candidates
+        self.max_rptree_depth = max_rptree_depth
+        self.n_iters = n_iters
+        self.delta = delta
+        self.n_jobs = n_jobs
+        self.low_memory = low_memory
+        self.compressed = compressed
+        self.verbose = verbose
+        self.random_state = random_state
+        self.dim = data.shape[1]
+
+        metric_id, dev_correction, host_correction, angular = pynnd_dist.resolve(metric)    # :1271-1292
+        self._distance_correction = host_correction
+        self._angular_trees = angular
+        data = check_array(data, dtype=np.float32, order="C")                                # :1054
+        self.tree_init = bool(tree_init) and n_trees != 0                                    # :1059-1062
+        current_random_state = check_random_state(self.random_state)
+        if metric == "dot":                                                                  # :1101-1103
+            from sklearn.preprocessing import normalize
+            data = normalize(data, norm="l2", copy=True)
+        self._raw_data = data
+        self.rng_state = current_random_state.randint(INT32_MIN, INT32_MAX, 3).astype(np.int64)          # :1105-1107
+        self.search_rng_state = current_random_state.randint(INT32_MIN, INT32_MAX, 3).astype(np.int64)  # :1108-1110
+        T = DEFAULT_EMULATED_THREADS if (n_jobs is None or n_jobs == -1) else int(n_jobs)
+        if T < 1:
+            raise ValueError("n_jobs must be a positive thread count (or None / -1)")
+        self.emulated_threads = T
+        eff_C = min(60, n_neighbors) if max_candidates is None else max_candidates           # :1135-1138
+
+        eng = Engine(data, metric_id, n_neighbors, device=device)
+        self._engine = eng
+        cap = push_capacity or eng.default_push_capacity()
+        self.timings = {}
+        t0 = time.perf_counter()
+        if leaf_array is not None:                      # test seam: reference-format leaves injected
+            eng.leaf_init_from_array(leaf_array, cap)
+        elif self.tree_init:
+            if verbose:
+                print(ts(), "Building RP forest with", str(n_trees), "trees")
+            if leaf_size is None:
+                leaf_size = max(60, min(256, 5 * int(n_neighbors)))                          # rp_trees.py:2845-2846
+            tree_states = current_random_state.randint(INT32_MIN, INT32_MAX, size=(n_trees, 3)).astype(np.int64)
+            self._tree_rng_states = tree_states                                              # rp_trees.py:2850-2852
+            lp, lo, n_leaves, max_leaf = eng.forest(tree_states, leaf_size, angular, max_rptree_depth)
+            self._leaf_csr = (lp, lo, n_leaves, max_leaf)
+            eng.stream.synchronize(); self.timings["forest"] = time.perf_counter() - t0; t0 = time.perf_counter()
+            eng.leaf_init(lp, lo, n_leaves, max_leaf, cap)
+        eng.stream.synchronize(); self.timings["leaf_init"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        eng.init_random(self.rng_state)                                                     # pynndescent_.py:345
+        if verbose:
+            print(ts(), "NN descent for", str(n_iters), "iterations")
+        iters, c_hist, stats = eng.descent(eff_C, self.rng_state, T, n_iters, delta, cap)    # :354
+        if verbose:
+            for it in range(iters):
+                print("\t", it + 1, " / ", n_iters)
+            if iters < n_iters or (c_hist and c_hist[-1] <= delta * n_neighbors * data.shape[0]):
+                print("\tStopping threshold met -- exiting after", iters, "iterations")
+        self.n_iters_run, self.c_hist, self.join_stats = iters, c_hist, stats
+        eng.stream.synchronize(); self.timings["descent"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        idx_t, dist_t = eng.deheap_sort(dev_correction)                                     # :366 + :2150-2154
+        self._graph_idx_t, self._graph_dist_t = idx_t, dist_t
+        self._neighbor_graph = (idx_t.cpu().numpy(), dist_t.cpu().numpy())
+        self.timings["sort_d2h"] = time.perf_counter() - t0
+        if np.any(self._neighbor_graph[0] < 0):                                             # :1262-1267
+            warn("Failed to correctly find n_neighbors for some samples."
+                 " Results may be less than ideal. Try re-running with"
+                 " different parameters.")
+
+    @property
+    def neighbor_graph(self):
+        """pynndescent_.py:2145-2158: (indices copy, corrected distances)."""
+        if self._distance_correction is not None:
+            return self._neighbor_graph[0].copy(), self._distance_correction(self._neighbor_graph[1])
+        return self._neighbor_graph[0].copy(), self._neighbor_graph[1].copy()
+
+    def prepare(self):
+        raise NotImplementedError("search-graph preparation + query walk are the next rows (SURVEY.md 8a-11, 8f-1)")
+
+    def query(self, query_data, k=10, epsilon=0.1):
+        raise NotImplementedError("search-graph preparation + query walk are the next rows (SURVEY.md 8a-11, 8f-1)")

@@ -1,0 +1,57 @@
+"""CPU-only: the C-ABI library loads and exports exactly what include/nnd_b200.h declares."""
+import os
+import re
+import subprocess
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "nnd_b200.h")).read()
+    return sorted(set(re.findall(r"^NND_API [\w \*]+?\b(nnd_\w+)\(", src, flags=re.M)))
+
+
+def test_header_declares_symbols():
+    syms = _header_symbols()
+    assert len(syms) >= 20 and "nnd_descent" in syms and "nnd_forest_build" in syms
+
+
+def test_library_exports_every_declared_symbol():
+    so = os.path.join(ROOT, "pynndescent_b200", "libnnd_b200.so")
+    assert os.path.exists(so), "libnnd_b200.so missing: run __graft_entry__.build()"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+    exported = set(re.findall(r" T (nnd_\w+)", out))
+    assert set(_header_symbols()) <= exported, sorted(set(_header_symbols()) - exported)
+    # nothing but the declared C-ABI leaks out
+    assert exported <= set(_header_symbols()), sorted(exported - set(_header_symbols()))
+
+
+def test_ctypes_binding_covers_header():
+    from pynndescent_b200 import _ffi
+    assert sorted(_ffi.SIGNATURES) == _header_symbols()
+    assert _ffi.lib.nnd_version() >= 100
+
+
+def test_metric_registry_matches_reference_names():
+    from pynndescent_b200 import distances as dist
+    import pytest
+    assert dist.resolve("euclidean")[0] == dist.NND_METRIC_SQEUCLIDEAN
+    assert dist.resolve("cosine")[3] is True
+    with pytest.raises(ValueError, match="neither callable, nor a recognised string"):
+        dist.resolve("no-such-metric")
+    with pytest.raises(NotImplementedError):
+        dist.resolve("manhattan")
+    with pytest.raises(NotImplementedError):
+        dist.resolve(lambda a, b: 0.0)
+
+
+def test_sm100a_sass_has_bulk_copy():
+    """The join kernel stages rows with the TMA engine's bulk copy: SASS must show UBLKCP."""
+    so = os.path.join(ROOT, "pynndescent_b200", "libnnd_b200.so")
+    try:
+        sass = subprocess.check_output(["cuobjdump", "-sass", so], text=True, stderr=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    assert "UBLKCP" in sass
