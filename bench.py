@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- kNN-graph build edges/sec (BASELINE.json metric) on synthetic float32 data.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU port of the reference path
+
+A "step" is one whole build (RP forest -> leaf init -> init_random -> NN-descent -> deheap_sort)
+of the workload named in config.workload with the data matrix already resident in HBM
+(`value`), and the same build through the public NNDescent(X_host) API with the H2D copy of X
+and the D2H copy of the graph inside the timed region (`e2e`).  Device time is measured with
+CUDA events on the launching stream; N>1 = one process per GPU, max over ranks.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on that fits one GPU
+    "cfg2": dict(n=1_000_000, d=128, k=15, metric="euclidean", name="1Mx128 float32 euclidean k=15 (SIFT-shape latent-16 synthetic)"),
+    "cfg3": dict(n=2_000_000, d=256, k=15, metric="cosine", name="2Mx256 float32 cosine k=15 (NYTimes-shape latent-16 synthetic)"),
+    "cfg1": dict(n=1000, d=16, k=10, metric="euclidean", name="1kx16 float32 euclidean k=10 (plumbing)"),
+    "small": dict(n=100_000, d=128, k=15, metric="euclidean", name="100kx128 float32 euclidean k=15 (latent-16 synthetic)"),
+}
+
+
+def latent(n, d, seed=0, latent_dim=16):
+    """SURVEY.md 8d 'latent-16' generator (iid Gaussian data gives the reference recall 0.12)."""
+    rs = np.random.RandomState(seed)
+    Z = rs.standard_normal((n, latent_dim)).astype(np.float32)
+    A = rs.standard_normal((latent_dim, d)).astype(np.float32) / np.sqrt(latent_dim)
+    X = Z @ A
+    X += 0.05 * rs.standard_normal((n, d)).astype(np.float32)
+    return X.astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) >= 6:
+                self.rows.append(p)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recall_at_k(X, graph_idx, k, metric, n_sample=1000, seed=0):
+    """recall@k against exact kNN of a row sample (brute force in float64 with torch on the GPU;
+    measurement utility, not part of the timed path)."""
+    import torch
+    rows = np.random.RandomState(seed).choice(X.shape[0], min(n_sample, X.shape[0]), replace=False)
+    Xd = torch.from_numpy(X).cuda().double()
+    if metric == "cosine":
+        Xd = Xd / Xd.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    hits = 0
+    for c0 in range(0, len(rows), 250):
+        r = torch.from_numpy(rows[c0:c0 + 250]).cuda()
+        q = Xd[r]
+        dm = (1.0 - q @ Xd.T) if metric == "cosine" else ((q * q).sum(1)[:, None] + (Xd * Xd).sum(1)[None, :] - 2.0 * q @ Xd.T)
+        true = dm.topk(k, dim=1, largest=False).indices.cpu().numpy()
+        for i, rr in enumerate(rows[c0:c0 + 250]):
+            hits += len(np.intersect1d(true[i], graph_idx[rr]))
+    del Xd
+    return hits / (len(rows) * k)
+
+
+def run_cpu_port(X, metric, k, seed, threads):
+    """One build with the oracle port on the host cores (the only place bench.py executes oracle/)."""
+    from oracle import nnd_oracle as orc
+    orc.lib().orc_set_num_threads(threads)
+    t0 = time.perf_counter()
+    o = orc.OracleNNDescent(X, metric, n_neighbors=k, random_state=seed, n_threads=threads, forest="dfs")
+    dt = time.perf_counter() - t0
+    return dt, o
+
+
+def reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_s = min(wl["n"], args.ref_sample)
+    X = latent(n_s, wl["d"], 0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, o = run_cpu_port(X, wl["metric"], wl["k"], 42, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = n_s * wl["k"] / t
+    sample = f"first {n_s} points of the workload generator, full build per step (oracle port of the numba path, OpenMP, T={cores})"
+    out = {"impl": "reference", "metric": "kNN-graph build edges/sec", "value": val, "unit": "edges/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic latent-16",
+           "config": {"workload": wl["name"], "n": wl["n"], "d": wl["d"], "k": wl["k"], "metric": wl["metric"]},
+           "cpu_baseline": {"value": val, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--ref-sample", type=int, default=100_000)
+    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return reference_arm(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from pynndescent_b200 import NNDescent
+    from pynndescent_b200 import distances as pdist
+    from pynndescent_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    n, d, k, metric = wl["n"], wl["d"], wl["k"], wl["metric"]
+    # independent partition per rank (weak scaling): rank r builds the graph of its own n points
+    X = latent(n, d, seed=rank)
+    metric_id, dev_corr, host_corr, angular = pdist.resolve(metric)
+    n_trees = max(3, min(12, int(round(2.0 * np.log10(n))))); n_iters = max(5, int(round(np.log2(n))))
+    leaf_size = max(60, min(256, 5 * k)); C_ = min(60, k); T = 8
+
+    eng = Engine(X, metric_id, k)
+    stream = eng.stream
+
+    def seeds():
+        rs = np.random.RandomState(42)
+        rng = rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, 3).astype(np.int64); rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, 3)
+        trees = rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, size=(n_trees, 3)).astype(np.int64)
+        return rng, trees
+
+    def one_build(timings=None):
+        rng, trees = seeds()
+        return eng.build(rng, trees, leaf_size, angular, C_, T, n_iters, 0.001, dev_corr, timings=timings)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_build()
+    eng.profile(reset=True)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {}
+    ev0.record(stream)
+    for _ in range(args.steps):
+        idx_t, dist_t, iters, c_hist, stats = one_build(stage)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    prof = eng.profile(reset=True)
+    launches = eng.launch_count() - launches0
+    gi = idx_t.cpu().numpy()
+
+    # ---- e2e: the public API with host buffers (H2D of X and D2H of the graph inside the timed region)
+    del eng, idx_t, dist_t
+    torch.cuda.empty_cache()
+    Xp = torch.from_numpy(X).pin_memory().numpy()
+    NNDescent(Xp, metric, n_neighbors=k, random_state=42)  # warm allocator
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        idx = NNDescent(Xp, metric, n_neighbors=k, random_state=42)
+        g = idx.neighbor_graph
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms / args.steps
+    value = world * n * k / (ms_step * 1e-3)
+    e2e = world * n * k / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_join, local-join launches), DESIGN.md section 7:
+    # algorithmic bytes = 4*ld*G (gathered rows) + 4*G (thresholds) + 8*N*C (candidate lists, per iteration)
+    #                     + 12*U (half-updates written), time = CUDA-event duration of those launches
+    peak, peak_src = measured_peaks()
+    ld = (d + 3) // 4 * 4
+    jj = prof["join"]
+    iters_total = iters * args.steps
+    bytes_alg = 4.0 * ld * jj["rows"] + 4.0 * jj["rows"] + 8.0 * n * C_ * iters_total + 12.0 * jj["pushes"]
+    ach = bytes_alg / (jj["ms"] * 1e-3) / 1e9 if jj["ms"] > 0 else 0.0
+    lf = prof["leaf"]
+    leaf_bytes = 4.0 * ld * lf["rows"] + 4.0 * lf["rows"] + 12.0 * lf["pushes"]
+    leaf_ach = leaf_bytes / (lf["ms"] * 1e-3) / 1e9 if lf["ms"] > 0 else 0.0
+    rec = recall_at_k(X, gi, k, metric)
+
+    out = {
+        "metric": "kNN-graph build edges/sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic latent-16 (SURVEY 8d), seed 0, index random_state 42",
+        "config": {"workload": wl["name"], "n": n, "d": d, "k": k, "metric": metric, "n_trees": n_trees,
+                   "leaf_size": leaf_size, "max_candidates": C_, "emulated_numba_threads": T, "iterations": iters,
+                   "multi_gpu": "independent partition per rank" if world > 1 else "single GPU",
+                   "l2": "inputs (X = %.0f MB) exceed the 126 MB L2; no explicit flush" % (n * ld * 4 / 1e6)},
+        "recall_at_k": rec,
+        "e2e": {"value": e2e, "unit": "edges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(n * d * 4),
+                "d2h_bytes_per_step": int(n * k * 8)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_join (local join, utils.py:536-658)", "bound": "hbm", "achieved": ach, "peak": peak,
+                     "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms_per_step": jj["ms"] / args.steps, "launches_per_step": jj["launches"] / args.steps,
+                     "rows_gathered_per_step": jj["rows"] / args.steps, "pairs_per_step": jj["pairs"] / args.steps,
+                     "leaf_join": {"achieved": leaf_ach, "frac": leaf_ach / peak, "kernel_ms_per_step": lf["ms"] / args.steps,
+                                   "pairs_per_step": lf["pairs"] / args.steps}},
+        "stage_ms_per_step": {kk: vv * 1e3 / args.steps for kk, vv in stage.items()},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "k_join_traffic.json")
+    if os.path.exists(traffic_file):
+        out["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_s = min(n, args.cpu_sample)
+        dt, o = run_cpu_port(X[:n_s].copy(), metric, k, 42, cores)
+        out["cpu_baseline"] = {"value": n_s * k / dt, "unit": "edges/s", "cores": cores, "kind": "port",
+                               "sample": f"one full build of the first {n_s} points of the same matrix by the oracle "
+                                         f"port of the numba path (OpenMP, T={cores}), {dt:.1f} s"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,10 @@ NND_API int nnd_rng_advance_host(nnd_ctx *ctx, int64_t *state_host, int64_t n);
 /* pair distances in the canonical order: out[i] = dist(X[a[i]], X[b[i]]) */
 NND_API int nnd_pair_distances(nnd_ctx *ctx, const nnd_problem *P, const int32_t *a, const int32_t *b, int64_t n, float *out,
                        void *stream);
+/* join-kernel profile, measured with CUDA events on the launching stream around every k_join
+ * launch: out10 = {ms, launches, rows gathered, pairs evaluated, half-updates} for the local join
+ * (utils.py:536-658) followed by the same five for the leaf join (pynndescent_.py:73-113).       */
+NND_API int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 NND_API int64_t nnd_launch_count(nnd_ctx *ctx);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "nnd_rng_stream": (C.c_int, [_vp, _pi64, _i64, _i64, _i32, _vp, _vp]),
     "nnd_rng_advance_host": (C.c_int, [_vp, _pi64, _i64]),
     "nnd_pair_distances": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _vp, _vp]),
+    "nnd_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), _i32]),
     "nnd_launch_count": (C.c_int64, [_vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

@@ -437,13 +437,24 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     J.thr = W.thr; J.unit_begin = u0; J.unit_end = u1;
     J.out_tgt = W.l_tgt; J.out_oth = W.l_oth; J.out_d = W.l_d; J.out_pos = W.l_pos; J.out_seq = W.l_seq;
     J.tgt_count = W.cnt; J.cursor = W.dev_scalars; J.capacity = (unsigned long long)cap;
-    J.stats = W.dev_scalars + 2; J.overflow = (int *)(W.dev_scalars + 4);
+    J.overflow = (int *)(W.dev_scalars + 4);
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars + 5, 0, sizeof(unsigned long long) * 2, st));
+    J.stats = W.dev_scalars + 5;
+    NND_CUDA(cudaEventRecord(ctx->ev0, st));
     NND_TRY(launch_join(ctx, J, u1 - u0, st));
-    unsigned long long h[5];
+    NND_CUDA(cudaEventRecord(ctx->ev1, st));
+    unsigned long long h[7];
     NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
     NND_CUDA(cudaStreamSynchronize(st));
     NND_CHECK(((int *)&h[4])[0] == 0, NND_ERR_OVERFLOW, "push list overflow (capacity %lld)", (long long)cap);
     *n_pushed = h[0];
+    {
+        float ms = 0.f;
+        NND_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        double *pf = ctx->prof[J.mode ? 1 : 0];
+        pf[0] += ms; pf[1] += 1; pf[2] += (double)h[5]; pf[3] += (double)h[6]; pf[4] += (double)h[0];
+        ctx->last_round_rows = h[5]; ctx->last_round_pairs = h[6];
+    }
     if (h[0] == 0) return NND_OK;
     NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, N, W.scan_tmp, st));  // offsets of power-of-two padded segments
     k_scatter<<<(unsigned)cdiv((int64_t)h[0], 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_pos, W.l_seq, h[0], W.off, W.rec);
@@ -544,17 +555,20 @@ extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_
     JoinParams J; memset(&J, 0, sizeof(J));
     J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
     J.mode = 0; J.newc = new_cand; J.oldc = old_cand; J.C = C; J.m_max = 2 * C < 4 ? 4 : 2 * C; J.slot_stride = 2 * C;
-    unsigned long long total = 0; int64_t blocks = 0;
+    unsigned long long total = 0, rows_g = 0, pairs_g = 0; int64_t blocks = 0;
     for (size_t b = 0; b + 1 < cuts.size(); ++b) {
         unsigned long long np = 0;
-        if (cuts[b] < cuts[b + 1]) { NND_TRY(route_round(ctx, P, J, cuts[b], cuts[b + 1], W, push_capacity, &np, st)); ++blocks; }
+        if (cuts[b] < cuts[b + 1]) {
+            NND_TRY(route_round(ctx, P, J, cuts[b], cuts[b + 1], W, push_capacity, &np, st)); ++blocks;
+            rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs;
+        }
         total += np;
     }
     unsigned long long h[5];
     NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
     NND_CUDA(cudaStreamSynchronize(st));
     if (c_host) *c_host = (int64_t)h[1];
-    if (stats_host) { stats_host[0] = (int64_t)h[2]; stats_host[1] = (int64_t)h[3]; stats_host[2] = (int64_t)total; stats_host[3] = blocks; }
+    if (stats_host) { stats_host[0] = (int64_t)rows_g; stats_host[1] = (int64_t)pairs_g; stats_host[2] = (int64_t)total; stats_host[3] = blocks; }
     return NND_OK;
 }
 

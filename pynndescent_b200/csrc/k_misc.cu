@@ -50,6 +50,9 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
     NND_CHECK(prop.major >= 10, NND_ERR_UNSUPPORTED, "libnnd_b200 needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor);
     nnd_ctx *c = new nnd_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->launches = 0;
+    memset(c->prof, 0, sizeof(c->prof));
+    NND_CUDA(cudaEventCreate(&c->ev0));
+    NND_CUDA(cudaEventCreate(&c->ev1));
     size_t n = (size_t)3 * NND_JUMP_POW * 64;
     c->h_jump = (uint64_t *)malloc(n * 8);
     build_jump_tables(c->h_jump);
@@ -61,8 +64,16 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
 extern "C" int nnd_destroy(nnd_ctx *ctx) {
     if (!ctx) return NND_OK;
     cudaFree(ctx->d_jump);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
     free(ctx->h_jump);
     delete ctx;
+    return NND_OK;
+}
+extern "C" int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset) {
+    NND_CHECK(ctx && out10, NND_ERR_INVALID, "nnd_profile_read: bad args");
+    memcpy(out10, ctx->prof, sizeof(ctx->prof));
+    if (reset) memset(ctx->prof, 0, sizeof(ctx->prof));
     return NND_OK;
 }
 extern "C" int nnd_rng_advance_host(nnd_ctx *ctx, int64_t *state_host, int64_t n) {

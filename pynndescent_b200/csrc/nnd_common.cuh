@@ -38,6 +38,10 @@ struct nnd_ctx {
     int64_t launches;
     uint64_t *d_jump;  // [3][NND_JUMP_POW][64] column-major GF(2) matrices M^(2^j)
     uint64_t *h_jump;
+    // profile accumulators per join mode (0 local join, 1 leaf): device ms, launches, rows, pairs, pushes
+    double prof[2][5];
+    cudaEvent_t ev0, ev1;
+    unsigned long long last_round_rows, last_round_pairs;
 };
 #define NND_JUMP_POW 44
 #define NND_LAUNCH(ctx) ((ctx)->launches++)

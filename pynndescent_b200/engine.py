@@ -39,10 +39,13 @@ class Engine:
         self.k = int(n_neighbors)
         self.metric_id = int(metric_id)
         self.stream = torch.cuda.current_stream(self.device)
-        if isinstance(data, np.ndarray):
-            host = torch.from_numpy(data)
-        self.X = torch.zeros((self.N, self.ld), dtype=torch.float32, device=self.device)
-        self.X[:, : self.d].copy_(host.pin_memory() if self.N * self.d > (1 << 22) else host, non_blocking=False)
+        host = torch.from_numpy(data)
+        if self.ld == self.d:
+            self.X = torch.empty((self.N, self.ld), dtype=torch.float32, device=self.device)
+            self.X.copy_(host, non_blocking=host.is_pinned())
+        else:  # pad rows to a multiple of 4 floats (16-byte vector loads / bulk copies); pad columns are zero
+            self.X = torch.zeros((self.N, self.ld), dtype=torch.float32, device=self.device)
+            self.X[:, : self.d].copy_(host, non_blocking=host.is_pinned())
         nb = C.c_size_t()
         check(lib.nnd_metric_aux_bytes(self.metric_id, self.N, C.byref(nb)))
         self.aux = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
@@ -191,6 +194,44 @@ class Engine:
         check(lib.nnd_deheap_sort(self._ctx, _ptr(self.heap_idx), _ptr(self.heap_dist), self.N, self.k, int(correction),
                                   _ptr(out), self._st()))
         return self.heap_idx, out
+
+    def build(self, rng_state, tree_rng_states, leaf_size, angular, max_candidates, n_threads, n_iters, delta,
+              correction, max_depth=200, push_capacity=None, leaf_array=None, timings=None):
+        """The whole seam-1 + seam-2 pipeline on device-resident data (pynndescent_.py:1118-1260):
+        forest -> leaf init -> init_random -> nn_descent_internal -> deheap_sort(+correction).
+        Returns (idx tensor, dist tensor, iters, c_hist, stats).  rng_state is advanced in place."""
+        import time
+        cap = push_capacity or self.default_push_capacity()
+        self.workspace(max_candidates, n_threads, cap)
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            if timings is not None:
+                self.stream.synchronize()
+                t1 = time.perf_counter(); timings[name] = timings.get(name, 0.0) + (t1 - t0); t0 = t1
+        self.make_heap()
+        if leaf_array is not None:
+            self.leaf_init_from_array(leaf_array, cap)
+        elif tree_rng_states is not None and len(tree_rng_states) > 0:
+            lp, lo, n_leaves, max_leaf = self.forest(tree_rng_states, leaf_size, angular, max_depth)
+            lap("forest")
+            self.leaf_init(lp, lo, n_leaves, max_leaf, cap)
+            del lp, lo
+        lap("leaf_init")
+        self.init_random(rng_state)
+        lap("init_random")
+        iters, c_hist, stats = self.descent(max_candidates, rng_state, n_threads, n_iters, delta, cap)
+        lap("descent")
+        idx_t, dist_t = self.deheap_sort(correction)
+        lap("deheap_sort")
+        return idx_t, dist_t, iters, c_hist, stats
+
+    def profile(self, reset=True):
+        out = (C.c_double * 10)()
+        check(lib.nnd_profile_read(self._ctx, out, int(bool(reset))))
+        keys = ("ms", "launches", "rows", "pairs", "pushes")
+        return {"join": dict(zip(keys, list(out)[:5])), "leaf": dict(zip(keys, list(out)[5:]))}
 
     # ------------------------------------------------------------------ small primitives
     def rng_stream(self, state, start, count, as_float):

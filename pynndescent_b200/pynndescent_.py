@@ -91,40 +91,32 @@ class NNDescent:
         self.emulated_threads = T
         eff_C = min(60, n_neighbors) if max_candidates is None else max_candidates           # :1135-1138
 
+        t0 = time.perf_counter()
         eng = Engine(data, metric_id, n_neighbors, device=device)
         self._engine = eng
-        cap = push_capacity or eng.default_push_capacity()
-        self.timings = {}
-        t0 = time.perf_counter()
-        if leaf_array is not None:                      # test seam: reference-format leaves injected
-            eng.leaf_init_from_array(leaf_array, cap)
-        elif self.tree_init:
+        self.timings = {"h2d_setup": time.perf_counter() - t0}
+        tree_states = None
+        if leaf_array is None and self.tree_init:
             if verbose:
                 print(ts(), "Building RP forest with", str(n_trees), "trees")
             if leaf_size is None:
                 leaf_size = max(60, min(256, 5 * int(n_neighbors)))                          # rp_trees.py:2845-2846
             tree_states = current_random_state.randint(INT32_MIN, INT32_MAX, size=(n_trees, 3)).astype(np.int64)
             self._tree_rng_states = tree_states                                              # rp_trees.py:2850-2852
-            lp, lo, n_leaves, max_leaf = eng.forest(tree_states, leaf_size, angular, max_rptree_depth)
-            self._leaf_csr = (lp, lo, n_leaves, max_leaf)
-            eng.stream.synchronize(); self.timings["forest"] = time.perf_counter() - t0; t0 = time.perf_counter()
-            eng.leaf_init(lp, lo, n_leaves, max_leaf, cap)
-        eng.stream.synchronize(); self.timings["leaf_init"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        eng.init_random(self.rng_state)                                                     # pynndescent_.py:345
         if verbose:
             print(ts(), "NN descent for", str(n_iters), "iterations")
-        iters, c_hist, stats = eng.descent(eff_C, self.rng_state, T, n_iters, delta, cap)    # :354
+        idx_t, dist_t, iters, c_hist, stats = eng.build(
+            self.rng_state, tree_states, leaf_size, angular, eff_C, T, n_iters, delta, dev_correction,
+            max_depth=max_rptree_depth, push_capacity=push_capacity, leaf_array=leaf_array, timings=self.timings)
         if verbose:
             for it in range(iters):
                 print("\t", it + 1, " / ", n_iters)
-            if iters < n_iters or (c_hist and c_hist[-1] <= delta * n_neighbors * data.shape[0]):
+            if c_hist and c_hist[-1] <= delta * n_neighbors * data.shape[0]:
                 print("\tStopping threshold met -- exiting after", iters, "iterations")
         self.n_iters_run, self.c_hist, self.join_stats = iters, c_hist, stats
-        eng.stream.synchronize(); self.timings["descent"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        idx_t, dist_t = eng.deheap_sort(dev_correction)                                     # :366 + :2150-2154
-        self._graph_idx_t, self._graph_dist_t = idx_t, dist_t
+        t0 = time.perf_counter()
         self._neighbor_graph = (idx_t.cpu().numpy(), dist_t.cpu().numpy())
-        self.timings["sort_d2h"] = time.perf_counter() - t0
+        self.timings["d2h"] = time.perf_counter() - t0
         if np.any(self._neighbor_graph[0] < 0):                                             # :1262-1267
             warn("Failed to correctly find n_neighbors for some samples."
                  " Results may be less than ideal. Try re-running with"

@@ -218,7 +218,7 @@ def test_thread_count_and_capacity_invariance(torch_cuda, oracle):
         o = oracle.OracleNNDescent(X, "euclidean", n_neighbors=10, random_state=4, n_threads=T, forest="level")
         assert np.array_equal(a.neighbor_graph[0], o.neighbor_graph[0])
         res[T] = a.neighbor_graph[0]
-    b = NNDescent(X, "euclidean", n_neighbors=10, random_state=4, n_jobs=8, push_capacity=1 << 16)
+    b = NNDescent(X, "euclidean", n_neighbors=10, random_state=4, n_jobs=8, push_capacity=1 << 18)
     assert np.array_equal(b.neighbor_graph[0], res[8])
 
 
