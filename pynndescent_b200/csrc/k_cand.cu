@@ -120,11 +120,12 @@ __global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int
     }
 }
 
+#define SEL_SMALL 32
 #define SEL_WARPS 8
 __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
                                                                 const uint32_t *indeg, const uint32_t *revoff,
                                                                 unsigned long long *rev, const float *fprio,
-                                                                int32_t *newc, int32_t *oldc) {
+                                                                int32_t *newc, int32_t *oldc, int skip_small) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t v = (int64_t)blockIdx.x * SEL_WARPS + warp;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *i
     int32_t *nind = (int32_t *)(opri + C), *oind = nind + C;
     for (int c = lane; c < C; c += 32) { npri[c] = CUDART_INF_F; opri[c] = CUDART_INF_F; nind[c] = -1; oind[c] = -1; }
     const uint32_t nrev = indeg[v];
+    if (skip_small && nrev <= SEL_SMALL) return;
     unsigned long long *seg = rev + revoff[v];
     unsigned long long *sorted;
     if (nrev <= NND_SEG_SMEM) {
@@ -182,6 +184,73 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *i
         if (found) flags[v * k + j] = 0;
     }
     for (int c = lane; c < C; c += 32) { newc[v * C + c] = nind[c]; oldc[v * C + c] = oind[c]; }
+}
+
+
+// ---- thread-per-vertex variant for vertices with <= SEL_SMALL reverse edges (the vast majority):
+// the reverse edges are staged in shared memory (column per thread), the next edge in scan order
+// is found by selection, and checked_heap_push is replayed by the thread on column-layout heaps.
+#define SEL_T 128
+__global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
+                                                             const uint32_t *indeg, const uint32_t *revoff,
+                                                             const unsigned long long *rev, const float *fprio,
+                                                             int32_t *newc, int32_t *oldc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int64_t v = (int64_t)blockIdx.x * SEL_T + tid;
+    unsigned long long *rs = (unsigned long long *)smem_raw + tid;              // [SEL_SMALL][SEL_T]
+    float *npri = (float *)(smem_raw + (size_t)SEL_SMALL * SEL_T * 8) + tid;       // [C][SEL_T]
+    float *opri = npri + (size_t)C * SEL_T;
+    int32_t *nind = (int32_t *)(opri + (size_t)C * SEL_T), *oind = nind + (size_t)C * SEL_T;
+    if (v >= N) return;
+    const uint32_t nrev = indeg[v];
+    if (nrev > SEL_SMALL) return;  // handled by the warp kernel
+    for (int c = 0; c < C; ++c) { npri[c * SEL_T] = CUDART_INF_F; opri[c * SEL_T] = CUDART_INF_F; nind[c * SEL_T] = -1; oind[c * SEL_T] = -1; }
+    const unsigned long long *seg = rev + revoff[v];
+    for (uint32_t j = 0; j < nrev; ++j) rs[j * SEL_T] = seg[j];
+    int jf = 0; uint32_t left = nrev;
+    const unsigned long long fbase = (unsigned long long)v * k;
+    for (;;) {
+        while (jf < k && ind[v * k + jf] < 0) ++jf;
+        const bool hasf = jf < k;
+        // smallest remaining reverse entry (keys are unique)
+        unsigned long long best = ~0ULL; int bj = -1;
+        if (left)
+            for (uint32_t j = 0; j < nrev; ++j) { unsigned long long x = rs[j * SEL_T]; if (x < best) { best = x; bj = (int)j; } }
+        const bool hasr = bj >= 0;
+        if (!hasf && !hasr) break;
+        const bool take_f = hasf && (!hasr || fbase + jf <= (best >> 33));
+        float p; int32_t cand; bool isnew;
+        if (take_f) { p = fprio[v * k + jf]; cand = ind[v * k + jf]; isnew = flags[v * k + jf] != 0; ++jf; }
+        else {
+            rs[bj * SEL_T] = ~0ULL; --left;
+            p = __uint_as_float((uint32_t)(best & 0xFFFFFFFFULL)); isnew = (best >> 32) & 1ULL;
+            cand = (int32_t)((best >> 33) / (unsigned long long)k);
+        }
+        float *pri = isnew ? npri : opri; int32_t *idx = isnew ? nind : oind;
+        if (p >= pri[0]) continue;
+        bool dup = false;
+        for (int c = 0; c < C; ++c) dup |= (idx[c * SEL_T] == cand);
+        if (dup) continue;
+        int i = 0, i_swap;
+        for (;;) {
+            int ic1 = 2 * i + 1, ic2 = ic1 + 1;
+            if (ic1 >= C) break;
+            else if (ic2 >= C) { if (pri[ic1 * SEL_T] > p) i_swap = ic1; else break; }
+            else if (pri[ic1 * SEL_T] >= pri[ic2 * SEL_T]) { if (p < pri[ic1 * SEL_T]) i_swap = ic1; else break; }
+            else { if (p < pri[ic2 * SEL_T]) i_swap = ic2; else break; }
+            pri[i * SEL_T] = pri[i_swap * SEL_T]; idx[i * SEL_T] = idx[i_swap * SEL_T];
+            i = i_swap;
+        }
+        pri[i * SEL_T] = p; idx[i * SEL_T] = cand;
+    }
+    for (int j = 0; j < k; ++j) {
+        int32_t x = ind[v * k + j];
+        bool found = false;
+        for (int c = 0; c < C; ++c) found |= (nind[c * SEL_T] == x);
+        if (found) flags[v * k + j] = 0;
+    }
+    for (int c = 0; c < C; ++c) { newc[v * C + c] = nind[c * SEL_T]; oldc[v * C + c] = oind[c * SEL_T]; }
 }
 
 __global__ void k_rng_table(const uint64_t *jump, long long s0, long long s1, long long s2, int64_t start, int64_t count,
@@ -247,9 +316,17 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
     size_t smem = (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)SEL_WARPS * hstride;
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
+    size_t smem_small = (size_t)SEL_SMALL * SEL_T * 8 + (size_t)C * SEL_T * 16;
+    const int use_small = smem_small <= 200 * 1024;
+    if (use_small) {
+        NND_CUDA(cudaFuncSetAttribute(k_cand_select_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        k_cand_select_small<<<(unsigned)cdiv(N, SEL_T), SEL_T, smem_small, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
+                                                                            W.revoff, W.rev, W.fprio, new_cand, old_cand);
+        NND_LAUNCH(ctx);
+    }
     NND_CUDA(cudaFuncSetAttribute(k_cand_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_cand_select<<<(unsigned)cdiv(N, SEL_WARPS), SEL_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
-                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand);
+                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand, use_small);
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
     return NND_OK;

@@ -15,6 +15,8 @@
 // re-checks dd < root(now) <= thr, so every half-update dropped here would have been rejected,
 // and the survivors are replayed per row in ascending emission sequence => identical heaps,
 // identical flags, identical accepted-push count.
+#include <stdlib.h>
+
 #include <type_traits>
 #include <vector>
 
@@ -27,7 +29,7 @@
 struct JoinParams {
     const float *X; int64_t N; int d, ld; int metric; const void *aux;
     const float *thr;
-    int mode;  // 0 local join, 1 leaf
+    int mode;  // 0 local join, 1 leaf (routed), 2 leaf fused with apply
     const int32_t *newc, *oldc; int C; int64_t unit_begin, unit_end;
     const int32_t *leaf_points; const int64_t *leaf_offsets;
     int m_max, slot_stride;
@@ -36,6 +38,8 @@ struct JoinParams {
     unsigned long long *cursor; unsigned long long capacity;
     unsigned long long *stats;  // [0] rows gathered [1] pairs evaluated
     int *overflow;
+    // mode 2 (fused leaf join + apply): heaps are updated in place by the leaf's own CTA
+    int32_t *heap_idx; float *heap_dist; uint8_t *heap_flag; int k; int d_alias;
 };
 
 static size_t join_smem_bytes(int m_max, int metric) {
@@ -46,6 +50,14 @@ static size_t join_smem_bytes(int m_max, int metric) {
     b = (b + 15) & ~size_t(15);
     b += (size_t)m_max * SD * 4;
     return b;
+}
+// fused leaf mode: + per-member heap columns [k][m_max] (f32,i32,u8) + distance matrix (aliased onto the
+// row tiles when it fits)
+static size_t fused_extra_bytes(int m_max, int k, int *alias) {
+    size_t heap = ((size_t)k * m_max * 9 + 15) & ~size_t(15);
+    int ds = m_max | 1;
+    *alias = (ds <= SD);
+    return heap + (*alias ? 0 : (size_t)m_max * ds * 4 + 16);
 }
 
 template <int METRIC, int TPT, int MAXT>
@@ -60,6 +72,13 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     if (METRIC == NND_METRIC_CORRELATION) {
         cur = (unsigned char *)(((uintptr_t)cur + 7) & ~uintptr_t(7));
         mu_s = (double *)cur; cur += (size_t)P.m_max * 16;
+    }
+    float *hpri = nullptr; int32_t *hind = nullptr; uint8_t *hflg = nullptr; float *dsep = nullptr;
+    if (P.mode == 2) {
+        cur = (unsigned char *)(((uintptr_t)cur + 15) & ~uintptr_t(15));
+        hpri = (float *)cur; hind = (int32_t *)(hpri + (size_t)P.k * P.m_max); hflg = (uint8_t *)(hind + (size_t)P.k * P.m_max);
+        cur += ((size_t)P.k * P.m_max * 9 + 15) & ~size_t(15);
+        if (!P.d_alias) { dsep = (float *)cur; cur += (size_t)P.m_max * (P.m_max | 1) * 4 + 16; }
     }
     float *rows = (float *)(((uintptr_t)cur + 15) & ~uintptr_t(15));
     __shared__ int s_nn, s_m;
@@ -93,10 +112,10 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     }
     __syncthreads();
     const int nn = s_nn, m = s_m;
-    if (nn == 0 || (P.mode == 1 && m < 2)) return;
+    if (nn == 0 || (P.mode != 0 && m < 2)) return;
     for (int j = tid; j < m; j += nthr) {
         int32_t id = ids[j];
-        thr_s[j] = P.thr[id];
+        thr_s[j] = (P.mode == 2) ? CUDART_INF_F : P.thr[id];
         if (METRIC == NND_METRIC_ALT_COSINE) n2_s[j] = ((const float *)P.aux)[id];
         if (METRIC == NND_METRIC_CORRELATION) {
             mu_s[2 * j] = ((const double *)P.aux)[2 * (int64_t)id];
@@ -217,6 +236,60 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                 dd[i][u * TILE + v] = r;
             }
         npush += __popc(pm[i]);
+    }
+    if (P.mode == 2) {
+        // ---- fused apply: distance matrix -> smem, then ONE THREAD PER MEMBER replays its pushes.
+        // Row ids[a] receives, in the reference's emission order (pairs (i,j), i<j, row-major), exactly
+        // the other members in ascending member position: (i,a) for i<a, then (a,j) for j>a.
+        float *Dm = P.d_alias ? rows : dsep;
+        const int ds = m | 1;
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            if (my_ta[i] < 0) continue;
+#pragma unroll
+            for (int u = 0; u < TILE; ++u)
+#pragma unroll
+                for (int v = 0; v < TILE; ++v) {
+                    int a = my_ta[i] * TILE + u, b = my_tb[i] * TILE + v;
+                    if (a < nn && b < m && b > a) { Dm[a * ds + b] = dd[i][u * TILE + v]; Dm[b * ds + a] = dd[i][u * TILE + v]; }
+                }
+        }
+        __syncthreads();
+        const int hs = P.m_max, k = P.k;
+        for (int a = tid; a < m; a += nthr) {
+            const int64_t row = ids[a];
+            float *pri = hpri + a; int32_t *ind = hind + a; uint8_t *flg = hflg + a;
+            for (int j = 0; j < k; ++j) {
+                pri[j * hs] = P.heap_dist[row * k + j]; ind[j * hs] = P.heap_idx[row * k + j]; flg[j * hs] = P.heap_flag[row * k + j];
+            }
+            bool changed = false;
+            for (int b = 0; b < m; ++b) {
+                if (b == a) continue;
+                const float p = Dm[a * ds + b];
+                if (p >= pri[0]) continue;
+                const int32_t nb = ids[b];
+                bool dup = false;
+                for (int j = 0; j < k; ++j) dup |= (ind[j * hs] == nb);
+                if (dup) continue;
+                int i = 0, i_swap;
+                for (;;) {
+                    int ic1 = 2 * i + 1, ic2 = ic1 + 1;
+                    if (ic1 >= k) break;
+                    else if (ic2 >= k) { if (pri[ic1 * hs] > p) i_swap = ic1; else break; }
+                    else if (pri[ic1 * hs] >= pri[ic2 * hs]) { if (p < pri[ic1 * hs]) i_swap = ic1; else break; }
+                    else { if (p < pri[ic2 * hs]) i_swap = ic2; else break; }
+                    pri[i * hs] = pri[i_swap * hs]; ind[i * hs] = ind[i_swap * hs]; flg[i * hs] = flg[i_swap * hs];
+                    i = i_swap;
+                }
+                pri[i * hs] = p; ind[i * hs] = nb; flg[i * hs] = 1;
+                changed = true;
+            }
+            if (changed)
+                for (int j = 0; j < k; ++j) {
+                    P.heap_dist[row * k + j] = pri[j * hs]; P.heap_idx[row * k + j] = ind[j * hs]; P.heap_flag[row * k + j] = flg[j * hs];
+                }
+        }
+        return;
     }
     // warp-aggregated slot allocation in the global push list
     int incl = npush;
@@ -393,9 +466,11 @@ template <int METRIC>
 static int launch_join_m(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaStream_t st) {
     // worst-case tile count for this launch decides (TPT, threads)
     int nn_max = (P.mode == 0) ? P.C : P.m_max;
+    if (P.mode == 2 && false) return NND_ERR_INVALID;
     int ntr = (nn_max + TILE - 1) / TILE, ntc = (P.m_max + TILE - 1) / TILE;
     int ntiles = ntr * ntc - ntr * (ntr - 1) / 2;
     size_t smem = join_smem_bytes(P.m_max, METRIC);
+    if (P.mode == 2) { int al; smem += fused_extra_bytes(P.m_max, P.k, &al) + 32; }
     NND_CHECK(smem <= 220 * 1024, NND_ERR_UNSUPPORTED, "join: %d members need %zu B of shared memory", P.m_max, smem);
     int tpt = (METRIC == NND_METRIC_CORRELATION) ? 1 : (ntiles <= 512 ? 1 : (ntiles <= 2048 ? 2 : 4));
     int threads = (int)(cdiv(cdiv(ntiles, tpt), 32) * 32);
@@ -514,6 +589,44 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
     else {
         NND_CUDA(cudaMemcpyAsync(offs.data(), leaf_offsets, sizeof(int64_t) * (n_leaves + 1), cudaMemcpyDeviceToHost, st));
         NND_CUDA(cudaStreamSynchronize(st));
+    }
+    // ---- fused path: when the leaves of each tree partition the points (true for every reference
+    // forest: offsets hit every multiple of N) a point lies in exactly ONE leaf per tree, so the leaf's
+    // own CTA can apply its pushes in place, tree after tree, with no routing at all.
+    {
+        const int64_t N = P->N, total = offs[n_leaves];
+        bool partition = (total % N == 0) && total > 0;
+        std::vector<int64_t> tree_cut; tree_cut.push_back(0);
+        if (partition) {
+            int64_t next = N;
+            for (int64_t i = 1; i <= n_leaves && partition; ++i) {
+                if (offs[i] == next) { tree_cut.push_back(i); next += N; }
+                else if (offs[i] > next) partition = false;
+            }
+        }
+        int mm = max_leaf < 4 ? 4 : max_leaf, al = 0;
+        size_t smem = join_smem_bytes(mm, P->metric) + fused_extra_bytes(mm, P->k, &al) + 32;
+        const char *force_routed = getenv("NND_LEAF_ROUTED");  // test switch: exercise the routed leaf path
+        if (partition && smem <= 200 * 1024 && !(force_routed && force_routed[0] == '1')) {
+            JoinParams J; memset(&J, 0, sizeof(J));
+            J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
+            J.mode = 2; J.leaf_points = leaf_points; J.leaf_offsets = leaf_offsets; J.m_max = mm; J.slot_stride = mm;
+            J.heap_idx = P->heap_idx; J.heap_dist = P->heap_dist; J.heap_flag = P->heap_flag; J.k = P->k; J.d_alias = al;
+            NND_CUDA(cudaEventRecord(ctx->ev0, st));
+            for (size_t t = 0; t + 1 < tree_cut.size(); ++t) {
+                J.unit_begin = tree_cut[t]; J.unit_end = tree_cut[t + 1];
+                NND_TRY(launch_join(ctx, J, J.unit_end - J.unit_begin, st));
+            }
+            NND_CUDA(cudaEventRecord(ctx->ev1, st));
+            NND_CUDA(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            NND_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            double pairs = 0;
+            for (int64_t i = 0; i < n_leaves; ++i) { double m = (double)(offs[i + 1] - offs[i]); pairs += m * (m - 1) / 2; }
+            double *pf = ctx->prof[1];
+            pf[0] += ms; pf[1] += (double)(tree_cut.size() - 1); pf[2] += (double)total; pf[3] += pairs;
+            return NND_OK;
+        }
     }
     std::vector<int64_t> cuts; cuts.push_back(0);
     int64_t accb = 0;

@@ -35,7 +35,8 @@ struct ForestWs {
     float *noff;          // [M]
     int32_t *tree_first;  // [n_trees]
     uint64_t *tree_seed;  // [n_trees]
-    int32_t *scalars;     // [0] n_degenerate [1] max_leaf
+    int32_t *scalars;     // [0] n_degenerate [1] max_leaf [2] next active count
+    int32_t *act[2];      // [TN] active positions (ping-pong, unordered)
     int64_t M_max;
 };
 
@@ -53,6 +54,7 @@ static int carve_forest_ws(void *ws, size_t ws_bytes, int64_t N, int ld, int n_t
     W->noff = A.get<float>(W->M_max);
     W->tree_first = A.get<int32_t>(n_trees); W->tree_seed = A.get<uint64_t>(n_trees);
     W->scalars = A.get<int32_t>(16);
+    for (int i = 0; i < 2; ++i) W->act[i] = A.get<int32_t>(TN);
     // hyperplanes: nodes that split hold > leaf_size points, but leaf_size is not known here;
     // active nodes of one level are disjoint and each has >= 2 points
     W->hyper = A.get<float>((size_t)0);  // sized by forest_hyper_elems() below (needs leaf_size)
@@ -103,13 +105,17 @@ __device__ __forceinline__ uint64_t node_key(uint64_t seed, int level, int64_t o
 }
 
 // ---------------------------------------------------------------- kernels
-__global__ void k_forest_init(int32_t *perm, int32_t *seg, uint8_t *segstart, int64_t N, int n_trees, int active) {
+__global__ void k_forest_init(int32_t *perm, int32_t *seg, uint8_t *segstart, int32_t *act, int32_t *leaf_points,
+                              uint32_t *flag32, int64_t N, int n_trees, int active) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)n_trees * N) return;
     int64_t t = i / N, p = i - t * N;
     perm[i] = (int32_t)p;
     seg[i] = active ? (int32_t)t : -1;
     segstart[i] = (p == 0);
+    act[i] = (int32_t)i;
+    flag32[i] = 0;
+    if (!active) leaf_points[i] = (int32_t)p;
 }
 
 // one warp per active node: choose the two members, build the hyperplane (rp_trees.py:351-367 / :88-118)
@@ -155,37 +161,66 @@ __global__ void k_forest_hyper(const float *X, int ld, int64_t N, int angular, i
     }
 }
 
-// one warp per position: side of the hyperplane (rp_trees.py:375-391)
-__global__ void k_forest_side(const float *X, int ld, int64_t TN, int64_t N, int level, const int32_t *perm,
-                              const int32_t *seg, const int32_t *nstart, const int32_t *tree_first,
+// one warp per SIDE_PW active positions: side of the hyperplane (rp_trees.py:375-391)
+#define SIDE_PW 4
+__global__ void k_forest_side(const float *X, int ld, int64_t n_act, const int32_t *act, int64_t N, int level,
+                              const int32_t *perm, const int32_t *seg, const int32_t *nstart, const int32_t *tree_first,
                               const uint64_t *tree_seed, const float *hyper, const float *noff, uint8_t *side,
                               uint32_t *flag32) {
     const int lane = threadIdx.x & 31;
-    const int64_t pos = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (pos >= TN) return;
-    const int o = seg[pos];
-    if (o < 0) { if (lane == 0) flag32[pos] = 0; return; }
-    const float *x = X + (int64_t)perm[pos] * ld;
-    float margin = __fadd_rn(noff[o], warp_lane_dot(hyper + (size_t)o * ld, x, ld, lane));
-    if (lane == 0) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t i0 = w * SIDE_PW;
+    if (i0 >= n_act) return;
+    int32_t pos[SIDE_PW], o[SIDE_PW];
+    const float *x[SIDE_PW];
+#pragma unroll
+    for (int q = 0; q < SIDE_PW; ++q) {
+        int64_t i = i0 + q < n_act ? i0 + q : n_act - 1;
+        pos[q] = act[i]; o[q] = seg[pos[q]];
+        x[q] = X + (int64_t)perm[pos[q]] * ld;
+    }
+    float acc[SIDE_PW];
+#pragma unroll
+    for (int q = 0; q < SIDE_PW; ++q) acc[q] = 0.0f;
+    for (int c = lane * 4; c < ld; c += 128) {
+        float4 b[SIDE_PW], a[SIDE_PW];
+#pragma unroll
+        for (int q = 0; q < SIDE_PW; ++q) { b[q] = *(const float4 *)(x[q] + c); a[q] = *(const float4 *)(hyper + (size_t)o[q] * ld + c); }
+#pragma unroll
+        for (int q = 0; q < SIDE_PW; ++q) {
+            acc[q] = __fmaf_rn(a[q].x, b[q].x, acc[q]); acc[q] = __fmaf_rn(a[q].y, b[q].y, acc[q]);
+            acc[q] = __fmaf_rn(a[q].z, b[q].z, acc[q]); acc[q] = __fmaf_rn(a[q].w, b[q].w, acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < SIDE_PW; ++q) {
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) acc[q] = __fadd_rn(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], sft));
+    }
+    if (lane < SIDE_PW && i0 + lane < n_act) {
+        float accq = acc[0]; int32_t pq = pos[0], oq = o[0];
+#pragma unroll
+        for (int q = 1; q < SIDE_PW; ++q) if (lane == q) { accq = acc[q]; pq = pos[q]; oq = o[q]; }
+        float margin = __fadd_rn(noff[oq], accq);
         uint8_t s;
         if (fabs((double)margin) < 1e-8) {
-            const int start = nstart[o];
+            const int start = nstart[oq];
             const int tree = (int)(start / N);
-            const uint64_t key = node_key(tree_seed[tree], level, (int64_t)(o - tree_first[tree]));
-            s = (uint8_t)(mix64(key ^ (0x100ULL + (uint64_t)(pos - start))) & 1ULL);
+            const uint64_t key = node_key(tree_seed[tree], level, (int64_t)(oq - tree_first[tree]));
+            s = (uint8_t)(mix64(key ^ (0x100ULL + (uint64_t)(pq - start))) & 1ULL);
         } else s = margin > 0 ? 0 : 1;
-        side[pos] = s;
-        flag32[pos] = (s == 0);
+        side[pq] = s;
+        flag32[pq] = (s == 0);
     }
 }
 
 // degenerate nodes (all points on one side): random split (rp_trees.py:395-403)
-__global__ void k_forest_fix_side(int64_t TN, int64_t N, int level, const int32_t *seg, const int32_t *nstart,
-                                  const uint8_t *ndegen, const int32_t *tree_first, const uint64_t *tree_seed,
-                                  uint8_t *side, uint32_t *flag32) {
-    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= TN) return;
+__global__ void k_forest_fix_side(int64_t n_act, const int32_t *act, int64_t N, int level, const int32_t *seg,
+                                  const int32_t *nstart, const uint8_t *ndegen, const int32_t *tree_first,
+                                  const uint64_t *tree_seed, uint8_t *side, uint32_t *flag32) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_act) return;
+    const int64_t pos = act[i];
     const int o = seg[pos];
     if (o < 0 || !ndegen[o]) return;
     const int start = nstart[o];
@@ -229,28 +264,42 @@ __global__ void k_forest_children(int M, const int32_t *nstart, const int32_t *n
     }
 }
 
-// stable partition of every active segment + relabel positions with the child's ordinal
-__global__ void k_forest_scatter(int64_t TN, const int32_t *perm, const int32_t *seg, const uint8_t *side,
-                                 const uint32_t *pl, const int32_t *nstart, const int32_t *nsize, const int32_t *nleft,
-                                 const uint32_t *nchild_scan, int leaf_size, int depth_left_after, int32_t *perm2,
-                                 int32_t *seg2) {
-    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= TN) return;
-    const int o = seg[pos];
-    if (o < 0) { perm2[pos] = perm[pos]; seg2[pos] = -1; return; }
-    const int start = nstart[o], n = nsize[o], nl = nleft[o];
-    const int lrank = (int)(pl[pos] - pl[start]);  // #left points before pos in this segment
-    const bool left = side[pos] == 0;
-    int64_t np = left ? (int64_t)start + lrank : (int64_t)start + nl + ((pos - start) - lrank);
-    perm2[np] = perm[pos];
-    int32_t child = -1;
-    if (depth_left_after > 0) {
-        uint32_t w = nchild_scan[o];
-        bool lact = nl > leaf_size, ract = (n - nl) > leaf_size;
-        if (left) child = lact ? (int32_t)w : -1;
-        else child = ract ? (int32_t)(w + (lact ? 1 : 0)) : -1;
+// stable partition of every active segment + relabel positions with the child's ordinal; points whose
+// child is a final leaf are written straight to leaf_points, the others go on the next active list
+__global__ void k_forest_scatter(int64_t n_act, const int32_t *act, const int32_t *perm, const int32_t *seg,
+                                 const uint8_t *side, const uint32_t *pl, const int32_t *nstart, const int32_t *nsize,
+                                 const int32_t *nleft, const uint32_t *nchild_scan, int leaf_size, int depth_left_after,
+                                 int32_t *perm2, int32_t *seg2, int32_t *act2, int32_t *n_act2, int32_t *leaf_points,
+                                 uint32_t *flag32) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool alive = false; int32_t np32 = 0;
+    if (i < n_act) {
+        const int64_t pos = act[i];
+        const int o = seg[pos];
+        const int start = nstart[o], n = nsize[o], nl = nleft[o];
+        const int lrank = (int)(pl[pos] - pl[start]);
+        const bool left = side[pos] == 0;
+        int64_t np = left ? (int64_t)start + lrank : (int64_t)start + nl + ((pos - start) - lrank);
+        int32_t child = -1;
+        if (depth_left_after > 0) {
+            uint32_t w = nchild_scan[o];
+            bool lact = nl > leaf_size, ract = (n - nl) > leaf_size;
+            if (left) child = lact ? (int32_t)w : -1;
+            else child = ract ? (int32_t)(w + (lact ? 1 : 0)) : -1;
+        }
+        const int32_t pt = perm[pos];
+        if (child >= 0) { perm2[np] = pt; seg2[np] = child; alive = true; np32 = (int32_t)np; }
+        else leaf_points[np] = pt;
+        flag32[pos] = 0;  // scan input must be zero outside the (new) active set
     }
-    seg2[np] = child;
+    unsigned mk = __ballot_sync(0xffffffffu, alive);
+    if (mk) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(n_act2, __popc(mk));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (alive) act2[base + __popc(mk & ((1u << lane) - 1))] = np32;
+    }
 }
 
 __global__ void k_forest_flags(int64_t TN, const uint8_t *segstart, uint32_t *flag32) {
@@ -298,7 +347,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
     NND_CUDA(cudaMemcpyAsync(W.tree_seed, seeds.data(), sizeof(uint64_t) * n_trees, cudaMemcpyHostToDevice, st));
     const bool root_active = (N > leaf_size && max_depth > 0);
     const unsigned gpos = (unsigned)cdiv(TN + 1, 256);
-    k_forest_init<<<gpos, 256, 0, st>>>(W.perm[0], W.seg[0], W.segstart, N, n_trees, root_active ? 1 : 0); NND_LAUNCH(ctx);
+    k_forest_init<<<gpos, 256, 0, st>>>(W.perm[0], W.seg[0], W.segstart, W.act[0], leaf_points, W.flag32, N, n_trees, root_active ? 1 : 0); NND_LAUNCH(ctx);
     NND_CUDA(cudaMemsetAsync(W.scalars, 0, sizeof(int32_t) * 16, st));
     int cur = 0;
     int M = 0;
@@ -312,6 +361,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
         M = n_trees;
     }
     int ncur = 0;
+    int64_t n_act = root_active ? TN : 0;
     for (int level = 0; M > 0; ++level) {
         NND_CHECK(M <= hyper_nodes, NND_ERR_OVERFLOW, "forest: %d active nodes exceed the hyperplane pool", M);
         const int depth_left_after = max_depth - (level + 1);
@@ -320,11 +370,13 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
                                                                                  W.nsize[ncur], W.perm[cur], W.tree_first,
                                                                                  W.tree_seed, W.hyper, W.noff);
         NND_LAUNCH(ctx);
-        k_forest_side<<<(unsigned)cdiv(TN * 32, 256), 256, 0, st>>>(X, ld, TN, N, level, W.perm[cur], W.seg[cur], W.nstart[ncur],
-                                                                    W.tree_first, W.tree_seed, W.hyper, W.noff, W.side, W.flag32);
+        k_forest_side<<<(unsigned)cdiv(cdiv(n_act, SIDE_PW) * 32, 256), 256, 0, st>>>(X, ld, n_act, W.act[cur], N, level, W.perm[cur],
+                                                                                   W.seg[cur], W.nstart[ncur], W.tree_first,
+                                                                                   W.tree_seed, W.hyper, W.noff, W.side, W.flag32);
         NND_LAUNCH(ctx);
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.flag32, W.pl, TN, W.scan_tmp, st));
         NND_CUDA(cudaMemsetAsync(W.scalars, 0, sizeof(int32_t), st));
+        NND_CUDA(cudaMemsetAsync(W.scalars + 2, 0, sizeof(int32_t), st));
         k_forest_node<<<(unsigned)cdiv(M, 256), 256, 0, st>>>(M, W.nstart[ncur], W.nsize[ncur], W.pl, leaf_size, depth_left_after,
                                                               W.nleft, W.ndegen, W.nchild, W.scalars, 0);
         NND_LAUNCH(ctx);
@@ -332,8 +384,8 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
         NND_CUDA(cudaMemcpyAsync(hsc, W.scalars, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
         NND_CUDA(cudaStreamSynchronize(st));
         if (hsc[0] > 0) {
-            k_forest_fix_side<<<(unsigned)cdiv(TN, 256), 256, 0, st>>>(TN, N, level, W.seg[cur], W.nstart[ncur], W.ndegen,
-                                                                       W.tree_first, W.tree_seed, W.side, W.flag32);
+            k_forest_fix_side<<<(unsigned)cdiv(n_act, 256), 256, 0, st>>>(n_act, W.act[cur], N, level, W.seg[cur], W.nstart[ncur],
+                                                                          W.ndegen, W.tree_first, W.tree_seed, W.side, W.flag32);
             NND_LAUNCH(ctx);
             NND_TRY(nnd_exclusive_scan_u32(ctx, W.flag32, W.pl, TN, W.scan_tmp, st));
             k_forest_node<<<(unsigned)cdiv(M, 256), 256, 0, st>>>(M, W.nstart[ncur], W.nsize[ncur], W.pl, leaf_size,
@@ -346,13 +398,16 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
                                                                   leaf_size, depth_left_after, N, W.nstart[ncur ^ 1],
                                                                   W.nsize[ncur ^ 1], W.segstart, W.tree_first);
         NND_LAUNCH(ctx);
-        k_forest_scatter<<<(unsigned)cdiv(TN, 256), 256, 0, st>>>(TN, W.perm[cur], W.seg[cur], W.side, W.pl, W.nstart[ncur],
-                                                                  W.nsize[ncur], W.nleft, W.nchild_scan, leaf_size,
-                                                                  depth_left_after, W.perm[cur ^ 1], W.seg[cur ^ 1]);
+        k_forest_scatter<<<(unsigned)cdiv(n_act, 256), 256, 0, st>>>(n_act, W.act[cur], W.perm[cur], W.seg[cur], W.side, W.pl,
+                                                                     W.nstart[ncur], W.nsize[ncur], W.nleft, W.nchild_scan, leaf_size,
+                                                                     depth_left_after, W.perm[cur ^ 1], W.seg[cur ^ 1], W.act[cur ^ 1],
+                                                                     W.scalars + 2, leaf_points, W.flag32);
         NND_LAUNCH(ctx);
-        uint32_t m_next = 0;
+        uint32_t m_next = 0; int32_t a_next = 0;
         NND_CUDA(cudaMemcpyAsync(&m_next, W.nchild_scan + M, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        NND_CUDA(cudaMemcpyAsync(&a_next, W.scalars + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         NND_CUDA(cudaStreamSynchronize(st));
+        n_act = a_next;
         cur ^= 1; ncur ^= 1;
         M = (int)m_next;
     }
@@ -362,7 +417,6 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
     k_forest_offsets<<<gpos, 256, 0, st>>>(TN, W.segstart, W.pl, leaf_offsets); NND_LAUNCH(ctx);
     uint32_t nl = 0;
     NND_CUDA(cudaMemcpyAsync(&nl, W.pl + TN, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    NND_CUDA(cudaMemcpyAsync(leaf_points, W.perm[cur], sizeof(int32_t) * TN, cudaMemcpyDeviceToDevice, st));
     NND_CUDA(cudaStreamSynchronize(st));
     NND_CUDA(cudaMemsetAsync(W.scalars + 1, 0, sizeof(int32_t), st));
     k_forest_maxleaf<<<(unsigned)cdiv((int64_t)nl, 256), 256, 0, st>>>((int64_t)nl, leaf_offsets, W.scalars); NND_LAUNCH(ctx);

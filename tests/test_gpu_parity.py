@@ -106,8 +106,14 @@ def test_leaf_init_from_reference_leaves(torch_cuda, oracle, name):
     oracle.init_rp_tree(Xh, metric, heap, G["leaf_array"])
     assert np.array_equal(hd, heap[1])                       # bit-exact vs the oracle, distances included
     # tiny push capacity -> many routing rounds -> same result (blocking invariance)
+    # the routed (counting-sort + ordered apply) leaf path with a tiny push capacity -> many rounds
+    import os
     eng.make_heap()
-    eng.leaf_init_from_array(G["leaf_array"], push_capacity=1 << 15)
+    os.environ["NND_LEAF_ROUTED"] = "1"
+    try:
+        eng.leaf_init_from_array(G["leaf_array"], push_capacity=1 << 15)
+    finally:
+        del os.environ["NND_LEAF_ROUTED"]
     hi2, hd2, hf2 = eng.get_heap()
     assert np.array_equal(hi2, hi) and np.array_equal(hd2, hd) and np.array_equal(hf2, hf)
 
