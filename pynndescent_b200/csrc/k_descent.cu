@@ -48,7 +48,7 @@ static size_t join_smem_bytes(int m_max, int metric) {
     if (metric == NND_METRIC_ALT_COSINE) b += (size_t)m_max * 4;
     if (metric == NND_METRIC_CORRELATION) b += (size_t)m_max * 16;
     b = (b + 15) & ~size_t(15);
-    b += (size_t)m_max * SD * 4;
+    b += (size_t)(m_max + 4) * SD * 4;  // slot permutation (j&3)*ntc + (j>>2) spans up to m+3 slots
     return b;
 }
 // fused leaf mode: + per-member heap columns [k][m_max] (f32,i32,u8) + distance matrix (aliased onto the
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
             if (lane == 0) mbar_expect_tx(bar, (uint32_t)m * (uint32_t)len * 4u);
             __syncwarp();
             for (int r = lane; r < m; r += 32)
-                bulk_g2s(rows + (size_t)r * SD, P.X + (int64_t)ids[r] * P.ld + c0, (uint32_t)len * 4u, bar);
+                bulk_g2s(rows + (size_t)((r & 3) * ntc + (r >> 2)) * SD, P.X + (int64_t)ids[r] * P.ld + c0, (uint32_t)len * 4u, bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
 #pragma unroll
             for (int u = 0; u < TILE; ++u) {
                 int ia = min(my_ta[i] * TILE + u, nn - 1), ib = min(my_tb[i] * TILE + u, m - 1);
-                ra[u] = rows + (size_t)ia * SD; rb[u] = rows + (size_t)ib * SD;
+                // member j lives at smem slot (j&3)*ntc + (j>>2): the 8 lanes of an LDS.128 phase (consecutive
+                // tile columns) then read consecutive slots = distinct bank groups (stride 132 floats)
+                ra[u] = rows + (size_t)((ia & 3) * ntc + (ia >> 2)) * SD; rb[u] = rows + (size_t)((ib & 3) * ntc + (ib >> 2)) * SD;
                 if (METRIC == NND_METRIC_CORRELATION) { ma[u] = (acc_t)mu_s[2 * ia]; mb[u] = (acc_t)mu_s[2 * ib]; }
                 else { ma[u] = 0; mb[u] = 0; }
             }
@@ -331,6 +333,227 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     }
 }
 
+
+// =====================================================================================================
+// k_join_batch: the local join for short rows (ld <= 256).  One 64-thread CTA handles a BATCH of consecutive
+// candidate rows chosen so that their member vectors fill the shared-memory budget; all 4x4 tiles of all rows
+// of the batch form one queue shared by the 64 threads, so lanes stay busy even when a single row has only a
+// handful of tiles (one-warp-per-row left 50-70 % of the lanes idle).  Member rows are resident in full (no
+// d-chunking), staged by the TMA bulk-copy engine.  Same arithmetic, same emission keys as k_join.
+// =====================================================================================================
+#define JB_THREADS 64
+#define JB_MAXU 40
+struct JoinBatchParams {
+    const float *X; int64_t N; int ld; int metric; const void *aux; const float *thr;
+    const int32_t *act_unit; const uint32_t *act_info; const uint32_t *act_poff; const int32_t *members;
+    int64_t n_active; uint32_t total_phys; int ps; int64_t batch_begin, batch_end; int slot_stride; int phys_max;
+    int32_t *out_tgt, *out_oth; float *out_d; uint32_t *out_pos; unsigned long long *out_seq;
+    uint32_t *tgt_count; unsigned long long *cursor; unsigned long long capacity; unsigned long long *stats; int *overflow;
+};
+
+// prepass 1: per row, number of new / old candidates -> physical slot count (0 for rows without new candidates)
+__global__ void k_jb_count(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *flag, uint32_t *phys,
+                           uint32_t *info) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int nn = 0, no = 0;
+    for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
+    int m = nn + no;
+    flag[i] = nn > 0;
+    phys[i] = nn > 0 ? (uint32_t)(((m + 3) >> 2) << 2) : 0u;
+    info[i] = (uint32_t)nn | ((uint32_t)m << 8);
+}
+// prepass 2: compacted active-row list + member ids in the reference's order (new k asc, then old k asc; holes dropped)
+__global__ void k_jb_fill(const int32_t *newc, const int32_t *oldc, int C, int64_t N, const uint32_t *flag,
+                          const uint32_t *pos, const uint32_t *poff, const uint32_t *info, int32_t *act_unit,
+                          uint32_t *act_info, uint32_t *act_poff, int32_t *members) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || !flag[i]) return;
+    uint32_t j = pos[i], o = poff[i];
+    act_unit[j] = (int32_t)i; act_info[j] = info[i]; act_poff[j] = o;
+    int w = 0;
+    for (int c = 0; c < C; ++c) { int32_t v = newc[i * C + c]; if (v >= 0) members[o + w++] = v; }
+    for (int c = 0; c < C; ++c) { int32_t v = oldc[i * C + c]; if (v >= 0) members[o + w++] = v; }
+    int pe = ((w + 3) >> 2) << 2;
+    for (; w < pe; ++w) members[o + w] = -1;
+}
+
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *a, int64_t n, uint32_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = (uint64_t *)smem_raw;
+    int *s_hdr = (int *)(smem_raw + 8);                     // [0] j0 [1] nunits [2] total tiles [3] total members
+    int32_t *s_uid = (int32_t *)(smem_raw + 32);            // [JB_MAXU]
+    int *s_unn = s_uid + JB_MAXU, *s_um = s_unn + JB_MAXU;  // nn, m
+    int *s_uoff = s_um + JB_MAXU;                           // [JB_MAXU+1] physical slot offset of the unit
+    int *s_utile = s_uoff + JB_MAXU + 1;                    // [JB_MAXU+1] tile prefix
+    int32_t *ids = (int32_t *)(s_utile + JB_MAXU + 1);      // [phys_max] logical order, padded per unit
+    float *thr_s = (float *)(ids + P.phys_max);
+    float *n2_s = thr_s + P.phys_max;                       // cosine only
+    float *rows = (float *)(((uintptr_t)(n2_s + (METRIC == NND_METRIC_ALT_COSINE ? P.phys_max : 0)) + 15) & ~uintptr_t(15));
+    const int sd = P.ld + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t B = P.batch_begin + blockIdx.x;
+    if (B >= P.batch_end) return;
+
+    if (tid == 0) {
+        int64_t j0 = lower_bound_u32(P.act_poff, P.n_active, (uint32_t)(B * P.ps));
+        int64_t j1 = lower_bound_u32(P.act_poff, P.n_active, (uint32_t)((B + 1) * P.ps));
+        s_hdr[0] = (int)j0; s_hdr[1] = (int)(j1 - j0);
+        mbar_init(bar, 1); mbar_fence_init();
+    }
+    __syncthreads();
+    const int j0 = s_hdr[0], nunits = s_hdr[1];
+    if (nunits <= 0) return;
+    const uint32_t base = P.act_poff[j0];
+    if (tid < nunits) {
+        uint32_t inf = P.act_info[j0 + tid];
+        s_uid[tid] = P.act_unit[j0 + tid]; s_unn[tid] = (int)(inf & 0xFF); s_um[tid] = (int)(inf >> 8);
+        s_uoff[tid] = (int)(P.act_poff[j0 + tid] - base);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0, mem = 0;
+        for (int u = 0; u < nunits; ++u) {
+            s_utile[u] = t;
+            int nn = s_unn[u], m = s_um[u];
+            int ntr = (nn + 3) >> 2, ntc = (m + 3) >> 2;
+            t += ntr * ntc - ntr * (ntr - 1) / 2;
+            mem += m;
+        }
+        s_utile[nunits] = t;
+        s_uoff[nunits] = s_uoff[nunits - 1] + (((s_um[nunits - 1] + 3) >> 2) << 2);
+        s_hdr[2] = t; s_hdr[3] = mem;
+        mbar_expect_tx(bar, (uint32_t)mem * (uint32_t)P.ld * 4u);
+        if (P.stats) {
+            unsigned long long pairs = 0;
+            for (int u = 0; u < nunits; ++u) { unsigned long long nn = s_unn[u], m = s_um[u]; pairs += nn * (nn + 1) / 2 + nn * (m - nn); }
+            atomicAdd(&P.stats[0], (unsigned long long)mem); atomicAdd(&P.stats[1], pairs);
+        }
+    }
+    __syncthreads();
+    const int totphys = s_uoff[nunits];
+    for (int e = tid; e < totphys; e += JB_THREADS) {
+        int32_t id = P.members[base + e];
+        ids[e] = id;
+        thr_s[e] = id >= 0 ? P.thr[id] : 0.0f;
+        if (METRIC == NND_METRIC_ALT_COSINE) n2_s[e] = id >= 0 ? ((const float *)P.aux)[id] : 0.0f;
+    }
+    __syncthreads();
+    // gather: member j of unit u -> physical slot uoff + (j&3)*ntc + (j>>2)   (bank-conflict-free tile reads)
+    for (int u = warp; u < nunits; u += JB_THREADS / 32) {
+        const int m = s_um[u], ntc = (m + 3) >> 2, uo = s_uoff[u];
+        for (int j = lane; j < m; j += 32)
+            bulk_g2s(rows + (size_t)(uo + (j & 3) * ntc + (j >> 2)) * sd, P.X + (int64_t)ids[uo + j] * P.ld, (uint32_t)P.ld * 4u, bar);
+    }
+    mbar_wait(bar, 0);
+
+    const int T = s_hdr[2];
+    const int rounds = (T + JB_THREADS - 1) / JB_THREADS;
+    for (int rd = 0; rd < rounds; ++rd) {
+        int t = rd * JB_THREADS + tid;
+        int u = -1, ta = 0, tb = 0, nn = 0, m = 0, uo = 0, ntc = 1;
+        float acc[TILE * TILE];
+#pragma unroll
+        for (int p = 0; p < TILE * TILE; ++p) acc[p] = 0.0f;
+        if (t < T) {
+            u = 0;
+            while (s_utile[u + 1] <= t) ++u;
+            nn = s_unn[u]; m = s_um[u]; uo = s_uoff[u]; ntc = (m + 3) >> 2;
+            int lt = t - s_utile[u];
+            while (lt >= ntc - ta) { lt -= ntc - ta; ++ta; }
+            tb = ta + lt;
+            const float *ra[TILE], *rb[TILE];
+#pragma unroll
+            for (int q = 0; q < TILE; ++q) {
+                int ia = min(ta * TILE + q, nn - 1), ib = min(tb * TILE + q, m - 1);
+                ra[q] = rows + (size_t)(uo + (ia & 3) * ntc + (ia >> 2)) * sd;
+                rb[q] = rows + (size_t)(uo + (ib & 3) * ntc + (ib >> 2)) * sd;
+            }
+#pragma unroll 2
+            for (int e = 0; e < P.ld; e += 4) {
+                float4 va[TILE], vb[TILE];
+#pragma unroll
+                for (int q = 0; q < TILE; ++q) { va[q] = *(const float4 *)(ra[q] + e); vb[q] = *(const float4 *)(rb[q] + e); }
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+#pragma unroll
+                    for (int qa = 0; qa < TILE; ++qa) {
+                        float xa = (w == 0) ? va[qa].x : (w == 1) ? va[qa].y : (w == 2) ? va[qa].z : va[qa].w;
+#pragma unroll
+                        for (int qb = 0; qb < TILE; ++qb) {
+                            float xb = (w == 0) ? vb[qb].x : (w == 1) ? vb[qb].y : (w == 2) ? vb[qb].z : vb[qb].w;
+                            if (METRIC == NND_METRIC_SQEUCLIDEAN) {
+                                float df = __fsub_rn(xa, xb);
+                                acc[qa * TILE + qb] = __fmaf_rn(df, df, acc[qa * TILE + qb]);
+                            } else {
+                                acc[qa * TILE + qb] = __fmaf_rn(xa, xb, acc[qa * TILE + qb]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- finalise + filter
+        uint32_t pm = 0;
+        if (u >= 0) {
+#pragma unroll
+            for (int qa = 0; qa < TILE; ++qa)
+#pragma unroll
+                for (int qb = 0; qb < TILE; ++qb) {
+                    int a = ta * TILE + qa, b = tb * TILE + qb;
+                    bool valid = (a < nn) && (b < m) && (b >= a);
+                    float r = 0.0f;
+                    if (valid) {
+                        if (METRIC == NND_METRIC_SQEUCLIDEAN) r = acc[qa * TILE + qb];
+                        else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine(acc[qa * TILE + qb], n2_s[uo + a], n2_s[uo + b]);
+                        else r = finish_alt_dot(acc[qa * TILE + qb]);
+                        if (r < thr_s[uo + a]) pm |= 1u << (2 * (qa * TILE + qb));
+                        if (b != a && r < thr_s[uo + b]) pm |= 2u << (2 * (qa * TILE + qb));
+                    }
+                    acc[qa * TILE + qb] = r;
+                }
+        }
+        int npush = __popc(pm), incl = npush;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long wbase = 0;
+        if (total > 0) {
+            if (lane == 31) wbase = atomicAdd(P.cursor, (unsigned long long)total);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        }
+        if (npush > 0) {
+            if (wbase + (unsigned long long)total > P.capacity) { *P.overflow = 1; }
+            else {
+                unsigned long long w = wbase + (unsigned long long)(incl - npush);
+                const unsigned long long unit = (unsigned long long)s_uid[u];
+                uint32_t mk = pm;
+                while (mk) {
+                    int bit = __ffs(mk) - 1; mk &= mk - 1;
+                    int pr = bit >> 1, side = bit & 1;
+                    int a = ta * TILE + pr / TILE, b = tb * TILE + pr % TILE;
+                    int32_t pa = ids[uo + a], pb = ids[uo + b];
+                    int32_t tgt = side ? pb : pa, oth = side ? pa : pb;
+                    float r = 0.0f;
+#pragma unroll
+                    for (int sidx = 0; sidx < TILE * TILE; ++sidx) if (sidx == pr) r = acc[sidx];
+                    P.out_tgt[w] = tgt; P.out_oth[w] = oth; P.out_d[w] = r;
+                    P.out_pos[w] = atomicAdd(&P.tgt_count[tgt], 1u);
+                    P.out_seq[w] = (unit << 20) | ((unsigned long long)(a * P.slot_stride + b) << 1) | (unsigned long long)side;
+                    ++w;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ routing
 __global__ void k_snapshot_thr(const float *heap_dist, int k, float *thr, int64_t N) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,6 +651,8 @@ struct DescentWs {
     // candidate-build scratch lives behind these (k_cand.cu)
     char *cand_base; size_t cand_bytes;
     int32_t *newc, *oldc;
+    // batched local join prepass
+    uint32_t *jb_flag, *jb_phys, *jb_info, *jb_pos, *jb_poff, *act_info, *act_poff; int32_t *act_unit, *members;
 };
 
 size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T);
@@ -449,6 +674,10 @@ static int carve_descent_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, 
     W->cand_bytes = nnd_cand_ws_bytes(N, k, C, T);
     W->cand_base = A.get<char>(W->cand_bytes);
     W->newc = A.get<int32_t>((size_t)Nb * C); W->oldc = A.get<int32_t>((size_t)Nb * C);
+    W->jb_flag = A.get<uint32_t>(Nb + 1); W->jb_phys = A.get<uint32_t>(Nb + 1); W->jb_info = A.get<uint32_t>(Nb + 1);
+    W->jb_pos = A.get<uint32_t>(Nb + 2); W->jb_poff = A.get<uint32_t>(Nb + 2);
+    W->act_info = A.get<uint32_t>(Nb + 1); W->act_poff = A.get<uint32_t>(Nb + 2); W->act_unit = A.get<int32_t>(Nb + 1);
+    W->members = A.get<int32_t>((size_t)Nb * (2 * C + 4));
     if (need) *need = A.off;
     return A.ok ? NND_OK : NND_ERR_WORKSPACE;
 }
@@ -503,8 +732,9 @@ static int launch_join(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaS
 }
 
 // one routing round: join over units [u0,u1) -> scan -> scatter -> apply.  Returns pushes routed.
+static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st);
 static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_t u0, int64_t u1, DescentWs &W,
-                       int64_t cap, unsigned long long *n_pushed, cudaStream_t st) {
+                       int64_t cap, unsigned long long *n_pushed, cudaStream_t st, JoinBatchParams *JB = nullptr) {
     const int64_t N = P->N;
     k_snapshot_thr<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_dist, P->k, W.thr, N); NND_LAUNCH(ctx);
     NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (N + 1), st));
@@ -516,7 +746,15 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     NND_CUDA(cudaMemsetAsync(W.dev_scalars + 5, 0, sizeof(unsigned long long) * 2, st));
     J.stats = W.dev_scalars + 5;
     NND_CUDA(cudaEventRecord(ctx->ev0, st));
-    NND_TRY(launch_join(ctx, J, u1 - u0, st));
+    if (JB) {
+        JB->thr = W.thr; JB->batch_begin = u0; JB->batch_end = u1;
+        JB->out_tgt = W.l_tgt; JB->out_oth = W.l_oth; JB->out_d = W.l_d; JB->out_pos = W.l_pos; JB->out_seq = W.l_seq;
+        JB->tgt_count = W.cnt; JB->cursor = W.dev_scalars; JB->capacity = (unsigned long long)cap;
+        JB->overflow = (int *)(W.dev_scalars + 4); JB->stats = W.dev_scalars + 5;
+        NND_TRY(launch_join_batch(ctx, *JB, st));
+    } else {
+        NND_TRY(launch_join(ctx, J, u1 - u0, st));
+    }
     NND_CUDA(cudaEventRecord(ctx->ev1, st));
     unsigned long long h[7];
     NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -539,6 +777,33 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
                                                                            W.cnt, W.off, W.rec, W.dev_scalars + 1);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+
+static size_t join_batch_smem(int phys_max, int ld, int metric) {
+    size_t b = 32 + (size_t)JB_MAXU * 4 * 3 + (size_t)(JB_MAXU + 1) * 4 * 2;
+    b += (size_t)phys_max * 4 * (metric == NND_METRIC_ALT_COSINE ? 3 : 2);
+    b = (b + 15) & ~size_t(15);
+    b += (size_t)phys_max * (ld + 4) * 4 + 16;
+    return b;
+}
+static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st) {
+    int64_t nb = JB.batch_end - JB.batch_begin;
+    if (nb <= 0) return NND_OK;
+    size_t smem = join_batch_smem(JB.phys_max, JB.ld, JB.metric);
+    dim3 grid((unsigned)nb);
+#define LB(M_)                                                                                                   \
+    do {                                                                                                         \
+        NND_CUDA(cudaFuncSetAttribute(k_join_batch<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_join_batch<M_><<<grid, JB_THREADS, smem, st>>>(JB);                                                     \
+    } while (0)
+    if (JB.metric == NND_METRIC_SQEUCLIDEAN) LB(NND_METRIC_SQEUCLIDEAN);
+    else if (JB.metric == NND_METRIC_ALT_COSINE) LB(NND_METRIC_ALT_COSINE);
+    else LB(NND_METRIC_ALT_DOT);
+#undef LB
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
     return NND_OK;
@@ -662,20 +927,60 @@ extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_
               "nnd_process_candidates: workspace too small");
     const int64_t N = P->N;
     NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long) * 16, st));
-    k_row_bound<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.bound); NND_LAUNCH(ctx);
-    std::vector<int64_t> cuts;
-    NND_TRY(plan_blocks(ctx, W.bound, N, W, push_capacity, cuts, st));
+    unsigned long long total = 0, rows_g = 0, pairs_g = 0; int64_t blocks = 0;
     JoinParams J; memset(&J, 0, sizeof(J));
     J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
     J.mode = 0; J.newc = new_cand; J.oldc = old_cand; J.C = C; J.m_max = 2 * C < 4 ? 4 : 2 * C; J.slot_stride = 2 * C;
-    unsigned long long total = 0, rows_g = 0, pairs_g = 0; int64_t blocks = 0;
-    for (size_t b = 0; b + 1 < cuts.size(); ++b) {
-        unsigned long long np = 0;
-        if (cuts[b] < cuts[b + 1]) {
-            NND_TRY(route_round(ctx, P, J, cuts[b], cuts[b + 1], W, push_capacity, &np, st)); ++blocks;
-            rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs;
+    const char *force_old = getenv("NND_JOIN_UNBATCHED");
+    const bool batched = P->metric != NND_METRIC_CORRELATION && P->ld <= 256 && 2 * C <= 120 &&
+                         !(force_old && force_old[0] == '1');
+    if (batched) {
+        // ---- batched path: compact the active rows and their members, then one CTA per member-budget batch
+        const int maxphys = ((2 * C + 3) >> 2) << 2;
+        int ps = (int)((56 * 1024) / ((size_t)(P->ld + 4) * 4)) - maxphys;   // physical slots per batch
+        if (ps < maxphys) ps = maxphys;
+        if (ps > (JB_MAXU - 1) * 4) ps = (JB_MAXU - 1) * 4;
+        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_info); NND_LAUNCH(ctx);
+        NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_flag, W.jb_pos, N, W.scan_tmp, st));
+        NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_phys, W.jb_poff, N, W.scan_tmp, st));
+        k_jb_fill<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_pos, W.jb_poff, W.jb_info,
+                                                          W.act_unit, W.act_info, W.act_poff, W.members);
+        NND_LAUNCH(ctx);
+        uint32_t hh[2];
+        NND_CUDA(cudaMemcpyAsync(&hh[0], W.jb_pos + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        NND_CUDA(cudaMemcpyAsync(&hh[1], W.jb_poff + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        NND_CUDA(cudaStreamSynchronize(st));
+        const int64_t n_active = hh[0]; const uint32_t total_phys = hh[1];
+        if (n_active > 0) {
+            JoinBatchParams JB; memset(&JB, 0, sizeof(JB));
+            JB.X = P->X; JB.N = N; JB.ld = P->ld; JB.metric = P->metric; JB.aux = P->aux;
+            JB.act_unit = W.act_unit; JB.act_info = W.act_info; JB.act_poff = W.act_poff; JB.members = W.members;
+            JB.n_active = n_active; JB.total_phys = total_phys; JB.ps = ps; JB.slot_stride = 2 * C; JB.phys_max = ps + maxphys;
+            const int64_t n_batches = cdiv((int64_t)total_phys, ps);
+            // worst case half-updates per member slot = (3C+1)/2  (full row: C(C+1)/2 + C^2 pairs over 2C members, x2)
+            const int64_t per_batch = (int64_t)(ps + maxphys) * ((3 * C + 1) / 2 + 1);
+            NND_CHECK(per_batch <= push_capacity, NND_ERR_OVERFLOW, "push_capacity %lld too small for one batch (%lld)",
+                      (long long)push_capacity, (long long)per_batch);
+            const int64_t bpb = push_capacity / per_batch;
+            for (int64_t b0 = 0; b0 < n_batches; b0 += bpb) {
+                int64_t b1 = b0 + bpb < n_batches ? b0 + bpb : n_batches;
+                unsigned long long np = 0;
+                NND_TRY(route_round(ctx, P, J, b0, b1, W, push_capacity, &np, st, &JB)); ++blocks;
+                rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs; total += np;
+            }
         }
-        total += np;
+    } else {
+        k_row_bound<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.bound); NND_LAUNCH(ctx);
+        std::vector<int64_t> cuts;
+        NND_TRY(plan_blocks(ctx, W.bound, N, W, push_capacity, cuts, st));
+        for (size_t b = 0; b + 1 < cuts.size(); ++b) {
+            unsigned long long np = 0;
+            if (cuts[b] < cuts[b + 1]) {
+                NND_TRY(route_round(ctx, P, J, cuts[b], cuts[b + 1], W, push_capacity, &np, st)); ++blocks;
+                rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs;
+            }
+            total += np;
+        }
     }
     unsigned long long h[5];
     NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
