@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
 // =====================================================================================================
 #define JB_THREADS 64
 #define JB_MAXU 40
+#define JB_CMAX 60  // members scratch is sized for the largest C so that its offset does not depend on C
 struct JoinBatchParams {
     const float *X; int64_t N; int ld; int metric; const void *aux; const float *thr;
     const int32_t *act_unit; const uint32_t *act_info; const uint32_t *act_poff; const int32_t *members;
@@ -671,13 +672,15 @@ static int carve_descent_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, 
     W->l_pos = A.get<uint32_t>(cap); W->l_seq = A.get<unsigned long long>(cap);
     W->rec = A.get<Rec16>((size_t)cap * 2 + NND_SEG_SMEM);
     W->dev_scalars = A.get<unsigned long long>(16);
-    W->cand_bytes = nnd_cand_ws_bytes(N, k, C, T);
-    W->cand_base = A.get<char>(W->cand_bytes);
-    W->newc = A.get<int32_t>((size_t)Nb * C); W->oldc = A.get<int32_t>((size_t)Nb * C);
+    // everything the stage calls share must sit BEFORE the T-dependent candidate scratch: nnd_descent carves
+    // with the real T, the stage entry points with T=1, and both must agree on these offsets
     W->jb_flag = A.get<uint32_t>(Nb + 1); W->jb_phys = A.get<uint32_t>(Nb + 1); W->jb_info = A.get<uint32_t>(Nb + 1);
     W->jb_pos = A.get<uint32_t>(Nb + 2); W->jb_poff = A.get<uint32_t>(Nb + 2);
     W->act_info = A.get<uint32_t>(Nb + 1); W->act_poff = A.get<uint32_t>(Nb + 2); W->act_unit = A.get<int32_t>(Nb + 1);
-    W->members = A.get<int32_t>((size_t)Nb * (2 * C + 4));
+    W->members = A.get<int32_t>((size_t)Nb * (2 * JB_CMAX + 4));
+    W->cand_bytes = nnd_cand_ws_bytes(N, k, C, T);
+    W->cand_base = A.get<char>(W->cand_bytes);
+    W->newc = A.get<int32_t>((size_t)Nb * C); W->oldc = A.get<int32_t>((size_t)Nb * C);
     if (need) *need = A.off;
     return A.ok ? NND_OK : NND_ERR_WORKSPACE;
 }
