@@ -335,82 +335,94 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
 
 
 // =====================================================================================================
-// k_join_batch: the local join for short rows (ld <= 256).  One 64-thread CTA handles a BATCH of consecutive
-// candidate rows chosen so that their member vectors fill the shared-memory budget; all 4x4 tiles of all rows
-// of the batch form one queue shared by the 64 threads, so lanes stay busy even when a single row has only a
-// handful of tiles (one-warp-per-row left 50-70 % of the lanes idle).  Member rows are resident in full (no
-// d-chunking), staged by the TMA bulk-copy engine.  Same arithmetic, same emission keys as k_join.
+// k_join_batch: the local join for short rows (ld <= 256).  One 128-thread CTA handles a BATCH of consecutive
+// candidate rows; every thread owns exactly one 4x4 tile of the batch's tile queue (batches are cut by a
+// per-row weight = max(#member slots, 1.5 x #tiles) so that <= 192 slots and <= 128 tiles fit), so lanes stay
+// busy even when one row has only a handful of tiles.  Member rows are staged by the TMA bulk-copy engine in
+// d-chunks of 32 floats, DOUBLE-BUFFERED on two mbarriers: chunk c+1 is in flight while chunk c is accumulated
+// (the sequential per-pair order is preserved because each thread walks the chunks in order).
+// Same arithmetic and the same emission keys as k_join.
 // =====================================================================================================
-#define JB_THREADS 64
-#define JB_MAXU 40
+#define JB_THREADS 128
+#define JB_TCAP 128      // tiles per batch
+#define JB_SCAP 176      // physical member slots per batch (2 buffers x 176 x 144 B -> 4 CTAs/SM)
+#define JB_MAXU 48       // units per batch (every unit weighs >= 4)
+#define JB_DK 32         // floats per staged chunk
+#define JB_SD (JB_DK + 4)
 #define JB_CMAX 60  // members scratch is sized for the largest C so that its offset does not depend on C
 struct JoinBatchParams {
     const float *X; int64_t N; int ld; int metric; const void *aux; const float *thr;
     const int32_t *act_unit; const uint32_t *act_info; const uint32_t *act_poff; const int32_t *members;
-    int64_t n_active; uint32_t total_phys; int ps; int64_t batch_begin, batch_end; int slot_stride; int phys_max;
+    const int32_t *batch_first;
+    int64_t n_active, n_batches; int64_t batch_begin, batch_end; int slot_stride;
     int32_t *out_tgt, *out_oth; float *out_d; uint32_t *out_pos; unsigned long long *out_seq;
     uint32_t *tgt_count; unsigned long long *cursor; unsigned long long capacity; unsigned long long *stats; int *overflow;
 };
 
-// prepass 1: per row, number of new / old candidates -> physical slot count (0 for rows without new candidates)
+__host__ __device__ __forceinline__ int jb_tiles(int nn, int m) {
+    int ntr = (nn + 3) >> 2, ntc = (m + 3) >> 2;
+    return ntr * ntc - ntr * (ntr - 1) / 2;
+}
+// prepass 1: per row -> active flag, physical slots, batching weight
 __global__ void k_jb_count(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *flag, uint32_t *phys,
-                           uint32_t *info) {
+                           uint32_t *wgt, uint32_t *info) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int nn = 0, no = 0;
     for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
     int m = nn + no;
+    uint32_t ph = nn > 0 ? (uint32_t)(((m + 3) >> 2) << 2) : 0u;
+    uint32_t tw = nn > 0 ? (uint32_t)((jb_tiles(nn, m) * 3 + 1) >> 1) : 0u;
     flag[i] = nn > 0;
-    phys[i] = nn > 0 ? (uint32_t)(((m + 3) >> 2) << 2) : 0u;
+    phys[i] = ph;
+    wgt[i] = ph > tw ? ph : tw;
     info[i] = (uint32_t)nn | ((uint32_t)m << 8);
 }
 // prepass 2: compacted active-row list + member ids in the reference's order (new k asc, then old k asc; holes dropped)
 __global__ void k_jb_fill(const int32_t *newc, const int32_t *oldc, int C, int64_t N, const uint32_t *flag,
-                          const uint32_t *pos, const uint32_t *poff, const uint32_t *info, int32_t *act_unit,
-                          uint32_t *act_info, uint32_t *act_poff, int32_t *members) {
+                          const uint32_t *pos, const uint32_t *poff, const uint32_t *woff, const uint32_t *info,
+                          int32_t *act_unit, uint32_t *act_info, uint32_t *act_poff, uint32_t *act_woff, int32_t *members) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N || !flag[i]) return;
     uint32_t j = pos[i], o = poff[i];
-    act_unit[j] = (int32_t)i; act_info[j] = info[i]; act_poff[j] = o;
+    act_unit[j] = (int32_t)i; act_info[j] = info[i]; act_poff[j] = o; act_woff[j] = woff[i];
     int w = 0;
     for (int c = 0; c < C; ++c) { int32_t v = newc[i * C + c]; if (v >= 0) members[o + w++] = v; }
     for (int c = 0; c < C; ++c) { int32_t v = oldc[i * C + c]; if (v >= 0) members[o + w++] = v; }
     int pe = ((w + 3) >> 2) << 2;
     for (; w < pe; ++w) members[o + w] = -1;
 }
-
-__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *a, int64_t n, uint32_t key) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
+// prepass 3: first active row of every batch (batch b = rows whose weight prefix lies in [b*ps,(b+1)*ps))
+__global__ void k_jb_bounds(const uint32_t *act_woff, int64_t n_active, uint32_t ps, int32_t *batch_first) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_active) return;
+    uint32_t b = act_woff[j] / ps;
+    if (j == 0 || act_woff[j - 1] / ps != b) batch_first[b] = (int32_t)j;
 }
 
 template <int METRIC>
 __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *bar = (uint64_t *)smem_raw;
-    int *s_hdr = (int *)(smem_raw + 8);                     // [0] j0 [1] nunits [2] total tiles [3] total members
+    uint64_t *bar = (uint64_t *)smem_raw;                  // [2]
+    int *s_hdr = (int *)(smem_raw + 16);                    // [0] nunits [1] tiles [2] members [3] total phys
     int32_t *s_uid = (int32_t *)(smem_raw + 32);            // [JB_MAXU]
-    int *s_unn = s_uid + JB_MAXU, *s_um = s_unn + JB_MAXU;  // nn, m
-    int *s_uoff = s_um + JB_MAXU;                           // [JB_MAXU+1] physical slot offset of the unit
-    int *s_utile = s_uoff + JB_MAXU + 1;                    // [JB_MAXU+1] tile prefix
-    int32_t *ids = (int32_t *)(s_utile + JB_MAXU + 1);      // [phys_max] logical order, padded per unit
-    float *thr_s = (float *)(ids + P.phys_max);
-    float *n2_s = thr_s + P.phys_max;                       // cosine only
-    float *rows = (float *)(((uintptr_t)(n2_s + (METRIC == NND_METRIC_ALT_COSINE ? P.phys_max : 0)) + 15) & ~uintptr_t(15));
-    const int sd = P.ld + 4;
+    int *s_unn = s_uid + JB_MAXU, *s_um = s_unn + JB_MAXU;
+    int *s_uoff = s_um + JB_MAXU;                           // [JB_MAXU+1]
+    int *s_utile = s_uoff + JB_MAXU + 1;                    // [JB_MAXU+1]
+    int32_t *ids = (int32_t *)(s_utile + JB_MAXU + 1);      // [JB_SCAP]
+    float *thr_s = (float *)(ids + JB_SCAP);
+    float *n2_s = thr_s + JB_SCAP;                          // cosine only
+    float *rows = (float *)(((uintptr_t)(n2_s + (METRIC == NND_METRIC_ALT_COSINE ? JB_SCAP : 0)) + 15) & ~uintptr_t(15));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t B = P.batch_begin + blockIdx.x;
     if (B >= P.batch_end) return;
-
-    if (tid == 0) {
-        int64_t j0 = lower_bound_u32(P.act_poff, P.n_active, (uint32_t)(B * P.ps));
-        int64_t j1 = lower_bound_u32(P.act_poff, P.n_active, (uint32_t)((B + 1) * P.ps));
-        s_hdr[0] = (int)j0; s_hdr[1] = (int)(j1 - j0);
-        mbar_init(bar, 1); mbar_fence_init();
-    }
-    __syncthreads();
-    const int j0 = s_hdr[0], nunits = s_hdr[1];
+    // batch_first[b] = first active row whose weight prefix starts in window b, or a sentinel (0x7f7f7f7f) when a
+    // heavy row of the previous window covers window b entirely (then this CTA has nothing to do)
+    int64_t j0 = P.batch_first[B];
+    if (j0 >= P.n_active) return;
+    int64_t j1 = P.n_active;
+    for (int64_t bb = B + 1; bb < P.n_batches; ++bb) { int64_t v = P.batch_first[bb]; if (v < P.n_active) { j1 = v; break; } }
+    const int nunits = (int)(j1 - j0);
     if (nunits <= 0) return;
     const uint32_t base = P.act_poff[j0];
     if (tid < nunits) {
@@ -418,70 +430,80 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
         s_uid[tid] = P.act_unit[j0 + tid]; s_unn[tid] = (int)(inf & 0xFF); s_um[tid] = (int)(inf >> 8);
         s_uoff[tid] = (int)(P.act_poff[j0 + tid] - base);
     }
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     if (tid == 0) {
         int t = 0, mem = 0;
+        unsigned long long pairs = 0;
         for (int u = 0; u < nunits; ++u) {
             s_utile[u] = t;
             int nn = s_unn[u], m = s_um[u];
-            int ntr = (nn + 3) >> 2, ntc = (m + 3) >> 2;
-            t += ntr * ntc - ntr * (ntr - 1) / 2;
+            t += jb_tiles(nn, m);
             mem += m;
+            pairs += (unsigned long long)nn * (nn + 1) / 2 + (unsigned long long)nn * (m - nn);
         }
         s_utile[nunits] = t;
         s_uoff[nunits] = s_uoff[nunits - 1] + (((s_um[nunits - 1] + 3) >> 2) << 2);
-        s_hdr[2] = t; s_hdr[3] = mem;
-        mbar_expect_tx(bar, (uint32_t)mem * (uint32_t)P.ld * 4u);
-        if (P.stats) {
-            unsigned long long pairs = 0;
-            for (int u = 0; u < nunits; ++u) { unsigned long long nn = s_unn[u], m = s_um[u]; pairs += nn * (nn + 1) / 2 + nn * (m - nn); }
-            atomicAdd(&P.stats[0], (unsigned long long)mem); atomicAdd(&P.stats[1], pairs);
-        }
+        s_hdr[1] = t; s_hdr[2] = mem;
+        if (P.stats) { atomicAdd(&P.stats[0], (unsigned long long)mem); atomicAdd(&P.stats[1], pairs); }
     }
     __syncthreads();
-    const int totphys = s_uoff[nunits];
+    const int totphys = s_uoff[nunits], mem = s_hdr[2], T = s_hdr[1];
     for (int e = tid; e < totphys; e += JB_THREADS) {
         int32_t id = P.members[base + e];
         ids[e] = id;
         thr_s[e] = id >= 0 ? P.thr[id] : 0.0f;
         if (METRIC == NND_METRIC_ALT_COSINE) n2_s[e] = id >= 0 ? ((const float *)P.aux)[id] : 0.0f;
     }
-    __syncthreads();
-    // gather: member j of unit u -> physical slot uoff + (j&3)*ntc + (j>>2)   (bank-conflict-free tile reads)
-    for (int u = warp; u < nunits; u += JB_THREADS / 32) {
-        const int m = s_um[u], ntc = (m + 3) >> 2, uo = s_uoff[u];
-        for (int j = lane; j < m; j += 32)
-            bulk_g2s(rows + (size_t)(uo + (j & 3) * ntc + (j >> 2)) * sd, P.X + (int64_t)ids[uo + j] * P.ld, (uint32_t)P.ld * 4u, bar);
+    // ---- my tile
+    int u = -1, ta = 0, tb = 0, nn = 0, m = 0, uo = 0, ntc = 1;
+    if (tid < T) {
+        int lo = 0, hi = nunits;                        // last u with s_utile[u] <= tid
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_utile[mid] <= tid) lo = mid; else hi = mid; }
+        u = lo;
+        nn = s_unn[u]; m = s_um[u]; uo = s_uoff[u]; ntc = (m + 3) >> 2;
+        int lt = tid - s_utile[u];
+        while (lt >= ntc - ta) { lt -= ntc - ta; ++ta; }
+        tb = ta + lt;
     }
-    mbar_wait(bar, 0);
+    int oa[TILE], ob[TILE];                                 // smem row offsets (floats) of my 4 + 4 member rows
+#pragma unroll
+    for (int q = 0; q < TILE; ++q) {
+        int ia = min(ta * TILE + q, max(nn - 1, 0)), ib = min(tb * TILE + q, max(m - 1, 0));
+        oa[q] = (uo + (ia & 3) * ntc + (ia >> 2)) * JB_SD;
+        ob[q] = (uo + (ib & 3) * ntc + (ib >> 2)) * JB_SD;
+    }
+    float acc[TILE * TILE];
+#pragma unroll
+    for (int p = 0; p < TILE * TILE; ++p) acc[p] = 0.0f;
+    __syncthreads();                                        // ids[] complete
 
-    const int T = s_hdr[2];
-    const int rounds = (T + JB_THREADS - 1) / JB_THREADS;
-    for (int rd = 0; rd < rounds; ++rd) {
-        int t = rd * JB_THREADS + tid;
-        int u = -1, ta = 0, tb = 0, nn = 0, m = 0, uo = 0, ntc = 1;
-        float acc[TILE * TILE];
-#pragma unroll
-        for (int p = 0; p < TILE * TILE; ++p) acc[p] = 0.0f;
-        if (t < T) {
-            u = 0;
-            while (s_utile[u + 1] <= t) ++u;
-            nn = s_unn[u]; m = s_um[u]; uo = s_uoff[u]; ntc = (m + 3) >> 2;
-            int lt = t - s_utile[u];
-            while (lt >= ntc - ta) { lt -= ntc - ta; ++ta; }
-            tb = ta + lt;
-            const float *ra[TILE], *rb[TILE];
-#pragma unroll
-            for (int q = 0; q < TILE; ++q) {
-                int ia = min(ta * TILE + q, nn - 1), ib = min(tb * TILE + q, m - 1);
-                ra[q] = rows + (size_t)(uo + (ia & 3) * ntc + (ia >> 2)) * sd;
-                rb[q] = rows + (size_t)(uo + (ib & 3) * ntc + (ib >> 2)) * sd;
-            }
+    // ---- chunk pipeline: gather chunk c+1 while accumulating chunk c
+    const int nchunks = (P.ld + JB_DK - 1) / JB_DK;
+    auto issue = [&](int c) {
+        const int c0 = c * JB_DK, len = min(JB_DK, P.ld - c0);
+        float *buf = rows + (size_t)(c & 1) * JB_SCAP * JB_SD;
+        if (tid == 0) mbar_expect_tx(&bar[c & 1], (uint32_t)mem * (uint32_t)len * 4u);
+        __syncthreads();
+        for (int uu = warp; uu < nunits; uu += JB_THREADS / 32) {
+            const int mm = s_um[uu], nt = (mm + 3) >> 2, o = s_uoff[uu];
+            for (int j = lane; j < mm; j += 32)
+                bulk_g2s(buf + (size_t)(o + (j & 3) * nt + (j >> 2)) * JB_SD, P.X + (int64_t)ids[o + j] * P.ld + c0,
+                         (uint32_t)len * 4u, &bar[c & 1]);
+        }
+    };
+    issue(0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) issue(c + 1);                  // buffer (c+1)&1 was released by the sync ending chunk c-1
+        mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
+        if (u >= 0) {
+            const float *buf = rows + (size_t)(c & 1) * JB_SCAP * JB_SD;
+            const int len = min(JB_DK, P.ld - c * JB_DK);
 #pragma unroll 2
-            for (int e = 0; e < P.ld; e += 4) {
+            for (int e = 0; e < len; e += 4) {
                 float4 va[TILE], vb[TILE];
 #pragma unroll
-                for (int q = 0; q < TILE; ++q) { va[q] = *(const float4 *)(ra[q] + e); vb[q] = *(const float4 *)(rb[q] + e); }
+                for (int q = 0; q < TILE; ++q) { va[q] = *(const float4 *)(buf + oa[q] + e); vb[q] = *(const float4 *)(buf + ob[q] + e); }
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
 #pragma unroll
@@ -501,56 +523,55 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
                 }
             }
         }
-        // ---- finalise + filter
-        uint32_t pm = 0;
-        if (u >= 0) {
+        __syncthreads();                                    // everyone done with buffer c&1
+    }
+    // ---- finalise + filter
+    uint32_t pm = 0;
+    if (u >= 0) {
 #pragma unroll
-            for (int qa = 0; qa < TILE; ++qa)
+        for (int qa = 0; qa < TILE; ++qa)
 #pragma unroll
-                for (int qb = 0; qb < TILE; ++qb) {
-                    int a = ta * TILE + qa, b = tb * TILE + qb;
-                    bool valid = (a < nn) && (b < m) && (b >= a);
-                    float r = 0.0f;
-                    if (valid) {
-                        if (METRIC == NND_METRIC_SQEUCLIDEAN) r = acc[qa * TILE + qb];
-                        else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine(acc[qa * TILE + qb], n2_s[uo + a], n2_s[uo + b]);
-                        else r = finish_alt_dot(acc[qa * TILE + qb]);
-                        if (r < thr_s[uo + a]) pm |= 1u << (2 * (qa * TILE + qb));
-                        if (b != a && r < thr_s[uo + b]) pm |= 2u << (2 * (qa * TILE + qb));
-                    }
-                    acc[qa * TILE + qb] = r;
+            for (int qb = 0; qb < TILE; ++qb) {
+                int a = ta * TILE + qa, b = tb * TILE + qb;
+                bool valid = (a < nn) && (b < m) && (b >= a);
+                float r = 0.0f;
+                if (valid) {
+                    if (METRIC == NND_METRIC_SQEUCLIDEAN) r = acc[qa * TILE + qb];
+                    else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine(acc[qa * TILE + qb], n2_s[uo + a], n2_s[uo + b]);
+                    else r = finish_alt_dot(acc[qa * TILE + qb]);
+                    if (r < thr_s[uo + a]) pm |= 1u << (2 * (qa * TILE + qb));
+                    if (b != a && r < thr_s[uo + b]) pm |= 2u << (2 * (qa * TILE + qb));
                 }
-        }
-        int npush = __popc(pm), incl = npush;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        int total = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned long long wbase = 0;
-        if (total > 0) {
-            if (lane == 31) wbase = atomicAdd(P.cursor, (unsigned long long)total);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        }
-        if (npush > 0) {
-            if (wbase + (unsigned long long)total > P.capacity) { *P.overflow = 1; }
-            else {
-                unsigned long long w = wbase + (unsigned long long)(incl - npush);
-                const unsigned long long unit = (unsigned long long)s_uid[u];
-                uint32_t mk = pm;
-                while (mk) {
-                    int bit = __ffs(mk) - 1; mk &= mk - 1;
-                    int pr = bit >> 1, side = bit & 1;
-                    int a = ta * TILE + pr / TILE, b = tb * TILE + pr % TILE;
-                    int32_t pa = ids[uo + a], pb = ids[uo + b];
-                    int32_t tgt = side ? pb : pa, oth = side ? pa : pb;
-                    float r = 0.0f;
-#pragma unroll
-                    for (int sidx = 0; sidx < TILE * TILE; ++sidx) if (sidx == pr) r = acc[sidx];
-                    P.out_tgt[w] = tgt; P.out_oth[w] = oth; P.out_d[w] = r;
-                    P.out_pos[w] = atomicAdd(&P.tgt_count[tgt], 1u);
-                    P.out_seq[w] = (unit << 20) | ((unsigned long long)(a * P.slot_stride + b) << 1) | (unsigned long long)side;
-                    ++w;
-                }
+                acc[qa * TILE + qb] = r;
             }
+    }
+    int npush = __popc(pm), incl = npush;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long wbase = 0;
+    if (total > 0) {
+        if (lane == 31) wbase = atomicAdd(P.cursor, (unsigned long long)total);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    }
+    if (npush > 0) {
+        if (wbase + (unsigned long long)total > P.capacity) { *P.overflow = 1; return; }
+        unsigned long long w = wbase + (unsigned long long)(incl - npush);
+        const unsigned long long unit = (unsigned long long)s_uid[u];
+        uint32_t mk = pm;
+        while (mk) {
+            int bit = __ffs(mk) - 1; mk &= mk - 1;
+            int pr = bit >> 1, side = bit & 1;
+            int a = ta * TILE + pr / TILE, b = tb * TILE + pr % TILE;
+            int32_t pa = ids[uo + a], pb = ids[uo + b];
+            int32_t tgt = side ? pb : pa, oth = side ? pa : pb;
+            float r = 0.0f;
+#pragma unroll
+            for (int sidx = 0; sidx < TILE * TILE; ++sidx) if (sidx == pr) r = acc[sidx];
+            P.out_tgt[w] = tgt; P.out_oth[w] = oth; P.out_d[w] = r;
+            P.out_pos[w] = atomicAdd(&P.tgt_count[tgt], 1u);
+            P.out_seq[w] = (unit << 20) | ((unsigned long long)(a * P.slot_stride + b) << 1) | (unsigned long long)side;
+            ++w;
         }
     }
 }
@@ -653,7 +674,8 @@ struct DescentWs {
     char *cand_base; size_t cand_bytes;
     int32_t *newc, *oldc;
     // batched local join prepass
-    uint32_t *jb_flag, *jb_phys, *jb_info, *jb_pos, *jb_poff, *act_info, *act_poff; int32_t *act_unit, *members;
+    uint32_t *jb_flag, *jb_phys, *jb_wgt, *jb_info, *jb_pos, *jb_poff, *jb_woff, *act_info, *act_poff, *act_woff;
+    int32_t *act_unit, *members, *batch_first;
 };
 
 size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T);
@@ -676,7 +698,15 @@ static int carve_descent_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, 
     // with the real T, the stage entry points with T=1, and both must agree on these offsets
     W->jb_flag = A.get<uint32_t>(Nb + 1); W->jb_phys = A.get<uint32_t>(Nb + 1); W->jb_info = A.get<uint32_t>(Nb + 1);
     W->jb_pos = A.get<uint32_t>(Nb + 2); W->jb_poff = A.get<uint32_t>(Nb + 2);
+    W->jb_wgt = A.get<uint32_t>(Nb + 1); W->jb_woff = A.get<uint32_t>(Nb + 2);
     W->act_info = A.get<uint32_t>(Nb + 1); W->act_poff = A.get<uint32_t>(Nb + 2); W->act_unit = A.get<int32_t>(Nb + 1);
+    W->act_woff = A.get<uint32_t>(Nb + 2);
+    {   // one entry per weight window: N * maxw / (JB_SCAP - maxw) windows at most (depends on C, not on T)
+        int Cc = C < 1 ? 1 : (C > JB_CMAX ? JB_CMAX : C);
+        int mp = ((2 * Cc + 3) >> 2) << 2, mt = (jb_tiles(Cc, 2 * Cc) * 3 + 1) >> 1, mw = mp > mt ? mp : mt;
+        int psw = JB_SCAP - mw; if (psw < 1) psw = 1;
+        W->batch_first = A.get<int32_t>((size_t)Nb * (size_t)(mw / psw + 1) + 8);
+    }
     W->members = A.get<int32_t>((size_t)Nb * (2 * JB_CMAX + 4));
     W->cand_bytes = nnd_cand_ws_bytes(N, k, C, T);
     W->cand_base = A.get<char>(W->cand_bytes);
@@ -786,17 +816,17 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
 }
 
 
-static size_t join_batch_smem(int phys_max, int ld, int metric) {
+static size_t join_batch_smem(int metric) {
     size_t b = 32 + (size_t)JB_MAXU * 4 * 3 + (size_t)(JB_MAXU + 1) * 4 * 2;
-    b += (size_t)phys_max * 4 * (metric == NND_METRIC_ALT_COSINE ? 3 : 2);
+    b += (size_t)JB_SCAP * 4 * (metric == NND_METRIC_ALT_COSINE ? 3 : 2);
     b = (b + 15) & ~size_t(15);
-    b += (size_t)phys_max * (ld + 4) * 4 + 16;
+    b += (size_t)2 * JB_SCAP * JB_SD * 4 + 16;
     return b;
 }
 static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st) {
     int64_t nb = JB.batch_end - JB.batch_begin;
     if (nb <= 0) return NND_OK;
-    size_t smem = join_batch_smem(JB.phys_max, JB.ld, JB.metric);
+    size_t smem = join_batch_smem(JB.metric);
     dim3 grid((unsigned)nb);
 #define LB(M_)                                                                                                   \
     do {                                                                                                         \
@@ -935,33 +965,36 @@ extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_
     J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
     J.mode = 0; J.newc = new_cand; J.oldc = old_cand; J.C = C; J.m_max = 2 * C < 4 ? 4 : 2 * C; J.slot_stride = 2 * C;
     const char *force_old = getenv("NND_JOIN_UNBATCHED");
-    const bool batched = P->metric != NND_METRIC_CORRELATION && P->ld <= 256 && 2 * C <= 120 &&
+    const bool batched = P->metric != NND_METRIC_CORRELATION && 2 * C <= 60 &&
                          !(force_old && force_old[0] == '1');
     if (batched) {
-        // ---- batched path: compact the active rows and their members, then one CTA per member-budget batch
+        // ---- batched path: compact the active rows and their members, cut batches by weight, one CTA per batch
         const int maxphys = ((2 * C + 3) >> 2) << 2;
-        int ps = (int)((56 * 1024) / ((size_t)(P->ld + 4) * 4)) - maxphys;   // physical slots per batch
-        if (ps < maxphys) ps = maxphys;
-        if (ps > (JB_MAXU - 1) * 4) ps = (JB_MAXU - 1) * 4;
-        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_info); NND_LAUNCH(ctx);
+        const int maxw_t = (jb_tiles(C, 2 * C) * 3 + 1) >> 1;
+        const int maxw = maxphys > maxw_t ? maxphys : maxw_t;
+        const uint32_t ps = (uint32_t)(JB_SCAP - maxw);                          // weight window per batch
+        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_wgt, W.jb_info); NND_LAUNCH(ctx);
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_flag, W.jb_pos, N, W.scan_tmp, st));
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_phys, W.jb_poff, N, W.scan_tmp, st));
-        k_jb_fill<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_pos, W.jb_poff, W.jb_info,
-                                                          W.act_unit, W.act_info, W.act_poff, W.members);
+        NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_wgt, W.jb_woff, N, W.scan_tmp, st));
+        k_jb_fill<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_pos, W.jb_poff, W.jb_woff, W.jb_info,
+                                                          W.act_unit, W.act_info, W.act_poff, W.act_woff, W.members);
         NND_LAUNCH(ctx);
         uint32_t hh[2];
         NND_CUDA(cudaMemcpyAsync(&hh[0], W.jb_pos + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        NND_CUDA(cudaMemcpyAsync(&hh[1], W.jb_poff + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        NND_CUDA(cudaMemcpyAsync(&hh[1], W.jb_woff + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         NND_CUDA(cudaStreamSynchronize(st));
-        const int64_t n_active = hh[0]; const uint32_t total_phys = hh[1];
+        const int64_t n_active = hh[0];
         if (n_active > 0) {
+            const int64_t n_batches = cdiv((int64_t)hh[1], (int64_t)ps);
+            NND_CUDA(cudaMemsetAsync(W.batch_first, 0x7f, sizeof(int32_t) * (n_batches + 2), st));
+            k_jb_bounds<<<(unsigned)cdiv(n_active, 256), 256, 0, st>>>(W.act_woff, n_active, ps, W.batch_first); NND_LAUNCH(ctx);
             JoinBatchParams JB; memset(&JB, 0, sizeof(JB));
             JB.X = P->X; JB.N = N; JB.ld = P->ld; JB.metric = P->metric; JB.aux = P->aux;
             JB.act_unit = W.act_unit; JB.act_info = W.act_info; JB.act_poff = W.act_poff; JB.members = W.members;
-            JB.n_active = n_active; JB.total_phys = total_phys; JB.ps = ps; JB.slot_stride = 2 * C; JB.phys_max = ps + maxphys;
-            const int64_t n_batches = cdiv((int64_t)total_phys, ps);
-            // worst case half-updates per member slot = (3C+1)/2  (full row: C(C+1)/2 + C^2 pairs over 2C members, x2)
-            const int64_t per_batch = (int64_t)(ps + maxphys) * ((3 * C + 1) / 2 + 1);
+            JB.batch_first = W.batch_first; JB.n_active = n_active; JB.n_batches = n_batches; JB.slot_stride = 2 * C;
+            // worst case half-updates per batch: every tile slot x 16 pairs x 2 sides
+            const int64_t per_batch = (int64_t)JB_TCAP * 32;
             NND_CHECK(per_batch <= push_capacity, NND_ERR_OVERFLOW, "push_capacity %lld too small for one batch (%lld)",
                       (long long)push_capacity, (long long)per_batch);
             const int64_t bpb = push_capacity / per_batch;
