@@ -198,8 +198,7 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int64_t v = (int64_t)blockIdx.x * SEL_T + tid;
-    unsigned long long *rs = (unsigned long long *)smem_raw + tid;              // [SEL_SMALL][SEL_T]
-    float *npri = (float *)(smem_raw + (size_t)SEL_SMALL * SEL_T * 8) + tid;       // [C][SEL_T]
+    float *npri = (float *)smem_raw + tid;                                         // [C][SEL_T]
     float *opri = npri + (size_t)C * SEL_T;
     int32_t *nind = (int32_t *)(opri + (size_t)C * SEL_T), *oind = nind + (size_t)C * SEL_T;
     if (v >= N) return;
@@ -207,8 +206,7 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
     if (nrev > SEL_SMALL) return;  // handled by the warp kernel
     for (int c = 0; c < C; ++c) { npri[c * SEL_T] = CUDART_INF_F; opri[c * SEL_T] = CUDART_INF_F; nind[c * SEL_T] = -1; oind[c * SEL_T] = -1; }
     const unsigned long long *seg = rev + revoff[v];
-    for (uint32_t j = 0; j < nrev; ++j) rs[j * SEL_T] = seg[j];
-    int jf = 0; uint32_t left = nrev;
+    int jf = 0; uint32_t left = nrev, used = 0;   // bit j of `used`: reverse edge j already consumed
     const unsigned long long fbase = (unsigned long long)v * k;
     for (;;) {
         while (jf < k && ind[v * k + jf] < 0) ++jf;
@@ -216,14 +214,18 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
         // smallest remaining reverse entry (keys are unique)
         unsigned long long best = ~0ULL; int bj = -1;
         if (left)
-            for (uint32_t j = 0; j < nrev; ++j) { unsigned long long x = rs[j * SEL_T]; if (x < best) { best = x; bj = (int)j; } }
+            for (uint32_t j = 0; j < nrev; ++j) {
+                if ((used >> j) & 1u) continue;
+                unsigned long long x = seg[j];
+                if (x < best) { best = x; bj = (int)j; }
+            }
         const bool hasr = bj >= 0;
         if (!hasf && !hasr) break;
         const bool take_f = hasf && (!hasr || fbase + jf <= (best >> 33));
         float p; int32_t cand; bool isnew;
         if (take_f) { p = fprio[v * k + jf]; cand = ind[v * k + jf]; isnew = flags[v * k + jf] != 0; ++jf; }
         else {
-            rs[bj * SEL_T] = ~0ULL; --left;
+            used |= 1u << bj; --left;
             p = __uint_as_float((uint32_t)(best & 0xFFFFFFFFULL)); isnew = (best >> 32) & 1ULL;
             cand = (int32_t)((best >> 33) / (unsigned long long)k);
         }
@@ -316,7 +318,7 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
     size_t smem = (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)SEL_WARPS * hstride;
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
-    size_t smem_small = (size_t)SEL_SMALL * SEL_T * 8 + (size_t)C * SEL_T * 16;
+    size_t smem_small = (size_t)C * SEL_T * 16;
     const int use_small = smem_small <= 200 * 1024;
     if (use_small) {
         NND_CUDA(cudaFuncSetAttribute(k_cand_select_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));

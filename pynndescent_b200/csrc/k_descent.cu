@@ -122,6 +122,16 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
             mu_s[2 * j + 1] = ((const double *)P.aux)[2 * (int64_t)id + 1];
         }
     }
+    if (P.mode == 2) {
+        // stage the members' heap rows now (column layout [j][member]); the loads complete behind the
+        // bulk copies and the distance phase
+        const int k = P.k, hs = P.m_max;
+        for (int idx = tid; idx < m * k; idx += nthr) {
+            int a = idx / k, j = idx - a * k;
+            const int64_t row = ids[a];
+            hpri[j * hs + a] = P.heap_dist[row * k + j]; hind[j * hs + a] = P.heap_idx[row * k + j]; hflg[j * hs + a] = P.heap_flag[row * k + j];
+        }
+    }
     if (tid == 0 && P.stats) {
         atomicAdd(&P.stats[0], (unsigned long long)m);
         unsigned long long np = (P.mode == 0) ? ((unsigned long long)nn * (nn + 1) / 2 + (unsigned long long)nn * (m - nn))
@@ -261,9 +271,6 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
         for (int a = tid; a < m; a += nthr) {
             const int64_t row = ids[a];
             float *pri = hpri + a; int32_t *ind = hind + a; uint8_t *flg = hflg + a;
-            for (int j = 0; j < k; ++j) {
-                pri[j * hs] = P.heap_dist[row * k + j]; ind[j * hs] = P.heap_idx[row * k + j]; flg[j * hs] = P.heap_flag[row * k + j];
-            }
             bool changed = false;
             for (int b = 0; b < m; ++b) {
                 if (b == a) continue;
@@ -286,10 +293,13 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                 pri[i * hs] = p; ind[i * hs] = nb; flg[i * hs] = 1;
                 changed = true;
             }
-            if (changed)
-                for (int j = 0; j < k; ++j) {
-                    P.heap_dist[row * k + j] = pri[j * hs]; P.heap_idx[row * k + j] = ind[j * hs]; P.heap_flag[row * k + j] = flg[j * hs];
-                }
+            (void)row; (void)changed;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < m * k; idx += nthr) {   // coalesced write-back of all member rows
+            int a = idx / k, j = idx - a * k;
+            const int64_t row = ids[a];
+            P.heap_dist[row * k + j] = hpri[j * hs + a]; P.heap_idx[row * k + j] = hind[j * hs + a]; P.heap_flag[row * k + j] = hflg[j * hs + a];
         }
         return;
     }
@@ -594,13 +604,13 @@ __global__ void k_scatter(const int32_t *tgt, const int32_t *oth, const float *d
 #define APPLY_WARPS 8
 __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag,
                                                             int k, int64_t N, const uint32_t *cnt, const uint32_t *off,
-                                                            Rec16 *rec, unsigned long long *c_total) {
+                                                            Rec16 *rec, unsigned long long *c_total, int skip_small) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * APPLY_WARPS + warp;
     if (row >= N) return;
     const uint32_t n = cnt[row];
-    if (n == 0) return;
+    if (n == 0 || (skip_small && n <= 48)) return;
     Rec16 *buf = (Rec16 *)smem_raw + (size_t)warp * NND_SEG_SMEM;
     unsigned char *hp = smem_raw + (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)warp * (((size_t)k * 9 + 15) & ~size_t(15));
     float *pri = (float *)hp; int32_t *ind = (int32_t *)(pri + k); uint8_t *flg = (uint8_t *)(ind + k);
@@ -647,6 +657,63 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
         }
         if (lane == 0) atomicAdd(c_total, (unsigned long long)c);
     }
+}
+
+
+// ---- thread-per-row apply for rows with few records (the common case): column-layout heap in smem, the
+// next record in emission order is found by selection among the records that can still be accepted
+// (d < current root), so no sort is needed.  Rows with more than APPLY_SMALL records go to k_apply.
+#define APPLY_SMALL 48
+#define APPLY_T 128
+__global__ void __launch_bounds__(APPLY_T) k_apply_small(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int k,
+                                                         int64_t N, const uint32_t *cnt, const uint32_t *off,
+                                                         const Rec16 *rec, unsigned long long *c_total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t row = (int64_t)blockIdx.x * APPLY_T + tid;
+    float *pri = (float *)smem_raw + tid;                                    // [k][APPLY_T]
+    int32_t *ind = (int32_t *)(smem_raw + (size_t)k * APPLY_T * 4) + tid;
+    uint8_t *flg = smem_raw + (size_t)k * APPLY_T * 8 + tid;
+    int c = 0;
+    uint32_t n = 0;
+    if (row < N) n = cnt[row];
+    if (n > 0 && n <= APPLY_SMALL) {
+        for (int j = 0; j < k; ++j) { pri[j * APPLY_T] = heap_dist[row * k + j]; ind[j * APPLY_T] = heap_idx[row * k + j]; flg[j * APPLY_T] = heap_flag[row * k + j]; }
+        const Rec16 *seg = rec + off[row];
+        unsigned long long last = 0; bool first = true;
+        for (;;) {
+            const float root = pri[0];
+            unsigned long long best = ~0ULL; int bj = -1;
+            for (uint32_t j = 0; j < n; ++j) {
+                Rec16 r = seg[j];
+                if (r.d < root && (first || r.key > last) && r.key < best) { best = r.key; bj = (int)j; }
+            }
+            if (bj < 0) break;
+            first = false; last = best;
+            const Rec16 r = seg[bj];
+            const float p = r.d; const int32_t nb = r.oth;
+            bool dup = false;
+            for (int j = 0; j < k; ++j) dup |= (ind[j * APPLY_T] == nb);
+            if (dup) continue;
+            int i = 0, i_swap;
+            for (;;) {
+                int ic1 = 2 * i + 1, ic2 = ic1 + 1;
+                if (ic1 >= k) break;
+                else if (ic2 >= k) { if (pri[ic1 * APPLY_T] > p) i_swap = ic1; else break; }
+                else if (pri[ic1 * APPLY_T] >= pri[ic2 * APPLY_T]) { if (p < pri[ic1 * APPLY_T]) i_swap = ic1; else break; }
+                else { if (p < pri[ic2 * APPLY_T]) i_swap = ic2; else break; }
+                pri[i * APPLY_T] = pri[i_swap * APPLY_T]; ind[i * APPLY_T] = ind[i_swap * APPLY_T]; flg[i * APPLY_T] = flg[i_swap * APPLY_T];
+                i = i_swap;
+            }
+            pri[i * APPLY_T] = p; ind[i * APPLY_T] = nb; flg[i * APPLY_T] = 1;
+            ++c;
+        }
+        if (c > 0)
+            for (int j = 0; j < k; ++j) { heap_dist[row * k + j] = pri[j * APPLY_T]; heap_idx[row * k + j] = ind[j * APPLY_T]; heap_flag[row * k + j] = flg[j * APPLY_T]; }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0 && c > 0) atomicAdd(c_total, (unsigned long long)c);
 }
 
 // ------------------------------------------------------------------ per-row worst-case push bound (for blocking)
@@ -808,8 +875,16 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "apply: k=%d too large", P->k);
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem_s = (size_t)P->k * APPLY_T * 9 + 16;
+    const int use_small = smem_s <= 64 * 1024;
+    if (use_small) {
+        NND_CUDA(cudaFuncSetAttribute(k_apply_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        k_apply_small<<<(unsigned)cdiv(N, APPLY_T), APPLY_T, smem_s, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N, W.cnt,
+                                                                        W.off, W.rec, W.dev_scalars + 1);
+        NND_LAUNCH(ctx);
+    }
     k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
-                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1);
+                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1, use_small);
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
     return NND_OK;

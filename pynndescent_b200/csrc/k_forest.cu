@@ -162,8 +162,8 @@ __global__ void k_forest_hyper(const float *X, int ld, int64_t N, int angular, i
 }
 
 // one warp per SIDE_PW active positions: side of the hyperplane (rp_trees.py:375-391)
-#define SIDE_PW 4
-__global__ void k_forest_side(const float *X, int ld, int64_t n_act, const int32_t *act, int64_t N, int level,
+#define SIDE_PW 2
+__global__ void __launch_bounds__(256, 6) k_forest_side(const float *X, int ld, int64_t n_act, const int32_t *act, int64_t N, int level,
                               const int32_t *perm, const int32_t *seg, const int32_t *nstart, const int32_t *tree_first,
                               const uint64_t *tree_seed, const float *hyper, const float *noff, uint8_t *side,
                               uint32_t *flag32) {

@@ -214,6 +214,22 @@ def test_full_build_bit_exact_vs_oracle(torch_cuda, oracle, metric, n, d, k, see
         assert _recall(gi, X, k) >= 0.95
 
 
+@pytest.mark.parametrize("metric,n,d,k,seed", [("cosine", 30000, 256, 15, 3),        # cfg3 shape: 2 staged d-chunks x 4
+                                               ("correlation", 12000, 784, 30, 4),   # cfg5 shape: chunked k_join, C=30
+                                               ("euclidean", 20000, 100, 40, 6)])    # C=40 > batched limit, d % 128 != 0
+def test_config_shapes_bit_exact_vs_oracle(torch_cuda, oracle, metric, n, d, k, seed):
+    """The BASELINE.json config shapes (reduced N) through every kernel variant: multi-chunk rows, the
+    chunked one-row-per-CTA join (correlation / large d / large C), routed leaf init for big leaves."""
+    from pynndescent_b200 import NNDescent
+    X = latent(n, d, seed)
+    idx = NNDescent(X, metric, n_neighbors=k, random_state=seed)
+    gi, gd = idx.neighbor_graph
+    o = oracle.OracleNNDescent(X, metric, n_neighbors=k, random_state=seed, n_threads=8, forest="level")
+    oi, od = o.neighbor_graph
+    assert idx.c_hist == [int(c) for c in o.c_hist[: o.n_iters_run]]
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
 def test_thread_count_and_capacity_invariance(torch_cuda, oracle):
     """T matters exactly as in the reference (oracle agrees for each T); push capacity never does."""
     from pynndescent_b200 import NNDescent
