@@ -357,8 +357,6 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
 #define JB_TCAP 128      // tiles per batch
 #define JB_SCAP 176      // physical member slots per batch (2 buffers x 176 x 144 B -> 4 CTAs/SM)
 #define JB_MAXU 48       // units per batch (every unit weighs >= 4)
-#define JB_DK 32         // floats per staged chunk
-#define JB_SD (JB_DK + 4)
 #define JB_CMAX 60  // members scratch is sized for the largest C so that its offset does not depend on C
 struct JoinBatchParams {
     const float *X; int64_t N; int ld; int metric; const void *aux; const float *thr;
@@ -410,8 +408,9 @@ __global__ void k_jb_bounds(const uint32_t *act_woff, int64_t n_active, uint32_t
     if (j == 0 || act_woff[j - 1] / ps != b) batch_first[b] = (int32_t)j;
 }
 
-template <int METRIC>
+template <int METRIC, int JB_DK>
 __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
+    constexpr int JB_SD = JB_DK + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = (uint64_t *)smem_raw;                  // [2]
     int *s_hdr = (int *)(smem_raw + 16);                    // [0] nunits [1] tiles [2] members [3] total phys
@@ -486,15 +485,15 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
     float acc[TILE * TILE];
 #pragma unroll
     for (int p = 0; p < TILE * TILE; ++p) acc[p] = 0.0f;
-    __syncthreads();                                        // ids[] complete
 
     // ---- chunk pipeline: gather chunk c+1 while accumulating chunk c
     const int nchunks = (P.ld + JB_DK - 1) / JB_DK;
-    auto issue = [&](int c) {
+    auto expect = [&](int c) {
+        if (tid == 0) mbar_expect_tx(&bar[c & 1], (uint32_t)mem * (uint32_t)min(JB_DK, P.ld - c * JB_DK) * 4u);
+    };
+    auto issue = [&](int c) {   // caller guarantees: expect(c) done and buffer c&1 free, both ordered by a __syncthreads
         const int c0 = c * JB_DK, len = min(JB_DK, P.ld - c0);
         float *buf = rows + (size_t)(c & 1) * JB_SCAP * JB_SD;
-        if (tid == 0) mbar_expect_tx(&bar[c & 1], (uint32_t)mem * (uint32_t)len * 4u);
-        __syncthreads();
         for (int uu = warp; uu < nunits; uu += JB_THREADS / 32) {
             const int mm = s_um[uu], nt = (mm + 3) >> 2, o = s_uoff[uu];
             for (int j = lane; j < mm; j += 32)
@@ -502,9 +501,12 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
                          (uint32_t)len * 4u, &bar[c & 1]);
         }
     };
+    expect(0);
+    if (nchunks > 1) expect(1);
+    __syncthreads();                                        // ids[] complete, expect_tx posted
     issue(0);
+    if (nchunks > 1) issue(1);
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) issue(c + 1);                  // buffer (c+1)&1 was released by the sync ending chunk c-1
         mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
         if (u >= 0) {
             const float *buf = rows + (size_t)(c & 1) * JB_SCAP * JB_SD;
@@ -533,7 +535,9 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
                 }
             }
         }
+        if (c + 2 < nchunks) expect(c + 2);                 // phase (c+2)>>1 of barrier c&1 (its previous phase completed: we waited on it)
         __syncthreads();                                    // everyone done with buffer c&1
+        if (c + 2 < nchunks) issue(c + 2);
     }
     // ---- finalise + filter
     uint32_t pm = 0;
@@ -811,7 +815,7 @@ static int launch_join_m(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cud
         NND_CUDA(cudaFuncSetAttribute(k_join<METRIC, T_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_join<METRIC, T_, M_><<<grid, threads, smem, st>>>(P);                                          \
     } while (0)
-    if (tpt == 1) { if (threads <= 128) LJ(1, 128); else LJ(1, 512); }
+    if (tpt == 1) { if (threads <= 128) LJ(1, 128); else if (threads <= 512) LJ(1, 512); else LJ(1, 1024); }
     else if (tpt == 2) { if (threads <= 512) LJ(2, 512); else LJ(2, 1024); }
     else LJ(4, 1024);
 #undef LJ
@@ -876,7 +880,8 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "apply: k=%d too large", P->k);
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t smem_s = (size_t)P->k * APPLY_T * 9 + 16;
-    const int use_small = smem_s <= 64 * 1024;
+    const char *e_small = getenv("NND_APPLY_SMALL");   // experimental: thread-per-row apply (slower on B200 as measured)
+    const int use_small = (e_small && e_small[0] == '1') && smem_s <= 64 * 1024;
     if (use_small) {
         NND_CUDA(cudaFuncSetAttribute(k_apply_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         k_apply_small<<<(unsigned)cdiv(N, APPLY_T), APPLY_T, smem_s, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N, W.cnt,
@@ -891,26 +896,32 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
 }
 
 
-static size_t join_batch_smem(int metric) {
+static size_t join_batch_smem(int metric, int dk, int ld) {
     size_t b = 32 + (size_t)JB_MAXU * 4 * 3 + (size_t)(JB_MAXU + 1) * 4 * 2;
     b += (size_t)JB_SCAP * 4 * (metric == NND_METRIC_ALT_COSINE ? 3 : 2);
     b = (b + 15) & ~size_t(15);
-    b += (size_t)2 * JB_SCAP * JB_SD * 4 + 16;
+    const int nbuf = (ld <= dk) ? 1 : 2;   // a single chunk needs no second buffer
+    b += (size_t)nbuf * JB_SCAP * (dk + 4) * 4 + 16;
     return b;
 }
 static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st) {
     int64_t nb = JB.batch_end - JB.batch_begin;
     if (nb <= 0) return NND_OK;
-    size_t smem = join_batch_smem(JB.metric);
+    static int dk_sel = -1;
+    if (dk_sel < 0) { const char *e = getenv("NND_JB_DK"); dk_sel = e ? atoi(e) : 32; if (dk_sel != 32 && dk_sel != 64 && dk_sel != 128) dk_sel = 32; }
+    const int dk = dk_sel;
+    size_t smem = join_batch_smem(JB.metric, dk, JB.ld);
     dim3 grid((unsigned)nb);
-#define LB(M_)                                                                                                   \
+#define LB(M_, D_)                                                                                                   \
     do {                                                                                                         \
-        NND_CUDA(cudaFuncSetAttribute(k_join_batch<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_join_batch<M_><<<grid, JB_THREADS, smem, st>>>(JB);                                                     \
+        NND_CUDA(cudaFuncSetAttribute(k_join_batch<M_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_join_batch<M_, D_><<<grid, JB_THREADS, smem, st>>>(JB);                                                     \
     } while (0)
-    if (JB.metric == NND_METRIC_SQEUCLIDEAN) LB(NND_METRIC_SQEUCLIDEAN);
-    else if (JB.metric == NND_METRIC_ALT_COSINE) LB(NND_METRIC_ALT_COSINE);
-    else LB(NND_METRIC_ALT_DOT);
+#define LBM(M_) do { if (dk == 32) LB(M_, 32); else if (dk == 64) LB(M_, 64); else LB(M_, 128); } while (0)
+    if (JB.metric == NND_METRIC_SQEUCLIDEAN) LBM(NND_METRIC_SQEUCLIDEAN);
+    else if (JB.metric == NND_METRIC_ALT_COSINE) LBM(NND_METRIC_ALT_COSINE);
+    else LBM(NND_METRIC_ALT_DOT);
+#undef LBM
 #undef LB
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());

@@ -214,6 +214,66 @@ __global__ void __launch_bounds__(256, 6) k_forest_side(const float *X, int ld, 
     }
 }
 
+
+// ld <= 128 fast path: one warp walks SIDE_RUN consecutive active entries; the node's hyperplane stays in
+// registers (one float4 per lane) while consecutive entries belong to the same node, which halves the L2
+// traffic of the pass (x is the only per-position stream left).
+#define SIDE_RUN 16
+__global__ void __launch_bounds__(256) k_forest_side128(const float *X, int ld, int64_t n_act, const int32_t *act, int64_t N,
+                                                        int level, const int32_t *perm, const int32_t *seg,
+                                                        const int32_t *nstart, const int32_t *tree_first,
+                                                        const uint64_t *tree_seed, const float *hyper, const float *noff,
+                                                        uint8_t *side, uint32_t *flag32) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t i0 = w * SIDE_RUN;
+    if (i0 >= n_act) return;
+    const int cnt = (int)min((int64_t)SIDE_RUN, n_act - i0);
+    const bool has = lane * 4 < ld;
+    // lanes 0..cnt-1 fetch the per-entry scalars, then broadcast
+    int32_t my_pos = 0, my_o = 0, my_pt = 0;
+    if (lane < cnt) { my_pos = act[i0 + lane]; my_o = seg[my_pos]; my_pt = perm[my_pos]; }
+    int cur_o = -1; float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f); float off = 0.f;
+    float4 xq[2];
+    {
+        int pt0 = __shfl_sync(0xffffffffu, my_pt, 0);
+        xq[0] = has ? *(const float4 *)(X + (int64_t)pt0 * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t sbits = 0;   // lane 0 collects the side bits of the run
+    for (int q = 0; q < cnt; ++q) {
+        if (q + 1 < cnt) {
+            int ptn = __shfl_sync(0xffffffffu, my_pt, q + 1);
+            xq[(q + 1) & 1] = has ? *(const float4 *)(X + (int64_t)ptn * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int o = __shfl_sync(0xffffffffu, my_o, q);
+        if (o != cur_o) {
+            cur_o = o;
+            h4 = has ? *(const float4 *)(hyper + (size_t)o * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            off = noff[o];
+        }
+        const float4 b = xq[q & 1];
+        float acc = 0.0f;
+        acc = __fmaf_rn(h4.x, b.x, acc); acc = __fmaf_rn(h4.y, b.y, acc); acc = __fmaf_rn(h4.z, b.z, acc); acc = __fmaf_rn(h4.w, b.w, acc);
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, sft));
+        const float margin = __fadd_rn(off, acc);
+        uint32_t s;
+        if (fabs((double)margin) < 1e-8) {
+            const int pos = __shfl_sync(0xffffffffu, my_pos, q);
+            const int start = nstart[o];
+            const int tree = (int)(start / N);
+            const uint64_t key = node_key(tree_seed[tree], level, (int64_t)(o - tree_first[tree]));
+            s = (uint32_t)(mix64(key ^ (0x100ULL + (uint64_t)(pos - start))) & 1ULL);
+        } else s = margin > 0 ? 0u : 1u;
+        sbits |= s << q;
+    }
+    if (lane < cnt) {
+        uint32_t s = (sbits >> lane) & 1u;
+        side[my_pos] = (uint8_t)s;
+        flag32[my_pos] = (s == 0);
+    }
+}
+
 // degenerate nodes (all points on one side): random split (rp_trees.py:395-403)
 __global__ void k_forest_fix_side(int64_t n_act, const int32_t *act, int64_t N, int level, const int32_t *seg,
                                   const int32_t *nstart, const uint8_t *ndegen, const int32_t *tree_first,
@@ -370,9 +430,15 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
                                                                                  W.nsize[ncur], W.perm[cur], W.tree_first,
                                                                                  W.tree_seed, W.hyper, W.noff);
         NND_LAUNCH(ctx);
-        k_forest_side<<<(unsigned)cdiv(cdiv(n_act, SIDE_PW) * 32, 256), 256, 0, st>>>(X, ld, n_act, W.act[cur], N, level, W.perm[cur],
-                                                                                   W.seg[cur], W.nstart[ncur], W.tree_first,
-                                                                                   W.tree_seed, W.hyper, W.noff, W.side, W.flag32);
+        if (ld <= 128)
+            k_forest_side128<<<(unsigned)cdiv(cdiv(n_act, SIDE_RUN) * 32, 256), 256, 0, st>>>(X, ld, n_act, W.act[cur], N, level,
+                                                                                         W.perm[cur], W.seg[cur], W.nstart[ncur],
+                                                                                         W.tree_first, W.tree_seed, W.hyper, W.noff,
+                                                                                         W.side, W.flag32);
+        else
+            k_forest_side<<<(unsigned)cdiv(cdiv(n_act, SIDE_PW) * 32, 256), 256, 0, st>>>(X, ld, n_act, W.act[cur], N, level, W.perm[cur],
+                                                                                       W.seg[cur], W.nstart[ncur], W.tree_first,
+                                                                                       W.tree_seed, W.hyper, W.noff, W.side, W.flag32);
         NND_LAUNCH(ctx);
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.flag32, W.pl, TN, W.scan_tmp, st));
         NND_CUDA(cudaMemsetAsync(W.scalars, 0, sizeof(int32_t), st));
