@@ -638,10 +638,40 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
             kept += __popc(mk);
         }
         if (kept == 0) return;
+        __syncwarp();
+        if (kept <= 32) {
+            // common case: sort (key, slot) pairs in registers with shuffles -- no shared-memory traffic
+            unsigned long long key = lane < kept ? buf[lane].key : ~0ULL;
+            int slot = lane;
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+                    int os = __shfl_xor_sync(0xffffffffu, slot, j);
+                    bool up = ((lane & k2) == 0), lower = ((lane & j) == 0);
+                    bool take = (lower == up) ? (ok < key) : (ok > key);
+                    if (take) { key = ok; slot = os; }
+                }
+            }
+            int c = 0;
+            for (int s2 = 0; s2 < kept; ++s2) {
+                int sl = __shfl_sync(0xffffffffu, slot, s2);
+                Rec16 r = buf[sl];
+                c += warp_heap_push(pri, ind, flg, k, r.d, r.oth, (uint8_t)1, lane);
+            }
+            if (c > 0) {
+                for (int j = lane; j < k; j += 32) {
+                    heap_dist[row * k + j] = pri[j]; heap_idx[row * k + j] = ind[j]; heap_flag[row * k + j] = flg[j];
+                }
+                if (lane == 0) atomicAdd(c_total, (unsigned long long)c);
+            }
+            return;
+        }
         int p2 = (int)next_pow2_u32((uint32_t)kept);
         for (int j = kept + lane; j < p2; j += 32) { buf[j].key = ~0ULL; buf[j].oth = -1; buf[j].d = CUDART_INF_F; }
         __syncwarp();
-        if (kept > 1) warp_bitonic_sort_rec(buf, p2, lane);
+        warp_bitonic_sort_rec(buf, p2, lane);
         sorted = buf; ns = kept;
     } else {
         uint32_t cap = padded_seg(n);
