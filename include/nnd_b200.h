@@ -140,6 +140,29 @@ NND_API int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int
                 int32_t n_iters, double delta, int64_t push_capacity, void *ws, size_t ws_bytes,
                 int32_t *iters_run_host, int64_t *c_hist_host, int64_t *stats_host, void *stream);
 
+/* ---- sharded build (one process per GPU) ----------------------------------------------
+ * Every process holds X and the whole heap; it samples candidates and joins only rows [lo,hi), exchanges the
+ * half-updates with the owners of their target rows and applies what it receives.                            */
+NND_API int nnd_set_row_range(nnd_ctx *ctx, int64_t lo, int64_t hi);
+/* prepass of one process_candidates call restricted to the row range; n_rounds_host = routing rounds needed */
+NND_API int nnd_join_prepare(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand, const int32_t *old_cand,
+                             int64_t push_capacity, void *ws, size_t ws_bytes, int32_t *n_rounds_host, void *stream);
+/* run the join of one round; the half-updates stay in the workspace (rounds beyond the plan emit nothing) */
+NND_API int nnd_join_emit_round(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int64_t push_capacity, void *ws, size_t ws_bytes,
+                                int32_t round, int64_t *n_pushed_host, void *stream);
+/* group them by owner process (owner = target / owner_block) into 24-byte records {tgt i32, oth i32, d f32, pad, seq u64} */
+NND_API int nnd_push_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int64_t push_capacity, void *ws, size_t ws_bytes,
+                            int64_t n_pushed, int64_t owner_block, int32_t R, void *out, int64_t *counts_host, void *stream);
+/* apply received records (any order) to the local heap; c_host = accepted pushes */
+NND_API int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const void *records, int64_t n,
+                              int64_t push_capacity, void *ws, size_t ws_bytes, int64_t *c_host, void *stream);
+/* fused leaf join + apply on leaves [l0,l1) of one tree (disjoint point sets) */
+NND_API int nnd_leaf_fused_range(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets,
+                                 int64_t l0, int64_t l1, int32_t max_leaf, void *stream);
+/* pack (unpack=0) / unpack (unpack=1) the heap rows listed in `rows` (NULL = rows 0..n-1) */
+NND_API int nnd_heap_pack_rows(nnd_ctx *ctx, const nnd_problem *P, const int32_t *rows, int64_t n, int32_t *out_idx,
+                               float *out_dist, uint8_t *out_flag, int32_t unpack, void *stream);
+
 /* ---- small exported primitives (unit tests / known-answer vectors) -------------------- */
 /* utils.py:17-57: out[i] = i-th tau_rand_int (as_float=0) or tau_rand (as_float=1) of the
  * stream starting at state_host, i in [start, start+count), via GF(2) jump-ahead.          */

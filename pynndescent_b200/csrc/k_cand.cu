@@ -93,14 +93,16 @@ __device__ __forceinline__ uint32_t draw_index(const uint32_t *pre, int64_t N, i
 
 __global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int64_t N, int T, int64_t B,
                             const uint32_t *pre, const float *table, int64_t table_len, const uint32_t *revoff,
-                            uint32_t *cursor, unsigned long long *rev, float *fprio) {
+                            uint32_t *cursor, unsigned long long *rev, float *fprio, int64_t lo, int64_t hi) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const bool mine = i >= lo && i < hi;
     const int ni = (int)(i / B);
     uint32_t wv = 0;  // valid edges before j in this row
     for (int j = 0; j < k; ++j) {
         int32_t x = ind[i * k + j];
         if (x < 0) { fprio[i * k + j] = 0.f; continue; }
+        if (!mine && (x < lo || x >= hi)) { ++wv; continue; }   // neither endpoint sampled by this process
         const int nx = (int)(x / B);
         uint32_t df = draw_index(pre, N, T, B, ni, i, wv, 0);
         float pf = table[(size_t)ni * table_len + df];
@@ -113,6 +115,7 @@ __global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int
             uint32_t dr = draw_index(pre, N, T, B, nx, i, 0, wn);
             pr = table[(size_t)nx * table_len + dr];
         }
+        if (x < lo || x >= hi) { ++wv; continue; }
         uint32_t slot = atomicAdd(&cursor[x], 1u);
         unsigned long long key = ((unsigned long long)(i * k + j) << 1) | (unsigned long long)(flags[i * k + j] != 0);
         rev[(size_t)revoff[x] + slot] = (key << 32) | (unsigned long long)__float_as_uint(pr);
@@ -125,11 +128,11 @@ __global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int
 __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
                                                                 const uint32_t *indeg, const uint32_t *revoff,
                                                                 unsigned long long *rev, const float *fprio,
-                                                                int32_t *newc, int32_t *oldc, int skip_small) {
+                                                                int32_t *newc, int32_t *oldc, int skip_small, int64_t lo, int64_t hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t v = (int64_t)blockIdx.x * SEL_WARPS + warp;
-    if (v >= N) return;
+    if (v >= N || v < lo || v >= hi) return;
     unsigned long long *buf = (unsigned long long *)smem_raw + (size_t)warp * NND_SEG_SMEM;
     const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
     unsigned char *hp = smem_raw + (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)warp * hstride;
@@ -194,14 +197,14 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *i
 __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
                                                              const uint32_t *indeg, const uint32_t *revoff,
                                                              const unsigned long long *rev, const float *fprio,
-                                                             int32_t *newc, int32_t *oldc) {
+                                                             int32_t *newc, int32_t *oldc, int64_t lo, int64_t hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int64_t v = (int64_t)blockIdx.x * SEL_T + tid;
     float *npri = (float *)smem_raw + tid;                                         // [C][SEL_T]
     float *opri = npri + (size_t)C * SEL_T;
     int32_t *nind = (int32_t *)(opri + (size_t)C * SEL_T), *oind = nind + (size_t)C * SEL_T;
-    if (v >= N) return;
+    if (v >= N || v < lo || v >= hi) return;
     const uint32_t nrev = indeg[v];
     if (nrev > SEL_SMALL) return;  // handled by the warp kernel
     for (int c = 0; c < C; ++c) { npri[c * SEL_T] = CUDART_INF_F; opri[c * SEL_T] = CUDART_INF_F; nind[c * SEL_T] = -1; oind[c * SEL_T] = -1; }
@@ -313,7 +316,7 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
     NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
     k_cand_fill<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.pre, W.table, W.table_len,
-                                                       W.revoff, W.cursor, W.rev, W.fprio);
+                                                       W.revoff, W.cursor, W.rev, W.fprio, ctx->row_lo, ctx->row_hi);
     NND_LAUNCH(ctx);
     const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
     size_t smem = (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)SEL_WARPS * hstride;
@@ -323,12 +326,12 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     if (use_small) {
         NND_CUDA(cudaFuncSetAttribute(k_cand_select_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         k_cand_select_small<<<(unsigned)cdiv(N, SEL_T), SEL_T, smem_small, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
-                                                                            W.revoff, W.rev, W.fprio, new_cand, old_cand);
+                                                                            W.revoff, W.rev, W.fprio, new_cand, old_cand, ctx->row_lo, ctx->row_hi);
         NND_LAUNCH(ctx);
     }
     NND_CUDA(cudaFuncSetAttribute(k_cand_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_cand_select<<<(unsigned)cdiv(N, SEL_WARPS), SEL_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
-                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand, use_small);
+                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand, use_small, ctx->row_lo, ctx->row_hi);
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
     return NND_OK;

@@ -40,6 +40,7 @@ struct JoinParams {
     int *overflow;
     // mode 2 (fused leaf join + apply): heaps are updated in place by the leaf's own CTA
     int32_t *heap_idx; float *heap_dist; uint8_t *heap_flag; int k; int d_alias;
+    int64_t row_lo, row_hi;   // mode 0: rows outside are skipped (sharded build)
 };
 
 static size_t join_smem_bytes(int m_max, int metric) {
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
     const int64_t unit = P.unit_begin + blockIdx.x;
     if (unit >= P.unit_end) return;
+    if (P.mode == 0 && (unit < P.row_lo || unit >= P.row_hi)) return;
 
     // ---- member list (order-preserving compaction of the -1 holes; warp 0) ----
     if (tid < 32) {
@@ -373,11 +375,12 @@ __host__ __device__ __forceinline__ int jb_tiles(int nn, int m) {
 }
 // prepass 1: per row -> active flag, physical slots, batching weight
 __global__ void k_jb_count(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *flag, uint32_t *phys,
-                           uint32_t *wgt, uint32_t *info) {
+                           uint32_t *wgt, uint32_t *info, int64_t lo, int64_t hi) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int nn = 0, no = 0;
-    for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
+    if (i >= lo && i < hi)
+        for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
     int m = nn + no;
     uint32_t ph = nn > 0 ? (uint32_t)(((m + 3) >> 2) << 2) : 0u;
     uint32_t tw = nn > 0 ? (uint32_t)((jb_tiles(nn, m) * 3 + 1) >> 1) : 0u;
@@ -751,10 +754,11 @@ __global__ void __launch_bounds__(APPLY_T) k_apply_small(int32_t *heap_idx, floa
 }
 
 // ------------------------------------------------------------------ per-row worst-case push bound (for blocking)
-__global__ void k_row_bound(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *bound) {
+__global__ void k_row_bound(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *bound, int64_t lo, int64_t hi) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int nn = 0, no = 0;
+    if (i >= lo && i < hi)
     for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
     bound[i] = (uint32_t)(nn * (nn + 1) + 2 * nn * no);  // 2 half-updates per pair (self pairs: 1, bounded by 2)
 }
@@ -868,7 +872,8 @@ static int launch_join(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaS
 // one routing round: join over units [u0,u1) -> scan -> scatter -> apply.  Returns pushes routed.
 static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st);
 static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_t u0, int64_t u1, DescentWs &W,
-                       int64_t cap, unsigned long long *n_pushed, cudaStream_t st, JoinBatchParams *JB = nullptr) {
+                       int64_t cap, unsigned long long *n_pushed, cudaStream_t st, JoinBatchParams *JB = nullptr,
+                       bool do_apply = true) {
     const int64_t N = P->N;
     k_snapshot_thr<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_dist, P->k, W.thr, N); NND_LAUNCH(ctx);
     NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (N + 1), st));
@@ -902,7 +907,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
         pf[0] += ms; pf[1] += 1; pf[2] += (double)h[5]; pf[3] += (double)h[6]; pf[4] += (double)h[0];
         ctx->last_round_rows = h[5]; ctx->last_round_pairs = h[6];
     }
-    if (h[0] == 0) return NND_OK;
+    if (h[0] == 0 || !do_apply) return NND_OK;
     NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, N, W.scan_tmp, st));  // offsets of power-of-two padded segments
     k_scatter<<<(unsigned)cdiv((int64_t)h[0], 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_pos, W.l_seq, h[0], W.off, W.rec);
     NND_LAUNCH(ctx);
@@ -1066,30 +1071,31 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
     return NND_OK;
 }
 
-extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand,
-                                      const int32_t *old_cand, int64_t push_capacity, void *ws, size_t ws_bytes,
-                                      int64_t *c_host, int64_t *stats_host, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    NND_CHECK(ctx && P && new_cand && old_cand && C > 0 && C <= 128, NND_ERR_INVALID, "nnd_process_candidates: bad args");
-    DescentWs W;
-    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
-              "nnd_process_candidates: workspace too small");
+// ---- join plan: the prepass of one process_candidates call + the list of routing rounds
+struct JoinPlan {
+    bool batched;
+    JoinParams J;
+    JoinBatchParams JB;
+    std::vector<std::pair<int64_t, int64_t>> rounds;   // unit (or batch) ranges, one per routing round
+};
+
+static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand, const int32_t *old_cand,
+                           int64_t push_capacity, DescentWs &W, cudaStream_t st, JoinPlan &PL) {
     const int64_t N = P->N;
-    NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long) * 16, st));
-    unsigned long long total = 0, rows_g = 0, pairs_g = 0; int64_t blocks = 0;
-    JoinParams J; memset(&J, 0, sizeof(J));
+    PL.rounds.clear();
+    JoinParams &J = PL.J; memset(&J, 0, sizeof(J));
     J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
     J.mode = 0; J.newc = new_cand; J.oldc = old_cand; J.C = C; J.m_max = 2 * C < 4 ? 4 : 2 * C; J.slot_stride = 2 * C;
+    J.row_lo = ctx->row_lo; J.row_hi = ctx->row_hi;
     const char *force_old = getenv("NND_JOIN_UNBATCHED");
-    const bool batched = P->metric != NND_METRIC_CORRELATION && 2 * C <= 60 &&
-                         !(force_old && force_old[0] == '1');
-    if (batched) {
+    PL.batched = P->metric != NND_METRIC_CORRELATION && 2 * C <= 60 && !(force_old && force_old[0] == '1');
+    if (PL.batched) {
         // ---- batched path: compact the active rows and their members, cut batches by weight, one CTA per batch
         const int maxphys = ((2 * C + 3) >> 2) << 2;
         const int maxw_t = (jb_tiles(C, 2 * C) * 3 + 1) >> 1;
         const int maxw = maxphys > maxw_t ? maxphys : maxw_t;
         const uint32_t ps = (uint32_t)(JB_SCAP - maxw);                          // weight window per batch
-        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_wgt, W.jb_info); NND_LAUNCH(ctx);
+        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_wgt, W.jb_info, ctx->row_lo, ctx->row_hi); NND_LAUNCH(ctx);
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_flag, W.jb_pos, N, W.scan_tmp, st));
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_phys, W.jb_poff, N, W.scan_tmp, st));
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_wgt, W.jb_woff, N, W.scan_tmp, st));
@@ -1105,7 +1111,7 @@ extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_
             const int64_t n_batches = cdiv((int64_t)hh[1], (int64_t)ps);
             NND_CUDA(cudaMemsetAsync(W.batch_first, 0x7f, sizeof(int32_t) * (n_batches + 2), st));
             k_jb_bounds<<<(unsigned)cdiv(n_active, 256), 256, 0, st>>>(W.act_woff, n_active, ps, W.batch_first); NND_LAUNCH(ctx);
-            JoinBatchParams JB; memset(&JB, 0, sizeof(JB));
+            JoinBatchParams &JB = PL.JB; memset(&JB, 0, sizeof(JB));
             JB.X = P->X; JB.N = N; JB.ld = P->ld; JB.metric = P->metric; JB.aux = P->aux;
             JB.act_unit = W.act_unit; JB.act_info = W.act_info; JB.act_poff = W.act_poff; JB.members = W.members;
             JB.batch_first = W.batch_first; JB.n_active = n_active; JB.n_batches = n_batches; JB.slot_stride = 2 * C;
@@ -1114,31 +1120,218 @@ extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_
             NND_CHECK(per_batch <= push_capacity, NND_ERR_OVERFLOW, "push_capacity %lld too small for one batch (%lld)",
                       (long long)push_capacity, (long long)per_batch);
             const int64_t bpb = push_capacity / per_batch;
-            for (int64_t b0 = 0; b0 < n_batches; b0 += bpb) {
-                int64_t b1 = b0 + bpb < n_batches ? b0 + bpb : n_batches;
-                unsigned long long np = 0;
-                NND_TRY(route_round(ctx, P, J, b0, b1, W, push_capacity, &np, st, &JB)); ++blocks;
-                rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs; total += np;
-            }
+            for (int64_t b0 = 0; b0 < n_batches; b0 += bpb) PL.rounds.push_back({b0, b0 + bpb < n_batches ? b0 + bpb : n_batches});
         }
     } else {
-        k_row_bound<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.bound); NND_LAUNCH(ctx);
+        k_row_bound<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.bound, ctx->row_lo, ctx->row_hi); NND_LAUNCH(ctx);
         std::vector<int64_t> cuts;
         NND_TRY(plan_blocks(ctx, W.bound, N, W, push_capacity, cuts, st));
-        for (size_t b = 0; b + 1 < cuts.size(); ++b) {
-            unsigned long long np = 0;
-            if (cuts[b] < cuts[b + 1]) {
-                NND_TRY(route_round(ctx, P, J, cuts[b], cuts[b + 1], W, push_capacity, &np, st)); ++blocks;
-                rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs;
-            }
-            total += np;
-        }
+        for (size_t b = 0; b + 1 < cuts.size(); ++b)
+            if (cuts[b] < cuts[b + 1]) PL.rounds.push_back({cuts[b], cuts[b + 1]});
+    }
+    return NND_OK;
+}
+
+extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand,
+                                      const int32_t *old_cand, int64_t push_capacity, void *ws, size_t ws_bytes,
+                                      int64_t *c_host, int64_t *stats_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && new_cand && old_cand && C > 0 && C <= 128, NND_ERR_INVALID, "nnd_process_candidates: bad args");
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_process_candidates: workspace too small");
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long) * 16, st));
+    unsigned long long total = 0, rows_g = 0, pairs_g = 0; int64_t blocks = 0;
+    JoinPlan PL;
+    NND_TRY(build_join_plan(ctx, P, C, new_cand, old_cand, push_capacity, W, st, PL));
+    for (auto &r : PL.rounds) {
+        unsigned long long np = 0;
+        NND_TRY(route_round(ctx, P, PL.J, r.first, r.second, W, push_capacity, &np, st, PL.batched ? &PL.JB : nullptr)); ++blocks;
+        rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs; total += np;
     }
     unsigned long long h[5];
     NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
     NND_CUDA(cudaStreamSynchronize(st));
     if (c_host) *c_host = (int64_t)h[1];
     if (stats_host) { stats_host[0] = (int64_t)rows_g; stats_host[1] = (int64_t)pairs_g; stats_host[2] = (int64_t)total; stats_host[3] = blocks; }
+    return NND_OK;
+}
+
+// =====================================================================================================
+// Sharded build (one process per GPU): the same join, but the half-updates of a round are handed to the
+// caller grouped by owner process (row ranges of `owner_block` rows, the reference's own ownership rule
+// utils.py:259-264), exchanged with an all-to-all, and applied by the owner.  Every record carries its global
+// emission sequence, so the result does not depend on the number of processes.
+// =====================================================================================================
+struct __align__(8) Rec24 { int32_t tgt, oth; float d; uint32_t pad; unsigned long long seq; };
+
+extern "C" int nnd_join_prepare(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand,
+                                const int32_t *old_cand, int64_t push_capacity, void *ws, size_t ws_bytes,
+                                int32_t *n_rounds_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && new_cand && old_cand && n_rounds_host, NND_ERR_INVALID, "nnd_join_prepare: bad args");
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_join_prepare: workspace too small");
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long) * 16, st));
+    if (!ctx->plan) ctx->plan = new JoinPlan();
+    JoinPlan &PL = *(JoinPlan *)ctx->plan;
+    NND_TRY(build_join_plan(ctx, P, C, new_cand, old_cand, push_capacity, W, st, PL));
+    *n_rounds_host = (int32_t)PL.rounds.size();
+    return NND_OK;
+}
+
+extern "C" int nnd_join_emit_round(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int64_t push_capacity, void *ws,
+                                   size_t ws_bytes, int32_t round, int64_t *n_pushed_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && ctx->plan && n_pushed_host, NND_ERR_INVALID, "nnd_join_emit_round: call nnd_join_prepare first");
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_join_emit_round: workspace too small");
+    JoinPlan &PL = *(JoinPlan *)ctx->plan;
+    *n_pushed_host = 0;
+    if (round < 0 || round >= (int32_t)PL.rounds.size()) return NND_OK;   // this process has fewer rounds: nothing to emit
+    unsigned long long np = 0;
+    NND_TRY(route_round(ctx, P, PL.J, PL.rounds[round].first, PL.rounds[round].second, W, push_capacity, &np, st,
+                        PL.batched ? &PL.JB : nullptr, /*do_apply=*/false));
+    *n_pushed_host = (int64_t)np;
+    return NND_OK;
+}
+
+__global__ void k_owner_count(const int32_t *tgt, unsigned long long n, int64_t owner_block, int R, unsigned long long *counts) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int o = -1;
+    if (i < n) { o = (int)(tgt[i] / owner_block); if (o >= R) o = R - 1; }
+    unsigned mk = __match_any_sync(0xffffffffu, o);
+    if (o >= 0 && (threadIdx.x & 31) == (__ffs(mk) - 1)) atomicAdd(&counts[o], (unsigned long long)__popc(mk));
+}
+__global__ void k_owner_scatter(const int32_t *tgt, const int32_t *oth, const float *dd, const unsigned long long *seq,
+                                unsigned long long n, int64_t owner_block, int R, unsigned long long *cursors, Rec24 *out) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int o = -1;
+    if (i < n) { o = (int)(tgt[i] / owner_block); if (o >= R) o = R - 1; }
+    unsigned mk = __match_any_sync(0xffffffffu, o);
+    const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
+    unsigned long long base = 0;
+    if (o >= 0 && lane == leader) base = atomicAdd(&cursors[o], (unsigned long long)__popc(mk));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (o >= 0) {
+        Rec24 r; r.tgt = tgt[i]; r.oth = oth[i]; r.d = dd[i]; r.pad = 0; r.seq = seq[i];
+        out[base + __popc(mk & ((1u << lane) - 1))] = r;
+    }
+}
+
+// group the half-updates emitted by the last nnd_join_emit_round by owner process; counts_host[R] receives the
+// bucket sizes, `out` (24-byte records, capacity n_pushed) the buckets back to back in rank order
+extern "C" int nnd_push_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int64_t push_capacity, void *ws, size_t ws_bytes,
+                               int64_t n_pushed, int64_t owner_block, int32_t R, void *out, int64_t *counts_host,
+                               void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && counts_host && R >= 1 && R <= 64 && owner_block > 0, NND_ERR_INVALID, "nnd_push_export: bad args");
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_push_export: workspace too small");
+    for (int r = 0; r < R; ++r) counts_host[r] = 0;
+    if (n_pushed <= 0) return NND_OK;
+    NND_CHECK(out, NND_ERR_INVALID, "nnd_push_export: out is null");
+    unsigned long long *dc = W.dev_scalars + 8;   // [64] counters live behind the 8 scalars... use the rec area instead
+    dc = (unsigned long long *)W.rec;              // routed-record area is free between emit and apply
+    NND_CUDA(cudaMemsetAsync(dc, 0, sizeof(unsigned long long) * 128, st));
+    k_owner_count<<<(unsigned)cdiv(n_pushed, 256), 256, 0, st>>>(W.l_tgt, (unsigned long long)n_pushed, owner_block, R, dc); NND_LAUNCH(ctx);
+    unsigned long long hc[64];
+    NND_CUDA(cudaMemcpyAsync(hc, dc, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    unsigned long long offs[64], acc = 0;
+    for (int r = 0; r < R; ++r) { offs[r] = acc; acc += hc[r]; counts_host[r] = (int64_t)hc[r]; }
+    NND_CUDA(cudaMemcpyAsync(dc + 64, offs, sizeof(unsigned long long) * R, cudaMemcpyHostToDevice, st));
+    k_owner_scatter<<<(unsigned)cdiv(n_pushed, 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_seq, (unsigned long long)n_pushed,
+                                                                  owner_block, R, dc + 64, (Rec24 *)out);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaStreamSynchronize(st));   // offs[] is a stack array
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+__global__ void k_rec_count(const Rec24 *in, unsigned long long n, uint32_t *cnt, uint32_t *pos) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = atomicAdd(&cnt[in[i].tgt], 1u);
+}
+__global__ void k_rec_scatter(const Rec24 *in, const uint32_t *pos, unsigned long long n, const uint32_t *off, Rec16 *rec) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rec24 a = in[i];
+    Rec16 r; r.key = a.seq; r.oth = a.oth; r.d = a.d;
+    rec[(size_t)off[a.tgt] + pos[i]] = r;
+}
+
+// apply received half-updates (any order) to the local heap rows: counting sort by target + ordered replay.
+// c_host = accepted pushes (utils.py:661-733 return value, local part)
+extern "C" int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const void *records, int64_t n,
+                                 int64_t push_capacity, void *ws, size_t ws_bytes, int64_t *c_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && c_host && n >= 0, NND_ERR_INVALID, "nnd_apply_records: bad args");
+    NND_CHECK(n <= push_capacity, NND_ERR_OVERFLOW, "nnd_apply_records: %lld records exceed push_capacity %lld", (long long)n,
+              (long long)push_capacity);
+    DescentWs W;
+    NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_apply_records: workspace too small");
+    *c_host = 0;
+    if (n == 0) return NND_OK;
+    const int64_t N = P->N;
+    NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (N + 1), st));
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars + 1, 0, sizeof(unsigned long long), st));
+    k_rec_count<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, (unsigned long long)n, W.cnt, W.l_pos); NND_LAUNCH(ctx);
+    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, N, W.scan_tmp, st));
+    k_rec_scatter<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, W.l_pos, (unsigned long long)n, W.off, W.rec); NND_LAUNCH(ctx);
+    size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
+    NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
+                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1, 0);
+    NND_LAUNCH(ctx);
+    unsigned long long hc = 0;
+    NND_CUDA(cudaMemcpyAsync(&hc, W.dev_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    *c_host = (int64_t)hc;
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+// fused leaf join + apply on leaves [l0,l1) of ONE tree (caller guarantees the leaves are disjoint point sets)
+extern "C" int nnd_leaf_fused_range(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets,
+                                    int64_t l0, int64_t l1, int32_t max_leaf, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && leaf_points && leaf_offsets && l0 >= 0 && l1 >= l0, NND_ERR_INVALID, "nnd_leaf_fused_range: bad args");
+    if (l1 == l0) return NND_OK;
+    int mm = max_leaf < 4 ? 4 : max_leaf, al = 0;
+    size_t smem = join_smem_bytes(mm, P->metric) + fused_extra_bytes(mm, P->k, &al) + 32;
+    NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "fused leaf join needs %zu B of shared memory (leaf %d, k %d)", smem, mm, P->k);
+    JoinParams J; memset(&J, 0, sizeof(J));
+    J.X = P->X; J.N = P->N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
+    J.mode = 2; J.leaf_points = leaf_points; J.leaf_offsets = leaf_offsets; J.m_max = mm; J.slot_stride = mm;
+    J.heap_idx = P->heap_idx; J.heap_dist = P->heap_dist; J.heap_flag = P->heap_flag; J.k = P->k; J.d_alias = al;
+    J.unit_begin = l0; J.unit_end = l1;
+    return launch_join(ctx, J, l1 - l0, st);
+}
+
+// pack / unpack heap rows listed in `rows` (sharded build: exchange of the rows a process has updated)
+__global__ void k_heap_pack(const int32_t *hi, const float *hd, const uint8_t *hf, int k, const int32_t *rows, int64_t n,
+                            int32_t *oi, float *od, uint8_t *of, int unpack, int32_t *whi, float *whd, uint8_t *whf) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * k) return;
+    int64_t r = e / k; int j = (int)(e - r * k);
+    int64_t row = rows ? (int64_t)rows[r] : r;
+    if (!unpack) { oi[e] = hi[row * k + j]; od[e] = hd[row * k + j]; of[e] = hf[row * k + j]; }
+    else { whi[row * k + j] = oi[e]; whd[row * k + j] = od[e]; whf[row * k + j] = of[e]; }
+}
+extern "C" int nnd_heap_pack_rows(nnd_ctx *ctx, const nnd_problem *P, const int32_t *rows, int64_t n, int32_t *out_idx,
+                                  float *out_dist, uint8_t *out_flag, int32_t unpack, void *stream) {
+    NND_CHECK(ctx && P && out_idx && out_dist && out_flag && n >= 0, NND_ERR_INVALID, "nnd_heap_pack_rows: bad args");
+    if (n == 0) return NND_OK;
+    k_heap_pack<<<(unsigned)cdiv(n * P->k, 256), 256, 0, (cudaStream_t)stream>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, rows, n,
+                                                                              out_idx, out_dist, out_flag, unpack, P->heap_idx,
+                                                                              P->heap_dist, P->heap_flag);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
     return NND_OK;
 }
 

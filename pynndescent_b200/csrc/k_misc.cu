@@ -51,6 +51,7 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
     nnd_ctx *c = new nnd_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->launches = 0;
     memset(c->prof, 0, sizeof(c->prof));
+    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr;
     NND_CUDA(cudaEventCreate(&c->ev0));
     NND_CUDA(cudaEventCreate(&c->ev1));
     size_t n = (size_t)3 * NND_JUMP_POW * 64;
@@ -68,6 +69,11 @@ extern "C" int nnd_destroy(nnd_ctx *ctx) {
     cudaEventDestroy(ctx->ev1);
     free(ctx->h_jump);
     delete ctx;
+    return NND_OK;
+}
+extern "C" int nnd_set_row_range(nnd_ctx *ctx, int64_t lo, int64_t hi) {
+    NND_CHECK(ctx && lo >= 0 && hi >= lo, NND_ERR_INVALID, "nnd_set_row_range: bad range");
+    ctx->row_lo = lo; ctx->row_hi = hi;
     return NND_OK;
 }
 extern "C" int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset) {

@@ -42,6 +42,8 @@ struct nnd_ctx {
     double prof[2][5];
     cudaEvent_t ev0, ev1;
     unsigned long long last_round_rows, last_round_pairs;
+    int64_t row_lo, row_hi;   // sharded build: this process joins / samples candidates only for rows in [row_lo,row_hi)
+    void *plan;               // JoinPlan of the sharded round API (k_descent.cu)
 };
 #define NND_JUMP_POW 44
 #define NND_LAUNCH(ctx) ((ctx)->launches++)

@@ -227,6 +227,48 @@ class Engine:
         lap("deheap_sort")
         return idx_t, dist_t, iters, c_hist, stats
 
+    # ------------------------------------------------------------------ sharded-build primitives (sharded.py)
+    def set_row_range(self, lo, hi):
+        check(lib.nnd_set_row_range(self._ctx, int(lo), int(hi)))
+
+    def join_prepare(self, newc, oldc, cap):
+        C_ = newc.shape[1]
+        ws = self.workspace(C_, 1, cap)
+        nr = C.c_int32()
+        check(lib.nnd_join_prepare(self._ctx, C.byref(self.problem()), C_, _ptr(newc), _ptr(oldc), cap, _ptr(ws), ws.numel(),
+                                   C.byref(nr), self._st()))
+        return int(nr.value)
+
+    def join_emit_round(self, C_, cap, rnd):
+        ws = self.workspace(C_, 1, cap)
+        n = C.c_int64()
+        check(lib.nnd_join_emit_round(self._ctx, C.byref(self.problem()), C_, cap, _ptr(ws), ws.numel(), int(rnd), C.byref(n),
+                                      self._st()))
+        return int(n.value)
+
+    def push_export(self, C_, cap, n_pushed, owner_block, world):
+        ws = self.workspace(C_, 1, cap)
+        out = torch.empty(max(n_pushed, 1) * 24, dtype=torch.uint8, device=self.device)
+        counts = (C.c_int64 * world)()
+        check(lib.nnd_push_export(self._ctx, C.byref(self.problem()), C_, cap, _ptr(ws), ws.numel(), int(n_pushed),
+                                  int(owner_block), int(world), _ptr(out), counts, self._st()))
+        return out, [int(c) for c in counts]
+
+    def apply_records(self, C_, cap, records, n):
+        ws = self.workspace(C_, 1, cap)
+        c = C.c_int64()
+        check(lib.nnd_apply_records(self._ctx, C.byref(self.problem()), C_, _ptr(records), int(n), cap, _ptr(ws), ws.numel(),
+                                    C.byref(c), self._st()))
+        return int(c.value)
+
+    def leaf_fused_range(self, leaf_points, leaf_offsets, l0, l1, max_leaf):
+        check(lib.nnd_leaf_fused_range(self._ctx, C.byref(self.problem()), _ptr(leaf_points), _ptr(leaf_offsets), int(l0), int(l1),
+                                       int(max_leaf), self._st()))
+
+    def heap_pack_rows(self, rows, n, oi, od, of, unpack):
+        check(lib.nnd_heap_pack_rows(self._ctx, C.byref(self.problem()), _ptr(rows), int(n), _ptr(oi), _ptr(od), _ptr(of),
+                                     int(bool(unpack)), self._st()))
+
     def profile(self, reset=True):
         out = (C.c_double * 10)()
         check(lib.nnd_profile_read(self._ctx, out, int(bool(reset))))

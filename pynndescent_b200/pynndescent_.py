@@ -41,7 +41,8 @@ class NNDescent:
                  search_tree_leaf_size=None, max_search_tree_depth=None, quantization=None, tree_init=True,
                  init_graph=None, init_dist=None, random_state=None, low_memory=True, max_candidates=None,
                  max_rptree_depth=200, n_iters=None, delta=0.001, n_jobs=None, compressed=False,
-                 parallel_batch_queries=False, verbose=False, device=None, push_capacity=None, leaf_array=None):
+                 parallel_batch_queries=False, verbose=False, device=None, push_capacity=None, leaf_array=None,
+                 sharded=False):
         from sklearn.utils import check_random_state, check_array
         from scipy.sparse import issparse
 
@@ -105,9 +106,19 @@ class NNDescent:
             self._tree_rng_states = tree_states                                              # rp_trees.py:2850-2852
         if verbose:
             print(ts(), "NN descent for", str(n_iters), "iterations")
-        idx_t, dist_t, iters, c_hist, stats = eng.build(
-            self.rng_state, tree_states, leaf_size, angular, eff_C, T, n_iters, delta, dev_correction,
-            max_depth=max_rptree_depth, push_capacity=push_capacity, leaf_array=leaf_array, timings=self.timings)
+        if sharded:
+            # one process per GPU (torch.distributed, NCCL): rows of the heap are sharded, see sharded.py
+            from .sharded import ShardedBuilder
+            sb = ShardedBuilder(eng)
+            self._sharded = sb
+            idx_t, dist_t, iters, c_hist = sb.build(self.rng_state, tree_states, leaf_size, angular, eff_C, T, n_iters, delta,
+                                                    dev_correction, max_depth=max_rptree_depth, cap=push_capacity,
+                                                    timings=self.timings)
+            stats = [0, 0, 0, 0]
+        else:
+            idx_t, dist_t, iters, c_hist, stats = eng.build(
+                self.rng_state, tree_states, leaf_size, angular, eff_C, T, n_iters, delta, dev_correction,
+                max_depth=max_rptree_depth, push_capacity=push_capacity, leaf_array=leaf_array, timings=self.timings)
         if verbose:
             for it in range(iters):
                 print("\t", it + 1, " / ", n_iters)

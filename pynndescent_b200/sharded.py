@@ -1,0 +1,172 @@
+"""Row-sharded NN-descent build across the GPUs of one node (one process per GPU, torch.distributed/NCCL).
+
+Every rank keeps X and the WHOLE heap (N x k x 9 B -- 1.35 GB at 10M x 15), but works only on its own
+contiguous row range [r*B, (r+1)*B), B = N // world + 1 -- the reference's own ownership rule for its
+threads (utils.py:259-264):
+
+  forest      trees t = rank, rank+world, ... are built locally, then every tree's leaves are broadcast
+  leaf init   per tree, the leaves are split by position among the ranks (disjoint point sets), each rank runs
+              the fused leaf join on its share, then the updated heap rows are all-gathered
+  candidates  sampled for the own rows only (reverse edges are found by scanning the replicated heap)
+  local join  own rows; the half-updates are grouped by owner(target) and exchanged with ONE all-to-all-v per
+              round; the owner replays them in emission-sequence order
+  end of it.  all-gather of the owners' heap rows, all-reduce(sum) of the accepted-push count `c`
+
+Every half-update carries its global emission sequence, so the graph is IDENTICAL to the single-GPU build
+(and to the oracle) for any world size -- tests/test_sharded_gpu.py checks exactly that.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import Engine
+
+
+class ShardedBuilder:
+    def __init__(self, engine: Engine):
+        assert dist.is_initialized(), "torch.distributed must be initialised (backend nccl)"
+        self.e = engine
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.N, self.k = engine.N, engine.k
+        self.B = self.N // self.world + 1                      # utils.py:259
+        self.lo = min(self.rank * self.B, self.N)
+        self.hi = min(self.lo + self.B, self.N)
+        # heap tensors with room for world*B rows so that the per-range all-gather lands in place
+        dev = engine.device
+        rows = self.world * self.B
+        self._full = (torch.empty((rows, self.k), dtype=torch.int32, device=dev),
+                      torch.empty((rows, self.k), dtype=torch.float32, device=dev),
+                      torch.empty((rows, self.k), dtype=torch.uint8, device=dev))
+        engine.heap_idx, engine.heap_dist, engine.heap_flag = (t[: self.N] for t in self._full)
+        self.comm_bytes = 0
+
+    # ------------------------------------------------------------------ collectives
+    def _allgather_heap(self):
+        """Owners' row ranges -> everyone (3 all-gathers of B x k rows)."""
+        for t in self._full:
+            send = t[self.rank * self.B: (self.rank + 1) * self.B].clone()
+            dist.all_gather_into_tensor(t, send)
+            self.comm_bytes += t.numel() * t.element_size()
+
+    def _bcast_tree(self, owner, pts, offs, n_leaves, max_leaf):
+        meta = torch.tensor([n_leaves, max_leaf], dtype=torch.int64, device=self.e.device)
+        dist.broadcast(meta, src=owner)
+        n_leaves, max_leaf = int(meta[0]), int(meta[1])
+        if self.rank != owner:
+            pts = torch.empty(self.N, dtype=torch.int32, device=self.e.device)
+            offs = torch.empty(n_leaves + 1, dtype=torch.int64, device=self.e.device)
+        dist.broadcast(pts, src=owner)
+        dist.broadcast(offs, src=owner)
+        self.comm_bytes += pts.numel() * 4 + offs.numel() * 8
+        return pts, offs, n_leaves, max_leaf
+
+    # ------------------------------------------------------------------ stages
+    def forest_and_leaf_init(self, tree_states, leaf_size, angular, max_depth, cap):
+        e, N = self.e, self.N
+        n_trees = len(tree_states)
+        mine = [t for t in range(n_trees) if t % self.world == self.rank]
+        local = {}
+        if mine:
+            lp, lo, n_leaves, max_leaf = e.forest(tree_states[mine], leaf_size, angular, max_depth)
+            lo_h = lo.cpu().numpy()
+            for j, t in enumerate(mine):                     # split the tree-major CSR back into trees
+                a = int(np.searchsorted(lo_h, j * N)); b = int(np.searchsorted(lo_h, (j + 1) * N))
+                local[t] = (lp[j * N: (j + 1) * N].contiguous(), (lo[a: b + 1] - j * N).contiguous(), b - a, max_leaf)
+        trees = []
+        for t in range(n_trees):
+            owner = t % self.world
+            pts, offs, nl, ml = local.get(t, (None, None, 0, 0))
+            trees.append(self._bcast_tree(owner, pts, offs, nl, ml))
+        max_leaf = max(tr[3] for tr in trees)
+        fused_ok = True
+        for t, (pts, offs, nl, _) in enumerate(trees):
+            offs_h = offs.cpu().numpy()
+            # rank r takes the leaves whose first position lies in [r*N/world, (r+1)*N/world)
+            cuts = [int(np.searchsorted(offs_h[:-1], (r * N) // self.world)) for r in range(self.world)] + [nl]
+            l0, l1 = cuts[self.rank], cuts[self.rank + 1]
+            if fused_ok:
+                try:
+                    e.leaf_fused_range(pts, offs, l0, l1, max_leaf)
+                except NotImplementedError:
+                    fused_ok = False
+            if not fused_ok:
+                break
+            # exchange the rows each rank has just updated (its leaves' points, in position order)
+            p0 = [int(offs_h[c]) for c in cuts]
+            maxn = max(p0[r + 1] - p0[r] for r in range(self.world))
+            k = self.k
+            si = torch.zeros((maxn, k), dtype=torch.int32, device=e.device); sd = torch.zeros((maxn, k), dtype=torch.float32, device=e.device)
+            sf = torch.zeros((maxn, k), dtype=torch.uint8, device=e.device)
+            n_mine = p0[self.rank + 1] - p0[self.rank]
+            e.heap_pack_rows(pts[p0[self.rank]: p0[self.rank + 1]], n_mine, si, sd, sf, False)
+            gi = torch.empty((self.world * maxn, k), dtype=torch.int32, device=e.device)
+            gd = torch.empty((self.world * maxn, k), dtype=torch.float32, device=e.device)
+            gf = torch.empty((self.world * maxn, k), dtype=torch.uint8, device=e.device)
+            dist.all_gather_into_tensor(gi, si); dist.all_gather_into_tensor(gd, sd); dist.all_gather_into_tensor(gf, sf)
+            self.comm_bytes += gi.numel() * 9
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                n_r = p0[r + 1] - p0[r]
+                e.heap_pack_rows(pts[p0[r]: p0[r + 1]], n_r, gi[r * maxn:], gd[r * maxn:], gf[r * maxn:], True)
+        if not fused_ok:
+            # leaves too large for the fused kernel: every rank runs the routed leaf init on all trees (replicated)
+            e.make_heap()
+            lp = torch.cat([tr[0] for tr in trees])
+            lo = torch.cat([tr[1][:-1] + t * N for t, tr in enumerate(trees)] +
+                           [torch.tensor([n_trees * N], dtype=torch.int64, device=e.device)])
+            e.leaf_init(lp, lo, lo.numel() - 1, max_leaf, cap)
+
+    def descent(self, C_, rng_state, T, n_iters, delta, cap):
+        e = self.e
+        c_hist = []
+        for it in range(n_iters):
+            e.set_row_range(self.lo, self.hi)
+            newc, oldc = e.build_candidates(C_, rng_state, T, tables_valid=(it > 0))
+            nr = torch.tensor([e.join_prepare(newc, oldc, cap)], dtype=torch.int64, device=e.device)
+            dist.all_reduce(nr, op=dist.ReduceOp.MAX)
+            c_loc = 0
+            for rnd in range(int(nr[0])):
+                n = e.join_emit_round(C_, cap, rnd)
+                send, counts = e.push_export(C_, cap, n, self.B, self.world)
+                cs = torch.tensor(counts, dtype=torch.int64, device=e.device)
+                cr = torch.empty_like(cs)
+                dist.all_to_all_single(cr, cs)
+                rc = [int(v) for v in cr.cpu()]
+                recv = torch.empty(max(sum(rc), 1) * 24, dtype=torch.uint8, device=e.device)
+                dist.all_to_all_single(recv[: sum(rc) * 24], send[: n * 24], output_split_sizes=[c * 24 for c in rc],
+                                       input_split_sizes=[c * 24 for c in counts])
+                self.comm_bytes += sum(rc) * 24
+                c_loc += e.apply_records(C_, cap, recv, sum(rc))
+            e.set_row_range(0, 2 ** 62)
+            self._allgather_heap()
+            ct = torch.tensor([c_loc], dtype=torch.int64, device=e.device)
+            dist.all_reduce(ct, op=dist.ReduceOp.SUM)
+            c_hist.append(int(ct[0]))
+            if c_hist[-1] <= delta * self.k * self.N:
+                break
+        return len(c_hist), c_hist
+
+    def build(self, rng_state, tree_states, leaf_size, angular, C_, T, n_iters, delta, correction, max_depth=200, cap=None,
+              timings=None):
+        import time
+        e = self.e
+        cap = cap or e.default_push_capacity()
+        e.workspace(C_, T, cap)
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            if timings is not None:
+                e.stream.synchronize()
+                t1 = time.perf_counter(); timings[name] = timings.get(name, 0.0) + (t1 - t0); t0 = t1
+        e.make_heap()
+        if tree_states is not None and len(tree_states) > 0:
+            self.forest_and_leaf_init(np.asarray(tree_states), leaf_size, angular, max_depth, cap)
+        lap("forest+leaf_init")
+        e.init_random(rng_state)
+        iters, c_hist = self.descent(C_, rng_state, T, n_iters, delta, cap)
+        lap("descent")
+        idx_t, dist_t = e.deheap_sort(correction)
+        lap("deheap_sort")
+        return idx_t, dist_t, iters, c_hist
