@@ -124,10 +124,20 @@ class ShardedBuilder:
             e.set_row_range(self.lo, self.hi)
             newc, oldc = e.build_candidates(C_, rng_state, T, tables_valid=(it > 0))
             nr = torch.tensor([e.join_prepare(newc, oldc, cap)], dtype=torch.int64, device=e.device)
-            dist.all_reduce(nr, op=dist.ReduceOp.MAX)
+            nrs = torch.empty(self.world, dtype=torch.int64, device=e.device)
+            dist.all_gather_into_tensor(nrs, nr)
+            nrs = [int(v) for v in nrs.cpu()]
+            # Canonical push order per target row = ascending join-row id.  One round per rank: all ranks emit at
+            # once and the owner's sort by emission sequence restores the order.  If some rank needs several
+            # rounds (push list larger than its capacity) the rounds are serialised rank-major, which is still
+            # ascending in the join-row id because ranks own ascending row ranges.
+            if max(nrs) <= 1:
+                schedule = [(None, 0)]
+            else:
+                schedule = [(src, rnd) for src in range(self.world) for rnd in range(nrs[src])]
             c_loc = 0
-            for rnd in range(int(nr[0])):
-                n = e.join_emit_round(C_, cap, rnd)
+            for src, rnd in schedule:
+                n = e.join_emit_round(C_, cap, rnd) if (src is None or src == self.rank) else 0
                 send, counts = e.push_export(C_, cap, n, self.B, self.world)
                 cs = torch.tensor(counts, dtype=torch.int64, device=e.device)
                 cr = torch.empty_like(cs)

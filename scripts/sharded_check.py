@@ -9,7 +9,8 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 rank, world = dist.get_rank(), dist.get_world_size()
-cases = [("euclidean", 20000, 32, 15, 42), ("cosine", 8000, 24, 10, 7), ("euclidean", 3000, 7, 30, 1)]
+cases = [("euclidean", 20000, 32, 15, 42), ("cosine", 8000, 24, 10, 7), ("euclidean", 3000, 7, 30, 1),
+         ("euclidean", 3000, 7, 15, 1), ("euclidean", 3000, 16, 30, 1), ("euclidean", 3000, 16, 20, 1)]
 if len(sys.argv) > 1:
     cases = [("euclidean", int(sys.argv[1]), 128, 15, 42)]
 ok = True
@@ -27,6 +28,9 @@ for metric, n, d, k, seed in cases:
         same = np.array_equal(gi, oi) and np.array_equal(gd, od) and sh.c_hist == one.c_hist
         print(f"[{metric} {n}x{d} k={k}] world={world} sharded==single: {same}  c_hist {sh.c_hist[:4]}.. t_sharded {t_sh:.3f}s t_single {t_one:.3f}s "
               f"timings {sh.timings} comm_MB {sh._sharded.comm_bytes/1e6:.1f}", flush=True)
+        if not same:
+            bad = np.where((gi != oi).any(1))[0]
+            print("   differing rows:", len(bad), bad[:10], "c_hist sharded", sh.c_hist, "single", one.c_hist, flush=True)
         ok = ok and same
     dist.barrier()
 if rank == 0:
