@@ -175,15 +175,21 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    n, d, k, metric = wl["n"], wl["d"], wl["k"], wl["metric"]
-    # independent partition per rank (weak scaling): rank r builds the graph of its own n points
-    X = latent(n, d, seed=rank)
+    n_per, d, k, metric = wl["n"], wl["d"], wl["k"], wl["metric"]
+    # weak scaling: ONE graph over n = world x n_per points; heap rows sharded by range across the ranks,
+    # X replicated, per-iteration NCCL exchange of half-updates (pynndescent_b200/sharded.py)
+    n = n_per * world
+    X = latent(n, d, seed=0)
     metric_id, dev_corr, host_corr, angular = pdist.resolve(metric)
     n_trees = max(3, min(12, int(round(2.0 * np.log10(n))))); n_iters = max(5, int(round(np.log2(n))))
     leaf_size = max(60, min(256, 5 * k)); C_ = min(60, k); T = 8
 
     eng = Engine(X, metric_id, k)
     stream = eng.stream
+    sb = None
+    if world > 1:
+        from pynndescent_b200.sharded import ShardedBuilder
+        sb = ShardedBuilder(eng)
 
     def seeds():
         rs = np.random.RandomState(42)
@@ -193,6 +199,9 @@ def main():
 
     def one_build(timings=None):
         rng, trees = seeds()
+        if sb is not None:
+            i_t, d_t, it_, ch_ = sb.build(rng, trees, leaf_size, angular, C_, T, n_iters, 0.001, dev_corr, timings=timings)
+            return i_t, d_t, it_, ch_, [0, 0, 0, 0]
         return eng.build(rng, trees, leaf_size, angular, C_, T, n_iters, 0.001, dev_corr, timings=timings)
 
     def barrier():
@@ -220,16 +229,17 @@ def main():
     gi = idx_t.cpu().numpy()
 
     # ---- e2e: the public API with host buffers (H2D of X and D2H of the graph inside the timed region)
-    del eng, idx_t, dist_t
+    comm_bytes = sb.comm_bytes if sb is not None else 0
+    del eng, idx_t, dist_t, sb
     torch.cuda.empty_cache()
     Xp = torch.from_numpy(X).pin_memory().numpy()
-    NNDescent(Xp, metric, n_neighbors=k, random_state=42)  # warm allocator
+    NNDescent(Xp, metric, n_neighbors=k, random_state=42, sharded=(world > 1))  # warm allocator
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = max(1, min(args.steps, 3))
     e0.record(stream)
     for _ in range(e2e_steps):
-        idx = NNDescent(Xp, metric, n_neighbors=k, random_state=42)
+        idx = NNDescent(Xp, metric, n_neighbors=k, random_state=42, sharded=(world > 1))
         g = idx.neighbor_graph
     e1.record(stream)
     barrier()
@@ -244,8 +254,8 @@ def main():
             dist.destroy_process_group()
         return
     ms_step = ms / args.steps
-    value = world * n * k / (ms_step * 1e-3)
-    e2e = world * n * k / (e2e_ms * 1e-3)
+    value = n * k / (ms_step * 1e-3)
+    e2e = n * k / (e2e_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (k_join, local-join launches), DESIGN.md section 7:
     # algorithmic bytes = 4*ld*G (gathered rows) + 4*G (thresholds) + 8*N*C (candidate lists, per iteration)
@@ -254,7 +264,7 @@ def main():
     ld = (d + 3) // 4 * 4
     jj = prof["join"]
     iters_total = iters * args.steps
-    bytes_alg = 4.0 * ld * jj["rows"] + 4.0 * jj["rows"] + 8.0 * n * C_ * iters_total + 12.0 * jj["pushes"]
+    bytes_alg = 4.0 * ld * jj["rows"] + 4.0 * jj["rows"] + 8.0 * (n / world) * C_ * iters_total + 12.0 * jj["pushes"]
     ach = bytes_alg / (jj["ms"] * 1e-3) / 1e9 if jj["ms"] > 0 else 0.0
     lf = prof["leaf"]
     leaf_bytes = 4.0 * ld * lf["rows"] + 4.0 * lf["rows"] + 12.0 * lf["pushes"]
@@ -265,9 +275,12 @@ def main():
         "metric": "kNN-graph build edges/sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic latent-16 (SURVEY 8d), seed 0, index random_state 42",
-        "config": {"workload": wl["name"], "n": n, "d": d, "k": k, "metric": metric, "n_trees": n_trees,
+        "config": {"workload": wl["name"] + ("" if world == 1 else " x %d (weak scaling)" % world), "n": n, "d": d, "k": k, "metric": metric, "n_trees": n_trees,
                    "leaf_size": leaf_size, "max_candidates": C_, "emulated_numba_threads": T, "iterations": iters,
-                   "multi_gpu": "independent partition per rank" if world > 1 else "single GPU",
+                   "multi_gpu": ("one graph over n_gpus x %d points: heap rows sharded by range, X replicated, NCCL "
+                                 "all-to-all-v of half-updates + all-gather of owners' heap rows per iteration; "
+                                 "%.1f MB/step/rank exchanged" % (n_per, comm_bytes / 1e6 / max(args.steps + args.warmup, 1)))
+                   if world > 1 else "single GPU",
                    "l2": "inputs (X = %.0f MB) exceed the 126 MB L2; no explicit flush" % (n * ld * 4 / 1e6)},
         "recall_at_k": rec,
         "e2e": {"value": e2e, "unit": "edges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(n * d * 4),

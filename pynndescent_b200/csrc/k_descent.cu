@@ -898,7 +898,11 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     unsigned long long h[7];
     NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
     NND_CUDA(cudaStreamSynchronize(st));
-    NND_CHECK(((int *)&h[4])[0] == 0, NND_ERR_OVERFLOW, "push list overflow (capacity %lld)", (long long)cap);
+    if (((int *)&h[4])[0] != 0) {   // the optimistic round did not fit: nothing was applied, the caller splits the round
+        NND_CUDA(cudaMemsetAsync(W.dev_scalars + 4, 0, sizeof(unsigned long long), st));
+        nnd_set_error("push list overflow (capacity %lld): raise push_capacity", (long long)cap);
+        return NND_ERR_OVERFLOW;
+    }
     *n_pushed = h[0];
     {
         float ms = 0.f;
@@ -1115,8 +1119,9 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
             JB.X = P->X; JB.N = N; JB.ld = P->ld; JB.metric = P->metric; JB.aux = P->aux;
             JB.act_unit = W.act_unit; JB.act_info = W.act_info; JB.act_poff = W.act_poff; JB.members = W.members;
             JB.batch_first = W.batch_first; JB.n_active = n_active; JB.n_batches = n_batches; JB.slot_stride = 2 * C;
-            // worst case half-updates per batch: every tile slot x 16 pairs x 2 sides
-            const int64_t per_batch = (int64_t)JB_TCAP * 32;
+            // rounds are planned optimistically (16 half-updates per tile slot; the worst case is 32 and the measured
+            // average 7); a round that overflows is detected (never silent) and split by the caller
+            const int64_t per_batch = (int64_t)JB_TCAP * 16;
             NND_CHECK(per_batch <= push_capacity, NND_ERR_OVERFLOW, "push_capacity %lld too small for one batch (%lld)",
                       (long long)push_capacity, (long long)per_batch);
             const int64_t bpb = push_capacity / per_batch;
@@ -1144,9 +1149,18 @@ extern "C" int nnd_process_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_
     unsigned long long total = 0, rows_g = 0, pairs_g = 0; int64_t blocks = 0;
     JoinPlan PL;
     NND_TRY(build_join_plan(ctx, P, C, new_cand, old_cand, push_capacity, W, st, PL));
-    for (auto &r : PL.rounds) {
+    std::vector<std::pair<int64_t, int64_t>> work(PL.rounds.rbegin(), PL.rounds.rend());   // stack, ascending order on top
+    while (!work.empty()) {
+        auto r = work.back(); work.pop_back();
         unsigned long long np = 0;
-        NND_TRY(route_round(ctx, P, PL.J, r.first, r.second, W, push_capacity, &np, st, PL.batched ? &PL.JB : nullptr)); ++blocks;
+        int rc = route_round(ctx, P, PL.J, r.first, r.second, W, push_capacity, &np, st, PL.batched ? &PL.JB : nullptr);
+        if (rc == NND_ERR_OVERFLOW && r.second - r.first > 1) {   // split, keep ascending unit order
+            int64_t mid = (r.first + r.second) / 2;
+            work.push_back({mid, r.second}); work.push_back({r.first, mid});
+            continue;
+        }
+        if (rc != NND_OK) return rc;
+        ++blocks;
         rows_g += ctx->last_round_rows; pairs_g += ctx->last_round_pairs; total += np;
     }
     unsigned long long h[5];

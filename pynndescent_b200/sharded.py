@@ -48,74 +48,70 @@ class ShardedBuilder:
             dist.all_gather_into_tensor(t, send)
             self.comm_bytes += t.numel() * t.element_size()
 
-    def _bcast_tree(self, owner, pts, offs, n_leaves, max_leaf):
-        meta = torch.tensor([n_leaves, max_leaf], dtype=torch.int64, device=self.e.device)
-        dist.broadcast(meta, src=owner)
-        n_leaves, max_leaf = int(meta[0]), int(meta[1])
-        if self.rank != owner:
-            pts = torch.empty(self.N, dtype=torch.int32, device=self.e.device)
-            offs = torch.empty(n_leaves + 1, dtype=torch.int64, device=self.e.device)
-        dist.broadcast(pts, src=owner)
-        dist.broadcast(offs, src=owner)
-        self.comm_bytes += pts.numel() * 4 + offs.numel() * 8
-        return pts, offs, n_leaves, max_leaf
-
     # ------------------------------------------------------------------ stages
     def forest_and_leaf_init(self, tree_states, leaf_size, angular, max_depth, cap):
-        e, N = self.e, self.N
+        e, N, k, dev = self.e, self.N, self.k, self.e.device
         n_trees = len(tree_states)
         mine = [t for t in range(n_trees) if t % self.world == self.rank]
+        meta = torch.zeros((n_trees, 2), dtype=torch.int64, device=dev)          # (n_leaves, max_leaf) per tree
         local = {}
         if mine:
             lp, lo, n_leaves, max_leaf = e.forest(tree_states[mine], leaf_size, angular, max_depth)
             lo_h = lo.cpu().numpy()
             for j, t in enumerate(mine):                     # split the tree-major CSR back into trees
                 a = int(np.searchsorted(lo_h, j * N)); b = int(np.searchsorted(lo_h, (j + 1) * N))
-                local[t] = (lp[j * N: (j + 1) * N].contiguous(), (lo[a: b + 1] - j * N).contiguous(), b - a, max_leaf)
-        trees = []
+                local[t] = (lp[j * N: (j + 1) * N], lo[a: b + 1] - j * N)
+                meta[t, 0] = b - a; meta[t, 1] = max_leaf
+        dist.all_reduce(meta, op=dist.ReduceOp.SUM)
+        meta_h = meta.cpu().numpy()
+        max_leaf = int(meta_h[:, 1].max())
+        # every tree's leaves to every rank: one points buffer + one offsets buffer, filled by broadcasts
+        pts_all = torch.empty((n_trees, N), dtype=torch.int32, device=dev)
+        offs_all = torch.empty(int(meta_h[:, 0].sum()) + n_trees, dtype=torch.int64, device=dev)
+        obase = np.concatenate([[0], np.cumsum(meta_h[:, 0] + 1)])
         for t in range(n_trees):
             owner = t % self.world
-            pts, offs, nl, ml = local.get(t, (None, None, 0, 0))
-            trees.append(self._bcast_tree(owner, pts, offs, nl, ml))
-        max_leaf = max(tr[3] for tr in trees)
+            ov = offs_all[obase[t]: obase[t + 1]]
+            if owner == self.rank:
+                pts_all[t].copy_(local[t][0]); ov.copy_(local[t][1])
+            dist.broadcast(pts_all[t], src=owner)
+            dist.broadcast(ov, src=owner)
+        self.comm_bytes += pts_all.numel() * 4 + offs_all.numel() * 8
+        offs_h = offs_all.cpu().numpy()
+        # rank r takes, in every tree, the leaves whose first position lies in [r*N/world, (r+1)*N/world)
+        plan = []
+        for t in range(n_trees):
+            oh = offs_h[obase[t]: obase[t + 1]]
+            cuts = [int(np.searchsorted(oh[:-1], (r * N) // self.world)) for r in range(self.world)] + [int(meta_h[t, 0])]
+            plan.append((cuts, [int(oh[c]) for c in cuts]))
+        maxn = max(p0[r + 1] - p0[r] for _, p0 in plan for r in range(self.world))
+        si = torch.zeros((maxn, k), dtype=torch.int32, device=dev); sd = torch.zeros((maxn, k), dtype=torch.float32, device=dev)
+        sf = torch.zeros((maxn, k), dtype=torch.uint8, device=dev)
+        gi = torch.empty((self.world * maxn, k), dtype=torch.int32, device=dev)
+        gd = torch.empty((self.world * maxn, k), dtype=torch.float32, device=dev)
+        gf = torch.empty((self.world * maxn, k), dtype=torch.uint8, device=dev)
         fused_ok = True
-        for t, (pts, offs, nl, _) in enumerate(trees):
-            offs_h = offs.cpu().numpy()
-            # rank r takes the leaves whose first position lies in [r*N/world, (r+1)*N/world)
-            cuts = [int(np.searchsorted(offs_h[:-1], (r * N) // self.world)) for r in range(self.world)] + [nl]
-            l0, l1 = cuts[self.rank], cuts[self.rank + 1]
-            if fused_ok:
-                try:
-                    e.leaf_fused_range(pts, offs, l0, l1, max_leaf)
-                except NotImplementedError:
-                    fused_ok = False
-            if not fused_ok:
+        for t in range(n_trees):
+            cuts, p0 = plan[t]
+            pts = pts_all[t]; offs = offs_all[obase[t]: obase[t + 1]]
+            try:
+                e.leaf_fused_range(pts, offs, cuts[self.rank], cuts[self.rank + 1], max_leaf)
+            except NotImplementedError:
+                fused_ok = False
                 break
             # exchange the rows each rank has just updated (its leaves' points, in position order)
-            p0 = [int(offs_h[c]) for c in cuts]
-            maxn = max(p0[r + 1] - p0[r] for r in range(self.world))
-            k = self.k
-            si = torch.zeros((maxn, k), dtype=torch.int32, device=e.device); sd = torch.zeros((maxn, k), dtype=torch.float32, device=e.device)
-            sf = torch.zeros((maxn, k), dtype=torch.uint8, device=e.device)
-            n_mine = p0[self.rank + 1] - p0[self.rank]
-            e.heap_pack_rows(pts[p0[self.rank]: p0[self.rank + 1]], n_mine, si, sd, sf, False)
-            gi = torch.empty((self.world * maxn, k), dtype=torch.int32, device=e.device)
-            gd = torch.empty((self.world * maxn, k), dtype=torch.float32, device=e.device)
-            gf = torch.empty((self.world * maxn, k), dtype=torch.uint8, device=e.device)
+            e.heap_pack_rows(pts[p0[self.rank]: p0[self.rank + 1]], p0[self.rank + 1] - p0[self.rank], si, sd, sf, False)
             dist.all_gather_into_tensor(gi, si); dist.all_gather_into_tensor(gd, sd); dist.all_gather_into_tensor(gf, sf)
             self.comm_bytes += gi.numel() * 9
             for r in range(self.world):
-                if r == self.rank:
-                    continue
-                n_r = p0[r + 1] - p0[r]
-                e.heap_pack_rows(pts[p0[r]: p0[r + 1]], n_r, gi[r * maxn:], gd[r * maxn:], gf[r * maxn:], True)
+                if r != self.rank:
+                    e.heap_pack_rows(pts[p0[r]: p0[r + 1]], p0[r + 1] - p0[r], gi[r * maxn:], gd[r * maxn:], gf[r * maxn:], True)
         if not fused_ok:
             # leaves too large for the fused kernel: every rank runs the routed leaf init on all trees (replicated)
             e.make_heap()
-            lp = torch.cat([tr[0] for tr in trees])
-            lo = torch.cat([tr[1][:-1] + t * N for t, tr in enumerate(trees)] +
-                           [torch.tensor([n_trees * N], dtype=torch.int64, device=e.device)])
-            e.leaf_init(lp, lo, lo.numel() - 1, max_leaf, cap)
+            lo = torch.cat([offs_all[obase[t]: obase[t + 1] - 1] + t * N for t in range(n_trees)] +
+                           [torch.tensor([n_trees * N], dtype=torch.int64, device=dev)])
+            e.leaf_init(pts_all.reshape(-1), lo, lo.numel() - 1, max_leaf, cap)
 
     def descent(self, C_, rng_state, T, n_iters, delta, cap):
         e = self.e
