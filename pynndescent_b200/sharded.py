@@ -113,16 +113,25 @@ class ShardedBuilder:
                            [torch.tensor([n_trees * N], dtype=torch.int64, device=dev)])
             e.leaf_init(pts_all.reshape(-1), lo, lo.numel() - 1, max_leaf, cap)
 
-    def descent(self, C_, rng_state, T, n_iters, delta, cap):
+    def descent(self, C_, rng_state, T, n_iters, delta, cap, timings=None):
+        import time
         e = self.e
         c_hist = []
+        tl = [time.perf_counter()]
+
+        def lap(name):
+            if timings is not None:
+                e.stream.synchronize()
+                t1 = time.perf_counter(); timings[name] = timings.get(name, 0.0) + (t1 - tl[0]); tl[0] = t1
         for it in range(n_iters):
             e.set_row_range(self.lo, self.hi)
             newc, oldc = e.build_candidates(C_, rng_state, T, tables_valid=(it > 0))
+            lap("d.candidates")
             nr = torch.tensor([e.join_prepare(newc, oldc, cap)], dtype=torch.int64, device=e.device)
             nrs = torch.empty(self.world, dtype=torch.int64, device=e.device)
             dist.all_gather_into_tensor(nrs, nr)
             nrs = [int(v) for v in nrs.cpu()]
+            lap("d.join_prepare")
             # Canonical push order per target row = ascending join-row id.  One round per rank: all ranks emit at
             # once and the owner's sort by emission sequence restores the order.  If some rank needs several
             # rounds (push list larger than its capacity) the rounds are serialised rank-major, which is still
@@ -134,7 +143,9 @@ class ShardedBuilder:
             c_loc = 0
             for src, rnd in schedule:
                 n = e.join_emit_round(C_, cap, rnd) if (src is None or src == self.rank) else 0
+                lap("d.join_emit")
                 send, counts = e.push_export(C_, cap, n, self.B, self.world)
+                lap("d.export")
                 cs = torch.tensor(counts, dtype=torch.int64, device=e.device)
                 cr = torch.empty_like(cs)
                 dist.all_to_all_single(cr, cs)
@@ -143,9 +154,12 @@ class ShardedBuilder:
                 dist.all_to_all_single(recv[: sum(rc) * 24], send[: n * 24], output_split_sizes=[c * 24 for c in rc],
                                        input_split_sizes=[c * 24 for c in counts])
                 self.comm_bytes += sum(rc) * 24
+                lap("d.all_to_all")
                 c_loc += e.apply_records(C_, cap, recv, sum(rc))
+                lap("d.apply")
             e.set_row_range(0, 2 ** 62)
             self._allgather_heap()
+            lap("d.allgather_heap")
             ct = torch.tensor([c_loc], dtype=torch.int64, device=e.device)
             dist.all_reduce(ct, op=dist.ReduceOp.SUM)
             c_hist.append(int(ct[0]))
@@ -171,7 +185,7 @@ class ShardedBuilder:
             self.forest_and_leaf_init(np.asarray(tree_states), leaf_size, angular, max_depth, cap)
         lap("forest+leaf_init")
         e.init_random(rng_state)
-        iters, c_hist = self.descent(C_, rng_state, T, n_iters, delta, cap)
+        iters, c_hist = self.descent(C_, rng_state, T, n_iters, delta, cap, timings=timings)
         lap("descent")
         idx_t, dist_t = e.deheap_sort(correction)
         lap("deheap_sort")
