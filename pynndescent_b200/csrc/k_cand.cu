@@ -217,10 +217,15 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
         // smallest remaining reverse entry (keys are unique)
         unsigned long long best = ~0ULL; int bj = -1;
         if (left)
-            for (uint32_t j = 0; j < nrev; ++j) {
-                if ((used >> j) & 1u) continue;
-                unsigned long long x = seg[j];
-                if (x < best) { best = x; bj = (int)j; }
+            {   // select on the 32-bit (scan position, isnew) word only; the priority word is fetched for the winner
+                const uint32_t *kw = (const uint32_t *)seg;
+                uint32_t bk = 0xFFFFFFFFu;
+                for (uint32_t j = 0; j < nrev; ++j) {
+                    if ((used >> j) & 1u) continue;
+                    uint32_t x = kw[2 * j + 1];
+                    if (x < bk) { bk = x; bj = (int)j; }
+                }
+                if (bj >= 0) best = seg[bj];
             }
         const bool hasr = bj >= 0;
         if (!hasf && !hasr) break;

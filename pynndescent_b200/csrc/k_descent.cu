@@ -840,6 +840,10 @@ static int launch_join_m(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cud
     if (P.mode == 2) { int al; smem += fused_extra_bytes(P.m_max, P.k, &al) + 32; }
     NND_CHECK(smem <= 220 * 1024, NND_ERR_UNSUPPORTED, "join: %d members need %zu B of shared memory", P.m_max, smem);
     int tpt = (METRIC == NND_METRIC_CORRELATION) ? 1 : (ntiles <= 512 ? 1 : (ntiles <= 2048 ? 2 : 4));
+    // leaves are on average ~60 % full: two tiles per thread keep more lanes busy than one thread per tile slot
+    static int leaf_tpt2 = -1;
+    if (leaf_tpt2 < 0) { const char *e = getenv("NND_LEAF_TPT2"); leaf_tpt2 = e ? atoi(e) : 0; }
+    if (P.mode == 2 && tpt == 1 && leaf_tpt2 && METRIC != NND_METRIC_CORRELATION && ntiles > 64) tpt = 2;
     int threads = (int)(cdiv(cdiv(ntiles, tpt), 32) * 32);
     NND_CHECK(threads <= 1024, NND_ERR_UNSUPPORTED, "join: %d tiles exceed one CTA (members=%d)", ntiles, P.m_max);
     if (threads < 32) threads = 32;

@@ -89,6 +89,18 @@ class Engine:
             self._ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def all_finite(self):
+        """NaN/inf scan of the resident matrix (input validation of check_array, done on the device)."""
+        return bool(torch.isfinite(self.X).all())
+
+    def to_host(self, idx_t, dist_t):
+        """Device -> host copy of the graph through pinned staging (torch caches the pinned blocks)."""
+        hi = torch.empty(idx_t.shape, dtype=idx_t.dtype, pin_memory=True)
+        hd = torch.empty(dist_t.shape, dtype=dist_t.dtype, pin_memory=True)
+        hi.copy_(idx_t, non_blocking=True); hd.copy_(dist_t, non_blocking=True)
+        self.stream.synchronize()
+        return hi.numpy(), hd.numpy()
+
     def launch_count(self):
         return int(lib.nnd_launch_count(self._ctx))
 

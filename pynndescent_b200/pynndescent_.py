@@ -77,7 +77,12 @@ class NNDescent:
         metric_id, dev_correction, host_correction, angular = pynnd_dist.resolve(metric)    # :1271-1292
         self._distance_correction = host_correction
         self._angular_trees = angular
-        data = check_array(data, dtype=np.float32, order="C")                                # :1054
+        # :1054 check_array -- dtype / layout conversion on the host; the NaN/inf scan (sklearn sums the whole
+        # matrix on one core, ~50 ms per 512 MB) is done on the device right after the H2D copy instead
+        try:
+            data = check_array(data, dtype=np.float32, order="C", ensure_all_finite=False)
+        except TypeError:  # older scikit-learn
+            data = check_array(data, dtype=np.float32, order="C", force_all_finite=False)
         self.tree_init = bool(tree_init) and n_trees != 0                                    # :1059-1062
         current_random_state = check_random_state(self.random_state)
         if metric == "dot":                                                                  # :1101-1103
@@ -95,6 +100,8 @@ class NNDescent:
         t0 = time.perf_counter()
         eng = Engine(data, metric_id, n_neighbors, device=device)
         self._engine = eng
+        if not eng.all_finite():
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float32').")
         self.timings = {"h2d_setup": time.perf_counter() - t0}
         tree_states = None
         if leaf_array is None and self.tree_init:
@@ -126,7 +133,7 @@ class NNDescent:
                 print("\tStopping threshold met -- exiting after", iters, "iterations")
         self.n_iters_run, self.c_hist, self.join_stats = iters, c_hist, stats
         t0 = time.perf_counter()
-        self._neighbor_graph = (idx_t.cpu().numpy(), dist_t.cpu().numpy())
+        self._neighbor_graph = eng.to_host(idx_t, dist_t)
         self.timings["d2h"] = time.perf_counter() - t0
         if np.any(self._neighbor_graph[0] < 0):                                             # :1262-1267
             warn("Failed to correctly find n_neighbors for some samples."
