@@ -279,3 +279,12 @@ def test_recall_close_to_reference_numbers(torch_cuda):
     np.testing.assert_allclose(gd[rows], exact, rtol=1e-5, atol=1e-6)
     srt = np.sort(gi[rows], axis=1)
     assert np.all(srt[:, 1:] != srt[:, :-1])
+
+
+def test_nan_input_raises_like_check_array(torch_cuda):
+    """pynndescent_.py:1054 check_array rejects NaN/inf; here the scan runs on the device."""
+    from pynndescent_b200 import NNDescent
+    X = latent(500, 8, 1)
+    X[17, 3] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        NNDescent(X, "euclidean", n_neighbors=5, random_state=0)
