@@ -163,6 +163,27 @@ NND_API int nnd_leaf_fused_range(nnd_ctx *ctx, const nnd_problem *P, const int32
 NND_API int nnd_heap_pack_rows(nnd_ctx *ctx, const nnd_problem *P, const int32_t *rows, int64_t n, int32_t *out_idx,
                                float *out_dist, uint8_t *out_flag, int32_t unpack, void *stream);
 
+/* ---- seam 3: query graph walk (pynndescent_.py:1770-1883 search_closure) ------------------------------------
+ * Prepared search structures in the reference's own format (pynndescent_.py:1664-1750): data re-ordered to
+ * tree-leaf order (:1629-1641), CSR search graph (:1746-1747), flat search tree (rp_trees.py:2926-3049: leaves
+ * encode -start/-end ranges of tree_indices in `children`).                                                    */
+typedef struct {
+    const float *data;   /* [N, ld] re-ordered, padded like nnd_problem.X           */
+    int64_t N; int32_t d, ld; int32_t metric; const void *aux; /* aux of the re-ordered data (nnd_metric_prepare) */
+    const int32_t *indptr, *indices;                      /* CSR search graph                                   */
+    const float *hyperplanes;                             /* [n_nodes, ld]                                       */
+    const float *offsets; const int32_t *children;        /* [n_nodes], [n_nodes, 2]                             */
+    const int32_t *tree_indices;                          /* [N]                                                 */
+    float min_distance; int32_t n_neighbors; int32_t normalize; /* :1539, :1748, :1762-1768 (cosine / dot)       */
+} nnd_search_index;
+NND_API int nnd_query_workspace_bytes(int64_t N, int64_t nq, int32_t k, size_t *bytes);
+/* Q: device [nq, ld] zero-padded.  out_idx/out_dist: raw result heaps [nq,k] (apply nnd_deheap_sort next,
+ * then vertex_order and the distance correction, :2361-2377).  rng_state_host = search_rng_state (:1796 copy).
+ * stats_host[3] (optional): distance evaluations, seed pops, queries replayed sequentially for the rng.        */
+NND_API int nnd_query(nnd_ctx *ctx, const nnd_search_index *S, const float *Q, int64_t nq, int32_t k, double epsilon,
+                      int64_t *rng_state_host, int32_t *out_idx, float *out_dist, void *ws, size_t ws_bytes,
+                      int64_t *stats_host, void *stream);
+
 /* ---- small exported primitives (unit tests / known-answer vectors) -------------------- */
 /* utils.py:17-57: out[i] = i-th tau_rand_int (as_float=0) or tau_rand (as_float=1) of the
  * stream starting at state_host, i in [start, start+count), via GF(2) jump-ahead.          */

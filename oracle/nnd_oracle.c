@@ -749,3 +749,104 @@ ORC_API void orc_set_num_threads(int n) {
     (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------- query walk ---- */
+/* pynndescent_.py:1770-1883 search_closure (+ :1716-1727 tree descent, rp_trees.py:2662-2677 select_side,
+ * utils.py:352-406 simple_heap_push, utils.py:323-349 visited bitset, CPython heapq on (d, idx) tuples).
+ * Canonical arithmetic: margins = offset + lane_dot (as in the forest), distances = the sequential chain.      */
+typedef struct { float d; int32_t i; } seed_t;
+static inline int seed_lt(seed_t a, seed_t b) { return a.d < b.d || (a.d == b.d && a.i < b.i); }
+/* heapq.heappush / heappop (Lib/heapq.py _siftdown / _siftup) */
+static void hq_push(seed_t *h, int *n, seed_t x) {
+    int pos = (*n)++;
+    h[pos] = x;
+    while (pos > 0) { int parent = (pos - 1) >> 1; if (seed_lt(x, h[parent])) { h[pos] = h[parent]; pos = parent; } else break; }
+    h[pos] = x;
+}
+static seed_t hq_pop(seed_t *h, int *n) {
+    seed_t last = h[--(*n)];
+    if (*n == 0) return last;
+    seed_t ret = h[0];
+    int pos = 0, end = *n, child = 1;
+    while (child < end) {                       /* _siftup: bubble the smaller child up to the leaf ... */
+        int right = child + 1;
+        if (right < end && !seed_lt(h[child], h[right])) child = right;
+        h[pos] = h[child]; pos = child; child = 2 * pos + 1;
+    }
+    h[pos] = last;
+    while (pos > 0) { int parent = (pos - 1) >> 1; if (seed_lt(last, h[parent])) { h[pos] = h[parent]; pos = parent; } else break; }
+    h[pos] = last;                              /* ... then _siftdown it into place */
+    return ret;
+}
+
+ORC_API void orc_search(const float *data, int64_t N, int d, int metric, const int32_t *indptr, const int32_t *indices,
+                        const float *hyperplanes, const float *offsets, const int32_t *children, const int32_t *tree_indices,
+                        const float *Q, int64_t nq, int k, double epsilon, float min_distance, int n_neighbors, int normalize,
+                        const int64_t *rng_state, int32_t *out_idx, float *out_dist) {
+    int64_t rng[3] = {rng_state[0], rng_state[1], rng_state[2]};   /* :1796 one copy, advanced across queries */
+    uint8_t *visited = (uint8_t *)malloc(N / 8 + 1);
+    seed_t *seeds = (seed_t *)malloc(sizeof(seed_t) * (N + 16));
+    float *q = (float *)malloc(sizeof(float) * d);
+    for (int64_t qi = 0; qi < nq; ++qi) {
+        float *hp = out_dist + qi * k; int32_t *hi = out_idx + qi * k;
+        for (int j = 0; j < k; ++j) { hp[j] = INFINITY; hi[j] = -1; }
+        memset(visited, 0, N / 8 + 1);
+        const float *qq = Q + qi * d;
+        if (normalize) {                                             /* :1806-1811 */
+            float s = 0.0f;
+            for (int e = 0; e < d; ++e) s = s + qq[e] * qq[e];
+            float norm = sqrtf(s);
+            if (!(norm > 0.0f)) continue;
+            for (int e = 0; e < d; ++e) q[e] = qq[e] / norm;
+        } else memcpy(q, qq, sizeof(float) * d);
+        int ns = 0;
+        int32_t node = 0;                                            /* :1716-1727 */
+        while (children[2 * node] > 0) {
+            float margin = offsets[node] + lane_dot(hyperplanes + (int64_t)node * d, q, d);
+            int side;
+            if (fabs((double)margin) < 1e-8) side = (int)(abs_i32(orc_tau_rand_int(rng)) % 2 != 0);
+            else side = margin > 0 ? 0 : 1;
+            node = children[2 * node + side];
+        }
+        int32_t b0 = -children[2 * node], b1 = -children[2 * node + 1];
+        for (int32_t j = b0; j < b1; ++j) {                          /* :1826-1832 */
+            int32_t c = tree_indices[j];
+            float dd = dist_fn(metric, q, data + (int64_t)c * d, d);
+            heap_push(hp, hi, NULL, k, dd, c, 0, 0);
+            seed_t s = {dd, c}; hq_push(seeds, &ns, s);
+            visited[c >> 3] |= (uint8_t)(1 << (c & 7));
+        }
+        int n_random = (k < n_neighbors ? k : n_neighbors) - (b1 - b0);   /* :1835-1847 */
+        for (int j = 0; j < n_random; ++j) {
+            int32_t c = (int32_t)floormod(abs_i32(orc_tau_rand_int(rng)), N);
+            int was = visited[c >> 3] & (1 << (c & 7));
+            visited[c >> 3] |= (uint8_t)(1 << (c & 7));
+            if (!was) {
+                float dd = dist_fn(metric, q, data + (int64_t)c * d, d);
+                heap_push(hp, hi, NULL, k, dd, c, 0, 0);
+                seed_t s = {dd, c}; hq_push(seeds, &ns, s);
+            }
+        }
+        float bound = (float)((double)hp[0] + epsilon * ((double)hp[0] - (double)min_distance));   /* :1850-1852 */
+        if (ns == 0) continue;
+        seed_t cur = hq_pop(seeds, &ns);
+        while (cur.d < bound) {                                      /* :1857-1881 */
+            for (int32_t j = indptr[cur.i]; j < indptr[cur.i + 1]; ++j) {
+                int32_t c = indices[j];
+                int was = visited[c >> 3] & (1 << (c & 7));
+                visited[c >> 3] |= (uint8_t)(1 << (c & 7));
+                if (!was) {
+                    float dd = dist_fn(metric, q, data + (int64_t)c * d, d);
+                    if (dd < bound) {
+                        heap_push(hp, hi, NULL, k, dd, c, 0, 0);
+                        seed_t s = {dd, c}; hq_push(seeds, &ns, s);
+                        bound = (float)((double)hp[0] + epsilon * ((double)hp[0] - (double)min_distance));
+                    }
+                }
+            }
+            if (ns == 0) break;
+            cur = hq_pop(seeds, &ns);
+        }
+    }
+    free(visited); free(seeds); free(q);
+}

@@ -72,6 +72,8 @@ def lib():
     L.orc_nn_descent_internal.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, C.c_int,
                                           _i64p, C.c_int, C.c_int, C.c_double, C.c_int64, _i64p]
     L.orc_nn_descent_internal.restype = C.c_int
+    L.orc_search.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _i32p, _f32p, _f32p, _i32p, _i32p, _f32p, C.c_int64,
+                             C.c_int, C.c_double, C.c_float, C.c_int, C.c_int, _i64p, _i32p, _f32p]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
     _LIB = L
@@ -158,6 +160,19 @@ def process_candidates(X, metric, heap, newc, oldc, n_threads, block_size=16384)
 def deheap_sort(ind, dist_):
     lib().orc_deheap_sort(ind, dist_, ind.shape[0], ind.shape[1])
     return ind, dist_
+
+
+def search(data, metric, indptr, indices, hyperplanes, offsets, children, tree_indices, Q, k, epsilon, min_distance,
+           n_neighbors, rng_state):
+    """pynndescent_.py:1793-1883 search_closure -> raw (heap_idx, heap_dist) (not yet deheap-sorted)."""
+    data = np.ascontiguousarray(data, np.float32); Q = np.ascontiguousarray(Q, np.float32)
+    hi = np.empty((Q.shape[0], k), np.int32); hd = np.empty((Q.shape[0], k), np.float32)
+    lib().orc_search(data, data.shape[0], data.shape[1], METRIC_IDS[metric], np.ascontiguousarray(indptr, np.int32),
+                     np.ascontiguousarray(indices, np.int32), np.ascontiguousarray(hyperplanes, np.float32),
+                     np.ascontiguousarray(offsets, np.float32), np.ascontiguousarray(children, np.int32),
+                     np.ascontiguousarray(tree_indices, np.int32), Q, Q.shape[0], int(k), float(epsilon), float(min_distance),
+                     int(n_neighbors), int(metric in ("cosine", "dot")), np.ascontiguousarray(rng_state, np.int64), hi, hd)
+    return hi, hd
 
 
 def correction(metric, d):

@@ -21,6 +21,14 @@ class Problem(C.Structure):
                 ("heap_flag", C.c_void_p)]
 
 
+class SearchIndex(C.Structure):
+    """nnd_search_index (include/nnd_b200.h)"""
+    _fields_ = [("data", C.c_void_p), ("N", C.c_int64), ("d", C.c_int32), ("ld", C.c_int32), ("metric", C.c_int32),
+                ("aux", C.c_void_p), ("indptr", C.c_void_p), ("indices", C.c_void_p), ("hyperplanes", C.c_void_p),
+                ("offsets", C.c_void_p), ("children", C.c_void_p), ("tree_indices", C.c_void_p),
+                ("min_distance", C.c_float), ("n_neighbors", C.c_int32), ("normalize", C.c_int32)]
+
+
 if not os.path.exists(LIB_PATH):
     raise NNDLibraryError(
         f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -61,6 +69,8 @@ SIGNATURES = {
     "nnd_apply_records": (C.c_int, [_vp, _PP, _i32, _vp, _i64, _i64, _vp, _sz, _pi64, _vp]),
     "nnd_leaf_fused_range": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _i64, _i32, _vp]),
     "nnd_heap_pack_rows": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "nnd_query_workspace_bytes": (C.c_int, [_i64, _i64, _i32, _psz]),
+    "nnd_query": (C.c_int, [_vp, C.POINTER(SearchIndex), _vp, _i64, _i32, C.c_double, _pi64, _vp, _vp, _vp, _sz, _pi64, _vp]),
     "nnd_rng_stream": (C.c_int, [_vp, _pi64, _i64, _i64, _i32, _vp, _vp]),
     "nnd_rng_advance_host": (C.c_int, [_vp, _pi64, _i64]),
     "nnd_pair_distances": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _vp, _vp]),

@@ -148,7 +148,23 @@ class NNDescent:
         return self._neighbor_graph[0].copy(), self._neighbor_graph[1].copy()
 
     def prepare(self):
-        raise NotImplementedError("search-graph preparation + query walk are the next rows (SURVEY.md 8a-11, 8f-1)")
+        """pynndescent_.py:2174-2273.  Building the search graph / hub tree on the GPU is a "next" row of the scope
+        table; until then the prepared structures can be injected with load_search_structures()."""
+        if getattr(self, "_search_gpu", None) is None:
+            raise NotImplementedError("search-graph preparation (diversify / degree prune / hub tree) is not built on the GPU "
+                                      "yet (SURVEY.md 8f-1); inject prepared structures with load_search_structures()")
+
+    def load_search_structures(self, data_reordered, indptr, indices, hyperplanes, offsets, children, tree_indices,
+                               vertex_order, min_distance, search_rng_state=None):
+        """Install search structures in the reference's array format (what prepare() computes,
+        pynndescent_.py:1670-1673, 1746-1750, 1629-1641, 1539) so that query() can run on the GPU."""
+        from .search import SearchIndexGPU
+        self._search_gpu = SearchIndexGPU(data_reordered, self.metric, indptr, indices, hyperplanes, offsets, children,
+                                          tree_indices, vertex_order, min_distance, self.n_neighbors,
+                                          self.search_rng_state if search_rng_state is None else search_rng_state)
+        return self
 
     def query(self, query_data, k=10, epsilon=0.1):
-        raise NotImplementedError("search-graph preparation + query walk are the next rows (SURVEY.md 8a-11, 8f-1)")
+        """pynndescent_.py:2275-2379."""
+        self.prepare()
+        return self._search_gpu.query(query_data, k=k, epsilon=epsilon)

@@ -103,3 +103,19 @@ def test_stage_candidates_and_join(oracle, name):
     heap2 = (G["init_heap_idx"].copy(), G["init_heap_dist"].copy(), G["it0_flag_after_cand"].copy())
     c2, _ = oracle.process_candidates(data, metric, heap2, newc, oldc, 3, block_size=10 ** 9)
     assert c2 == c and np.array_equal(heap2[0], heap[0]) and np.array_equal(heap2[1], heap[1])
+
+
+@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24"])
+def test_query_walk_matches_reference(oracle, name):
+    """Seam 3: orc_search on the reference's prepared structures reproduces the reference's raw result heaps
+    (layout included) and its final query() answers."""
+    G = load_golden(name)
+    metric = str(G["metric"])
+    hi, hd = oracle.search(G["data"], metric, G["indptr"], G["indices"], G["hyperplanes"], G["offsets"], G["children"],
+                           G["tree_indices"], G["Q"], int(G["k_query"]), float(G["epsilon"]), float(G["min_distance"]),
+                           int(G["n_neighbors"]), G["search_rng_state"])
+    assert np.array_equal(hi, G["heap_idx"])
+    np.testing.assert_allclose(hd, G["heap_dist"], rtol=1e-5, atol=1e-6)
+    si, sd = oracle.deheap_sort(hi, hd)
+    assert np.array_equal(G["vertex_order"][si], G["out_idx"])
+    np.testing.assert_allclose(oracle.correction(metric, sd), G["out_dist"], rtol=1e-5, atol=1e-6)
