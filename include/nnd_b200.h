@@ -184,6 +184,20 @@ NND_API int nnd_query(nnd_ctx *ctx, const nnd_search_index *S, const float *Q, i
                       int64_t *rng_state_host, int32_t *out_idx, float *out_dist, void *ws, size_t ws_bytes,
                       int64_t *stats_host, void *stream);
 
+/* ---- search-graph preparation, GPU parts (pynndescent_.py:1333-1662) ------------------------------------------
+ * hub tree (rp_trees.py:714-1309 make_hub_tree): node table of capacity 2N (node 0 = root; left/right = -1 for a
+ * leaf whose points are indices[start:start+size]); hyperplane of an internal node = node_hyper[node_hyper_row[n]].
+ * The host flattens this to the reference's pre-order arrays (rp_trees.py:2926-3049).                            */
+NND_API int nnd_hub_tree_workspace_bytes(int64_t N, int32_t d, size_t *bytes);
+NND_API int nnd_hub_tree_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t d, int32_t ld, int32_t angular,
+                               const int32_t *ng_idx, int32_t k, int32_t leaf_size, int32_t max_depth, int32_t *indices,
+                               int32_t *node_start, int32_t *node_size, int32_t *node_left, int32_t *node_right,
+                               int32_t *node_hyper_row, float *node_hyper, float *node_off, int64_t hyper_cap,
+                               int32_t *n_nodes_host, int32_t *n_hyper_host, void *ws, size_t ws_bytes, void *stream);
+/* pynndescent_.py:369-403 diversify (prune_probability 1) on a [N,k] neighbour table in ascending distance order
+ * (in place, rows compacted, -1/+inf padded); applied to already-compacted rows it is diversify_csr :549-588.     */
+NND_API int nnd_diversify(nnd_ctx *ctx, const nnd_problem *P, int32_t *ind, float *dist, void *stream);
+
 /* ---- small exported primitives (unit tests / known-answer vectors) -------------------- */
 /* utils.py:17-57: out[i] = i-th tau_rand_int (as_float=0) or tau_rand (as_float=1) of the
  * stream starting at state_host, i in [start, start+count), via GF(2) jump-ahead.          */

@@ -850,3 +850,177 @@ ORC_API void orc_search(const float *data, int64_t N, int d, int metric, const i
     }
     free(visited); free(seeds); free(q);
 }
+
+/* ------------------------------------------------------- search preparation ---- */
+/* rp_trees.py:747-803 get_top_k_hub_indices (k=3): insertion by strictly larger degree, first-come on ties */
+static int top3_hubs(const int32_t *indices, int64_t n, const int32_t *deg, int32_t *top) {
+    int ak = n < 3 ? (int)n : 3;
+    int32_t td[3] = {-1, -1, -1};
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t dg = deg[indices[i]];
+        if (dg > td[ak - 1]) {
+            int pos = ak - 1;
+            while (pos > 0 && dg > td[pos - 1]) --pos;
+            for (int j = ak - 1; j > pos; --j) { td[j] = td[j - 1]; top[j] = top[j - 1]; }
+            td[pos] = dg; top[pos] = indices[i];
+        }
+    }
+    return ak;
+}
+
+/* rp_trees.py:806-932 euclidean_hub_split / :935-1052 angular_hub_split + :1059-1230 recursive builders.
+ * Deterministic (the rng is touched only by the degenerate fallback, whose node then becomes a leaf because its
+ * balance is 0 < MIN_SPLIT_BALANCE).                                                                          */
+static void hub_tree_rec(tree_t *t, const float *X, int d, int angular, const int32_t *deg, int32_t *indices, int64_t n,
+                         int64_t *rng, int leaf_size, int max_depth) {
+    int is_leaf = !(n > leaf_size && max_depth > 0);
+    float *bh = NULL; float boff = 0.0f; int8_t *bside = NULL; int64_t bnl = 0, bnr = 0;
+    if (!is_leaf) {
+        int32_t top[3]; int nh = top3_hubs(indices, n, deg, top);
+        bh = (float *)calloc(d, sizeof(float)); bside = (int8_t *)calloc(n, 1);
+        float *h = (float *)malloc(sizeof(float) * d); int8_t *side = (int8_t *)malloc(n);
+        float best_balance = 0.0f;
+        for (int hi = 0; hi < nh; ++hi)
+            for (int hj = hi + 1; hj < nh; ++hj) {
+                float off;
+                make_hyperplane(X, d, angular, top[hi], top[hj], h, &off);
+                int64_t nl = 0, nr = 0;
+                for (int64_t i = 0; i < n; ++i) {
+                    float margin = off + lane_dot(h, X + (int64_t)indices[i] * d, d);
+                    if ((double)margin > 1e-8) { side[i] = 0; nl++; }
+                    else if ((double)margin < -1e-8) { side[i] = 1; nr++; }
+                    else { side[i] = (int8_t)(i % 2); if (side[i] == 0) nl++; else nr++; }
+                }
+                if (nl == 0 || nr == 0) continue;
+                float balance = (float)(nl < nr ? nl : nr) / (float)n;
+                if (balance > best_balance) {
+                    best_balance = balance; bnl = nl; bnr = nr; boff = off;
+                    memcpy(bh, h, sizeof(float) * d); memcpy(bside, side, n);
+                }
+            }
+        free(h); free(side);
+        if (bnl == 0 || bnr == 0) {           /* fallback: random assignment, balance stays 0 -> leaf */
+            for (int64_t i = 0; i < n; ++i) (void)orc_tau_rand_int(rng);
+            is_leaf = 1;
+        } else if (best_balance < 0.1f) is_leaf = 1;
+    }
+    if (!is_leaf) {
+        int32_t *L = (int32_t *)malloc(sizeof(int32_t) * bnl), *R = (int32_t *)malloc(sizeof(int32_t) * bnr);
+        int64_t a = 0, b = 0;
+        for (int64_t i = 0; i < n; ++i) { if (bside[i] == 0) L[a++] = indices[i]; else R[b++] = indices[i]; }
+        hub_tree_rec(t, X, d, angular, deg, L, bnl, rng, leaf_size, max_depth - 1);
+        int32_t left_node = (int32_t)(t->n_nodes - 1);
+        hub_tree_rec(t, X, d, angular, deg, R, bnr, rng, leaf_size, max_depth - 1);
+        int32_t right_node = (int32_t)(t->n_nodes - 1);
+        free(L); free(R);
+        int64_t id = tree_add_node(t);
+        t->child_l[id] = left_node; t->child_r[id] = right_node; t->offsets[id] = boff;
+        memcpy(t->hyper + id * d, bh, sizeof(float) * d);
+        t->leaf_start[id] = -1; t->leaf_size[id] = 0;
+    } else {
+        int64_t id = tree_add_node(t);
+        t->child_l[id] = -1; t->child_r[id] = -1; t->offsets[id] = -INFINITY;
+        t->leaf_start[id] = t->n_leaf_points; t->leaf_size[id] = (int32_t)n;
+        if (t->n_leaf_points + n > t->cap_leaf_points) {
+            t->cap_leaf_points = (t->n_leaf_points + n) * 2 + 64;
+            t->leaf_points = (int32_t *)realloc(t->leaf_points, sizeof(int32_t) * t->cap_leaf_points);
+        }
+        memcpy(t->leaf_points + t->n_leaf_points, indices, sizeof(int32_t) * n);
+        t->n_leaf_points += n;
+    }
+    free(bh); free(bside);
+}
+
+/* rp_trees.py:2926-2961 recursive_convert (pre-order flat tree) */
+static void flat_rec(const tree_t *t, int d, float *hyper, float *offsets, int32_t *children, int32_t *indices,
+                     int32_t *node_num, int32_t *leaf_start, int32_t tree_node) {
+    int32_t me = *node_num;
+    if (t->child_l[tree_node] < 0) {
+        int32_t leaf_end = *leaf_start + t->leaf_size[tree_node];
+        children[2 * me] = -*leaf_start; children[2 * me + 1] = -leaf_end;
+        memcpy(indices + *leaf_start, t->leaf_points + t->leaf_start[tree_node], sizeof(int32_t) * t->leaf_size[tree_node]);
+        *leaf_start = leaf_end;
+    } else {
+        memcpy(hyper + (int64_t)me * d, t->hyper + (int64_t)tree_node * d, sizeof(float) * d);
+        offsets[me] = t->offsets[tree_node];
+        children[2 * me] = me + 1;
+        *node_num = me + 1;
+        flat_rec(t, d, hyper, offsets, children, indices, node_num, leaf_start, t->child_l[tree_node]);
+        children[2 * me + 1] = *node_num + 1;
+        *node_num = *node_num + 1;
+        flat_rec(t, d, hyper, offsets, children, indices, node_num, leaf_start, t->child_r[tree_node]);
+    }
+}
+
+/* rp_trees.py:1233-1309 make_hub_tree + :3019-3049 convert_tree_format.  Two-call protocol: returns a handle. */
+ORC_API void *orc_hub_tree(const float *X, int64_t N, int d, int angular, const int32_t *ng_idx, int k, int leaf_size,
+                           int max_depth, const int64_t *rng_state, int64_t *n_nodes) {
+    int32_t *deg = (int32_t *)calloc(N, sizeof(int32_t));      /* rp_trees.py:714-744 compute_global_degrees */
+    for (int64_t i = 0; i < N; ++i)
+        for (int j = 0; j < k; ++j) { int32_t v = ng_idx[i * k + j]; if (v >= 0 && v < N) deg[v]++; }
+    tree_t *t = (tree_t *)calloc(1, sizeof(tree_t)); t->d = d;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * N);
+    for (int64_t i = 0; i < N; ++i) idx[i] = (int32_t)i;
+    int64_t rng[3] = {rng_state[0], rng_state[1], rng_state[2]};
+    hub_tree_rec(t, X, d, angular, deg, idx, N, rng, leaf_size, max_depth);
+    free(idx); free(deg);
+    *n_nodes = t->n_nodes;
+    return t;
+}
+ORC_API void orc_hub_tree_flatten(void *tp, int d, int64_t N, float *hyper, float *offsets, int32_t *children, int32_t *indices) {
+    tree_t *t = (tree_t *)tp;
+    for (int64_t i = 0; i < t->n_nodes; ++i) { offsets[i] = 0.0f; children[2 * i] = -1; children[2 * i + 1] = -1; }
+    memset(hyper, 0, sizeof(float) * t->n_nodes * d);
+    for (int64_t i = 0; i < N; ++i) indices[i] = -1;
+    int32_t node_num = 0, leaf_start = 0;
+    flat_rec(t, d, hyper, offsets, children, indices, &node_num, &leaf_start, (int32_t)(t->n_nodes - 1));
+    free(t->child_l); free(t->child_r); free(t->offsets); free(t->hyper); free(t->leaf_start); free(t->leaf_size); free(t->leaf_points);
+    free(t);
+}
+
+/* pynndescent_.py:369-403 diversify (prune_probability = 1: the racy tau_rand draw is always < 1) */
+ORC_API void orc_diversify(int32_t *ind, float *dist, int64_t N, int k, const float *X, int d, int metric) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        int32_t *ri = ind + i * k; float *rd = dist + i * k;
+        int32_t ni[256]; float nd[256]; int nn = 0;
+        ni[nn] = ri[0]; nd[nn] = rd[0]; nn++;
+        for (int j = 1; j < k; ++j) {
+            if (ri[j] < 0) break;
+            int flag = 1;
+            for (int c = 0; c < nn; ++c) {
+                float dd = dist_fn(metric, X + (int64_t)ri[j] * d, X + (int64_t)ni[c] * d, d);
+                if (nd[c] > FLT_EPSILON && dd < rd[j]) { flag = 0; break; }
+            }
+            if (flag) { ni[nn] = ri[j]; nd[nn] = rd[j]; nn++; }
+        }
+        for (int j = 0; j < k; ++j) { if (j < nn) { ri[j] = ni[j]; rd[j] = nd[j]; } else { ri[j] = -1; rd[j] = INFINITY; } }
+    }
+}
+
+/* pynndescent_.py:549-588 diversify_csr, literally (note the reference indexes the second point with k, not order[k]).
+ * argsort ties: stable order here (numba's quicksort tie order is unspecified).                                   */
+ORC_API void orc_diversify_csr(const int32_t *indptr, const int32_t *indices, float *data, int64_t n_nodes, const float *X,
+                               int d, int metric) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        int32_t s = indptr[i], m = indptr[i + 1] - indptr[i];
+        if (m <= 1) continue;
+        const int32_t *ci = indices + s; float *cd = data + s;
+        int32_t *order = (int32_t *)malloc(sizeof(int32_t) * m); int8_t *ret = (int8_t *)malloc(m);
+        for (int a = 0; a < m; ++a) { order[a] = a; ret[a] = 1; }
+        for (int a = 1; a < m; ++a) { int32_t v = order[a]; int b = a - 1; while (b >= 0 && cd[order[b]] > cd[v]) { order[b + 1] = order[b]; --b; } order[b + 1] = v; }
+        for (int a = 1; a < m; ++a) {
+            int32_t j = order[a];
+            for (int kk = 0; kk < a; ++kk) {
+                int32_t l = order[kk];
+                if (ret[l] == 1) {
+                    float dd = dist_fn(metric, X + (int64_t)ci[j] * d, X + (int64_t)ci[kk] * d, d);
+                    if (cd[l] > FLT_EPSILON && dd < cd[j]) { ret[j] = 0; break; }
+                }
+            }
+        }
+        for (int a = 0; a < m; ++a) if (ret[order[a]] == 0) cd[order[a]] = 0.0f;
+        free(order); free(ret);
+    }
+}

@@ -74,6 +74,11 @@ def lib():
     L.orc_nn_descent_internal.restype = C.c_int
     L.orc_search.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _i32p, _f32p, _f32p, _i32p, _i32p, _f32p, C.c_int64,
                              C.c_int, C.c_double, C.c_float, C.c_int, C.c_int, _i64p, _i32p, _f32p]
+    L.orc_hub_tree.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, _i64p, C.POINTER(C.c_int64)]
+    L.orc_hub_tree.restype = C.c_void_p
+    L.orc_hub_tree_flatten.argtypes = [C.c_void_p, C.c_int, C.c_int64, _f32p, _f32p, _i32p, _i32p]
+    L.orc_diversify.argtypes = [_i32p, _f32p, C.c_int64, C.c_int, _f32p, C.c_int, C.c_int]
+    L.orc_diversify_csr.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _f32p, C.c_int, C.c_int]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
     _LIB = L
@@ -173,6 +178,66 @@ def search(data, metric, indptr, indices, hyperplanes, offsets, children, tree_i
                      np.ascontiguousarray(tree_indices, np.int32), Q, Q.shape[0], int(k), float(epsilon), float(min_distance),
                      int(n_neighbors), int(metric in ("cosine", "dot")), np.ascontiguousarray(rng_state, np.int64), hi, hd)
     return hi, hd
+
+
+def hub_tree(X, ng_idx, rng_state, leaf_size, angular, max_depth=200):
+    """rp_trees.py:1233 make_hub_tree + :3019 convert_tree_format -> (hyperplanes, offsets, children, indices)."""
+    L = lib(); n, d = X.shape
+    nn = C.c_int64()
+    t = L.orc_hub_tree(X, n, d, int(angular), np.ascontiguousarray(ng_idx, np.int32), ng_idx.shape[1], int(leaf_size), int(max_depth),
+                       np.ascontiguousarray(rng_state, np.int64), C.byref(nn))
+    hyper = np.zeros((nn.value, d), np.float32); offs = np.zeros(nn.value, np.float32)
+    children = np.empty((nn.value, 2), np.int32); indices = np.empty(n, np.int32)
+    L.orc_hub_tree_flatten(t, d, n, hyper, offs, children, indices)
+    return hyper, offs, children, indices
+
+
+def prepare(X, metric, ng_idx, ng_dist, n_neighbors, rng_state, leaf_size=None, pruning_degree_multiplier=1.5, max_depth=200):
+    """pynndescent_.py:1333-1662 _init_search_graph (dense, tree_init, standard diversification, diversify_prob=1).
+    Returns the structures query() walks: data (leaf order), indptr, indices, tree arrays, vertex_order, min_distance."""
+    import scipy.sparse as sp
+    L = lib()
+    X = np.ascontiguousarray(X, np.float32); n, d = X.shape
+    angular = metric in ANGULAR_METRICS
+    search_leaf_size = leaf_size if leaf_size is not None else 30                        # :1341-1345
+    hyper, offs, children, tree_idx = hub_tree(X, ng_idx, rng_state, search_leaf_size, angular, max_depth)
+    di = np.ascontiguousarray(ng_idx, np.int32).copy(); dd = np.ascontiguousarray(ng_dist, np.float32).copy()
+    L.orc_diversify(di, dd, n, di.shape[1], X, d, METRIC_IDS[metric])                  # :1502-1519
+    dd[dd == 0.0] = np.finfo(np.float32).eps                                           # :1526
+    g = sp.coo_array((n, n), dtype=np.float32)                                         # :1521-1537, built exactly like the
+    g.row = np.repeat(np.arange(n, dtype=np.int32), di.shape[1])                       # reference does: the CSR rows keep the
+    g.col = di.ravel(); g.data = dd.ravel()                                            # ascending-distance entry order
+    g = g.tocsr()
+    g.data[g.indices == -1] = 0.0
+    g.eliminate_zeros()
+    min_distance = np.min(g.data)                                                      # :1539
+    # :1552-1587  `reverse_graph = self._search_graph.transpose()` is a CSC VIEW that shares indptr / indices / data with
+    # the forward CSR graph, so diversify_csr walks the FORWARD rows and zeroes entries of the shared data array;
+    # eliminate_zeros then compacts both.  Restated literally: prune the forward rows, then transpose.
+    gdata = np.ascontiguousarray(g.data, np.float32)
+    L.orc_diversify_csr(np.ascontiguousarray(g.indptr, np.int32), np.ascontiguousarray(g.indices, np.int32), gdata, n, X, d,
+                        METRIC_IDS[metric])
+    g = sp.csr_array((gdata, g.indices, g.indptr), shape=(n, n)); g.eliminate_zeros()
+    rev = g.transpose().tocsr()
+    rev.sort_indices(); g.sort_indices()
+    g = g.maximum(rev).tocsr()                                                         # :1601
+    g.setdiag(0.0); g.eliminate_zeros()
+    max_degree = int(np.round(pruning_degree_multiplier * n_neighbors))                # :1608-1611, :728-760
+    for i in range(n):
+        row = g.data[g.indptr[i]: g.indptr[i + 1]]
+        if row.shape[0] > max_degree:
+            cut = np.sort(row)[max_degree]
+            row[row > cut] = 0.0
+    g.eliminate_zeros()
+    g = (g != 0).astype(np.uint8)                                                      # :1613
+    vertex_order = tree_idx                                                            # :1630
+    g = g[vertex_order, :].tocsc()[:, vertex_order].tocsr(); g.sort_indices()          # :1631-1634
+    data = np.ascontiguousarray(X[vertex_order, :])                                    # :1639-1641
+    tree_order = np.argsort(vertex_order)
+    new_tree_idx = tree_idx[tree_order].astype(np.int32)                               # :763-771 resort_tree_indices
+    return dict(data=data, indptr=g.indptr.astype(np.int32), indices=g.indices.astype(np.int32), hyperplanes=hyper, offsets=offs,
+                children=children, tree_indices=new_tree_idx, vertex_order=vertex_order.astype(np.int32),
+                min_distance=np.float32(min_distance))
 
 
 def correction(metric, d):

@@ -71,6 +71,10 @@ SIGNATURES = {
     "nnd_heap_pack_rows": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "nnd_query_workspace_bytes": (C.c_int, [_i64, _i64, _i32, _psz]),
     "nnd_query": (C.c_int, [_vp, C.POINTER(SearchIndex), _vp, _i64, _i32, C.c_double, _pi64, _vp, _vp, _vp, _sz, _pi64, _vp]),
+    "nnd_hub_tree_workspace_bytes": (C.c_int, [_i64, _i32, _psz]),
+    "nnd_hub_tree_build": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _i64, _pi32, _pi32, _vp, _sz, _vp]),
+    "nnd_diversify": (C.c_int, [_vp, _PP, _vp, _vp, _vp]),
     "nnd_rng_stream": (C.c_int, [_vp, _pi64, _i64, _i64, _i32, _vp, _vp]),
     "nnd_rng_advance_host": (C.c_int, [_vp, _pi64, _i64]),
     "nnd_pair_distances": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _vp, _vp]),

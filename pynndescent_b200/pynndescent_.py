@@ -22,6 +22,20 @@ INT32_MAX = np.iinfo(np.int32).max - 1
 DEFAULT_EMULATED_THREADS = 8
 
 
+def _tau_advance(state, n):
+    """utils.py:17-40 tau_rand_int applied n times (int64 state words, arithmetic >>)."""
+    s = [int(v) for v in state]
+
+    def wrap(x):
+        x &= (1 << 64) - 1
+        return x - (1 << 64) if x >= (1 << 63) else x
+    for _ in range(n):
+        s[0] = wrap((((s[0] & 4294967294) << 12) & 0xFFFFFFFF) ^ ((((s[0] << 13) & 0xFFFFFFFF) ^ s[0]) >> 19))
+        s[1] = wrap((((s[1] & 4294967288) << 4) & 0xFFFFFFFF) ^ ((((s[1] << 2) & 0xFFFFFFFF) ^ s[1]) >> 25))
+        s[2] = wrap((((s[2] & 4294967280) << 17) & 0xFFFFFFFF) ^ ((((s[2] << 3) & 0xFFFFFFFF) ^ s[2]) >> 11))
+    return np.array(s, np.int64)
+
+
 def ts():
     return time.ctime(time.time())
 
@@ -63,6 +77,7 @@ class NNDescent:
         self.metric = metric
         self.metric_kwds = metric_kwds
         self.leaf_size = leaf_size
+        self.pruning_degree_multiplier = pruning_degree_multiplier
         self.max_candidates = max_candidates
         self.max_rptree_depth = max_rptree_depth
         self.n_iters = n_iters
@@ -91,6 +106,8 @@ class NNDescent:
         self._raw_data = data
         self.rng_state = current_random_state.randint(INT32_MIN, INT32_MAX, 3).astype(np.int64)          # :1105-1107
         self.search_rng_state = current_random_state.randint(INT32_MIN, INT32_MAX, 3).astype(np.int64)  # :1108-1110
+        # :1111-1113 warm up the search rng by 10 draws (host-side replica of tau_rand_int)
+        self.search_rng_state = _tau_advance(self.search_rng_state, 10)
         T = DEFAULT_EMULATED_THREADS if (n_jobs is None or n_jobs == -1) else int(n_jobs)
         if T < 1:
             raise ValueError("n_jobs must be a positive thread count (or None / -1)")
@@ -148,11 +165,21 @@ class NNDescent:
         return self._neighbor_graph[0].copy(), self._neighbor_graph[1].copy()
 
     def prepare(self):
-        """pynndescent_.py:2174-2273.  Building the search graph / hub tree on the GPU is a "next" row of the scope
-        table; until then the prepared structures can be injected with load_search_structures()."""
-        if getattr(self, "_search_gpu", None) is None:
-            raise NotImplementedError("search-graph preparation (diversify / degree prune / hub tree) is not built on the GPU "
-                                      "yet (SURVEY.md 8f-1); inject prepared structures with load_search_structures()")
+        """pynndescent_.py:2174-2273 (dense, no quantisation): hub search tree + diversified, degree-pruned search graph,
+        data re-ordered to leaf order; then the GPU search index (seam 3)."""
+        if getattr(self, "_search_gpu", None) is not None:
+            return
+        if self.pruning_degree_multiplier is None:
+            raise ValueError("pruning_degree_multiplier must be a number")
+        from .prepare import prepare_search_structures
+        eng = self._engine
+        S = prepare_search_structures(eng, self.metric, eng.heap_idx, eng.heap_dist, self.n_neighbors, self._angular_trees,
+                                      leaf_size=self.leaf_size, pruning_degree_multiplier=self.pruning_degree_multiplier,
+                                      max_depth=self.max_rptree_depth)
+        self._search_structures = S
+        data_reordered = np.ascontiguousarray(self._raw_data[S["vertex_order"], :])                 # :1639-1641
+        self.load_search_structures(data_reordered, S["indptr"], S["indices"], S["hyperplanes"], S["offsets"], S["children"],
+                                    S["tree_indices"], S["vertex_order"], S["min_distance"])
 
     def load_search_structures(self, data_reordered, indptr, indices, hyperplanes, offsets, children, tree_indices,
                                vertex_order, min_distance, search_rng_state=None):

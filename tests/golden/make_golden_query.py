@@ -30,6 +30,8 @@ def dump(name, metric, n, d, k_index, seed, nq, k_query, eps):
     both = latent(n + nq, d, seed)
     X, Q = both[:n], both[n:]
     idx = pynndescent.NNDescent(X, metric, n_neighbors=k_index, random_state=seed)
+    ng_idx, ng_dist = idx._neighbor_graph[0].copy(), idx._neighbor_graph[1].copy()   # raw (alternative) distances
+    rng_before_prepare = idx.rng_state.copy()
     idx.prepare()
     tree = idx._search_forest[0]
     out = dict(
@@ -38,7 +40,8 @@ def dump(name, metric, n, d, k_index, seed, nq, k_query, eps):
         hyperplanes=np.asarray(tree.hyperplanes, np.float32), offsets=np.asarray(tree.offsets, np.float32),
         children=np.asarray(tree.children, np.int32), tree_indices=np.asarray(tree.indices, np.int32),
         vertex_order=np.asarray(idx._vertex_order, np.int32), min_distance=np.float32(idx._min_distance),
-        search_rng_state=idx.search_rng_state.copy(), n_neighbors=k_index,
+        search_rng_state=idx.search_rng_state.copy(), n_neighbors=k_index, ng_idx=ng_idx, ng_dist=ng_dist,
+        rng_before_prepare=rng_before_prepare,
     )
     Qc = np.asarray(Q).astype(np.float32, order="C")
     hi, hd, _ = idx._search_function(Qc, k_query, eps, idx._visited, idx.search_rng_state)

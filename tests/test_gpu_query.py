@@ -52,3 +52,46 @@ def test_query_rng_fallback_and_edge_cases(oracle):
     got = qi.copy()
     assert np.array_equal(got[np.arange(40) != 3], want[np.arange(40) != 3])
     assert np.all(hi[3] == -1)
+
+
+@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24"])
+def test_prepare_matches_reference_structures(name):
+    """prepare(): from the reference's kNN graph, the GPU hub tree + diversification + the scipy bookkeeping give
+    the reference's search graph, search tree, leaf order and min_distance."""
+    from pynndescent_b200.engine import Engine
+    from pynndescent_b200.prepare import prepare_search_structures
+    from pynndescent_b200 import distances as pdist
+    import torch
+    G = load_golden(name)
+    metric = str(G["metric"])
+    metric_id, _, _, angular = pdist.resolve(metric)
+    eng = Engine(G["X"], metric_id, int(G["n_neighbors"]))
+    gi = torch.from_numpy(G["ng_idx"]).to(eng.device); gd = torch.from_numpy(G["ng_dist"]).to(eng.device)
+    S = prepare_search_structures(eng, metric, gi, gd, int(G["n_neighbors"]), angular)
+    for key in ("vertex_order", "tree_indices", "children", "indptr", "indices"):
+        assert np.array_equal(S[key], G[key]), key
+    np.testing.assert_allclose(S["hyperplanes"], G["hyperplanes"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(S["offsets"], G["offsets"], rtol=1e-5, atol=1e-5)
+    assert np.float32(S["min_distance"]) == np.float32(G["min_distance"])
+
+
+def test_build_prepare_query_end_to_end(oracle):
+    """NNDescent(...).query(): GPU build -> GPU prepare -> GPU walk, against the oracle's prepare + search on the same
+    graph, and against brute force (reference's own bar: query recall >= 0.95 on easy data, test_pynndescent_.py:133)."""
+    from pynndescent_b200 import NNDescent
+    from conftest import latent
+    both = latent(6200, 24, 3)
+    X, Q = both[:6000], both[6000:]
+    idx = NNDescent(X, "euclidean", n_neighbors=15, random_state=5)
+    qi, qd = idx.query(Q, k=10, epsilon=0.2)
+    gi, _ = idx.neighbor_graph
+    raw_d = idx._engine.heap_dist.cpu().numpy()                      # sorted raw (squared) distances of the built graph
+    P = oracle.prepare(X, "euclidean", gi, raw_d, 15, idx.rng_state)
+    hi, hd = oracle.search(P["data"], "euclidean", P["indptr"], P["indices"], P["hyperplanes"], P["offsets"], P["children"],
+                           P["tree_indices"], Q, 10, 0.2, float(P["min_distance"]), 15, idx.search_rng_state)
+    si, sd = oracle.deheap_sort(hi, hd)
+    assert np.array_equal(qi, P["vertex_order"][si])
+    assert np.array_equal(qd, np.sqrt(sd))
+    true = np.argsort(((Q[:, None, :].astype(np.float64) - X[None, :, :]) ** 2).sum(-1), 1)[:, :10]
+    rec = np.mean([len(np.intersect1d(true[i], qi[i])) / 10 for i in range(len(Q))])
+    assert rec >= 0.95, rec
