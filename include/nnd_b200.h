@@ -147,7 +147,10 @@ NND_API int nnd_set_row_range(nnd_ctx *ctx, int64_t lo, int64_t hi);
 /* prepass of one process_candidates call restricted to the row range; n_rounds_host = routing rounds needed */
 NND_API int nnd_join_prepare(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand, const int32_t *old_cand,
                              int64_t push_capacity, void *ws, size_t ws_bytes, int32_t *n_rounds_host, void *stream);
-/* run the join of one round; the half-updates stay in the workspace (rounds beyond the plan emit nothing) */
+/* run the join of one round; the half-updates stay in the workspace (rounds beyond the plan emit nothing).
+ * Rounds are planned optimistically: if this one does not fit push_capacity it is split in two (the plan grows
+ * by one round), *n_pushed_host = -1 and the caller emits the same round index again.  NND_ERR_OVERFLOW only
+ * when a single unit does not fit.                                                                             */
 NND_API int nnd_join_emit_round(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int64_t push_capacity, void *ws, size_t ws_bytes,
                                 int32_t round, int64_t *n_pushed_host, void *stream);
 /* group them by owner process (owner = target / owner_block) into 24-byte records {tgt i32, oth i32, d f32, pad, seq u64} */

@@ -1210,8 +1210,19 @@ extern "C" int nnd_join_emit_round(nnd_ctx *ctx, const nnd_problem *P, int32_t C
     *n_pushed_host = 0;
     if (round < 0 || round >= (int32_t)PL.rounds.size()) return NND_OK;   // this process has fewer rounds: nothing to emit
     unsigned long long np = 0;
-    NND_TRY(route_round(ctx, P, PL.J, PL.rounds[round].first, PL.rounds[round].second, W, push_capacity, &np, st,
-                        PL.batched ? &PL.JB : nullptr, /*do_apply=*/false));
+    const std::pair<int64_t, int64_t> r = PL.rounds[round];
+    int rc = route_round(ctx, P, PL.J, r.first, r.second, W, push_capacity, &np, st, PL.batched ? &PL.JB : nullptr,
+                         /*do_apply=*/false);
+    if (rc == NND_ERR_OVERFLOW && r.second - r.first > 1) {
+        // the optimistically planned round did not fit the push list: split it in two (the plan grows by one
+        // round, ascending unit order kept) and tell the caller to emit the same round index again
+        const int64_t mid = (r.first + r.second) / 2;
+        PL.rounds[round] = {r.first, mid};
+        PL.rounds.insert(PL.rounds.begin() + round + 1, {mid, r.second});
+        *n_pushed_host = -1;
+        return NND_OK;
+    }
+    if (rc != NND_OK) return rc;
     *n_pushed_host = (int64_t)np;
     return NND_OK;
 }
@@ -1270,16 +1281,23 @@ extern "C" int nnd_push_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, in
     return NND_OK;
 }
 
-__global__ void k_rec_count(const Rec24 *in, unsigned long long n, uint32_t *cnt, uint32_t *pos) {
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pos[i] = atomicAdd(&cnt[in[i].tgt], 1u);
-}
-__global__ void k_rec_scatter(const Rec24 *in, const uint32_t *pos, unsigned long long n, const uint32_t *off, Rec16 *rec) {
+// cnt / off are indexed by (target - row_lo): only the rows this process owns are histogrammed and replayed
+__global__ void k_rec_count(const Rec24 *in, unsigned long long n, uint32_t *cnt, uint32_t *pos, int64_t row_lo, int64_t row_hi,
+                            unsigned long long *bad) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int64_t t = in[i].tgt;
+    if (t < row_lo || t >= row_hi) { pos[i] = 0xffffffffu; atomicAdd(bad, 1ULL); return; }
+    pos[i] = atomicAdd(&cnt[t - row_lo], 1u);
+}
+__global__ void k_rec_scatter(const Rec24 *in, const uint32_t *pos, unsigned long long n, const uint32_t *off, Rec16 *rec,
+                              int64_t row_lo) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (pos[i] == 0xffffffffu) return;
     Rec24 a = in[i];
     Rec16 r; r.key = a.seq; r.oth = a.oth; r.d = a.d;
-    rec[(size_t)off[a.tgt] + pos[i]] = r;
+    rec[(size_t)off[a.tgt - row_lo] + pos[i]] = r;
 }
 
 // apply received half-updates (any order) to the local heap rows: counting sort by target + ordered replay.
@@ -1295,22 +1313,34 @@ extern "C" int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, 
               "nnd_apply_records: workspace too small");
     *c_host = 0;
     if (n == 0) return NND_OK;
+    // only the rows this process owns ([row_lo,row_hi), nnd_set_row_range) can be targets: histogram, scan and
+    // replay over that range instead of all N rows
     const int64_t N = P->N;
-    NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (N + 1), st));
+    const int64_t lo = ctx->row_lo > 0 ? (ctx->row_lo < N ? ctx->row_lo : N) : 0;
+    const int64_t hi = ctx->row_hi < N ? (ctx->row_hi > lo ? ctx->row_hi : lo) : N;
+    const int64_t Nr = hi - lo;
+    NND_CHECK(Nr > 0, NND_ERR_INVALID, "nnd_apply_records: %lld records but the row range [%lld,%lld) is empty", (long long)n,
+              (long long)lo, (long long)hi);
+    NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (Nr + 1), st));
     NND_CUDA(cudaMemsetAsync(W.dev_scalars + 1, 0, sizeof(unsigned long long), st));
-    k_rec_count<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, (unsigned long long)n, W.cnt, W.l_pos); NND_LAUNCH(ctx);
-    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, N, W.scan_tmp, st));
-    k_rec_scatter<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, W.l_pos, (unsigned long long)n, W.off, W.rec); NND_LAUNCH(ctx);
+    NND_CUDA(cudaMemsetAsync(W.dev_scalars + 9, 0, sizeof(unsigned long long), st));
+    k_rec_count<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, (unsigned long long)n, W.cnt, W.l_pos, lo, hi, W.dev_scalars + 9); NND_LAUNCH(ctx);
+    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, Nr, W.scan_tmp, st));
+    k_rec_scatter<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, W.l_pos, (unsigned long long)n, W.off, W.rec, lo); NND_LAUNCH(ctx);
     size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
-                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1, 0);
+    k_apply<<<(unsigned)cdiv(Nr, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx + lo * P->k, P->heap_dist + lo * P->k,
+                                                                            P->heap_flag + lo * P->k, P->k, Nr, W.cnt, W.off, W.rec,
+                                                                            W.dev_scalars + 1, 0);
     NND_LAUNCH(ctx);
-    unsigned long long hc = 0;
+    unsigned long long hc = 0, hbad = 0;
     NND_CUDA(cudaMemcpyAsync(&hc, W.dev_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaMemcpyAsync(&hbad, W.dev_scalars + 9, sizeof(hbad), cudaMemcpyDeviceToHost, st));
     NND_CUDA(cudaStreamSynchronize(st));
     *c_host = (int64_t)hc;
     NND_CUDA(cudaGetLastError());
+    NND_CHECK(hbad == 0, NND_ERR_INVALID, "nnd_apply_records: %llu records target rows outside this process's range [%lld,%lld)",
+              hbad, (long long)lo, (long long)hi);
     return NND_OK;
 }
 

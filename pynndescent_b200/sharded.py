@@ -113,6 +113,41 @@ class ShardedBuilder:
                            [torch.tensor([n_trees * N], dtype=torch.int64, device=dev)])
             e.leaf_init(pts_all.reshape(-1), lo, lo.numel() - 1, max_leaf, cap)
 
+    def _replay(self, C_, cap, inbox):
+        """Apply the collected 24-byte records to the own heap rows; returns the accepted-push count.
+
+        One call when they fit the routing workspace (`cap` records).  Otherwise the own row range is halved
+        recursively and each half replayed on its own -- pushes to different rows commute, so any split BY
+        TARGET ROW keeps the result identical.
+        """
+        e = self.e
+        if not inbox:
+            return 0
+        buf = inbox[0] if len(inbox) == 1 else torch.cat(inbox)
+        n = buf.numel() // 24
+        if n <= cap:
+            return e.apply_records(C_, cap, buf, n)
+        recs = buf.view(n, 24)
+        tgt = buf.view(torch.int32).view(n, 6)[:, 0]
+        c = 0
+        work = [(self.lo, self.hi, recs, tgt)]
+        while work:
+            a, b, r, t = work.pop()
+            m = r.shape[0]
+            if m == 0:
+                continue
+            if m <= cap:
+                c += e.apply_records(C_, cap, r.reshape(-1), m)
+                continue
+            if b - a <= 1:
+                raise OverflowError("push_capacity %d is smaller than the %d half-updates of ONE heap row" % (cap, m))
+            mid = (a + b) // 2
+            left = t < mid
+            rl = r[left].contiguous(); rr = r[~left].contiguous()
+            work.append((mid, b, rr, rr.view(-1).view(torch.int32).view(-1, 6)[:, 0]))
+            work.append((a, mid, rl, rl.view(-1).view(torch.int32).view(-1, 6)[:, 0]))
+        return c
+
     def descent(self, C_, rng_state, T, n_iters, delta, cap, timings=None):
         import time
         e = self.e
@@ -127,36 +162,45 @@ class ShardedBuilder:
             e.set_row_range(self.lo, self.hi)
             newc, oldc = e.build_candidates(C_, rng_state, T, tables_valid=(it > 0))
             lap("d.candidates")
-            nr = torch.tensor([e.join_prepare(newc, oldc, cap)], dtype=torch.int64, device=e.device)
-            nrs = torch.empty(self.world, dtype=torch.int64, device=e.device)
-            dist.all_gather_into_tensor(nrs, nr)
-            nrs = [int(v) for v in nrs.cpu()]
+            my_rounds = e.join_prepare(newc, oldc, cap)
             lap("d.join_prepare")
-            # Canonical push order per target row = ascending join-row id.  One round per rank: all ranks emit at
-            # once and the owner's sort by emission sequence restores the order.  If some rank needs several
-            # rounds (push list larger than its capacity) the rounds are serialised rank-major, which is still
-            # ascending in the join-row id because ranks own ascending row ranges.
-            if max(nrs) <= 1:
-                schedule = [(None, 0)]
-            else:
-                schedule = [(src, rnd) for src in range(self.world) for rnd in range(nrs[src])]
-            c_loc = 0
-            for src, rnd in schedule:
-                n = e.join_emit_round(C_, cap, rnd) if (src is None or src == self.rank) else 0
+            # Canonical push order per target row = ascending emission sequence.  All ranks emit their round r at
+            # the same time; the owner only COLLECTS the records of every round and replays them once at the end
+            # of the iteration, where the sort by emission sequence restores the canonical order no matter which
+            # rank / round a record came from.  (Emission only reads the replicated heap's thresholds, which do
+            # not change before the all-gather, so nothing depends on the replay having happened.)  Ranks may
+            # need different numbers of rounds (and a round that overflows the push list is split on the spot):
+            # the count exchange carries a "more rounds follow" flag and the loop ends when no rank raises it.
+            inbox = []
+            rnd = 0
+            while True:
+                n = 0
+                while rnd < my_rounds:
+                    n = e.join_emit_round(C_, cap, rnd)
+                    if n >= 0:
+                        break
+                    my_rounds += 1                                   # round split in two: emit its first half
                 lap("d.join_emit")
                 send, counts = e.push_export(C_, cap, n, self.B, self.world)
                 lap("d.export")
-                cs = torch.tensor(counts, dtype=torch.int64, device=e.device)
+                more = 1 if rnd + 1 < my_rounds else 0
+                cs = torch.tensor([[c, more] for c in counts], dtype=torch.int64, device=e.device)
                 cr = torch.empty_like(cs)
                 dist.all_to_all_single(cr, cs)
-                rc = [int(v) for v in cr.cpu()]
+                crh = cr.cpu().numpy()
+                rc = [int(v) for v in crh[:, 0]]
                 recv = torch.empty(max(sum(rc), 1) * 24, dtype=torch.uint8, device=e.device)
                 dist.all_to_all_single(recv[: sum(rc) * 24], send[: n * 24], output_split_sizes=[c * 24 for c in rc],
                                        input_split_sizes=[c * 24 for c in counts])
                 self.comm_bytes += sum(rc) * 24
+                if sum(rc) > 0:
+                    inbox.append(recv[: sum(rc) * 24])
                 lap("d.all_to_all")
-                c_loc += e.apply_records(C_, cap, recv, sum(rc))
-                lap("d.apply")
+                rnd += 1
+                if not crh[:, 1].any():
+                    break
+            c_loc = self._replay(C_, cap, inbox)
+            lap("d.apply")
             e.set_row_range(0, 2 ** 62)
             self._allgather_heap()
             lap("d.allgather_heap")

@@ -55,3 +55,88 @@ def test_world_size_2_gloo_reductions(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
     assert int(line[1]) == 1001 * 15 and float(line[2]) == 2.0
+
+
+SHARDED_WORKER = r'''
+"""Drive pynndescent_b200.sharded.ShardedBuilder.descent over gloo with a scripted engine: checks the exchange
+protocol only (unequal round counts, rounds split on overflow, the "more rounds" flag, the replay split by
+target row) -- every emitted record must reach the owner of its target exactly once."""
+import os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+dist.init_process_group("gloo")
+from pynndescent_b200.sharded import ShardedBuilder
+r, w = dist.get_rank(), dist.get_world_size()
+N, K, CAP = 1001, 4, 64
+
+
+class ScriptedEngine:
+    """Stands in for engine.Engine: emits seeded records instead of running the CUDA join."""
+    def __init__(self):
+        self.N, self.k, self.device = N, K, torch.device("cpu")
+        self.heap_idx = self.heap_dist = self.heap_flag = None
+        self.emitted, self.received, self.it = [], [], 0
+        self.lo = self.hi = None
+    def set_row_range(self, lo, hi): self.lo, self.hi = lo, hi
+    def build_candidates(self, C_, rng, T, tables_valid=False): return None, None
+    def join_prepare(self, newc, oldc, cap):
+        self.it += 1
+        rs = np.random.RandomState(100 * self.it + r)
+        # rank 0 plans 3 rounds, rank 1 one round (iteration 2: rank 0 none at all)
+        n_rounds = (3 if r == 0 else 1) if self.it == 1 else (0 if r == 0 else 2)
+        self.rounds = [rs.randint(0, N, size=rs.randint(20, 60)) for _ in range(n_rounds)]
+        self.split_pending = (self.it == 1 and r == 0)
+        return n_rounds
+    def join_emit_round(self, C_, cap, rnd):
+        if rnd >= len(self.rounds): return 0
+        if self.split_pending and rnd == 1:           # this round "overflows" once: split in two, caller retries
+            self.split_pending = False
+            t = self.rounds[rnd]; self.rounds[rnd: rnd + 1] = [t[: len(t) // 2], t[len(t) // 2:]]
+            return -1
+        self.cur = self.rounds[rnd]
+        return len(self.cur)
+    def push_export(self, C_, cap, n, B, world):
+        if n == 0: return torch.zeros(24, dtype=torch.uint8), [0] * world
+        tgt = np.sort(self.cur.astype(np.int32), kind="stable")          # grouped by owner since owners own ranges
+        rec = np.zeros((n, 6), np.int32)
+        rec[:, 0] = tgt; rec[:, 1] = r; rec[:, 4] = np.arange(n) + 1000 * len(self.emitted); rec[:, 5] = self.it
+        self.emitted.append(rec.copy())
+        counts = [int(((tgt // B).clip(max=world - 1) == o).sum()) for o in range(world)]
+        return torch.from_numpy(rec).view(torch.uint8).reshape(-1), counts
+    def apply_records(self, C_, cap, buf, n):
+        assert n <= cap, "replay must split by row below the capacity"
+        rec = buf[: n * 24].view(torch.int32).view(n, 6).numpy()
+        assert ((rec[:, 0] >= self.lo) & (rec[:, 0] < self.hi)).all(), "record delivered to the wrong owner"
+        self.received.append(rec.copy())
+        return n
+
+
+e = ScriptedEngine()
+sb = ShardedBuilder(e)
+for t in sb._full:
+    t.zero_()
+iters, c_hist = sb.descent(4, None, 1, 2, -1.0, CAP)
+sent = np.concatenate(e.emitted) if e.emitted else np.zeros((0, 6), np.int32)
+got = np.concatenate(e.received) if e.received else np.zeros((0, 6), np.int32)
+allsent, allgot = [None] * w, [None] * w
+dist.all_gather_object(allsent, sent); dist.all_gather_object(allgot, got)
+if r == 0:
+    S = np.concatenate(allsent); G = np.concatenate(allgot)
+    key = lambda a: sorted(map(tuple, a.tolist()))
+    ok = key(S) == key(G) and iters == 2 and c_hist == [len(np.concatenate([x[x[:, 5] == i] for x in allsent])) for i in (1, 2)]
+    print("RESULT", "OK" if ok else "BAD", len(S), len(G), c_hist, flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_exchange_protocol_gloo(tmp_path):
+    """world_size 2 over gloo: ShardedBuilder.descent's round / flag / replay logic with a scripted engine."""
+    script = tmp_path / "sharded_worker.py"
+    script.write_text(SHARDED_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    assert line[1] == "OK", out.stdout[-2000:]
