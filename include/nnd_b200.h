@@ -48,6 +48,22 @@ extern "C" {
 #define NND_METRIC_ALT_COSINE 1  /* distances.py:583-630 (cosine)                       */
 #define NND_METRIC_ALT_DOT 2     /* distances.py:665-701 (dot; data pre-normalised)     */
 #define NND_METRIC_CORRELATION 3 /* distances.py:1283-1320                              */
+/* SURVEY 8f-2 "more named metrics": computed by the generic (unbatched) join, the query walk and prepare() */
+#define NND_METRIC_MANHATTAN 4   /* distances.py manhattan / taxicab / l1   (f64 accumulator like the reference) */
+#define NND_METRIC_CHEBYSHEV 5   /* distances.py chebyshev / linfinity / linfty / linf                           */
+#define NND_METRIC_CANBERRA 6    /* distances.py canberra                   (f64 accumulator)                     */
+#define NND_METRIC_HAMMING 7     /* distances.py hamming                                                         */
+/* binary family: one accumulator tt = #{x_i != 0 and y_i != 0} + the per-row non-zero counts (metric aux) */
+#define NND_METRIC_ALT_JACCARD 8 /* distances.py:303-326 alternative_jaccard (jaccard; correction 1 - 2^-d)       */
+#define NND_METRIC_DICE 9
+#define NND_METRIC_MATCHING 10
+#define NND_METRIC_KULSINSKI 11
+#define NND_METRIC_ROGERSTANIMOTO 12 /* also sokalmichener (same formula in the reference)                       */
+#define NND_METRIC_RUSSELLRAO 13
+#define NND_METRIC_SOKALSNEATH 14
+#define NND_METRIC_YULE 15
+#define NND_METRIC_ALT_HELLINGER 16 /* distances.py:1387-1416 alternative_hellinger (correction sqrt(1 - 2^-d)) */
+#define NND_METRIC_MAX 16
 
 #define NND_CORRECT_NONE 0
 #define NND_CORRECT_SQRT 1   /* distances.py:2171       np.sqrt                         */

@@ -31,7 +31,11 @@
 #define ORC_API __attribute__((visibility("default")))
 
 /* metric ids (restated; the product's copy lives in include/nnd_b200.h) */
-enum { ORC_SQEUCLIDEAN = 0, ORC_ALT_COSINE = 1, ORC_ALT_DOT = 2, ORC_CORRELATION = 3 };
+enum { ORC_SQEUCLIDEAN = 0, ORC_ALT_COSINE = 1, ORC_ALT_DOT = 2, ORC_CORRELATION = 3,
+       /* SURVEY 8f-2 */
+       ORC_MANHATTAN = 4, ORC_CHEBYSHEV = 5, ORC_CANBERRA = 6, ORC_HAMMING = 7, ORC_ALT_JACCARD = 8, ORC_DICE = 9,
+       ORC_MATCHING = 10, ORC_KULSINSKI = 11, ORC_ROGERSTANIMOTO = 12, ORC_RUSSELLRAO = 13, ORC_SOKALSNEATH = 14,
+       ORC_YULE = 15, ORC_ALT_HELLINGER = 16 };
 
 /* ------------------------------------------------------------------ RNG ---- */
 /* utils.py:17-40 tau_rand_int.  State words are int64 and are NOT confined to 32
@@ -138,12 +142,89 @@ static inline float d_correlation(const float *x, const float *y, int d) {
     if (dp == 0.0) return 1.0f;
     return (float)(1.0 - dp / sqrt(nx * ny));
 }
+/* distances.py manhattan: the reference's accumulator is a float64 `result`, terms are f32 |x_i - y_i| */
+static inline float d_manhattan(const float *x, const float *y, int d) {
+    double acc = 0.0;
+    for (int e = 0; e < d; ++e) acc += (double)fabsf(x[e] - y[e]);
+    return (float)acc;
+}
+/* distances.py chebyshev */
+static inline float d_chebyshev(const float *x, const float *y, int d) {
+    float acc = 0.0f;
+    for (int e = 0; e < d; ++e) { float t = fabsf(x[e] - y[e]); acc = t > acc ? t : acc; }
+    return acc;
+}
+/* distances.py canberra: f32 quotient |x-y| / (|x|+|y|) added to a float64 result when the denominator is > 0 */
+static inline float d_canberra(const float *x, const float *y, int d) {
+    double acc = 0.0;
+    for (int e = 0; e < d; ++e) {
+        float den = fabsf(x[e]) + fabsf(y[e]);
+        if (den > 0.0f) acc += (double)(fabsf(x[e] - y[e]) / den);
+    }
+    return (float)acc;
+}
+/* distances.py hamming */
+static inline float d_hamming(const float *x, const float *y, int d) {
+    double acc = 0.0;
+    for (int e = 0; e < d; ++e) if (x[e] != y[e]) acc += 1.0;
+    return (float)(acc / (double)d);
+}
+/* the binary family (distances.py jaccard..yule): every one is a function of tt = #{both non-zero}, the two
+ * non-zero counts and the dimension; the reference forms the final quotient in float64                        */
+static inline float d_binary(int metric, const float *x, const float *y, int d) {
+    double tt = 0.0, nx = 0.0, ny = 0.0, n = (double)d;
+    for (int e = 0; e < d; ++e) {
+        int xt = x[e] != 0.0f, yt = y[e] != 0.0f;
+        tt += (double)(xt && yt); nx += (double)xt; ny += (double)yt;
+    }
+    double neq = nx + ny - 2.0 * tt; /* num_not_equal */
+    switch (metric) {
+    case ORC_ALT_JACCARD: { /* distances.py:303-326 */
+        double nnz = nx + ny - tt;
+        if (nnz == 0.0) return 0.0f;
+        if (tt == 0.0) return INFINITY; /* -log2(0) */
+        return (float)(-det_log2((double)((float)tt / (float)nnz))); /* f32 quotient: numba locals are float32 */
+    }
+    case ORC_DICE: return neq == 0.0 ? 0.0f : (float)(neq / (2.0 * tt + neq));
+    case ORC_MATCHING: return (float)(neq / n);
+    case ORC_KULSINSKI: return neq == 0.0 ? 0.0f : (float)((neq - tt + n) / (neq + n));
+    case ORC_ROGERSTANIMOTO: return (float)((2.0 * neq) / (n + neq));
+    case ORC_RUSSELLRAO: return (tt == nx && tt == ny) ? 0.0f : (float)((n - tt) / n);
+    case ORC_SOKALSNEATH: return neq == 0.0 ? 0.0f : (float)(neq / (0.5 * tt + neq));
+    default: { /* ORC_YULE */
+        double tf = nx - tt, ft = ny - tt, ff = n - tt - tf - ft;
+        if (tf == 0.0 || ft == 0.0) return 0.0f;
+        return (float)((2.0 * tf * ft) / (tt * ff + tf * ft));
+    }
+    }
+}
+/* distances.py:1387-1416 alternative_hellinger: result and both l1 norms are float32 locals in the reference
+ * (numba `locals`), summed here in the canonical sequential order; the tail is alternative_cosine's        */
+static inline float d_alt_hellinger(const float *x, const float *y, int d) {
+    float s = 0.0f, lx = 0.0f, ly = 0.0f;
+    for (int e = 0; e < d; ++e) {
+        s = s + sqrtf(x[e] * y[e]);
+        lx = lx + x[e];
+        ly = ly + y[e];
+    }
+    if (lx == 0.0f && ly == 0.0f) return 0.0f;
+    if (lx == 0.0f || ly == 0.0f) return FLT_MAX;
+    if (s <= 0.0f) return FLT_MAX;
+    float r = sqrtf(lx * ly) / s;
+    return (float)det_log2((double)r);
+}
 static inline float dist_fn(int metric, const float *x, const float *y, int d) {
     switch (metric) {
     case ORC_SQEUCLIDEAN: return d_sqeuclid(x, y, d);
     case ORC_ALT_COSINE: return d_alt_cosine(x, y, d);
     case ORC_ALT_DOT: return d_alt_dot(x, y, d);
-    default: return d_correlation(x, y, d);
+    case ORC_CORRELATION: return d_correlation(x, y, d);
+    case ORC_MANHATTAN: return d_manhattan(x, y, d);
+    case ORC_CHEBYSHEV: return d_chebyshev(x, y, d);
+    case ORC_CANBERRA: return d_canberra(x, y, d);
+    case ORC_HAMMING: return d_hamming(x, y, d);
+    case ORC_ALT_HELLINGER: return d_alt_hellinger(x, y, d);
+    default: return d_binary(metric, x, y, d);
     }
 }
 ORC_API float orc_dist(int metric, const float *x, const float *y, int d) { return dist_fn(metric, x, y, d); }
@@ -507,11 +588,28 @@ static void dfs_tree(tree_t *t, const float *X, int d, int angular, int32_t *ind
         float *h = (float *)malloc(sizeof(float) * d);
         float off;
         make_hyperplane(X, d, angular, indices[li], indices[ri], h, &off);
+        /* The reference accumulates offset and margin in float32 under fastmath=True (rp_trees.py:303-321
+         * `locals`), i.e. in whatever order LLVM vectorises them -- unknowable here.  This restatement
+         * accumulates the f32 products in float64, which yields the EXACT sign of the margin; every f32
+         * summation order reproduces that sign except for points within rounding of the hyperplane, so this is
+         * the best predictor of the reference's split (all continuous-data goldens in tests/golden agree; a
+         * plain f32 chain misplaced one point of latent_manhattan_1500x20).  On integer / binary data with
+         * angular trees margins are EXACTLY zero for many points and the reference's coin flips then depend on
+         * its rounding noise: those goldens pin the path from the reference's leaf_array onwards instead.
+         * (The "level" scheme below -- the GPU forest's formulation -- keeps its own canonical f32 lane order.) */
+        double off64 = 0.0;
+        if (!angular) {
+            const float *xl = X + (int64_t)indices[li] * d, *xr = X + (int64_t)indices[ri] * d;
+            for (int e = 0; e < d; ++e) off64 -= (double)(h[e] * (xl[e] + xr[e])) / 2.0;
+            off = (float)off64;
+        }
         int8_t *side = (int8_t *)malloc(n);
         int64_t nl = 0, nr = 0;
         for (int64_t i = 0; i < n; ++i) {
-            float margin = off + lane_dot(h, X + (int64_t)indices[i] * d, d);
-            if (fabs((double)margin) < 1e-8) {
+            const float *xi = X + (int64_t)indices[i] * d;
+            double margin = off64;
+            for (int e = 0; e < d; ++e) margin += (double)(h[e] * xi[e]);
+            if (fabs(margin) < 1e-8) {
                 int32_t r = orc_tau_rand_int(rng);
                 side[i] = angular ? (int8_t)floormod(r, 2) : (int8_t)(abs_i32(r) % 2 != 0);
                 if (side[i] == 0) nl++; else nr++;

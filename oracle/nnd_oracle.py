@@ -17,7 +17,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-METRIC_IDS = {"sqeuclidean": 0, "euclidean": 0, "l2": 0, "cosine": 1, "dot": 2, "correlation": 3}
+METRIC_IDS = {"sqeuclidean": 0, "euclidean": 0, "l2": 0, "cosine": 1, "dot": 2, "correlation": 3,
+              # SURVEY 8f-2 (ids restate include/nnd_b200.h)
+              "manhattan": 4, "taxicab": 4, "l1": 4, "chebyshev": 5, "linfinity": 5, "linfty": 5, "linf": 5,
+              "canberra": 6, "hamming": 7, "jaccard": 8, "dice": 9, "matching": 10, "kulsinski": 11,
+              "rogerstanimoto": 12, "sokalmichener": 12, "russellrao": 13, "sokalsneath": 14, "yule": 15,
+              "hellinger": 16}
 ANGULAR_METRICS = ("cosine", "dot", "correlation", "dice", "jaccard", "hellinger", "hamming")
 INT32_MIN = np.iinfo(np.int32).min + 1
 INT32_MAX = np.iinfo(np.int32).max - 1
@@ -245,8 +250,10 @@ def correction(metric, d):
     pow-based cosine/dot correction, as the reference's numba.vectorize gives)."""
     if metric in ("euclidean", "l2"):
         return np.sqrt(d)
-    if metric in ("cosine", "dot"):
+    if metric in ("cosine", "dot", "jaccard"):            # correct_alternative_cosine / _jaccard: 1 - 2^-d
         return 1.0 - np.power(2.0, -d.astype(np.float64))
+    if metric == "hellinger":                             # correct_alternative_hellinger: sqrt(1 - 2^-d)
+        return np.sqrt(1.0 - np.power(2.0, -d.astype(np.float64)))
     return d.copy()
 
 

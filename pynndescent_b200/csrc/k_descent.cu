@@ -43,11 +43,16 @@ struct JoinParams {
     int64_t row_lo, row_hi;   // mode 0: rows outside are skipped (sharded build)
 };
 
+// compile-time views of a metric CLASS (nnd_metric_class): per-row auxiliaries in shared memory, accumulator type
+#define MC_AUX1(M) ((M) == NND_METRIC_ALT_COSINE || (M) == NND_METRIC_ALT_JACCARD || (M) == NND_METRIC_ALT_HELLINGER)
+#define MC_AUX2(M) ((M) == NND_METRIC_CORRELATION)
+#define MC_F64(M) ((M) == NND_METRIC_CORRELATION || (M) == NND_METRIC_MANHATTAN || (M) == NND_METRIC_CANBERRA)
+
 static size_t join_smem_bytes(int m_max, int metric) {
     size_t b = 16;                       // mbarrier
     b += (size_t)m_max * 4 * 2;          // ids, thr
-    if (metric == NND_METRIC_ALT_COSINE) b += (size_t)m_max * 4;
-    if (metric == NND_METRIC_CORRELATION) b += (size_t)m_max * 16;
+    if (nnd_metric_aux_kind(metric) == 1) b += (size_t)m_max * 4;
+    if (nnd_metric_aux_kind(metric) == 2) b += (size_t)m_max * 16;
     b = (b + 15) & ~size_t(15);
     b += (size_t)(m_max + 4) * SD * 4;  // slot permutation (j&3)*ntc + (j>>2) spans up to m+3 slots
     return b;
@@ -69,8 +74,8 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     float *thr_s = (float *)(ids + P.m_max);
     unsigned char *cur = (unsigned char *)(thr_s + P.m_max);
     float *n2_s = nullptr; double *mu_s = nullptr;
-    if (METRIC == NND_METRIC_ALT_COSINE) { n2_s = (float *)cur; cur += (size_t)P.m_max * 4; }
-    if (METRIC == NND_METRIC_CORRELATION) {
+    if (MC_AUX1(METRIC)) { n2_s = (float *)cur; cur += (size_t)P.m_max * 4; }
+    if (MC_AUX2(METRIC)) {
         cur = (unsigned char *)(((uintptr_t)cur + 7) & ~uintptr_t(7));
         mu_s = (double *)cur; cur += (size_t)P.m_max * 16;
     }
@@ -118,8 +123,8 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     for (int j = tid; j < m; j += nthr) {
         int32_t id = ids[j];
         thr_s[j] = (P.mode == 2) ? CUDART_INF_F : P.thr[id];
-        if (METRIC == NND_METRIC_ALT_COSINE) n2_s[j] = ((const float *)P.aux)[id];
-        if (METRIC == NND_METRIC_CORRELATION) {
+        if (MC_AUX1(METRIC)) n2_s[j] = ((const float *)P.aux)[id];
+        if (MC_AUX2(METRIC)) {
             mu_s[2 * j] = ((const double *)P.aux)[2 * (int64_t)id];
             mu_s[2 * j + 1] = ((const double *)P.aux)[2 * (int64_t)id + 1];
         }
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
         }
     }
 
-    typedef typename std::conditional<METRIC == NND_METRIC_CORRELATION, double, float>::type acc_t;
+    typedef typename std::conditional<MC_F64(METRIC), double, float>::type acc_t;
     acc_t acc[TPT][TILE * TILE];
 #pragma unroll
     for (int i = 0; i < TPT; ++i)
@@ -213,8 +218,10 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                                     double sy = __dadd_rn((double)xb, -(double)mb[v]);
                                     acc[i][u * TILE + v] = __fma_rn(sx, sy, (double)acc[i][u * TILE + v]);
                                 }
-                            } else {
+                            } else if (METRIC == NND_METRIC_ALT_COSINE || METRIC == NND_METRIC_ALT_DOT) {
                                 acc[i][u * TILE + v] = __fmaf_rn(xa, xb, (float)acc[i][u * TILE + v]);
+                            } else {
+                                acc[i][u * TILE + v] = nnd_metric_step<METRIC, acc_t>(acc[i][u * TILE + v], xa, xb);
                             }
                         }
                     }
@@ -243,7 +250,11 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                     if (METRIC == NND_METRIC_SQEUCLIDEAN) r = (float)acc[i][u * TILE + v];
                     else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine((float)acc[i][u * TILE + v], n2_s[a], n2_s[b]);
                     else if (METRIC == NND_METRIC_ALT_DOT) r = finish_alt_dot((float)acc[i][u * TILE + v]);
-                    else r = finish_correlation((double)acc[i][u * TILE + v], mu_s[2 * a + 1], mu_s[2 * b + 1]);
+                    else if (METRIC == NND_METRIC_CORRELATION) r = finish_correlation((double)acc[i][u * TILE + v], mu_s[2 * a + 1], mu_s[2 * b + 1]);
+                    else if (METRIC == NND_METRIC_ALT_JACCARD) r = finish_binary(P.metric, (float)acc[i][u * TILE + v], n2_s[a], n2_s[b], P.d);
+                    else if (METRIC == NND_METRIC_ALT_HELLINGER) r = finish_alt_hellinger((float)acc[i][u * TILE + v], n2_s[a], n2_s[b]);
+                    else if (METRIC == NND_METRIC_CHEBYSHEV) r = (float)acc[i][u * TILE + v];
+                    else r = finish_plain(METRIC, (double)acc[i][u * TILE + v], P.d);
                     if (r < thr_s[a]) pm[i] |= 1u << (2 * (u * TILE + v));
                     if (b != a && r < thr_s[b]) pm[i] |= 2u << (2 * (u * TILE + v));
                 }
@@ -839,11 +850,11 @@ static int launch_join_m(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cud
     size_t smem = join_smem_bytes(P.m_max, METRIC);
     if (P.mode == 2) { int al; smem += fused_extra_bytes(P.m_max, P.k, &al) + 32; }
     NND_CHECK(smem <= 220 * 1024, NND_ERR_UNSUPPORTED, "join: %d members need %zu B of shared memory", P.m_max, smem);
-    int tpt = (METRIC == NND_METRIC_CORRELATION) ? 1 : (ntiles <= 512 ? 1 : (ntiles <= 2048 ? 2 : 4));
+    int tpt = MC_F64(METRIC) ? 1 : (ntiles <= 512 ? 1 : (ntiles <= 2048 ? 2 : 4));
     // leaves are on average ~60 % full: two tiles per thread keep more lanes busy than one thread per tile slot
     static int leaf_tpt2 = -1;
     if (leaf_tpt2 < 0) { const char *e = getenv("NND_LEAF_TPT2"); leaf_tpt2 = e ? atoi(e) : 0; }
-    if (P.mode == 2 && tpt == 1 && leaf_tpt2 && METRIC != NND_METRIC_CORRELATION && ntiles > 64) tpt = 2;
+    if (P.mode == 2 && tpt == 1 && leaf_tpt2 && !MC_F64(METRIC) && ntiles > 64) tpt = 2;
     int threads = (int)(cdiv(cdiv(ntiles, tpt), 32) * 32);
     NND_CHECK(threads <= 1024, NND_ERR_UNSUPPORTED, "join: %d tiles exceed one CTA (members=%d)", ntiles, P.m_max);
     if (threads < 32) threads = 32;
@@ -854,8 +865,10 @@ static int launch_join_m(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cud
         k_join<METRIC, T_, M_><<<grid, threads, smem, st>>>(P);                                          \
     } while (0)
     if (tpt == 1) { if (threads <= 128) LJ(1, 128); else if (threads <= 512) LJ(1, 512); else LJ(1, 1024); }
-    else if (tpt == 2) { if (threads <= 512) LJ(2, 512); else LJ(2, 1024); }
-    else LJ(4, 1024);
+    else if constexpr (!MC_F64(METRIC)) {           // f64 classes always run one tile per thread
+        if (tpt == 2) { if (threads <= 512) LJ(2, 512); else LJ(2, 1024); }
+        else LJ(4, 1024);
+    }
 #undef LJ
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
@@ -868,7 +881,13 @@ static int launch_join(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaS
     case NND_METRIC_ALT_COSINE: return launch_join_m<NND_METRIC_ALT_COSINE>(ctx, P, n_units, st);
     case NND_METRIC_ALT_DOT: return launch_join_m<NND_METRIC_ALT_DOT>(ctx, P, n_units, st);
     case NND_METRIC_CORRELATION: return launch_join_m<NND_METRIC_CORRELATION>(ctx, P, n_units, st);
+    case NND_METRIC_MANHATTAN: return launch_join_m<NND_METRIC_MANHATTAN>(ctx, P, n_units, st);
+    case NND_METRIC_CHEBYSHEV: return launch_join_m<NND_METRIC_CHEBYSHEV>(ctx, P, n_units, st);
+    case NND_METRIC_CANBERRA: return launch_join_m<NND_METRIC_CANBERRA>(ctx, P, n_units, st);
+    case NND_METRIC_HAMMING: return launch_join_m<NND_METRIC_HAMMING>(ctx, P, n_units, st);
+    case NND_METRIC_ALT_HELLINGER: return launch_join_m<NND_METRIC_ALT_HELLINGER>(ctx, P, n_units, st);
     }
+    if (nnd_metric_class(P.metric) == NND_METRIC_ALT_JACCARD) return launch_join_m<NND_METRIC_ALT_JACCARD>(ctx, P, n_units, st);
     nnd_set_error("join: unknown metric %d", P.metric);
     return NND_ERR_UNSUPPORTED;
 }
@@ -1096,7 +1115,8 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
     J.mode = 0; J.newc = new_cand; J.oldc = old_cand; J.C = C; J.m_max = 2 * C < 4 ? 4 : 2 * C; J.slot_stride = 2 * C;
     J.row_lo = ctx->row_lo; J.row_hi = ctx->row_hi;
     const char *force_old = getenv("NND_JOIN_UNBATCHED");
-    PL.batched = P->metric != NND_METRIC_CORRELATION && 2 * C <= 60 && !(force_old && force_old[0] == '1');
+    // the batched kernel is instantiated for the three f32 dot/difference metrics; everything else runs the generic join
+    PL.batched = P->metric <= NND_METRIC_ALT_DOT && 2 * C <= 60 && !(force_old && force_old[0] == '1');
     if (PL.batched) {
         // ---- batched path: compact the active rows and their members, cut batches by weight, one CTA per batch
         const int maxphys = ((2 * C + 3) >> 2) << 2;

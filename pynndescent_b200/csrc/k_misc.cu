@@ -190,13 +190,13 @@ extern "C" int nnd_make_heap(nnd_ctx *ctx, int32_t *heap_idx, float *heap_dist, 
 
 extern "C" int nnd_metric_aux_bytes(int32_t metric, int64_t N, size_t *bytes) {
     NND_CHECK(bytes && N > 0, NND_ERR_INVALID, "nnd_metric_aux_bytes: bad args");
-    switch (metric) {
-    case NND_METRIC_SQEUCLIDEAN: case NND_METRIC_ALT_DOT: *bytes = 16; return NND_OK;
-    case NND_METRIC_ALT_COSINE: *bytes = (size_t)N * 4 + 16; return NND_OK;
-    case NND_METRIC_CORRELATION: *bytes = (size_t)N * 16 + 16; return NND_OK;
+    if (metric < 0 || metric > NND_METRIC_MAX) {
+        nnd_set_error("unknown metric id %d", metric);
+        return NND_ERR_UNSUPPORTED;
     }
-    nnd_set_error("unknown metric id %d", metric);
-    return NND_ERR_UNSUPPORTED;
+    const int kind = nnd_metric_aux_kind(metric);
+    *bytes = (kind == 1 ? (size_t)N * 4 : kind == 2 ? (size_t)N * 16 : 0) + 16;
+    return NND_OK;
 }
 __global__ void k_metric_prepare(const float *X, int64_t N, int d, int ld, int metric, void *aux) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,13 +212,21 @@ __global__ void k_metric_prepare(const float *X, int64_t N, int d, int ld, int m
         double mu = __ddiv_rn(s, (double)d), nn = 0.0;
         for (int e = 0; e < d; ++e) { double sx = __dadd_rn((double)x[e], -mu); nn = __fma_rn(sx, sx, nn); }
         ((double *)aux)[2 * i] = mu; ((double *)aux)[2 * i + 1] = nn;
+    } else if (nnd_metric_class(metric) == NND_METRIC_ALT_JACCARD) {
+        float nz = 0.0f;                               // number of non-zero coordinates (exact small integer)
+        for (int e = 0; e < d; ++e) if (x[e] != 0.0f) nz += 1.0f;
+        ((float *)aux)[i] = nz;
+    } else if (metric == NND_METRIC_ALT_HELLINGER) {
+        float s = 0.0f;                                // distances.py:1405 l1 norm (f32 local in the reference)
+        for (int e = 0; e < d; ++e) s = __fadd_rn(s, x[e]);
+        ((float *)aux)[i] = s;
     }
 }
 extern "C" int nnd_metric_prepare(nnd_ctx *ctx, const float *X, int64_t N, int32_t d, int32_t ld, int32_t metric, void *aux,
                                   void *stream) {
     NND_CHECK(ctx && X && N > 0 && d > 0 && ld >= d, NND_ERR_INVALID, "nnd_metric_prepare: bad args");
-    NND_CHECK(metric >= 0 && metric <= 3, NND_ERR_UNSUPPORTED, "metric id %d not supported on the GPU path", metric);
-    if (metric == NND_METRIC_SQEUCLIDEAN || metric == NND_METRIC_ALT_DOT) return NND_OK;
+    NND_CHECK(metric >= 0 && metric <= NND_METRIC_MAX, NND_ERR_UNSUPPORTED, "metric id %d not supported on the GPU path", metric);
+    if (nnd_metric_aux_kind(metric) == 0) return NND_OK;
     NND_CHECK(aux, NND_ERR_INVALID, "nnd_metric_prepare: aux is null");
     k_metric_prepare<<<(unsigned)cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(X, N, d, ld, metric, aux);
     NND_LAUNCH(ctx);

@@ -64,11 +64,39 @@ __device__ __forceinline__ float query_distance(const QueryParams &P, const floa
             dp = __fma_rn(sx, sy, dp);
         }
         return finish_correlation(dp, nq2, mu[2 * (int64_t)c + 1]);
-    } else {
+    } else if (P.metric == NND_METRIC_ALT_COSINE || P.metric == NND_METRIC_ALT_DOT) {
         float acc = 0.0f;
         for (int e = 0; e < P.d; ++e) acc = __fmaf_rn(q[e], y[e], acc);
         if (P.metric == NND_METRIC_ALT_DOT) return finish_alt_dot(acc);
         return finish_alt_cosine(acc, qn2, ((const float *)P.aux)[c]);
+    }
+    // SURVEY 8f-2 metrics: the same per-element steps and tails as the join (nnd_common.cuh); the query-side
+    // auxiliaries arrive in qn2 (non-zero count / l1 norm)
+    const int mc = nnd_metric_class(P.metric);
+    if (mc == NND_METRIC_MANHATTAN) {
+        double acc = 0.0;
+        for (int e = 0; e < P.d; ++e) acc = nnd_metric_step<NND_METRIC_MANHATTAN, double>(acc, q[e], y[e]);
+        return finish_plain(P.metric, acc, P.d);
+    } else if (mc == NND_METRIC_CHEBYSHEV) {
+        float acc = 0.0f;
+        for (int e = 0; e < P.d; ++e) acc = nnd_metric_step<NND_METRIC_CHEBYSHEV, float>(acc, q[e], y[e]);
+        return acc;
+    } else if (mc == NND_METRIC_CANBERRA) {
+        double acc = 0.0;
+        for (int e = 0; e < P.d; ++e) acc = nnd_metric_step<NND_METRIC_CANBERRA, double>(acc, q[e], y[e]);
+        return finish_plain(P.metric, acc, P.d);
+    } else if (mc == NND_METRIC_HAMMING) {
+        float acc = 0.0f;
+        for (int e = 0; e < P.d; ++e) acc = nnd_metric_step<NND_METRIC_HAMMING, float>(acc, q[e], y[e]);
+        return finish_plain(P.metric, (double)acc, P.d);
+    } else if (mc == NND_METRIC_ALT_JACCARD) {
+        float acc = 0.0f;
+        for (int e = 0; e < P.d; ++e) acc = nnd_metric_step<NND_METRIC_ALT_JACCARD, float>(acc, q[e], y[e]);
+        return finish_binary(P.metric, acc, qn2, ((const float *)P.aux)[c], P.d);
+    } else {
+        float acc = 0.0f;
+        for (int e = 0; e < P.d; ++e) acc = nnd_metric_step<NND_METRIC_ALT_HELLINGER, float>(acc, q[e], y[e]);
+        return finish_alt_hellinger(acc, qn2, ((const float *)P.aux)[c]);
     }
 }
 
@@ -154,6 +182,8 @@ __device__ int run_query(const QueryParams &P, int64_t qi, float *q, float *pri,
     if (inv_ok == 0.0f) return 0;   // zero query under cosine/dot: the reference `continue`s (row stays -1 / inf)
     float qn2 = 0.0f; double mq = 0.0, nq2 = 0.0;
     if (P.metric == NND_METRIC_ALT_COSINE) for (int e = 0; e < P.d; ++e) qn2 = __fmaf_rn(q[e], q[e], qn2);
+    if (nnd_metric_class(P.metric) == NND_METRIC_ALT_JACCARD) for (int e = 0; e < P.d; ++e) if (q[e] != 0.0f) qn2 += 1.0f;
+    if (P.metric == NND_METRIC_ALT_HELLINGER) for (int e = 0; e < P.d; ++e) qn2 = __fadd_rn(qn2, q[e]);
     if (P.metric == NND_METRIC_CORRELATION) {
         double sq = 0.0;
         for (int e = 0; e < P.d; ++e) sq = __dadd_rn(sq, (double)q[e]);
@@ -326,7 +356,7 @@ extern "C" int nnd_query(nnd_ctx *ctx, const nnd_search_index *S, const float *Q
                          int64_t *stats_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     NND_CHECK(ctx && S && Q && out_idx && out_dist && rng_state_host && ws && nq >= 0 && k > 0, NND_ERR_INVALID, "nnd_query: bad args");
-    NND_CHECK(S->metric >= 0 && S->metric <= 3, NND_ERR_UNSUPPORTED, "nnd_query: metric id %d", S->metric);
+    NND_CHECK(S->metric >= 0 && S->metric <= NND_METRIC_MAX, NND_ERR_UNSUPPORTED, "nnd_query: metric id %d", S->metric);
     NND_CHECK(S->ld % 4 == 0 && S->ld >= S->d, NND_ERR_INVALID, "nnd_query: ld must be a multiple of 4 and >= d");
     if (nq == 0) return NND_OK;
     WsAlloc A(ws, ws_bytes);

@@ -117,6 +117,71 @@ __device__ __forceinline__ float finish_correlation(double dp, double nx, double
     return (float)__dadd_rn(1.0, -__ddiv_rn(dp, __dsqrt_rn(__dmul_rn(nx, ny))));
 }
 
+// ---- SURVEY 8f-2 metrics ---------------------------------------------------------------------------------
+// metric class = which per-element accumulation a kernel instantiation runs; the binary family shares one
+__host__ __device__ __forceinline__ int nnd_metric_class(int metric) {
+    return (metric >= NND_METRIC_ALT_JACCARD && metric <= NND_METRIC_YULE) ? NND_METRIC_ALT_JACCARD : metric;
+}
+// classes whose accumulator is f64 (the reference accumulates these in a float64 `result`)
+__host__ __device__ __forceinline__ bool nnd_metric_acc_f64(int metric) {
+    return metric == NND_METRIC_CORRELATION || metric == NND_METRIC_MANHATTAN || metric == NND_METRIC_CANBERRA;
+}
+// per-row auxiliary: 0 none, 1 one f32 per row (cosine: squared norm; binary family: non-zero count;
+// hellinger: l1 norm), 2 two f64 per row (correlation: mean, centred squared norm)
+__host__ __device__ __forceinline__ int nnd_metric_aux_kind(int metric) {
+    const int c = nnd_metric_class(metric);
+    if (c == NND_METRIC_ALT_COSINE || c == NND_METRIC_ALT_JACCARD || c == NND_METRIC_ALT_HELLINGER) return 1;
+    if (c == NND_METRIC_CORRELATION) return 2;
+    return 0;
+}
+// one element of the accumulation (template class MC); padded columns (both 0) contribute nothing
+template <int MC, typename ACC>
+__device__ __forceinline__ ACC nnd_metric_step(ACC acc, float xa, float xb) {
+    if (MC == NND_METRIC_MANHATTAN) return (ACC)__dadd_rn((double)acc, (double)fabsf(__fsub_rn(xa, xb)));
+    if (MC == NND_METRIC_CHEBYSHEV) return (ACC)fmaxf((float)acc, fabsf(__fsub_rn(xa, xb)));
+    if (MC == NND_METRIC_CANBERRA) {
+        const float den = __fadd_rn(fabsf(xa), fabsf(xb));
+        return den > 0.0f ? (ACC)__dadd_rn((double)acc, (double)__fdiv_rn(fabsf(__fsub_rn(xa, xb)), den)) : acc;
+    }
+    if (MC == NND_METRIC_HAMMING) return (xa != xb) ? (ACC)__fadd_rn((float)acc, 1.0f) : acc;
+    if (MC == NND_METRIC_ALT_JACCARD) return (xa != 0.0f && xb != 0.0f) ? (ACC)__fadd_rn((float)acc, 1.0f) : acc;
+    if (MC == NND_METRIC_ALT_HELLINGER) return (ACC)__fadd_rn((float)acc, __fsqrt_rn(__fmul_rn(xa, xb)));
+    return acc;
+}
+// tails of the binary family from tt = #{both non-zero}, the two non-zero counts and the dimension (all exact
+// small integers; the reference does the final division in float64)
+__device__ __forceinline__ float finish_binary(int metric, float ttf, float nxf, float nyf, int dim) {
+    const double tt = (double)ttf, nx = (double)nxf, ny = (double)nyf, n = (double)dim;
+    const double neq = nx + ny - 2.0 * tt;      // #{exactly one non-zero}
+    switch (metric) {
+    case NND_METRIC_ALT_JACCARD: {              // distances.py:303-326
+        const double nnz = nx + ny - tt;
+        if (nnz == 0.0) return 0.0f;
+        if (tt == 0.0) return CUDART_INF_F;     // -log2(0)
+        return (float)(-det_log2((double)__fdiv_rn(ttf, (float)nnz)));   // the reference divides in f32 (locals)
+    }
+    case NND_METRIC_DICE: return neq == 0.0 ? 0.0f : (float)__ddiv_rn(neq, 2.0 * tt + neq);
+    case NND_METRIC_MATCHING: return (float)__ddiv_rn(neq, n);
+    case NND_METRIC_KULSINSKI: return neq == 0.0 ? 0.0f : (float)__ddiv_rn(neq - tt + n, neq + n);
+    case NND_METRIC_ROGERSTANIMOTO: return (float)__ddiv_rn(2.0 * neq, n + neq);
+    case NND_METRIC_RUSSELLRAO: return (tt == nx && tt == ny) ? 0.0f : (float)__ddiv_rn(n - tt, n);
+    case NND_METRIC_SOKALSNEATH: return neq == 0.0 ? 0.0f : (float)__ddiv_rn(neq, 0.5 * tt + neq);
+    default: {                                  // NND_METRIC_YULE
+        const double tf = nx - tt, ft = ny - tt, ff = n - tt - tf - ft;
+        if (tf == 0.0 || ft == 0.0) return 0.0f;
+        return (float)__ddiv_rn(2.0 * tf * ft, tt * ff + tf * ft);
+    }
+    }
+}
+// distances.py:1387-1416 tail of alternative_hellinger given s = sum sqrt(x_i y_i) and the two l1 norms: all
+// f32 in the reference (numba locals) and literally the tail of alternative_cosine with (dot, nx, ny) = (s, lx, ly)
+__device__ __forceinline__ float finish_alt_hellinger(float s, float lx, float ly) { return finish_alt_cosine(s, lx, ly); }
+// tail for the classes without per-row auxiliaries
+__device__ __forceinline__ float finish_plain(int metric, double acc, int dim) {
+    if (metric == NND_METRIC_HAMMING) return (float)__ddiv_rn(acc, (double)dim);
+    return (float)acc;   // manhattan, canberra (f64 -> f32), chebyshev
+}
+
 // one whole pair distance by ONE thread straight from global memory (canonical sequential
 // chain).  Used by the low-volume paths (init_random, tests); the join kernel has its own
 // shared-memory tiled loop with the same per-pair operation order.
@@ -132,7 +197,7 @@ __device__ __forceinline__ float pair_distance_seq(const float *__restrict__ x, 
         if (metric == NND_METRIC_ALT_DOT) return finish_alt_dot(acc);
         const float *n2 = (const float *)aux;
         return finish_alt_cosine(acc, n2[ix], n2[iy]);
-    } else {
+    } else if (metric == NND_METRIC_CORRELATION) {
         const double *mu = (const double *)aux;
         double mx = mu[2 * ix], my = mu[2 * iy], dp = 0.0;
         for (int e = 0; e < d; ++e) {
@@ -140,6 +205,34 @@ __device__ __forceinline__ float pair_distance_seq(const float *__restrict__ x, 
             dp = __fma_rn(sx, sy, dp);
         }
         return finish_correlation(dp, mu[2 * ix + 1], mu[2 * iy + 1]);
+    }
+    const int mc = nnd_metric_class(metric);
+    if (mc == NND_METRIC_MANHATTAN) {
+        double acc = 0.0;
+        for (int e = 0; e < d; ++e) acc = nnd_metric_step<NND_METRIC_MANHATTAN, double>(acc, x[e], y[e]);
+        return finish_plain(metric, acc, d);
+    } else if (mc == NND_METRIC_CHEBYSHEV) {
+        float acc = 0.0f;
+        for (int e = 0; e < d; ++e) acc = nnd_metric_step<NND_METRIC_CHEBYSHEV, float>(acc, x[e], y[e]);
+        return acc;
+    } else if (mc == NND_METRIC_CANBERRA) {
+        double acc = 0.0;
+        for (int e = 0; e < d; ++e) acc = nnd_metric_step<NND_METRIC_CANBERRA, double>(acc, x[e], y[e]);
+        return finish_plain(metric, acc, d);
+    } else if (mc == NND_METRIC_HAMMING) {
+        float acc = 0.0f;
+        for (int e = 0; e < d; ++e) acc = nnd_metric_step<NND_METRIC_HAMMING, float>(acc, x[e], y[e]);
+        return finish_plain(metric, (double)acc, d);
+    } else if (mc == NND_METRIC_ALT_JACCARD) {
+        float acc = 0.0f;
+        for (int e = 0; e < d; ++e) acc = nnd_metric_step<NND_METRIC_ALT_JACCARD, float>(acc, x[e], y[e]);
+        const float *nz = (const float *)aux;
+        return finish_binary(metric, acc, nz[ix], nz[iy], d);
+    } else {
+        float acc = 0.0f;
+        for (int e = 0; e < d; ++e) acc = nnd_metric_step<NND_METRIC_ALT_HELLINGER, float>(acc, x[e], y[e]);
+        const float *l1 = (const float *)aux;
+        return finish_alt_hellinger(acc, l1[ix], l1[iy]);
     }
 }
 

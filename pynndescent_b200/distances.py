@@ -9,6 +9,10 @@ raise the reference's ValueError (pynndescent_.py:1292).
 import numpy as np
 
 NND_METRIC_SQEUCLIDEAN, NND_METRIC_ALT_COSINE, NND_METRIC_ALT_DOT, NND_METRIC_CORRELATION = 0, 1, 2, 3
+# SURVEY 8f-2 (include/nnd_b200.h)
+(NND_METRIC_MANHATTAN, NND_METRIC_CHEBYSHEV, NND_METRIC_CANBERRA, NND_METRIC_HAMMING, NND_METRIC_ALT_JACCARD,
+ NND_METRIC_DICE, NND_METRIC_MATCHING, NND_METRIC_KULSINSKI, NND_METRIC_ROGERSTANIMOTO, NND_METRIC_RUSSELLRAO,
+ NND_METRIC_SOKALSNEATH, NND_METRIC_YULE, NND_METRIC_ALT_HELLINGER) = range(4, 17)
 NND_CORRECT_NONE, NND_CORRECT_SQRT = 0, 1
 
 
@@ -16,6 +20,14 @@ def correct_alternative_cosine(d):
     """distances.py:704-711: 1 - 2^-d (float64 result like the reference's numba.vectorize)."""
     return 1.0 - np.power(2.0, -np.asarray(d).astype(np.float64))
 
+
+def correct_alternative_hellinger(d):
+    """distances.py:1419-1426: sqrt(1 - 2^-d)."""
+    return np.sqrt(1.0 - np.power(2.0, -np.asarray(d).astype(np.float64)))
+
+
+# correct_alternative_jaccard (distances.py:329-336) is the same map as correct_alternative_cosine
+correct_alternative_jaccard = correct_alternative_cosine
 
 # name -> (kernel metric id, device-side correction, host-side correction or None, angular trees)
 gpu_distances = {
@@ -25,6 +37,26 @@ gpu_distances = {
     "cosine": (NND_METRIC_ALT_COSINE, NND_CORRECT_NONE, correct_alternative_cosine, True),
     "dot": (NND_METRIC_ALT_DOT, NND_CORRECT_NONE, correct_alternative_cosine, True),
     "correlation": (NND_METRIC_CORRELATION, NND_CORRECT_NONE, None, True),
+    # SURVEY 8f-2; angular-tree membership from pynndescent_.py:1074-1085
+    "manhattan": (NND_METRIC_MANHATTAN, NND_CORRECT_NONE, None, False),
+    "taxicab": (NND_METRIC_MANHATTAN, NND_CORRECT_NONE, None, False),
+    "l1": (NND_METRIC_MANHATTAN, NND_CORRECT_NONE, None, False),
+    "chebyshev": (NND_METRIC_CHEBYSHEV, NND_CORRECT_NONE, None, False),
+    "linfinity": (NND_METRIC_CHEBYSHEV, NND_CORRECT_NONE, None, False),
+    "linfty": (NND_METRIC_CHEBYSHEV, NND_CORRECT_NONE, None, False),
+    "linf": (NND_METRIC_CHEBYSHEV, NND_CORRECT_NONE, None, False),
+    "canberra": (NND_METRIC_CANBERRA, NND_CORRECT_NONE, None, False),
+    "hamming": (NND_METRIC_HAMMING, NND_CORRECT_NONE, None, True),
+    "jaccard": (NND_METRIC_ALT_JACCARD, NND_CORRECT_NONE, correct_alternative_jaccard, True),
+    "dice": (NND_METRIC_DICE, NND_CORRECT_NONE, None, True),
+    "matching": (NND_METRIC_MATCHING, NND_CORRECT_NONE, None, False),
+    "kulsinski": (NND_METRIC_KULSINSKI, NND_CORRECT_NONE, None, False),
+    "rogerstanimoto": (NND_METRIC_ROGERSTANIMOTO, NND_CORRECT_NONE, None, False),
+    "sokalmichener": (NND_METRIC_ROGERSTANIMOTO, NND_CORRECT_NONE, None, False),
+    "russellrao": (NND_METRIC_RUSSELLRAO, NND_CORRECT_NONE, None, False),
+    "sokalsneath": (NND_METRIC_SOKALSNEATH, NND_CORRECT_NONE, None, False),
+    "yule": (NND_METRIC_YULE, NND_CORRECT_NONE, None, False),
+    "hellinger": (NND_METRIC_ALT_HELLINGER, NND_CORRECT_NONE, correct_alternative_hellinger, True),
 }
 
 # every key of the reference's named_distances (distances.py:2103-2162)

@@ -15,7 +15,25 @@ GOLDEN_CASES = {
     "latent_cosine_2k24": "cosine",
     "latent_corr_1500x20": "correlation",
     "latent_dot_1500x20": "dot",
+    # SURVEY 8f-2 metrics (tests/golden/make_golden_metrics.py): one case per accumulation class
+    "latent_manhattan_1500x20": "manhattan",
+    "latent_chebyshev_1200x12": "chebyshev",
+    "binary_jaccard_1200x40": "jaccard",
+    "cat_hamming_1200x30": "hamming",
+    "nonneg_hellinger_1200x24": "hellinger",
 }
+
+# Goldens whose RP forest cannot be re-derived bit-exactly by ANY independent implementation: integer / binary
+# data under angular trees puts many points exactly on the hyperplane (margin == 0 up to the reference's own
+# fastmath rounding noise, rp_trees.py:126-131), so the coin flips -- and with them the whole rng stream -- depend
+# on LLVM's summation order.  For these the parity tests start from the reference's leaf_array.
+FOREST_FROM_REFERENCE = ("binary_jaccard_1200x40", "cat_hamming_1200x30")
+
+# name -> input matrix key in tests/golden/kat_metrics.npz (pairwise KATs of the reference's numba functions)
+METRIC_KATS = {"manhattan": "real_A", "chebyshev": "real_A", "canberra": "real_A", "hamming": "cat_A",
+               "jaccard": "bin_A", "dice": "bin_A", "matching": "bin_A", "kulsinski": "bin_A", "rogerstanimoto": "bin_A",
+               "sokalmichener": "bin_A", "russellrao": "bin_A", "sokalsneath": "bin_A", "yule": "bin_A",
+               "hellinger": "nonneg_A"}
 
 
 def pytest_configure(config):
@@ -32,6 +50,26 @@ def latent(n, d, seed=0, latent_dim=16):
     Z = rs.standard_normal((n, latent_dim)).astype(np.float32)
     A = rs.standard_normal((latent_dim, d)).astype(np.float32) / np.sqrt(latent_dim)
     return (Z @ A + 0.05 * rs.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
+
+
+# input domains of the SURVEY 8f-2 metrics (same generators as tests/golden/make_golden_metrics.py)
+def binary_data(n, d, seed):
+    return (latent(n, d, seed) > 0.35).astype(np.float32)
+
+
+def categorical_data(n, d, seed):
+    return np.clip(np.round(latent(n, d, seed) * 1.2), -2, 2).astype(np.float32)
+
+
+def nonneg_data(n, d, seed):
+    X = np.abs(latent(n, d, seed)).astype(np.float32)
+    X[X < 0.15] = 0.0
+    return X
+
+
+def metric_data(metric, n, d, seed):
+    kind = METRIC_KATS.get(metric, "real_A")
+    return {"real_A": latent, "cat_A": categorical_data, "bin_A": binary_data, "nonneg_A": nonneg_data}[kind](n, d, seed)
 
 
 @pytest.fixture(scope="session")

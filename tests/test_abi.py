@@ -39,8 +39,15 @@ def test_metric_registry_matches_reference_names():
     assert dist.resolve("cosine")[3] is True
     with pytest.raises(ValueError, match="neither callable, nor a recognised string"):
         dist.resolve("no-such-metric")
+    # SURVEY 8f-2 metrics: ids, aliases, angular-tree membership (pynndescent_.py:1074-1085), corrections
+    assert dist.resolve("manhattan")[0] == dist.resolve("l1")[0] == dist.resolve("taxicab")[0] == dist.NND_METRIC_MANHATTAN
+    assert dist.resolve("linf")[0] == dist.NND_METRIC_CHEBYSHEV and dist.resolve("sokalmichener")[0] == dist.NND_METRIC_ROGERSTANIMOTO
+    assert [dist.resolve(m)[3] for m in ("jaccard", "dice", "hellinger", "hamming", "manhattan", "yule")] == [True] * 4 + [False] * 2
+    assert dist.resolve("jaccard")[2] is not None and dist.resolve("hellinger")[2] is not None and dist.resolve("dice")[2] is None
     with pytest.raises(NotImplementedError):
-        dist.resolve("manhattan")
+        dist.resolve("minkowski")          # needs metric_kwds
+    with pytest.raises(NotImplementedError):
+        dist.resolve("bit_jaccard")
     with pytest.raises(NotImplementedError):
         dist.resolve(lambda a, b: 0.0)
 

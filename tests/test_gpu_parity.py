@@ -8,11 +8,19 @@ the oracle (same defined summation order) and within 1e-5 relative of the refere
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, latent, load_golden
+from conftest import GOLDEN_CASES, METRIC_KATS, latent, load_golden, metric_data
 
 pytestmark = pytest.mark.gpu
 
-METRIC_ID = {"euclidean": 0, "sqeuclidean": 0, "cosine": 1, "dot": 2, "correlation": 3}
+
+class _MetricIds(dict):
+    """metric name -> C enum through the product's own registry (pynndescent_b200.distances.resolve)."""
+    def __missing__(self, name):
+        from pynndescent_b200 import distances
+        return distances.resolve(name)[0]
+
+
+METRIC_ID = _MetricIds()
 
 
 @pytest.fixture(scope="module")
@@ -90,6 +98,54 @@ def test_distance_kat_vs_reference(torch_cuda):
         big = R > 1e30
         assert np.array_equal(big, got > 1e30)
         np.testing.assert_allclose(got[~big], R[~big], rtol=1e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------ SURVEY 8f-2 metrics
+@pytest.mark.parametrize("metric", list(METRIC_KATS))
+def test_more_metrics_pair_distances(torch_cuda, oracle, metric):
+    """nnd_pair_distances for every added metric: bit-exact vs the oracle on domain data of three widths, and vs the
+    reference's own numba functions on the KAT matrix (exact for the integer-valued / max / f64-summed ones)."""
+    for d in (5, 37, 130):
+        X = metric_data(metric, 64, d, d)
+        X[5] = 0.0; X[6] = X[7]
+        eng, Xh = _engine(X, metric, 4)
+        rs = np.random.RandomState(d)
+        a = rs.randint(0, 64, 400).astype(np.int32); b = rs.randint(0, 64, 400).astype(np.int32)
+        got = eng.pair_distances(a, b)
+        want = np.array([oracle.dist(metric, Xh[i], Xh[j]) for i, j in zip(a, b)], np.float32)
+        assert np.array_equal(got, want, equal_nan=True), metric
+    g = load_golden("kat_metrics")
+    A = g[METRIC_KATS[metric]]
+    ii, jj = np.meshgrid(np.arange(24), np.arange(24), indexing="ij")
+    eng, _ = _engine(A, metric, 4)
+    got = eng.pair_distances(ii.ravel(), jj.ravel()).reshape(24, 24)
+    R = g[f"dist_{metric}"]
+    special = ~np.isfinite(R) | (R > 1e30)
+    assert np.array_equal(special, ~np.isfinite(got) | (got > 1e30))
+    if metric in ("jaccard", "hellinger", "canberra"):
+        np.testing.assert_allclose(got[~special], R[~special], rtol=1e-5, atol=2e-6)
+    else:
+        assert np.array_equal(got, R)
+
+
+@pytest.mark.parametrize("metric,n,d,k,seed", [("manhattan", 3000, 20, 10, 3), ("chebyshev", 2000, 12, 10, 4),
+                                               ("canberra", 2000, 16, 8, 5), ("hamming", 2000, 30, 10, 6),
+                                               ("jaccard", 2500, 40, 10, 7), ("dice", 1500, 40, 10, 8),
+                                               ("yule", 1500, 33, 6, 9), ("russellrao", 1200, 40, 10, 10),
+                                               ("hellinger", 2000, 24, 10, 11), ("kulsinski", 1200, 130, 12, 12)])
+def test_more_metrics_full_build_bit_exact_vs_oracle(torch_cuda, oracle, metric, n, d, k, seed):
+    """Forest (euclidean or angular per pynndescent_.py:1074-1085) + leaf init + descent under the added metrics ==
+    the oracle's level-scheme build, indices and distances bit for bit -- binary / categorical data makes almost every
+    comparison a tie, so this also pins the push ORDER."""
+    from pynndescent_b200 import NNDescent
+    X = metric_data(metric, n, d, seed)
+    idx = NNDescent(X, metric, n_neighbors=k, random_state=seed)
+    gi, gd = idx.neighbor_graph
+    o = oracle.OracleNNDescent(X, metric, n_neighbors=k, random_state=seed, n_threads=8, forest="level")
+    oi, od = o.neighbor_graph
+    assert idx.c_hist == [int(c) for c in o.c_hist[: o.n_iters_run]]
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(gd, od, equal_nan=True)
 
 
 # ------------------------------------------------------------------ stage-injected parity vs the reference

@@ -95,3 +95,25 @@ def test_build_prepare_query_end_to_end(oracle):
     true = np.argsort(((Q[:, None, :].astype(np.float64) - X[None, :, :]) ** 2).sum(-1), 1)[:, :10]
     rec = np.mean([len(np.intersect1d(true[i], qi[i])) / 10 for i in range(len(Q))])
     assert rec >= 0.90, rec
+
+
+@pytest.mark.parametrize("metric,n,d,k", [("manhattan", 4000, 20, 12), ("jaccard", 3000, 40, 10), ("hellinger", 3000, 24, 10)])
+def test_more_metrics_build_prepare_query(oracle, metric, n, d, k):
+    """SURVEY 8f-2 metrics through prepare() and query(): GPU structures and answers == the oracle's on the same graph."""
+    from pynndescent_b200 import NNDescent
+    from conftest import metric_data
+    both = metric_data(metric, n + 150, d, 3)
+    X, Q = both[:n], both[n:]
+    idx = NNDescent(X, metric, n_neighbors=k, random_state=5)
+    qi, qd = idx.query(Q, k=8, epsilon=0.15)
+    gi, _ = idx.neighbor_graph
+    raw_d = idx._engine.heap_dist.cpu().numpy()
+    P = oracle.prepare(X, metric, gi, raw_d, k, idx.rng_state)
+    S = idx._search_structures
+    assert np.array_equal(S["indptr"], P["indptr"]) and np.array_equal(S["indices"], P["indices"])
+    assert np.array_equal(S["vertex_order"], P["vertex_order"]) and np.array_equal(S["children"], P["children"])
+    hi, hd = oracle.search(P["data"], metric, P["indptr"], P["indices"], P["hyperplanes"], P["offsets"], P["children"],
+                           P["tree_indices"], Q, 8, 0.15, float(P["min_distance"]), k, idx.search_rng_state)
+    si, sd = oracle.deheap_sort(hi, hd)
+    assert np.array_equal(qi, P["vertex_order"][si])            # -1 (unfilled) wraps like the reference's fancy index
+    assert np.array_equal(qd, oracle.correction(metric, sd), equal_nan=True)

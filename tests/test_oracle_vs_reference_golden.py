@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, load_golden
+from conftest import FOREST_FROM_REFERENCE, GOLDEN_CASES, METRIC_KATS, load_golden
 
 
 def test_tau_rand_kat(oracle):
@@ -64,6 +64,26 @@ def test_distance_kat(oracle, metric):
     np.testing.assert_allclose(D[~big], R[~big], rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("metric", list(METRIC_KATS))
+def test_distance_kat_more_metrics(oracle, metric):
+    """SURVEY 8f-2 metrics vs the reference's own numba functions: the integer-valued ones (hamming, the binary
+    family) and max / f64-accumulated sums must be EXACT, the f32-accumulated log2 ones within 1e-5."""
+    g = load_golden("kat_metrics")
+    A = g[METRIC_KATS[metric]]
+    D = np.array([[oracle.dist(metric, A[i], A[j]) for j in range(24)] for i in range(24)], np.float32)
+    R = g[f"dist_{metric}"]
+    special = ~np.isfinite(R) | (R > 1e30)      # -log2(0) = inf (jaccard), FLOAT32_MAX sentinel (hellinger)
+    assert np.array_equal(special, ~np.isfinite(D) | (D > 1e30))
+    assert np.array_equal(R[special], D[special])
+    if metric in ("jaccard", "hellinger", "canberra"):
+        np.testing.assert_allclose(D[~special], R[~special], rtol=1e-5, atol=2e-6)
+    else:
+        assert np.array_equal(D, R)
+    if metric in ("jaccard", "hellinger"):
+        fin = np.isfinite(D) & (D < 1e30)
+        np.testing.assert_allclose(oracle.correction(metric, D[fin]), g[f"corr_{metric}"][fin], rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
 def test_end_to_end_matches_reference(oracle, name):
     """Full build replay: leaf_array, heaps after each init stage, candidates, per-iteration
@@ -71,8 +91,9 @@ def test_end_to_end_matches_reference(oracle, name):
     distances rtol 1e-5)."""
     G = load_golden(name)
     metric = GOLDEN_CASES[name]
+    inject = G["leaf_array"] if name in FOREST_FROM_REFERENCE else None      # see conftest.FOREST_FROM_REFERENCE
     o = oracle.OracleNNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_threads=int(G["T"]),
-                               keep_stages=True)
+                               keep_stages=True, leaf_array=inject)
     assert np.array_equal(o.leaf_array, G["leaf_array"])
     assert np.array_equal(o.heap_after_leaf[0], G["leaf_heap_idx"])
     assert np.array_equal(o.heap_after_leaf[2], G["leaf_heap_flag"])
