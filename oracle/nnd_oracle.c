@@ -483,6 +483,20 @@ ORC_API void orc_init_rp_tree(const float *X, int64_t N, int d, int metric, int3
     free(lists); free(caps); free(counts); free(thr);
 }
 
+/* utils.py:836-860 initalize_heap_from_graph_indices(_and_distances): warm start from a user-supplied graph
+ * (pynndescent_.py:1225-1242).  Row i receives, in column order, a flagged checked push of every j >= 0 with
+ * d = metric(data[i], data[j]) -- or the caller's init_dist[i, idx] verbatim when given.                      */
+ORC_API void orc_init_from_graph(const float *X, int64_t N, int d, int metric, int32_t *ind, float *dist, uint8_t *flg,
+                                 int k, const int32_t *graph, int w, const float *init_dist) {
+    for (int64_t i = 0; i < N; ++i)
+        for (int c = 0; c < w; ++c) {
+            int32_t j = graph[i * w + c];
+            if (j < 0) continue;
+            float dd = init_dist ? init_dist[i * w + c] : dist_fn(metric, X + i * d, X + (int64_t)j * d, d);
+            heap_push(dist + i * k, ind + i * k, flg + i * k, k, dd, j, 1, 1);
+        }
+}
+
 /* pynndescent_.py:188-203 init_random (serial; advances rng_state) */
 ORC_API void orc_init_random(const float *X, int64_t N, int d, int metric, int32_t *ind, float *dist, uint8_t *flg,
                              int k, int64_t *rng_state) {

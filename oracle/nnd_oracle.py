@@ -67,6 +67,8 @@ def lib():
     L.orc_init_rp_tree.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i32p, C.c_int64,
                                    C.c_int]
     L.orc_init_random.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i64p]
+    L.orc_init_from_graph.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i32p, C.c_int,
+                                      C.c_void_p]
     L.orc_make_forest.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_make_forest.restype = C.c_void_p
     L.orc_forest_free.argtypes = [C.c_void_p]
@@ -140,6 +142,14 @@ def init_rp_tree(X, metric, heap, leaf_array):
 def init_random(X, metric, heap, rng_state):
     lib().orc_init_random(X, X.shape[0], X.shape[1], METRIC_IDS[metric], heap[0], heap[1], heap[2], heap[0].shape[1],
                           rng_state)
+
+
+def init_from_graph(X, metric, heap, init_graph, init_dist=None):
+    """utils.py:836-860 warm start (distances from `metric`, or the caller's init_dist pushed verbatim)."""
+    g = np.ascontiguousarray(init_graph, np.int32)
+    dd = None if init_dist is None else np.ascontiguousarray(init_dist, np.float32)
+    lib().orc_init_from_graph(X, X.shape[0], X.shape[1], METRIC_IDS[metric], heap[0], heap[1], heap[2], heap[0].shape[1],
+                              g, g.shape[1], None if dd is None else dd.ctypes.data_as(C.c_void_p))
 
 
 def new_build_candidates(heap, max_candidates, rng_state, n_threads):
@@ -267,7 +277,7 @@ class OracleNNDescent:
 
     def __init__(self, data, metric="euclidean", n_neighbors=30, n_trees=None, leaf_size=None, random_state=None,
                  max_candidates=None, n_iters=None, delta=0.001, tree_init=True, max_rptree_depth=200, n_threads=8,
-                 forest="dfs", leaf_array=None, keep_stages=False, block_size=16384):
+                 forest="dfs", leaf_array=None, keep_stages=False, block_size=16384, init_graph=None, init_dist=None):
         from sklearn.utils import check_random_state
         data = np.ascontiguousarray(data, np.float32)
         n = data.shape[0]
@@ -295,11 +305,19 @@ class OracleNNDescent:
         C_ = min(60, n_neighbors) if max_candidates is None else max_candidates
         self.max_candidates = C_
         heap = make_heap(n, n_neighbors)
-        if tree_init:
+        if init_graph is not None:
+            # pynndescent_.py:1225-1242 + nn_descent :339-350: the supplied graph REPLACES leaf init and init_random
+            if np.shape(init_graph)[0] != n:
+                raise ValueError("Init graph size does not match dataset size!")
+            if init_dist is not None and np.shape(init_graph) != np.shape(init_dist):
+                raise ValueError("The shapes of init graph and init distances do not match!")
+            init_from_graph(data, metric, heap, init_graph, init_dist)
+        elif tree_init:
             init_rp_tree(data, metric, heap, self.leaf_array)
         if keep_stages:
             self.heap_after_leaf = tuple(a.copy() for a in heap)
-        init_random(data, metric, heap, self.rng_state)
+        if init_graph is None:
+            init_random(data, metric, heap, self.rng_state)
         if keep_stages:
             self.heap_after_init = tuple(a.copy() for a in heap)
             self.rng_state_after_init = self.rng_state.copy()

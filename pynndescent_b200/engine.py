@@ -167,6 +167,42 @@ class Engine:
         check(lib.nnd_init_random(self._ctx, C.byref(self.problem()), st, _ptr(ws), ws.numel(), self._st()))
         rng_state[:] = np.array(list(st), np.int64)
 
+    def init_from_graph(self, init_graph, init_dist=None, push_capacity=None):
+        """Warm start (pynndescent_.py:1225-1242, utils.py:836-860): row i receives, in column order, a flagged checked
+        push of every init_graph[i, c] >= 0 with d = metric(data[i], data[j]) (nnd_pair_distances) or init_dist[i, c]
+        verbatim.  The ordered replay is nnd_apply_records with the column position as emission sequence."""
+        dev = self.device
+        g = torch.from_numpy(np.ascontiguousarray(init_graph, np.int32)).to(dev)
+        N, w = g.shape
+        if int(g.max()) >= self.N:
+            raise ValueError("init_graph refers to a point outside the dataset")
+        cols = g.reshape(-1)
+        valid = cols >= 0
+        a = torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(w)[valid].contiguous()
+        b = cols[valid].contiguous()
+        n = int(a.numel())
+        if n == 0:
+            return 0
+        if init_dist is None:
+            d = torch.empty(n, dtype=torch.float32, device=dev)
+            check(lib.nnd_pair_distances(self._ctx, C.byref(self.problem()), _ptr(a), _ptr(b), n, _ptr(d), self._st()))
+        else:
+            d = torch.from_numpy(np.ascontiguousarray(init_dist, np.float32)).to(dev).reshape(-1)[valid].contiguous()
+        seq = torch.arange(N * w, device=dev, dtype=torch.int64)[valid].contiguous()
+        rec = torch.zeros((n, 6), dtype=torch.int32, device=dev)          # {tgt, oth, d, pad, seq lo, seq hi} = 24 B
+        rec[:, 0] = a; rec[:, 1] = b; rec[:, 2] = d.view(torch.int32); rec[:, 4:6] = seq.view(torch.int32).view(n, 2)
+        cap = push_capacity or self.default_push_capacity()
+        accepted = 0
+        if n <= cap:
+            accepted = self.apply_records(1, cap, rec.view(torch.uint8).reshape(-1), n)
+        else:                                   # records are grouped by target row: cut at row boundaries
+            rows_per = max(1, cap // w)
+            for r0 in range(0, N, rows_per):
+                m = (a >= r0) & (a < r0 + rows_per)
+                sub = rec[m].contiguous()
+                accepted += self.apply_records(1, cap, sub.view(torch.uint8).reshape(-1), sub.shape[0])
+        return accepted
+
     def build_candidates(self, max_candidates, rng_state, n_threads, tables_valid=False):
         nb = C.c_size_t()
         check(lib.nnd_cand_workspace_bytes(self.N, self.k, max_candidates, n_threads, C.byref(nb)))
@@ -208,7 +244,8 @@ class Engine:
         return self.heap_idx, out
 
     def build(self, rng_state, tree_rng_states, leaf_size, angular, max_candidates, n_threads, n_iters, delta,
-              correction, max_depth=200, push_capacity=None, leaf_array=None, timings=None):
+              correction, max_depth=200, push_capacity=None, leaf_array=None, timings=None, init_graph=None,
+              init_dist=None):
         """The whole seam-1 + seam-2 pipeline on device-resident data (pynndescent_.py:1118-1260):
         forest -> leaf init -> init_random -> nn_descent_internal -> deheap_sort(+correction).
         Returns (idx tensor, dist tensor, iters, c_hist, stats).  rng_state is advanced in place."""
@@ -223,6 +260,16 @@ class Engine:
                 self.stream.synchronize()
                 t1 = time.perf_counter(); timings[name] = timings.get(name, 0.0) + (t1 - t0); t0 = t1
         self.make_heap()
+        if init_graph is not None:
+            # nn_descent :339-350: a supplied graph replaces BOTH the leaf init and init_random
+            self.workspace(max(1, max_candidates), n_threads, cap)
+            self.init_from_graph(init_graph, init_dist, cap)
+            lap("init_graph")
+            iters, c_hist, stats = self.descent(max_candidates, rng_state, n_threads, n_iters, delta, cap)
+            lap("descent")
+            idx_t, dist_t = self.deheap_sort(correction)
+            lap("deheap_sort")
+            return idx_t, dist_t, iters, c_hist, stats
         if leaf_array is not None:
             self.leaf_init_from_array(leaf_array, cap)
         elif tree_rng_states is not None and len(tree_rng_states) > 0:

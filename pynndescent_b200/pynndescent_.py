@@ -66,8 +66,13 @@ class NNDescent:
             raise NotImplementedError("metric_kwds are not supported by the GPU metrics")
         if quantization is not None or bit_metric:
             raise NotImplementedError("quantized / bit metrics are outside the sm_100a hot path")
-        if init_graph is not None or init_dist is not None:
-            raise NotImplementedError("init_graph warm start is a 'next' row (SURVEY.md 8f-4)")
+        if init_graph is not None:                                                   # pynndescent_.py:1228-1236
+            if np.shape(init_graph)[0] != data.shape[0]:
+                raise ValueError("Init graph size does not match dataset size!")
+            if init_dist is not None and np.shape(init_graph) != np.shape(init_dist):
+                raise ValueError("The shapes of init graph and init distances do not match!")
+            if sharded:
+                raise NotImplementedError("init_graph with the sharded build")
         if n_trees is None:
             n_trees = max(3, min(12, int(round(2.0 * np.log10(data.shape[0])))))      # pynndescent_.py:1009-1010
         if n_iters is None:
@@ -142,7 +147,8 @@ class NNDescent:
         else:
             idx_t, dist_t, iters, c_hist, stats = eng.build(
                 self.rng_state, tree_states, leaf_size, angular, eff_C, T, n_iters, delta, dev_correction,
-                max_depth=max_rptree_depth, push_capacity=push_capacity, leaf_array=leaf_array, timings=self.timings)
+                max_depth=max_rptree_depth, push_capacity=push_capacity, leaf_array=leaf_array, timings=self.timings,
+                init_graph=init_graph, init_dist=init_dist if init_graph is not None else None)
         if verbose:
             for it in range(iters):
                 print("\t", it + 1, " / ", n_iters)

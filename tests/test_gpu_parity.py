@@ -344,3 +344,27 @@ def test_nan_input_raises_like_check_array(torch_cuda):
     X[17, 3] = np.nan
     with pytest.raises(ValueError, match="NaN"):
         NNDescent(X, "euclidean", n_neighbors=5, random_state=0)
+
+
+@pytest.mark.parametrize("case", ["rand", "knn", "knn_dist"])
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_warm_start_init_graph(torch_cuda, oracle, case, metric):
+    """init_graph / init_dist (pynndescent_.py:1225-1242): nnd_pair_distances + ordered nnd_apply_records build the start
+    heap; the final graph equals the reference's (golden) and the oracle's bit for bit; tiny push capacity -> same."""
+    from pynndescent_b200 import NNDescent
+    G = load_golden("warm_start_1500x16")
+    kw = {"rand": dict(init_graph=G["g_rand"]), "knn": dict(init_graph=G["g_knn"]),
+          "knn_dist": dict(init_graph=G["g_knn"], init_dist=G["d_knn"])}[case]
+    idx = NNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_jobs=int(G["T"]), **kw)
+    gi, gd = idx.neighbor_graph
+    assert np.array_equal(gi, G[f"{case}_{metric}_idx"])
+    np.testing.assert_allclose(gd, G[f"{case}_{metric}_dist"], rtol=1e-5, atol=1e-6)
+    o = oracle.OracleNNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_threads=int(G["T"]), **kw)
+    oi, od = o.neighbor_graph
+    assert idx.c_hist == [int(c) for c in o.c_hist[: o.n_iters_run]]
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    idx2 = NNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_jobs=int(G["T"]),
+                     push_capacity=1 << 13, **kw)
+    assert np.array_equal(idx2.neighbor_graph[0], gi)
+    with pytest.raises(ValueError, match="Init graph size does not match dataset size!"):
+        NNDescent(G["X"], metric, n_neighbors=10, random_state=1, init_graph=G["g_knn"][:-1])

@@ -140,3 +140,21 @@ def test_query_walk_matches_reference(oracle, name):
     si, sd = oracle.deheap_sort(hi, hd)
     assert np.array_equal(G["vertex_order"][si], G["out_idx"])
     np.testing.assert_allclose(oracle.correction(metric, sd), G["out_dist"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["rand", "knn", "knn_dist"])
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_warm_start_matches_reference(oracle, case, metric):
+    """init_graph / init_dist (pynndescent_.py:1225-1242, utils.py:836-860): the supplied graph replaces leaf init AND
+    init_random; init_dist is pushed verbatim.  Final graph identical to the reference's (tests/golden/make_golden_warm.py)."""
+    G = load_golden("warm_start_1500x16")
+    kw = {"rand": dict(init_graph=G["g_rand"]), "knn": dict(init_graph=G["g_knn"]),
+          "knn_dist": dict(init_graph=G["g_knn"], init_dist=G["d_knn"])}[case]
+    o = oracle.OracleNNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_threads=int(G["T"]), **kw)
+    gi, gd = o.neighbor_graph
+    assert np.array_equal(gi, G[f"{case}_{metric}_idx"])
+    np.testing.assert_allclose(gd, G[f"{case}_{metric}_dist"], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError, match="Init graph size does not match dataset size!"):
+        oracle.OracleNNDescent(G["X"], metric, n_neighbors=10, random_state=1, init_graph=G["g_knn"][:-1])
+    with pytest.raises(ValueError, match="shapes of init graph and init distances do not match"):
+        oracle.OracleNNDescent(G["X"], metric, n_neighbors=10, random_state=1, init_graph=G["g_knn"], init_dist=G["d_knn"][:, :-1])
