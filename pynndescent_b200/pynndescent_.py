@@ -197,6 +197,16 @@ class NNDescent:
                                           self.search_rng_state if search_rng_state is None else search_rng_state)
         return self
 
+    def reference_state(self):
+        """The reference's pickle-state dict (pynndescent_.py:1306-1320) for this index; see persistence.py."""
+        from .persistence import reference_state
+        return reference_state(self)
+
+    def save_for_reference(self, file):
+        """Pickle this index so that a stock pynndescent installation can `pickle.load` and query it on the CPU."""
+        from .persistence import dump_reference_pickle
+        dump_reference_pickle(self, file)
+
     def query(self, query_data, k=10, epsilon=0.1):
         """pynndescent_.py:2275-2379."""
         self.prepare()
