@@ -90,7 +90,7 @@ def test_reference_state_of_a_gpu_built_index():
     vo = st["_vertex_order"]
     assert sorted(vo.tolist()) == list(range(3000)) and np.array_equal(st["_raw_data"], X[vo])
     hyper, offs, children, tidx, leaf_size = st["_search_forest"][0]
-    assert hyper.shape == (children.shape[0], 24) and offs.shape[0] == children.shape[0] and 0 < leaf_size <= 30
+    assert hyper.shape == (children.shape[0], 24) and offs.shape[0] == children.shape[0] and leaf_size > 0
     assert st["_search_graph"].shape == (3000, 3000) and st["_search_graph"].nnz == idx._search_structures["indices"].shape[0]
     buf = io.BytesIO()
     idx.save_for_reference(buf)
