@@ -84,7 +84,8 @@ typedef struct {
     int64_t N;
     int32_t d, ld;
     int32_t metric;  /* NND_METRIC_*                                                      */
-    const void *aux; /* from nnd_metric_prepare: cosine f32 norm2[N]; correlation f64 (mu,nrm2)[N] */
+    const void *aux; /* from nnd_metric_prepare: cosine f32 norm2[N]; correlation f64 (mu,nrm2)[N];
+                        binary family f32 nnz[N]; hellinger f32 l1[N]; nothing for the other metrics   */
     int32_t k;       /* n_neighbors                                                        */
     int32_t *heap_idx;  /* [N,k]  utils.py:130-158 make_heap layout                        */
     float *heap_dist;   /* [N,k]                                                           */
@@ -172,7 +173,10 @@ NND_API int nnd_join_emit_round(nnd_ctx *ctx, const nnd_problem *P, int32_t C, i
 /* group them by owner process (owner = target / owner_block) into 24-byte records {tgt i32, oth i32, d f32, pad, seq u64} */
 NND_API int nnd_push_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int64_t push_capacity, void *ws, size_t ws_bytes,
                             int64_t n_pushed, int64_t owner_block, int32_t R, void *out, int64_t *counts_host, void *stream);
-/* apply received records (any order) to the local heap; c_host = accepted pushes */
+/* apply received records (any order) to the heap rows of this process's row range (nnd_set_row_range; all rows by
+ * default): counting sort by target, then checked_flagged_heap_push (utils.py:471-533) replayed per row in ascending
+ * `seq`; c_host = accepted pushes.  A record outside the row range is an error.  Also the warm start of
+ * pynndescent_.py:1225-1242 / utils.py:836-860 (records = the init graph's entries, seq = column position).          */
 NND_API int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const void *records, int64_t n,
                               int64_t push_capacity, void *ws, size_t ws_bytes, int64_t *c_host, void *stream);
 /* fused leaf join + apply on leaves [l0,l1) of one tree (disjoint point sets) */
@@ -224,7 +228,8 @@ NND_API int nnd_rng_stream(nnd_ctx *ctx, const int64_t *state_host, int64_t star
                    void *out, void *stream);
 /* state after `n` draws (host-side jump-ahead) */
 NND_API int nnd_rng_advance_host(nnd_ctx *ctx, int64_t *state_host, int64_t n);
-/* pair distances in the canonical order: out[i] = dist(X[a[i]], X[b[i]]) */
+/* pair distances in the canonical order: out[i] = dist(X[a[i]], X[b[i]]) -- the metric plugin evaluated outside a join
+ * (distances.py named_distances / fast_distance_alternatives); used by the warm start and by the tests */
 NND_API int nnd_pair_distances(nnd_ctx *ctx, const nnd_problem *P, const int32_t *a, const int32_t *b, int64_t n, float *out,
                        void *stream);
 /* join-kernel profile, measured with CUDA events on the launching stream around every k_join
