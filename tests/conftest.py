@@ -52,6 +52,9 @@ def latent(n, d, seed=0, latent_dim=16):
     return (Z @ A + 0.05 * rs.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
 
 
+# query goldens (tests/golden/make_golden_query.py): the reference's prepared search structures + its query() answers
+QUERY_GOLDENS = ("query_euclid_3k32", "query_cosine_2k24", "query_manhattan_2k20", "query_jaccard_2k40", "query_hellinger_2k24")
+
 # input domains of the SURVEY 8f-2 metrics (same generators as tests/golden/make_golden_metrics.py)
 def binary_data(n, d, seed):
     return (latent(n, d, seed) > 0.35).astype(np.float32)

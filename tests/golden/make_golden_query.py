@@ -26,8 +26,8 @@ def latent(n, d, seed=0, latent_dim=16):
     return (Z @ A + 0.05 * rs.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
 
 
-def dump(name, metric, n, d, k_index, seed, nq, k_query, eps):
-    both = latent(n + nq, d, seed)
+def dump(name, metric, n, d, k_index, seed, nq, k_query, eps, data_fn=None):
+    both = (data_fn or latent)(n + nq, d, seed)
     X, Q = both[:n], both[n:]
     idx = pynndescent.NNDescent(X, metric, n_neighbors=k_index, random_state=seed)
     ng_idx, ng_dist = idx._neighbor_graph[0].copy(), idx._neighbor_graph[1].copy()   # raw (alternative) distances
@@ -58,6 +58,22 @@ def dump(name, metric, n, d, k_index, seed, nq, k_query, eps):
     print(name, "saved: graph nnz", out["indices"].shape[0], "tree nodes", out["children"].shape[0])
 
 
+def binary(n, d, seed):
+    return (latent(n, d, seed) > 0.35).astype(np.float32)
+
+
+def nonneg(n, d, seed):
+    X = np.abs(latent(n, d, seed)).astype(np.float32)
+    X[X < 0.15] = 0.0
+    return X
+
+
 if __name__ == "__main__":
-    dump("query_euclid_3k32", "euclidean", 3000, 32, 15, 42, 200, 10, 0.1)
-    dump("query_cosine_2k24", "cosine", 2000, 24, 10, 7, 150, 10, 0.1)
+    which = sys.argv[1:] or ["base", "metrics"]
+    if "base" in which:
+        dump("query_euclid_3k32", "euclidean", 3000, 32, 15, 42, 200, 10, 0.1)
+        dump("query_cosine_2k24", "cosine", 2000, 24, 10, 7, 150, 10, 0.1)
+    if "metrics" in which:      # SURVEY 8f-2 metrics through prepare() and query()
+        dump("query_manhattan_2k20", "manhattan", 2000, 20, 12, 11, 150, 10, 0.1)
+        dump("query_jaccard_2k40", "jaccard", 2000, 40, 10, 12, 150, 10, 0.1, data_fn=binary)
+        dump("query_hellinger_2k24", "hellinger", 2000, 24, 10, 13, 150, 10, 0.1, data_fn=nonneg)

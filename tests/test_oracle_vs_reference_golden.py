@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import FOREST_FROM_REFERENCE, GOLDEN_CASES, METRIC_KATS, load_golden
+from conftest import FOREST_FROM_REFERENCE, GOLDEN_CASES, METRIC_KATS, QUERY_GOLDENS, load_golden
 
 
 def test_tau_rand_kat(oracle):
@@ -126,7 +126,22 @@ def test_stage_candidates_and_join(oracle, name):
     assert c2 == c and np.array_equal(heap2[0], heap[0]) and np.array_equal(heap2[1], heap[1])
 
 
-@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24"])
+@pytest.mark.parametrize("name", list(QUERY_GOLDENS))
+def test_prepare_matches_reference(oracle, name):
+    """_init_search_graph (pynndescent_.py:1333-1662) restated: from the reference's built graph (raw distances) and rng
+    state, the oracle's hub tree, diversified + degree-pruned search graph, leaf order and min_distance are the
+    reference's own arrays."""
+    G = load_golden(name)
+    P = oracle.prepare(G["X"], str(G["metric"]), G["ng_idx"], G["ng_dist"], int(G["n_neighbors"]), G["rng_before_prepare"].copy())
+    for key in ("indptr", "indices", "children", "tree_indices", "vertex_order"):
+        assert np.array_equal(P[key], G[key]), key
+    assert np.array_equal(P["data"], G["data"])
+    np.testing.assert_allclose(P["hyperplanes"], G["hyperplanes"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(P["offsets"], G["offsets"], rtol=1e-5, atol=1e-6)
+    assert np.float32(P["min_distance"]) == np.float32(G["min_distance"])
+
+
+@pytest.mark.parametrize("name", list(QUERY_GOLDENS))
 def test_query_walk_matches_reference(oracle, name):
     """Seam 3: orc_search on the reference's prepared structures reproduces the reference's raw result heaps
     (layout included) and its final query() answers."""
