@@ -157,6 +157,15 @@ NND_API int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int
                 int32_t n_iters, double delta, int64_t push_capacity, void *ws, size_t ws_bytes,
                 int32_t *iters_run_host, int64_t *c_hist_host, int64_t *stats_host, void *stream);
 
+/* ---- schedule of the local join (no reference counterpart: the numba path visits rows in ascending order per thread,
+ * utils.py:558-658).  `perm` = a permutation of 0..n-1 in DEVICE memory, kept alive by the caller until replaced
+ * (NULL / n = 0 restores ascending order).  Half-updates carry their emission sequence (row, pair slot, side), so the
+ * visiting order never changes a result; visiting rows in RP-tree leaf order keeps the rows gathered by concurrently
+ * running batches inside one neighbourhood (L2 hits instead of HBM reads).  Schedule switches read from the
+ * environment by nnd_create (all default off, none changes a result): NND_JOIN_PIPE, NND_PIPE_DK, NND_PIPE_STAGES,
+ * NND_PIPE_CTAS, NND_RANK_SCATTER (csrc/nnd_common.cuh).                                                            */
+NND_API int nnd_set_join_order(nnd_ctx *ctx, const int32_t *perm, int64_t n);
+
 /* ---- sharded build (one process per GPU) ----------------------------------------------
  * Every process holds X and the whole heap; it samples candidates and joins only rows [lo,hi), exchanges the
  * half-updates with the owners of their target rows and applies what it receives.                            */

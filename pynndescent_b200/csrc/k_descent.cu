@@ -21,8 +21,8 @@
 #include <vector>
 
 #include "nnd_common.cuh"
+#include "join_batch.cuh"
 
-#define TILE 4
 #define DK 128  // d-chunk staged per pass (floats)
 #define SD (DK + 4)  // padded smem row stride: consecutive rows shift by 4 banks
 
@@ -366,48 +366,35 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
 // (the sequential per-pair order is preserved because each thread walks the chunks in order).
 // Same arithmetic and the same emission keys as k_join.
 // =====================================================================================================
-#define JB_THREADS 128
-#define JB_TCAP 128      // tiles per batch
-#define JB_SCAP 176      // physical member slots per batch (2 buffers x 176 x 144 B -> 4 CTAs/SM)
-#define JB_MAXU 48       // units per batch (every unit weighs >= 4)
-#define JB_CMAX 60  // members scratch is sized for the largest C so that its offset does not depend on C
-struct JoinBatchParams {
-    const float *X; int64_t N; int ld; int metric; const void *aux; const float *thr;
-    const int32_t *act_unit; const uint32_t *act_info; const uint32_t *act_poff; const int32_t *members;
-    const int32_t *batch_first;
-    int64_t n_active, n_batches; int64_t batch_begin, batch_end; int slot_stride;
-    int32_t *out_tgt, *out_oth; float *out_d; uint32_t *out_pos; unsigned long long *out_seq;
-    uint32_t *tgt_count; unsigned long long *cursor; unsigned long long capacity; unsigned long long *stats; int *overflow;
-};
-
-__host__ __device__ __forceinline__ int jb_tiles(int nn, int m) {
-    int ntr = (nn + 3) >> 2, ntc = (m + 3) >> 2;
-    return ntr * ntc - ntr * (ntr - 1) / 2;
-}
 // prepass 1: per row -> active flag, physical slots, batching weight
+// `order` (nnd_set_join_order): position p of the scan visits row order[p]; every array written here and consumed by the
+// scans / k_jb_fill is indexed by POSITION, only the candidate lists are indexed by row
 __global__ void k_jb_count(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *flag, uint32_t *phys,
-                           uint32_t *wgt, uint32_t *info, int64_t lo, int64_t hi) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+                           uint32_t *wgt, uint32_t *info, int64_t lo, int64_t hi, const int32_t *order) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int64_t i = order ? (int64_t)order[p] : p;
     int nn = 0, no = 0;
     if (i >= lo && i < hi)
         for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
     int m = nn + no;
     uint32_t ph = nn > 0 ? (uint32_t)(((m + 3) >> 2) << 2) : 0u;
     uint32_t tw = nn > 0 ? (uint32_t)((jb_tiles(nn, m) * 3 + 1) >> 1) : 0u;
-    flag[i] = nn > 0;
-    phys[i] = ph;
-    wgt[i] = ph > tw ? ph : tw;
-    info[i] = (uint32_t)nn | ((uint32_t)m << 8);
+    flag[p] = nn > 0;
+    phys[p] = ph;
+    wgt[p] = ph > tw ? ph : tw;
+    info[p] = (uint32_t)nn | ((uint32_t)m << 8);
 }
 // prepass 2: compacted active-row list + member ids in the reference's order (new k asc, then old k asc; holes dropped)
 __global__ void k_jb_fill(const int32_t *newc, const int32_t *oldc, int C, int64_t N, const uint32_t *flag,
                           const uint32_t *pos, const uint32_t *poff, const uint32_t *woff, const uint32_t *info,
-                          int32_t *act_unit, uint32_t *act_info, uint32_t *act_poff, uint32_t *act_woff, int32_t *members) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N || !flag[i]) return;
-    uint32_t j = pos[i], o = poff[i];
-    act_unit[j] = (int32_t)i; act_info[j] = info[i]; act_poff[j] = o; act_woff[j] = woff[i];
+                          int32_t *act_unit, uint32_t *act_info, uint32_t *act_poff, uint32_t *act_woff, int32_t *members,
+                          const int32_t *order) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N || !flag[p]) return;
+    const int64_t i = order ? (int64_t)order[p] : p;
+    uint32_t j = pos[p], o = poff[p];
+    act_unit[j] = (int32_t)i; act_info[j] = info[p]; act_poff[j] = o; act_woff[j] = woff[p];
     int w = 0;
     for (int c = 0; c < C; ++c) { int32_t v = newc[i * C + c]; if (v >= 0) members[o + w++] = v; }
     for (int c = 0; c < C; ++c) { int32_t v = oldc[i * C + c]; if (v >= 0) members[o + w++] = v; }
@@ -597,7 +584,10 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
 #pragma unroll
             for (int sidx = 0; sidx < TILE * TILE; ++sidx) if (sidx == pr) r = acc[sidx];
             P.out_tgt[w] = tgt; P.out_oth[w] = oth; P.out_d[w] = r;
-            P.out_pos[w] = atomicAdd(&P.tgt_count[tgt], 1u);
+            // out_pos == nullptr (NND_RANK_SCATTER): k_scatter_rank takes the rank inside the target's segment, so this is
+            // a fire-and-forget reduction (RED) instead of an atomic whose result the store has to wait for
+            if (P.out_pos) P.out_pos[w] = atomicAdd(&P.tgt_count[tgt], 1u);
+            else atomicAdd(&P.tgt_count[tgt], 1u);
             P.out_seq[w] = (unit << 20) | ((unsigned long long)(a * P.slot_stride + b) << 1) | (unsigned long long)side;
             ++w;
         }
@@ -616,6 +606,17 @@ __global__ void k_scatter(const int32_t *tgt, const int32_t *oth, const float *d
     if (i >= n) return;
     Rec16 r; r.key = seq[i]; r.oth = oth[i]; r.d = dd[i];
     rec[(size_t)off[tgt[i]] + pos[i]] = r;
+}
+
+// NND_RANK_SCATTER: the join only counted its targets; the rank inside the target's segment is taken here, where every
+// thread has one independent record in flight (segment order is arbitrary either way: k_apply sorts by sequence)
+__global__ void k_scatter_rank(const int32_t *tgt, const int32_t *oth, const float *dd, const unsigned long long *seq,
+                               unsigned long long n, const uint32_t *off, uint32_t *rank, Rec16 *rec) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t t = tgt[i];
+    Rec16 r; r.key = seq[i]; r.oth = oth[i]; r.d = dd[i];
+    rec[(size_t)off[t] + atomicAdd(&rank[t], 1u)] = r;
 }
 
 // ------------------------------------------------------------------ apply
@@ -792,6 +793,7 @@ struct DescentWs {
     // batched local join prepass
     uint32_t *jb_flag, *jb_phys, *jb_wgt, *jb_info, *jb_pos, *jb_poff, *jb_woff, *act_info, *act_poff, *act_woff;
     int32_t *act_unit, *members, *batch_first;
+    char *jp_meta; size_t jp_meta_bytes;   // k_join_pipe batch descriptors of one routing round
 };
 
 size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T);
@@ -824,6 +826,15 @@ static int carve_descent_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, 
         W->batch_first = A.get<int32_t>((size_t)Nb * (size_t)(mw / psw + 1) + 8);
     }
     W->members = A.get<int32_t>((size_t)Nb * (2 * JB_CMAX + 4));
+    {   // descriptors of ONE routing round: a round holds at most cap / (JB_TCAP*16) batches (build_join_plan) and never more
+        // than there are weight windows
+        int Cc = C < 1 ? 1 : (C > JB_CMAX ? JB_CMAX : C);
+        int mp = ((2 * Cc + 3) >> 2) << 2, mt = (jb_tiles(Cc, 2 * Cc) * 3 + 1) >> 1, mw = mp > mt ? mp : mt;
+        int psw = JB_SCAP - mw; if (psw < 1) psw = 1;
+        int64_t windows = (int64_t)Nb * (mw / psw + 1) + 8, per_round = cap / ((int64_t)JB_TCAP * 16) + 1;
+        W->jp_meta_bytes = join_pipe_meta_bytes(windows < per_round ? windows : per_round);
+        W->jp_meta = A.get<char>(W->jp_meta_bytes);
+    }
     W->cand_bytes = nnd_cand_ws_bytes(N, k, C, T);
     W->cand_base = A.get<char>(W->cand_bytes);
     W->newc = A.get<int32_t>((size_t)Nb * C); W->oldc = A.get<int32_t>((size_t)Nb * C);
@@ -908,12 +919,19 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     NND_CUDA(cudaMemsetAsync(W.dev_scalars + 5, 0, sizeof(unsigned long long) * 2, st));
     J.stats = W.dev_scalars + 5;
     NND_CUDA(cudaEventRecord(ctx->ev0, st));
+    // schedule options (nnd_ctx): neither changes what is emitted, only how
+    const bool rank_scatter = JB && do_apply && ctx->opt_rank_scatter;
     if (JB) {
         JB->thr = W.thr; JB->batch_begin = u0; JB->batch_end = u1;
-        JB->out_tgt = W.l_tgt; JB->out_oth = W.l_oth; JB->out_d = W.l_d; JB->out_pos = W.l_pos; JB->out_seq = W.l_seq;
+        JB->out_tgt = W.l_tgt; JB->out_oth = W.l_oth; JB->out_d = W.l_d; JB->out_pos = rank_scatter ? nullptr : W.l_pos; JB->out_seq = W.l_seq;
         JB->tgt_count = W.cnt; JB->cursor = W.dev_scalars; JB->capacity = (unsigned long long)cap;
         JB->overflow = (int *)(W.dev_scalars + 4); JB->stats = W.dev_scalars + 5;
-        NND_TRY(launch_join_batch(ctx, *JB, st));
+        if (ctx->opt_join_pipe) {
+            JoinPipeOpts po; po.dk = ctx->opt_pipe_dk; po.stages = ctx->opt_pipe_stages; po.ctas_per_sm = ctx->opt_pipe_ctas;
+            NND_TRY(launch_join_pipe(ctx, *JB, W.jp_meta, W.jp_meta_bytes, po, st));
+        } else {
+            NND_TRY(launch_join_batch(ctx, *JB, st));
+        }
     } else {
         NND_TRY(launch_join(ctx, J, u1 - u0, st));
     }
@@ -936,7 +954,12 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     }
     if (h[0] == 0 || !do_apply) return NND_OK;
     NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, N, W.scan_tmp, st));  // offsets of power-of-two padded segments
-    k_scatter<<<(unsigned)cdiv((int64_t)h[0], 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_pos, W.l_seq, h[0], W.off, W.rec);
+    if (rank_scatter) {   // W.bound is only used by the unbatched plan
+        NND_CUDA(cudaMemsetAsync(W.bound, 0, sizeof(uint32_t) * (N + 1), st));
+        k_scatter_rank<<<(unsigned)cdiv((int64_t)h[0], 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_seq, h[0], W.off, W.bound, W.rec);
+    } else {
+        k_scatter<<<(unsigned)cdiv((int64_t)h[0], 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_pos, W.l_seq, h[0], W.off, W.rec);
+    }
     NND_LAUNCH(ctx);
     size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "apply: k=%d too large", P->k);
@@ -1123,12 +1146,13 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
         const int maxw_t = (jb_tiles(C, 2 * C) * 3 + 1) >> 1;
         const int maxw = maxphys > maxw_t ? maxphys : maxw_t;
         const uint32_t ps = (uint32_t)(JB_SCAP - maxw);                          // weight window per batch
-        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_wgt, W.jb_info, ctx->row_lo, ctx->row_hi); NND_LAUNCH(ctx);
+        const int32_t *order = (ctx->join_order && ctx->join_order_n == N) ? ctx->join_order : nullptr;
+        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_wgt, W.jb_info, ctx->row_lo, ctx->row_hi, order); NND_LAUNCH(ctx);
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_flag, W.jb_pos, N, W.scan_tmp, st));
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_phys, W.jb_poff, N, W.scan_tmp, st));
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_wgt, W.jb_woff, N, W.scan_tmp, st));
         k_jb_fill<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_pos, W.jb_poff, W.jb_woff, W.jb_info,
-                                                          W.act_unit, W.act_info, W.act_poff, W.act_woff, W.members);
+                                                          W.act_unit, W.act_info, W.act_poff, W.act_woff, W.members, order);
         NND_LAUNCH(ctx);
         uint32_t hh[2];
         NND_CUDA(cudaMemcpyAsync(&hh[0], W.jb_pos + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1212,7 +1236,7 @@ extern "C" int nnd_join_prepare(nnd_ctx *ctx, const nnd_problem *P, int32_t C, c
     NND_CHECK(carve_descent_ws(ws, ws_bytes, P->N, P->k, C, 1, push_capacity, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
               "nnd_join_prepare: workspace too small");
     NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long) * 16, st));
-    if (!ctx->plan) ctx->plan = new JoinPlan();
+    if (!ctx->plan) { ctx->plan = new JoinPlan(); ctx->plan_free = [](void *p) { delete (JoinPlan *)p; }; }
     JoinPlan &PL = *(JoinPlan *)ctx->plan;
     NND_TRY(build_join_plan(ctx, P, C, new_cand, old_cand, push_capacity, W, st, PL));
     *n_rounds_host = (int32_t)PL.rounds.size();

@@ -51,7 +51,16 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
     nnd_ctx *c = new nnd_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->launches = 0;
     memset(c->prof, 0, sizeof(c->prof));
-    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr;
+    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr; c->plan_free = nullptr;
+    {
+        auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
+        c->opt_join_pipe = env_int("NND_JOIN_PIPE", 0);
+        c->opt_pipe_dk = env_int("NND_PIPE_DK", 32);
+        c->opt_pipe_stages = env_int("NND_PIPE_STAGES", 4);
+        c->opt_pipe_ctas = env_int("NND_PIPE_CTAS", 0);
+        c->opt_rank_scatter = env_int("NND_RANK_SCATTER", 0);
+        c->join_order = nullptr; c->join_order_n = 0;
+    }
     NND_CUDA(cudaEventCreate(&c->ev0));
     NND_CUDA(cudaEventCreate(&c->ev1));
     size_t n = (size_t)3 * NND_JUMP_POW * 64;
@@ -64,6 +73,7 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
 }
 extern "C" int nnd_destroy(nnd_ctx *ctx) {
     if (!ctx) return NND_OK;
+    if (ctx->plan && ctx->plan_free) ctx->plan_free(ctx->plan);
     cudaFree(ctx->d_jump);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -74,6 +84,15 @@ extern "C" int nnd_destroy(nnd_ctx *ctx) {
 extern "C" int nnd_set_row_range(nnd_ctx *ctx, int64_t lo, int64_t hi) {
     NND_CHECK(ctx && lo >= 0 && hi >= lo, NND_ERR_INVALID, "nnd_set_row_range: bad range");
     ctx->row_lo = lo; ctx->row_hi = hi;
+    return NND_OK;
+}
+// Row visiting order of the batched local join (a permutation of 0..n-1 in device memory that must stay alive until it
+// is replaced; nullptr = ascending row id).  Half-updates carry their emission sequence (row, pair slot, side), so
+// the order in which rows are joined never changes a result -- it only decides which rows are gathered at about the
+// same time (RP-tree leaf order keeps the gathers of concurrently running batches inside one neighbourhood = L2 hits).
+extern "C" int nnd_set_join_order(nnd_ctx *ctx, const int32_t *perm, int64_t n) {
+    NND_CHECK(ctx && n >= 0 && (perm || n == 0), NND_ERR_INVALID, "nnd_set_join_order: bad args");
+    ctx->join_order = n > 0 ? perm : nullptr; ctx->join_order_n = n > 0 ? n : 0;
     return NND_OK;
 }
 extern "C" int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset) {

@@ -44,6 +44,12 @@ struct nnd_ctx {
     unsigned long long last_round_rows, last_round_pairs;
     int64_t row_lo, row_hi;   // sharded build: this process joins / samples candidates only for rows in [row_lo,row_hi)
     void *plan;               // JoinPlan of the sharded round API (k_descent.cu)
+    void (*plan_free)(void *);
+    // ---- schedule options (read from the environment by nnd_create; none of them changes any result)
+    int opt_join_pipe;        // NND_JOIN_PIPE=1: persistent warp-specialised local join (k_join_pipe.cu) instead of k_join_batch
+    int opt_pipe_dk, opt_pipe_stages, opt_pipe_ctas;   // NND_PIPE_DK (32|64), NND_PIPE_STAGES (2..6), NND_PIPE_CTAS (per SM, 0 = max)
+    int opt_rank_scatter;     // NND_RANK_SCATTER=1: joins count targets with fire-and-forget reductions, k_scatter_rank ranks
+    const int32_t *join_order; int64_t join_order_n;   // nnd_set_join_order: row visiting order of the batched local join
 };
 #define NND_JUMP_POW 44
 #define NND_LAUNCH(ctx) ((ctx)->launches++)

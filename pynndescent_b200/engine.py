@@ -13,6 +13,7 @@ of the reference so that tests can inject the reference's intermediates at any s
     deheap_sort()        utils.py:189-218
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -260,6 +261,7 @@ class Engine:
                 self.stream.synchronize()
                 t1 = time.perf_counter(); timings[name] = timings.get(name, 0.0) + (t1 - t0); t0 = t1
         self.make_heap()
+        self.set_join_order(None)
         if init_graph is not None:
             # nn_descent :339-350: a supplied graph replaces BOTH the leaf init and init_random
             self.workspace(max(1, max_candidates), n_threads, cap)
@@ -274,6 +276,9 @@ class Engine:
             self.leaf_init_from_array(leaf_array, cap)
         elif tree_rng_states is not None and len(tree_rng_states) > 0:
             lp, lo, n_leaves, max_leaf = self.forest(tree_rng_states, leaf_size, angular, max_depth)
+            if os.environ.get("NND_JOIN_ORDER", "") == "leaf":
+                # schedule only (results are order-independent, include/nnd_b200.h): join rows in the first tree's leaf order
+                self.set_join_order(lp[: self.N].clone())
             lap("forest")
             self.leaf_init(lp, lo, n_leaves, max_leaf, cap)
             del lp, lo
@@ -289,6 +294,11 @@ class Engine:
     # ------------------------------------------------------------------ sharded-build primitives (sharded.py)
     def set_row_range(self, lo, hi):
         check(lib.nnd_set_row_range(self._ctx, int(lo), int(hi)))
+
+    def set_join_order(self, perm):
+        """perm: int32 device tensor holding a permutation of 0..N-1 (kept alive here), or None for ascending rows."""
+        self._join_order = perm
+        check(lib.nnd_set_join_order(self._ctx, _ptr(perm), 0 if perm is None else int(perm.numel())))
 
     def join_prepare(self, newc, oldc, cap):
         C_ = newc.shape[1]
