@@ -497,6 +497,16 @@ ORC_API void orc_init_from_graph(const float *X, int64_t N, int d, int metric, i
         }
 }
 
+/* pynndescent_.py:207-214 init_from_neighbor_graph (update(), :2512-2515): row p of the OLD graph (n_rows <= rows of
+ * the heap) receives, in column order, an UNFLAGGED checked push of every entry -- invalidated entries are (-1, inf)
+ * and fall out at the `d >= root` test of the push itself, exactly as in the reference.                           */
+ORC_API void orc_init_from_neighbor_graph(int32_t *ind, float *dist, uint8_t *flg, int k, int64_t n_rows,
+                                          const int32_t *graph, const float *gdist, int w) {
+    for (int64_t p = 0; p < n_rows; ++p)
+        for (int c = 0; c < w; ++c)
+            heap_push(dist + p * k, ind + p * k, flg + p * k, k, gdist[p * w + c], graph[p * w + c], 0, 1);
+}
+
 /* pynndescent_.py:188-203 init_random (serial; advances rng_state) */
 ORC_API void orc_init_random(const float *X, int64_t N, int d, int metric, int32_t *ind, float *dist, uint8_t *flg,
                              int k, int64_t *rng_state) {

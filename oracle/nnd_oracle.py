@@ -69,6 +69,7 @@ def lib():
     L.orc_init_random.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i64p]
     L.orc_init_from_graph.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i32p, _f32p, _u8p, C.c_int, _i32p, C.c_int,
                                       C.c_void_p]
+    L.orc_init_from_neighbor_graph.argtypes = [_i32p, _f32p, _u8p, C.c_int, C.c_int64, _i32p, _f32p, C.c_int]
     L.orc_make_forest.argtypes = [_f32p, C.c_int64, C.c_int, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_make_forest.restype = C.c_void_p
     L.orc_forest_free.argtypes = [C.c_void_p]
@@ -150,6 +151,12 @@ def init_from_graph(X, metric, heap, init_graph, init_dist=None):
     dd = None if init_dist is None else np.ascontiguousarray(init_dist, np.float32)
     lib().orc_init_from_graph(X, X.shape[0], X.shape[1], METRIC_IDS[metric], heap[0], heap[1], heap[2], heap[0].shape[1],
                               g, g.shape[1], None if dd is None else dd.ctypes.data_as(C.c_void_p))
+
+
+def init_from_neighbor_graph(heap, indices, distances):
+    """pynndescent_.py:207-214 (update()): unflagged pushes of the old graph's rows into the first rows of `heap`."""
+    g = np.ascontiguousarray(indices, np.int32); dd = np.ascontiguousarray(distances, np.float32)
+    lib().orc_init_from_neighbor_graph(heap[0], heap[1], heap[2], heap[0].shape[1], g.shape[0], g, dd, g.shape[1])
 
 
 def new_build_candidates(heap, max_candidates, rng_state, n_threads):
@@ -287,6 +294,11 @@ class OracleNNDescent:
             n_iters = max(5, int(round(np.log2(n))))
         self.metric = metric
         self.n_neighbors = n_neighbors
+        self.random_state = random_state
+        self.n_trees = n_trees
+        self.n_trees_after_update = max(2, int(np.round(n_trees / 3)))                 # pynndescent_.py:1016
+        self.leaf_size, self.n_iters, self.delta, self.max_rptree_depth = leaf_size, n_iters, delta, max_rptree_depth
+        self.n_threads, self.forest_scheme, self.block_size = n_threads, forest, block_size
         rs = check_random_state(random_state)
         if metric == "dot":
             from sklearn.preprocessing import normalize  # pynndescent_.py:1101-1103
@@ -328,6 +340,52 @@ class OracleNNDescent:
         if keep_stages:
             self.heap_final = tuple(a.copy() for a in heap)
         deheap_sort(heap[0], heap[1])
+        self._neighbor_graph = (heap[0], heap[1])
+
+    def update(self, xs_fresh=None, xs_updated=None, updated_indices=None, leaf_array=None):
+        """pynndescent_.py:2381-2553 update() (dense): replace rows, append rows, invalidate the graph entries that
+        touch a replaced row, then forest (n_trees_after_update trees) -> init_from_neighbor_graph -> init_rp_tree ->
+        nn_descent_internal on the index's own (already advanced) rng_state.  `leaf_array` injects a forest."""
+        from sklearn.utils import check_random_state
+        rs = check_random_state(self.random_state)                                      # :2407-2410
+        rs.randint(INT32_MIN, INT32_MAX, 3)                                             # rng_state handed to make_forest (unused there)
+        if xs_updated is not None and updated_indices is None:
+            raise ValueError("If xs_updated are provided, updated_indices must also be provided!")
+        upd = [] if (xs_updated is None or updated_indices is None) else list(map(int, updated_indices))
+        data = self._raw_data.copy()
+        if upd:
+            xs_updated = np.ascontiguousarray(xs_updated, np.float32)
+            if len(upd) != xs_updated.shape[0]:
+                raise ValueError("Number of updated indices must match number of rows of xs_updated.")
+            for x, i in zip(xs_updated, upd):                                           # :2472-2473
+                data[i] = x
+        if xs_fresh is not None and len(xs_fresh):
+            data = np.vstack([data, np.ascontiguousarray(xs_fresh, np.float32)])        # :2474
+        data = np.ascontiguousarray(data, np.float32)
+        ns, ds = self._neighbor_graph[0].copy(), self._neighbor_graph[1].copy()
+        if upd:                                                                         # :2475-2488
+            changed = np.zeros(data.shape[0], bool); changed[upd] = True
+            hit = changed[np.where(ns >= 0, ns, 0)] & (ns >= 0)
+            hit[np.asarray(upd, np.int64)[np.asarray(upd) < ns.shape[0]], :] = True
+            ns[hit] = -1; ds[hit] = np.inf
+        self.n_trees = self.n_trees_after_update                                        # :2498
+        angular = self.metric in ANGULAR_METRICS
+        if leaf_array is not None:
+            self.leaf_array = np.ascontiguousarray(leaf_array, np.int32)
+        else:
+            self.leaf_array, self.tree_rng_states = make_forest(data, self.n_neighbors, self.n_trees, self.leaf_size, rs,
+                                                                angular, self.max_rptree_depth, self.forest_scheme)
+        n = data.shape[0]
+        heap = make_heap(n, self.n_neighbors)                                           # :2511
+        init_from_neighbor_graph(heap, ns, ds)                                          # :2512-2514
+        init_rp_tree(data, self.metric, heap, self.leaf_array)                          # :2515
+        self.c_hist = np.zeros(self.n_iters, np.int64)
+        self.n_iters_run = lib().orc_nn_descent_internal(data, n, data.shape[1], METRIC_IDS[self.metric], heap[0], heap[1],
+                                                         heap[2], self.n_neighbors, self.max_candidates, self.rng_state,
+                                                         self.n_threads, self.n_iters, self.delta, self.block_size,
+                                                         self.c_hist)                   # :2522-2535
+        deheap_sort(heap[0], heap[1])
+        self._raw_data = data
         self._neighbor_graph = (heap[0], heap[1])
 
     @property

@@ -118,6 +118,9 @@ class NNDescent:
             raise ValueError("n_jobs must be a positive thread count (or None / -1)")
         self.emulated_threads = T
         eff_C = min(60, n_neighbors) if max_candidates is None else max_candidates           # :1135-1138
+        self.n_trees_after_update = max(2, int(np.round(self.n_trees / 3)))                  # :1016
+        self._build_args = dict(metric_id=metric_id, dev_correction=dev_correction, eff_C=eff_C, device=device,
+                                push_capacity=push_capacity, sharded=bool(sharded))
 
         t0 = time.perf_counter()
         eng = Engine(data, metric_id, n_neighbors, device=device)
@@ -169,6 +172,91 @@ class NNDescent:
         if self._distance_correction is not None:
             return self._neighbor_graph[0].copy(), self._distance_correction(self._neighbor_graph[1])
         return self._neighbor_graph[0].copy(), self._neighbor_graph[1].copy()
+
+    def update(self, xs_fresh=None, xs_updated=None, updated_indices=None, leaf_array=None):
+        """pynndescent_.py:2381-2553 (dense): append `xs_fresh`, replace rows `updated_indices` by `xs_updated`, then
+        re-run the hot path from the old graph: every entry that touches a replaced row is invalidated (:2475-2488), a
+        forest of n_trees_after_update trees is grown on the new data (:2498-2509), the heap is seeded with the old
+        graph (init_from_neighbor_graph :207-214, unflagged pushes), refined by the leaf join (init_rp_tree) and by
+        nn_descent on the index's own rng_state (:2522-2535).  All of it runs on the kernels of the build path.
+
+        The old entries are re-pushed with their RAW distances.  The reference keeps those on the host; here they are
+        recomputed on the device from the (index, index) pairs -- the canonical summation order makes that bit-identical
+        to what the heap held -- because the host copy holds the corrected distances.  `leaf_array` (extra, optional)
+        injects a forest in the reference's format, as in the constructor.
+        """
+        from sklearn.utils import check_array, check_random_state
+        if self._build_args["sharded"]:
+            raise NotImplementedError("update() of a sharded index")
+        current_random_state = check_random_state(self.random_state)                             # :2407
+        current_random_state.randint(INT32_MIN, INT32_MAX, 3)     # :2408-2410 the rng_state make_forest receives and ignores
+        if xs_updated is not None:                                                                 # :2413-2434
+            xs_updated = check_array(xs_updated, dtype=np.float32, order="C")
+            if updated_indices is None:
+                raise ValueError("If xs_updated are provided, updated_indices must also be provided!")
+            try:
+                updated_indices = list(map(int, updated_indices))
+            except (TypeError, ValueError):
+                raise ValueError("Could not convert updated indices to list of int(s).")
+            if len(updated_indices) != xs_updated.shape[0]:
+                raise ValueError(f"Number of updated indices ({len(updated_indices)}) must match "
+                                 f"number of rows of xs_updated ({xs_updated.shape[0]}).")
+        else:
+            if updated_indices is not None:                                                        # :2435-2441
+                warn("xs_updated not provided, while update_indices provided. They will be ignored.")
+            updated_indices = None
+        if updated_indices is None:
+            xs_updated, updated_indices = [], []
+        if xs_fresh is None:
+            xs_fresh = np.zeros((0, self._raw_data.shape[1]), dtype=np.float32)                   # :2453-2456
+        else:
+            xs_fresh = check_array(xs_fresh, dtype=np.float32, order="C")
+        data = np.array(self._raw_data, dtype=np.float32, order="C", copy=True)                   # :2471-2474
+        for x_updated, i_fresh in zip(xs_updated, updated_indices):
+            data[i_fresh] = x_updated
+        data = np.ascontiguousarray(np.vstack([data, xs_fresh]))
+        ns = self._neighbor_graph[0].copy()                                                       # :2475-2488
+        if updated_indices:
+            changed = np.zeros(data.shape[0], dtype=bool)
+            changed[updated_indices] = True
+            ns[(ns >= 0) & changed[np.where(ns >= 0, ns, 0)]] = -1
+            ns[np.asarray(updated_indices, dtype=np.int64), :] = -1
+        self.n_trees = self.n_trees_after_update                                                  # :2498
+        a = self._build_args
+        old = self._engine
+        self._engine = None
+        old.close()
+        del old
+        t0 = time.perf_counter()
+        eng = Engine(data, a["metric_id"], self.n_neighbors, device=a["device"])
+        self._engine = eng
+        if not eng.all_finite():
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float32').")
+        self.timings = {"h2d_setup": time.perf_counter() - t0}
+        cap = a["push_capacity"] or eng.default_push_capacity()
+        eng.workspace(a["eff_C"], self.emulated_threads, cap)
+        eng.set_join_order(None)
+        # :2511-2514 make_heap + init_from_neighbor_graph: the old rows in column order; -1 entries push nothing
+        eng.init_from_graph(ns, None, cap)
+        eng.heap_flag.zero_()                  # init_from_neighbor_graph pushes with flag 0 (the warm-start replay sets 1)
+        if leaf_array is not None:                                                                # :2515 init_rp_tree
+            eng.leaf_init_from_array(leaf_array, cap)
+        else:
+            leaf_size = self.leaf_size if self.leaf_size is not None else max(60, min(256, 5 * int(self.n_neighbors)))
+            tree_states = current_random_state.randint(INT32_MIN, INT32_MAX, size=(self.n_trees, 3)).astype(np.int64)
+            lp, lo, n_leaves, max_leaf = eng.forest(tree_states, leaf_size, self._angular_trees, self.max_rptree_depth)
+            eng.leaf_init(lp, lo, n_leaves, max_leaf, cap)
+            del lp, lo
+        iters, c_hist, stats = eng.descent(a["eff_C"], self.rng_state, self.emulated_threads, self.n_iters, self.delta, cap)
+        idx_t, dist_t = eng.deheap_sort(a["dev_correction"])
+        self.n_iters_run, self.c_hist, self.join_stats = iters, c_hist, stats
+        self._raw_data = data
+        self._neighbor_graph = eng.to_host(idx_t, dist_t)
+        self.timings["update"] = time.perf_counter() - t0
+        if getattr(self, "_search_gpu", None) is not None:                                        # :2539-2553
+            self._search_gpu = None
+            self._search_structures = None
+            self.prepare()
 
     def prepare(self):
         """pynndescent_.py:2174-2273 (dense, no quantisation): hub search tree + diversified, degree-pruned search graph,

@@ -1,0 +1,47 @@
+"""Full-size GPU test: BASELINE.json configs[1] (1M x 128 float32 euclidean k=15, latent-16 synthetic) through the public
+API, checked by the size-independent properties of a kNN graph (the oracle needs minutes at this size):
+
+* every row sorted by ascending distance, the point itself first at distance 0, no duplicate neighbours
+  (reference tests/test_pynndescent_.py:299-369 check the same on their data);
+* the reported distances are the true euclidean distances of the reported neighbours (rtol 1e-5, the bar of
+  BASELINE.json's north_star);
+* determinism: a second build from the same (data, random_state) is bit-identical (reference test_deterministic
+  :279-292);
+* recall@15 against brute force on a 1000-row sample >= the reference's 0.885 minus sampling slack.
+
+Runs last (file name) so that the small, oracle-checked parity tests report first.
+"""
+import numpy as np
+import pytest
+
+from conftest import latent
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg2_full_size_properties_and_determinism():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from bench import recall_at_k
+    from pynndescent_b200 import NNDescent
+    n, d, k = 1_000_000, 128, 15
+    X = latent(n, d, 0)
+    idx = NNDescent(X, "euclidean", n_neighbors=k, random_state=42)
+    gi, gd = idx.neighbor_graph
+    assert gi.shape == (n, k) and gi.dtype == np.int32 and gd.shape == (n, k) and gd.dtype == np.float32
+    assert gi.min() >= 0 and gi.max() < n                                   # every row filled
+    assert np.all(gi[:, 0] == np.arange(n)) and np.all(gd[:, 0] == 0)       # self first
+    assert np.all(np.diff(gd, axis=1) >= 0)                                 # ascending
+    srt = np.sort(gi, axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])                                # no duplicate neighbours
+    rows = np.random.RandomState(1).choice(n, 4000, replace=False)
+    exact = np.sqrt(((X[rows, None, :].astype(np.float64) - X[gi[rows]].astype(np.float64)) ** 2).sum(-1))
+    np.testing.assert_allclose(gd[rows], exact, rtol=1e-5, atol=1e-6)
+    rec = recall_at_k(X, gi, k, "euclidean", n_sample=1000, seed=0)
+    assert rec >= 0.885 - 0.015, rec
+    iters, c_hist = idx.n_iters_run, list(idx.c_hist)
+    del idx
+    idx2 = NNDescent(X, "euclidean", n_neighbors=k, random_state=42)
+    gi2, gd2 = idx2.neighbor_graph
+    assert idx2.n_iters_run == iters and list(idx2.c_hist) == c_hist
+    assert np.array_equal(gi, gi2) and np.array_equal(gd, gd2)
