@@ -1,0 +1,44 @@
+#!/bin/bash
+# First GPU commands of round 2 (run under gpurun from the repo root; everything lands in gpurun_out/).
+#   gpurun --timeout 2400 -- 'bash scripts/r2_measure.sh all'          # or one of: tests ab bench cfg3 cfg5 ncu
+# Every step runs under its own `timeout` so that a hung experimental kernel cannot hold the box to gpurun's limit.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+what="${1:-all}"
+run() { echo "=== $*" | tee -a gpurun_out/r2.log; "$@" >> gpurun_out/r2.log 2>&1; echo "    rc=$?" | tee -a gpurun_out/r2.log; }
+
+if [ "$what" = all ] || [ "$what" = tests ]; then
+  # the suite that was green at the end of round 1 first, then the files added without a GPU
+  run timeout 900 python -m pytest tests -m gpu -x -q -n 4 --deselect tests/test_sharded_gpu.py \
+      --ignore tests/test_update.py --ignore tests/test_transformer.py --ignore tests/test_zfull_size_gpu.py
+  run timeout 600 python -m pytest tests/test_update.py tests/test_transformer.py tests/test_zfull_size_gpu.py -m gpu -q
+fi
+if [ "$what" = all ] || [ "$what" = ab ]; then
+  # schedule experiments: bit-equality + timing, small first (a wrong kernel shows up in seconds), then the bench size
+  run timeout 900 python scripts/r2_ab.py 100000 128 15 euclidean --reps=1 --timeout=120
+  run timeout 900 python scripts/r2_ab.py 60000 256 15 cosine --reps=1 --timeout=120 --configs=default,rank,leaf,pipe,pipe+rank+leaf
+  cp gpurun_out/ab_summary.json gpurun_out/ab_summary_small.json 2>/dev/null
+  run timeout 1500 python scripts/r2_ab.py 1000000 128 15 euclidean --reps=2 --timeout=200
+fi
+if [ "$what" = all ] || [ "$what" = bench ]; then
+  run timeout 900 python bench.py --steps 5 --warmup 3
+  run timeout 600 python bench.py --impl reference --steps 1 --warmup 0
+fi
+if [ "$what" = all ] || [ "$what" = cfg3 ]; then
+  run timeout 900 python bench.py --workload cfg3 --steps 3 --warmup 2 --no-cpu-baseline
+fi
+if [ "$what" = all ] || [ "$what" = cfg5 ]; then
+  # BASELINE.json configs[4]: 1M x 784 correlation k=30 build + query() of 100k held-out points
+  run timeout 1500 python scripts/query_bench.py 1000000 784 30 100000 correlation
+fi
+if [ "$what" = all ] || [ "$what" = ncu ]; then
+  # launch list of one warm build (shares), then --set full of the join kernels (default and experimental)
+  run timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_r02.csv \
+      python scripts/one_build.py 1000000 128 15 euclidean 2
+  run timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_join_batch -s 17 -c 2 -o gpurun_out/join_batch_r02 -f \
+      python scripts/one_build.py 1000000 128 15 euclidean 2
+  NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 run timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_join_pipe -s 17 -c 2 \
+      -o gpurun_out/join_pipe_r02 -f python scripts/one_build.py 1000000 128 15 euclidean 2
+fi
+tail -n 60 gpurun_out/r2.log
