@@ -27,6 +27,7 @@ struct CandWs {
     float *table;       // [T * table_len]
     uint32_t *scan_tmp;
     int64_t table_len;
+    uint8_t *act;       // [N+1] NND_CAND_SKIP: 1 = the vertex touches a new-flagged edge (= will have new candidates)
 };
 
 static int64_t cand_table_len(int64_t N, int k) { return N * (int64_t)k; }
@@ -45,6 +46,7 @@ static int carve_cand_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, int
     W->table_len = cand_table_len(Nb, k);
     W->table = A.get<float>((size_t)T * W->table_len);
     W->scan_tmp = A.get<uint32_t>(nnd_scan_tmp_elems((int64_t)(T + 1) * Nb + 2));
+    W->act = A.get<uint8_t>(Nb + 1);
     if (need) *need = A.off;
     return A.ok ? NND_OK : NND_ERR_WORKSPACE;
 }
@@ -59,7 +61,12 @@ size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T) {
     return need + 1024;
 }
 
-__global__ void k_cand_count(const int32_t *ind, int k, int64_t N, int T, int64_t B, uint32_t *cnt, uint32_t *indeg) {
+// act (NND_CAND_SKIP, may be null): a vertex gets at least one NEW candidate iff it is an endpoint of a new-flagged edge
+// (the first push into its empty new-heap is always accepted, utils.py:289-306), and the local join skips every vertex
+// without new candidates (utils.py:575-577 loops over new candidates only) -- so the candidate lists of all other vertices
+// are never read and need not be sampled.
+__global__ void k_cand_count(const int32_t *ind, const uint8_t *flags, int k, int64_t N, int T, int64_t B, uint32_t *cnt,
+                             uint32_t *indeg, uint8_t *act) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t valid = 0;
@@ -69,10 +76,15 @@ __global__ void k_cand_count(const int32_t *ind, int k, int64_t N, int T, int64_
         for (int j = 0; j < k; ++j) { int32_t x = ind[i * k + j]; c += (x >= bs && x < be && x >= 0); }
         cnt[(size_t)n * N + i] = c;
     }
+    bool anynew = false;
     for (int j = 0; j < k; ++j) {
         int32_t x = ind[i * k + j];
-        if (x >= 0) { ++valid; atomicAdd(&indeg[x], 1u); }
+        if (x >= 0) {
+            ++valid; atomicAdd(&indeg[x], 1u);
+            if (act && flags[i * k + j]) { anynew = true; act[x] = 1; }
+        }
     }
+    if (anynew) act[i] = 1;
     cnt[(size_t)T * N + i] = valid;
 }
 
@@ -93,16 +105,24 @@ __device__ __forceinline__ uint32_t draw_index(const uint32_t *pre, int64_t N, i
 
 __global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int64_t N, int T, int64_t B,
                             const uint32_t *pre, const float *table, int64_t table_len, const uint32_t *revoff,
-                            uint32_t *cursor, unsigned long long *rev, float *fprio, int64_t lo, int64_t hi) {
+                            uint32_t *cursor, unsigned long long *rev, float *fprio, int64_t lo, int64_t hi,
+                            const uint8_t *act) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const bool mine = i >= lo && i < hi;
     const int ni = (int)(i / B);
+    const bool ai = !act || act[i];
     uint32_t wv = 0;  // valid edges before j in this row
     for (int j = 0; j < k; ++j) {
         int32_t x = ind[i * k + j];
         if (x < 0) { fprio[i * k + j] = 0.f; continue; }
         if (!mine && (x < lo || x >= hi)) { ++wv; continue; }   // neither endpoint sampled by this process
+        if (act) {
+            // NND_CAND_SKIP: the forward priority is only read by select(i), the reverse entry only by select(x); both are
+            // skipped for vertices without new candidates (draw indices are closed forms, nothing else depends on them)
+            const bool ax = act[x] && x >= lo && x < hi;
+            if (!(ai && mine) && !ax) { ++wv; continue; }
+        }
         const int nx = (int)(x / B);
         uint32_t df = draw_index(pre, N, T, B, ni, i, wv, 0);
         float pf = table[(size_t)ni * table_len + df];
@@ -116,6 +136,7 @@ __global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int
             pr = table[(size_t)nx * table_len + dr];
         }
         if (x < lo || x >= hi) { ++wv; continue; }
+        if (act && !act[x]) { ++wv; continue; }
         uint32_t slot = atomicAdd(&cursor[x], 1u);
         unsigned long long key = ((unsigned long long)(i * k + j) << 1) | (unsigned long long)(flags[i * k + j] != 0);
         rev[(size_t)revoff[x] + slot] = (key << 32) | (unsigned long long)__float_as_uint(pr);
@@ -128,7 +149,8 @@ __global__ void k_cand_fill(const int32_t *ind, const uint8_t *flags, int k, int
 __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
                                                                 const uint32_t *indeg, const uint32_t *revoff,
                                                                 unsigned long long *rev, const float *fprio,
-                                                                int32_t *newc, int32_t *oldc, int skip_small, int64_t lo, int64_t hi) {
+                                                                int32_t *newc, int32_t *oldc, int skip_small, int64_t lo, int64_t hi,
+                                                                const uint8_t *act) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t v = (int64_t)blockIdx.x * SEL_WARPS + warp;
@@ -141,6 +163,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *i
     for (int c = lane; c < C; c += 32) { npri[c] = CUDART_INF_F; opri[c] = CUDART_INF_F; nind[c] = -1; oind[c] = -1; }
     const uint32_t nrev = indeg[v];
     if (skip_small && nrev <= SEL_SMALL) return;
+    if (act && !act[v]) {     // no new candidates: the join never looks at this vertex
+        for (int c = lane; c < C; c += 32) { newc[v * C + c] = -1; oldc[v * C + c] = -1; }
+        return;
+    }
     unsigned long long *seg = rev + revoff[v];
     unsigned long long *sorted;
     if (nrev <= NND_SEG_SMEM) {
@@ -197,7 +223,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *i
 __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
                                                              const uint32_t *indeg, const uint32_t *revoff,
                                                              const unsigned long long *rev, const float *fprio,
-                                                             int32_t *newc, int32_t *oldc, int64_t lo, int64_t hi) {
+                                                             int32_t *newc, int32_t *oldc, int64_t lo, int64_t hi,
+                                                             const uint8_t *act) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int64_t v = (int64_t)blockIdx.x * SEL_T + tid;
@@ -207,6 +234,10 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
     if (v >= N || v < lo || v >= hi) return;
     const uint32_t nrev = indeg[v];
     if (nrev > SEL_SMALL) return;  // handled by the warp kernel
+    if (act && !act[v]) {          // no new candidates: the join never looks at this vertex
+        for (int c = 0; c < C; ++c) { newc[v * C + c] = -1; oldc[v * C + c] = -1; }
+        return;
+    }
     for (int c = 0; c < C; ++c) { npri[c * SEL_T] = CUDART_INF_F; opri[c * SEL_T] = CUDART_INF_F; nind[c * SEL_T] = -1; oind[c * SEL_T] = -1; }
     const unsigned long long *seg = rev + revoff[v];
     int jf = 0; uint32_t left = nrev, used = 0;   // bit j of `used`: reverse edge j already consumed
@@ -317,11 +348,13 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     }
     NND_CUDA(cudaMemsetAsync(W.indeg, 0, sizeof(uint32_t) * (N + 1), st));
     NND_CUDA(cudaMemsetAsync(W.cursor, 0, sizeof(uint32_t) * (N + 1), st));
-    k_cand_count<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, k, N, T, B, W.cnt, W.indeg); NND_LAUNCH(ctx);
+    uint8_t *act = ctx->opt_cand_skip ? W.act : nullptr;
+    if (act) NND_CUDA(cudaMemsetAsync(act, 0, (size_t)N + 1, st));
+    k_cand_count<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.cnt, W.indeg, act); NND_LAUNCH(ctx);
     NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
     NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
     k_cand_fill<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.pre, W.table, W.table_len,
-                                                       W.revoff, W.cursor, W.rev, W.fprio, ctx->row_lo, ctx->row_hi);
+                                                       W.revoff, W.cursor, W.rev, W.fprio, ctx->row_lo, ctx->row_hi, act);
     NND_LAUNCH(ctx);
     const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
     size_t smem = (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)SEL_WARPS * hstride;
@@ -331,12 +364,12 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     if (use_small) {
         NND_CUDA(cudaFuncSetAttribute(k_cand_select_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         k_cand_select_small<<<(unsigned)cdiv(N, SEL_T), SEL_T, smem_small, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
-                                                                            W.revoff, W.rev, W.fprio, new_cand, old_cand, ctx->row_lo, ctx->row_hi);
+                                                                            W.revoff, W.rev, W.fprio, new_cand, old_cand, ctx->row_lo, ctx->row_hi, act);
         NND_LAUNCH(ctx);
     }
     NND_CUDA(cudaFuncSetAttribute(k_cand_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_cand_select<<<(unsigned)cdiv(N, SEL_WARPS), SEL_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
-                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand, use_small, ctx->row_lo, ctx->row_hi);
+                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand, use_small, ctx->row_lo, ctx->row_hi, act);
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
     return NND_OK;
