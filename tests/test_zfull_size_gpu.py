@@ -7,7 +7,9 @@ API, checked by the size-independent properties of a kNN graph (the oracle needs
   BASELINE.json's north_star);
 * determinism: a second build from the same (data, random_state) is bit-identical (reference test_deterministic
   :279-292);
-* recall@15 against brute force on a 1000-row sample >= the reference's 0.885 minus sampling slack.
+* recall@15 against brute force on a 1000-row sample >= the reference's 0.885 (SURVEY.md section 8d) minus sampling slack;
+* the whole 1,000,000 x 15 graph equals the CPU oracle's, bit for bit (sha256 of indices and of distances, per-iteration
+  accepted-push counts; fixture tests/golden/cfg2_full_oracle.json written by tests/golden/make_full_size_checksum.py).
 
 Runs last (file name) so that the small, oracle-checked parity tests report first.
 """
@@ -41,6 +43,18 @@ def test_cfg2_full_size_properties_and_determinism():
     rec = recall_at_k(X, gi, k, "euclidean", n_sample=1000, seed=0)
     assert rec >= 0.885 - 0.015, rec
     iters, c_hist = idx.n_iters_run, list(idx.c_hist)
+    # bit-for-bit against the CPU oracle's build of the same 1M-point workload (tests/golden/make_full_size_checksum.py):
+    # per-iteration accepted-push counts, four literal rows, then sha256 of all 15M indices and of all 15M distances
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "cfg2_full_oracle.json")))
+    assert iters == g["iters"] and [int(c) for c in c_hist] == g["c_hist"]
+    for r, row in g["rows"].items():
+        assert gi[int(r)].tolist() == row["idx"] and [float(v) for v in gd[int(r)]] == row["dist"]
+    assert hashlib.sha256(np.ascontiguousarray(gi, np.int32).tobytes()).hexdigest() == g["idx_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(gd, np.float32).tobytes()).hexdigest() == g["dist_sha256"]
     del idx
     idx2 = NNDescent(X, "euclidean", n_neighbors=k, random_state=42)
     gi2, gd2 = idx2.neighbor_graph
