@@ -28,6 +28,7 @@ WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on that fits one GPU
     "cfg2": dict(n=1_000_000, d=128, k=15, metric="euclidean", name="1Mx128 float32 euclidean k=15 (SIFT-shape latent-16 synthetic)"),
     "cfg3": dict(n=2_000_000, d=256, k=15, metric="cosine", name="2Mx256 float32 cosine k=15 (NYTimes-shape latent-16 synthetic)"),
+    "cfg5": dict(n=1_000_000, d=784, k=30, metric="correlation", name="1Mx784 float32 correlation k=30 (MNIST-shape latent-16 synthetic)"),
     "cfg1": dict(n=1000, d=16, k=10, metric="euclidean", name="1kx16 float32 euclidean k=10 (plumbing)"),
     "small": dict(n=100_000, d=128, k=15, metric="euclidean", name="100kx128 float32 euclidean k=15 (latent-16 synthetic)"),
 }
@@ -106,13 +107,15 @@ def recall_at_k(X, graph_idx, k, metric, n_sample=1000, seed=0):
     import torch
     rows = np.random.RandomState(seed).choice(X.shape[0], min(n_sample, X.shape[0]), replace=False)
     Xd = torch.from_numpy(X).cuda().double()
-    if metric == "cosine":
+    if metric == "correlation":     # correlation distance = cosine distance of the row-centred vectors
+        Xd = Xd - Xd.mean(dim=1, keepdim=True)
+    if metric in ("cosine", "correlation"):
         Xd = Xd / Xd.norm(dim=1, keepdim=True).clamp_min(1e-30)
     hits = 0
     for c0 in range(0, len(rows), 250):
         r = torch.from_numpy(rows[c0:c0 + 250]).cuda()
         q = Xd[r]
-        dm = (1.0 - q @ Xd.T) if metric == "cosine" else ((q * q).sum(1)[:, None] + (Xd * Xd).sum(1)[None, :] - 2.0 * q @ Xd.T)
+        dm = (1.0 - q @ Xd.T) if metric in ("cosine", "correlation") else ((q * q).sum(1)[:, None] + (Xd * Xd).sum(1)[None, :] - 2.0 * q @ Xd.T)
         true = dm.topk(k, dim=1, largest=False).indices.cpu().numpy()
         for i, rr in enumerate(rows[c0:c0 + 250]):
             hits += len(np.intersect1d(true[i], graph_idx[rr]))

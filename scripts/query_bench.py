@@ -18,6 +18,8 @@ torch.cuda.synchronize(); t4 = time.perf_counter()
 st = idx._search_gpu.last_stats
 rows = np.random.RandomState(0).choice(nq, min(nq, 500), replace=False)
 Xd = torch.from_numpy(X).cuda().double(); Qd = torch.from_numpy(Q[rows]).cuda().double()
+if metric == "correlation":      # correlation distance = cosine distance of the row-centred vectors
+    Xd = Xd - Xd.mean(dim=1, keepdim=True); Qd = Qd - Qd.mean(dim=1, keepdim=True)
 dm = (Qd * Qd).sum(1)[:, None] + (Xd * Xd).sum(1)[None, :] - 2 * Qd @ Xd.T if metric == "euclidean" else \
     1 - (Qd / Qd.norm(dim=1, keepdim=True)) @ (Xd / Xd.norm(dim=1, keepdim=True)).T
 true = dm.topk(10, dim=1, largest=False).indices.cpu().numpy()
