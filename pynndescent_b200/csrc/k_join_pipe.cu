@@ -310,6 +310,7 @@ static int launch_pipe_t(nnd_ctx *ctx, const JoinBatchParams &JB, const JpRec *r
 
 template <int METRIC>
 static int launch_pipe_m(nnd_ctx *ctx, const JoinBatchParams &JB, const JpRec *recs, const JoinPipeOpts &o, cudaStream_t st) {
+    if (o.dk == 128) return launch_pipe_t<METRIC, 128, 2>(ctx, JB, recs, o.ctas_per_sm, st);   // whole 512-byte rows, 1 CTA/SM
     if (o.dk == 64) {
         if (o.stages <= 2) return launch_pipe_t<METRIC, 64, 2>(ctx, JB, recs, o.ctas_per_sm, st);
         if (o.stages == 3) return launch_pipe_t<METRIC, 64, 3>(ctx, JB, recs, o.ctas_per_sm, st);

@@ -31,6 +31,7 @@ CONFIGS = {
     "pipe-s2c3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "2", "NND_PIPE_CTAS": "3"},
     "pipe-s6": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "6"},
     "pipe-dk64s2": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_DK": "64", "NND_PIPE_STAGES": "2"},
+    "pipe-dk128": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_DK": "128"},
     "pipe-dk64s3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_DK": "64", "NND_PIPE_STAGES": "3"},
 }
 
