@@ -188,10 +188,13 @@ class NNDescent:
         from sklearn.utils import check_array, check_random_state
         if self._build_args["sharded"]:
             raise NotImplementedError("update() of a sharded index")
+        import inspect
+        _nofinite = ({"ensure_all_finite": False} if "ensure_all_finite" in inspect.signature(check_array).parameters
+                     else {"force_all_finite": False})
         current_random_state = check_random_state(self.random_state)                             # :2407
         current_random_state.randint(INT32_MIN, INT32_MAX, 3)     # :2408-2410 the rng_state make_forest receives and ignores
         if xs_updated is not None:                                                                 # :2413-2434
-            xs_updated = check_array(xs_updated, dtype=np.float32, order="C")
+            xs_updated = check_array(xs_updated, dtype=np.float32, order="C", **_nofinite)
             if updated_indices is None:
                 raise ValueError("If xs_updated are provided, updated_indices must also be provided!")
             try:
@@ -210,7 +213,10 @@ class NNDescent:
         if xs_fresh is None:
             xs_fresh = np.zeros((0, self._raw_data.shape[1]), dtype=np.float32)                   # :2453-2456
         else:
-            xs_fresh = check_array(xs_fresh, dtype=np.float32, order="C")
+            xs_fresh = check_array(xs_fresh, dtype=np.float32, order="C", **_nofinite)
+        # check_array's NaN/inf rejection (:2414, :2458), on the rows that are new, BEFORE any state is touched
+        if not (np.isfinite(xs_fresh).all() and (len(updated_indices) == 0 or np.isfinite(xs_updated).all())):
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float32').")
         data = np.array(self._raw_data, dtype=np.float32, order="C", copy=True)                   # :2471-2474
         for x_updated, i_fresh in zip(xs_updated, updated_indices):
             data[i_fresh] = x_updated
@@ -230,8 +236,6 @@ class NNDescent:
         t0 = time.perf_counter()
         eng = Engine(data, a["metric_id"], self.n_neighbors, device=a["device"])
         self._engine = eng
-        if not eng.all_finite():
-            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float32').")
         self.timings = {"h2d_setup": time.perf_counter() - t0}
         cap = a["push_capacity"] or eng.default_push_capacity()
         eng.workspace(a["eff_C"], self.emulated_threads, cap)

@@ -88,6 +88,11 @@ def test_update_argument_errors(monkeypatch):
         idx.update(xs_updated=g["xs_updated"], updated_indices=[1, 2, 3])
     with pytest.raises(ValueError, match="Could not convert"):
         idx.update(xs_updated=g["xs_updated"][:1], updated_indices=["a"])
+    bad = g["xs_updated"][:1].copy(); bad[0, 0] = np.nan
+    before = idx.neighbor_graph[0].copy()
+    with pytest.raises(ValueError, match="NaN"):
+        idx.update(xs_fresh=bad)
+    assert np.array_equal(idx.neighbor_graph[0], before) and idx._raw_data.shape[0] == 800   # a rejected update changes nothing
     with pytest.warns(UserWarning, match="will be ignored"):
         idx.update(updated_indices=[1, 2], leaf_array=g["leaf_array_update"])
 
