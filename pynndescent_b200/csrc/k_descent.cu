@@ -855,7 +855,6 @@ template <int METRIC>
 static int launch_join_m(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaStream_t st) {
     // worst-case tile count for this launch decides (TPT, threads)
     int nn_max = (P.mode == 0) ? P.C : P.m_max;
-    if (P.mode == 2 && false) return NND_ERR_INVALID;
     int ntr = (nn_max + TILE - 1) / TILE, ntc = (P.m_max + TILE - 1) / TILE;
     int ntiles = ntr * ntc - ntr * (ntr - 1) / 2;
     size_t smem = join_smem_bytes(P.m_max, METRIC);
@@ -1307,8 +1306,7 @@ extern "C" int nnd_push_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, in
     for (int r = 0; r < R; ++r) counts_host[r] = 0;
     if (n_pushed <= 0) return NND_OK;
     NND_CHECK(out, NND_ERR_INVALID, "nnd_push_export: out is null");
-    unsigned long long *dc = W.dev_scalars + 8;   // [64] counters live behind the 8 scalars... use the rec area instead
-    dc = (unsigned long long *)W.rec;              // routed-record area is free between emit and apply
+    unsigned long long *dc = (unsigned long long *)W.rec;   // [128] owner counters + offsets: the routed-record area is free between emit and apply
     NND_CUDA(cudaMemsetAsync(dc, 0, sizeof(unsigned long long) * 128, st));
     k_owner_count<<<(unsigned)cdiv(n_pushed, 256), 256, 0, st>>>(W.l_tgt, (unsigned long long)n_pushed, owner_block, R, dc); NND_LAUNCH(ctx);
     unsigned long long hc[64];
