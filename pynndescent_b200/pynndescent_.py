@@ -262,6 +262,16 @@ class NNDescent:
             self._search_structures = None
             self.prepare()
 
+    def compress_index(self):
+        """pynndescent_.py:2160-2172: prepare the search structures, then drop what only construction needed (the host
+        copy of the kNN graph; `neighbor_graph` raises AttributeError afterwards exactly like the reference's)."""
+        import gc
+        self.prepare()
+        self.compressed = True
+        if hasattr(self, "_neighbor_graph"):
+            del self._neighbor_graph
+        gc.collect()
+
     def prepare(self):
         """pynndescent_.py:2174-2273 (dense, no quantisation): hub search tree + diversified, degree-pruned search graph,
         data re-ordered to leaf order; then the GPU search index (seam 3)."""
