@@ -28,6 +28,8 @@ WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on that fits one GPU
     "cfg2": dict(n=1_000_000, d=128, k=15, metric="euclidean", name="1Mx128 float32 euclidean k=15 (SIFT-shape latent-16 synthetic)"),
     "cfg3": dict(n=2_000_000, d=256, k=15, metric="cosine", name="2Mx256 float32 cosine k=15 (NYTimes-shape latent-16 synthetic)"),
+    # BASELINE.json configs[3] is ONE 10M-point graph on 8 GPUs: `--gpus 8 --workload cfg4` = 8 x 1.25M rows per rank
+    "cfg4": dict(n=1_250_000, d=128, k=15, metric="euclidean", name="10Mx128 float32 euclidean k=15 at 8 GPUs (1.25M rows per GPU, latent-16 synthetic)"),
     "cfg5": dict(n=1_000_000, d=784, k=30, metric="correlation", name="1Mx784 float32 correlation k=30 (MNIST-shape latent-16 synthetic)"),
     "cfg1": dict(n=1000, d=16, k=10, metric="euclidean", name="1kx16 float32 euclidean k=10 (plumbing)"),
     "small": dict(n=100_000, d=128, k=15, metric="euclidean", name="100kx128 float32 euclidean k=15 (latent-16 synthetic)"),
