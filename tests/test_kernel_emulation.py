@@ -1,0 +1,188 @@
+"""CPU emulation of the SOURCE of the batched local-join kernels (tests/emu/cuda_emu.h).
+
+The schedule experiments of DESIGN.md 10a were written when no GPU time was left, so this test runs their actual source on
+the CPU: the kernels are cut out of pynndescent_b200/csrc/*.cu by their section markers (the test fails loudly if a marker
+disappears), compiled with g++ against a small emulation of the CUDA execution model (one OS thread per CUDA thread, real
+barriers, PTX-semantics mbarriers, an asynchronous "TMA" thread serving the bulk copies) and driven through the same
+prepass as build_join_plan.  Checked against the oracle, half-update by half-update in emission order:
+
+* k_join_batch (the kernel that IS verified on hardware) -- validates the emulator itself;
+* k_jp_meta + k_join_pipe for several (chunk, stage-ring, grid) shapes, with and without NND_RANK_SCATTER's RED path, with
+  a permuted row order (nnd_set_join_order) and with a push list that overflows.
+
+This is an emulation of the programming model, not of the hardware: it proves indexing, tiling, descriptor packing, the
+producer/consumer protocol and the arithmetic order, not performance and not memory-model subtleties of the async proxy.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, latent
+
+CSRC = os.path.join(ROOT, "pynndescent_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+def _between(text, start, end, what):
+    a = text.find(start)
+    b = text.find(end, a + 1)
+    assert a >= 0 and b > a, f"section markers of {what} not found -- update tests/test_kernel_emulation.py"
+    return text[a:b]
+
+
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    tmp = str(tmp_path_factory.mktemp("emu"))
+    common = open(os.path.join(CSRC, "nnd_common.cuh")).read()
+    ptx = _between(common, "// ------------------------------------------------------------------ PTX: mbarrier",
+                   "// ------------------------------------------------------------------ host-visible kernels", "the PTX helpers")
+    common = common.replace(ptx, "")
+    for inc in ("#include <cuda_runtime.h>\n", "#include <math_constants.h>\n"):
+        assert inc in common
+        common = common.replace(inc, "")
+    common = common.replace('#include "../../include/nnd_b200.h"', '#include "%s"' % os.path.join(ROOT, "include", "nnd_b200.h"))
+    open(os.path.join(tmp, "nnd_common.cuh"), "w").write(common)
+    open(os.path.join(tmp, "join_batch.cuh"), "w").write(open(os.path.join(CSRC, "join_batch.cuh")).read())
+    desc = open(os.path.join(CSRC, "k_descent.cu")).read()
+    batch = _between(desc, "// prepass 1: per row -> active flag", "// ------------------------------------------------------------------ routing",
+                     "k_jb_* / k_join_batch")
+    pipe = open(os.path.join(CSRC, "k_join_pipe.cu")).read()
+    pipe_defs = _between(pipe, "#define JP_CWARPS", "__device__ __forceinline__ void mbar_arrive", "k_join_pipe's constants")
+    pipe = pipe_defs + _between(pipe, "// ------------------------------------------------------------------------------------------------ descriptor prepass",
+                    "// ------------------------------------------------------------------------------------------------ host", "k_jp_meta / k_join_pipe")
+    kernels = batch + "\n" + pipe
+    n_ext = kernels.count("extern __shared__")
+    for al in ("16", "128"):
+        kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
+    assert n_ext == 2 and "extern __shared__" not in kernels
+    src = os.path.join(tmp, "emu_kernels.cpp")
+    with open(src, "w") as f:
+        f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
+        f.write(kernels)
+        f.write(open(os.path.join(EMU, "emu_driver.inc")).read())
+    so = os.path.join(tmp, "libemu.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-shared", "-fPIC",
+                           "-I", tmp, "-o", so, src])
+    lib = C.CDLL(so)
+    f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"); i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+    u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"); u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+    i64 = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+    lib.emu_join.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_void_p, f32, i32, i32, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                             C.c_int, C.c_long, i32, i32, f32, u32, u64, u32, i64]
+    lib.emu_norms.argtypes = [f32, C.c_long, C.c_int, f32]
+    return lib
+
+
+class Case:
+    """One local-join input (heap thresholds + candidate lists from the oracle) and the expected half-updates."""
+
+    def __init__(self, n, d, k, metric, seed):
+        from sklearn.utils import check_random_state
+        from oracle import nnd_oracle as orc
+        self.metric, self.C = metric, k
+        X = latent(n, d, seed)
+        self.ld = (d + 3) // 4 * 4
+        self.X = np.zeros((n, self.ld), np.float32); self.X[:, :d] = X
+        rs = check_random_state(seed)
+        rng_state = rs.randint(orc.INT32_MIN, orc.INT32_MAX, 3).astype(np.int64)
+        la, _ = orc.make_forest(X, k, 3, None, rs, metric == "cosine", 200, "level")
+        heap = orc.make_heap(n, k)
+        orc.init_rp_tree(X, metric, heap, la); orc.init_random(X, metric, heap, rng_state)
+        newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)
+        orc.process_candidates(X, metric, heap, newc, oldc, 8)             # second iteration: mixed new / old lists, holes
+        self.newc, self.oldc = orc.new_build_candidates(heap, k, rng_state, 8)
+        self.thr = np.ascontiguousarray(heap[1][:, 0], np.float32)
+        # expected half-updates in emission order (utils.py:575-658 loop order, the kernels' sequence key)
+        exp = []
+        stride = 2 * k
+        for i in range(n):
+            nw = self.newc[i][self.newc[i] >= 0]; ol = self.oldc[i][self.oldc[i] >= 0]
+            mem = np.concatenate([nw, ol]); nn = len(nw)
+            for a in range(nn):
+                for b in range(a, len(mem)):
+                    p, q = int(mem[a]), int(mem[b])
+                    dd = np.float32(orc.dist(metric, X[p], X[q]))
+                    base = (i << 20) | ((a * stride + b) << 1)
+                    if dd < self.thr[p]:
+                        exp.append((base, p, q, dd))
+                    if b != a and dd < self.thr[q]:
+                        exp.append((base | 1, q, p, dd))
+        self.expected = exp
+        self.n = n
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return {"euclid40": Case(500, 40, 10, "euclidean", 3), "euclid128": Case(300, 128, 15, "euclidean", 4),
+            "cosine72": Case(400, 72, 10, "cosine", 5)}
+
+
+def _run(lib, case, kernel, dk=32, nst=4, grid=3, rank_scatter=0, order=None, capacity=None):
+    n = case.n
+    cap = capacity or (len(case.expected) + 64)
+    aux = None
+    if case.metric == "cosine":
+        aux = np.zeros(n, np.float32); lib.emu_norms(case.X, n, case.ld, aux)
+    tgt = np.zeros(cap, np.int32); oth = np.zeros(cap, np.int32); dd = np.zeros(cap, np.float32)
+    pos = np.full(cap, 0xFFFFFFFF, np.uint32); seq = np.zeros(cap, np.uint64); cnt = np.zeros(n + 1, np.uint32)
+    info = np.zeros(8, np.int64)
+    rc = lib.emu_join(case.X, n, case.ld, 1 if case.metric == "cosine" else 0, None if aux is None else aux.ctypes.data_as(C.c_void_p),
+                      case.thr, case.newc, case.oldc, case.C, None if order is None else order.ctypes.data_as(C.c_void_p), kernel, dk, nst,
+                      grid, rank_scatter, cap, tgt, oth, dd, pos, seq, cnt, info)
+    assert rc == 0
+    return dict(tgt=tgt, oth=oth, d=dd, pos=pos, seq=seq, cnt=cnt, n_active=int(info[0]), n_batches=int(info[1]), n_out=int(info[2]),
+                overflow=int(info[3]), rows=int(info[4]), pairs=int(info[5]))
+
+
+def _check(case, r, rank_scatter=False):
+    exp = case.expected
+    assert r["overflow"] == 0 and r["n_out"] == len(exp)
+    m = r["n_out"]
+    order = np.argsort(r["seq"][:m], kind="stable")
+    got = [(int(r["seq"][j]), int(r["tgt"][j]), int(r["oth"][j]), np.float32(r["d"][j])) for j in order]
+    assert len({g[0] for g in got}) == m                                    # emission keys are unique
+    assert got == [(int(s), p, q, dd) for s, p, q, dd in exp]               # same records, same order, same distance bits
+    cnt = np.bincount(r["tgt"][:m], minlength=case.n)
+    assert np.array_equal(cnt, r["cnt"][: case.n])                          # per-target counts (RED or ATOM path)
+    if not rank_scatter:                                                    # ranks inside every target's segment: a permutation
+        for t in np.unique(r["tgt"][:m])[:200]:
+            assert sorted(r["pos"][:m][r["tgt"][:m] == t].tolist()) == list(range(int(cnt[t])))
+    mem = sum(int((case.newc[i] >= 0).sum() + (case.oldc[i] >= 0).sum()) for i in range(case.n) if (case.newc[i] >= 0).any())
+    assert r["rows"] == mem                                                 # profile counter: rows gathered
+
+
+@pytest.mark.parametrize("name", ["euclid40", "euclid128", "cosine72"])
+def test_emulator_reproduces_the_hardware_verified_kernel(emu_lib, cases, name):
+    _check(cases[name], _run(emu_lib, cases[name], kernel=0))
+
+
+@pytest.mark.parametrize("name,dk,nst,grid", [("euclid40", 32, 4, 3), ("euclid40", 32, 2, 1), ("euclid40", 64, 2, 5), ("euclid128", 32, 3, 2),
+                                             ("euclid128", 128, 2, 4), ("cosine72", 32, 4, 2), ("cosine72", 64, 2, 3)])
+def test_k_join_pipe_equals_oracle(emu_lib, cases, name, dk, nst, grid):
+    _check(cases[name], _run(emu_lib, cases[name], kernel=1, dk=dk, nst=nst, grid=grid))
+
+
+def test_rank_scatter_red_path_and_join_order(emu_lib, cases):
+    case = cases["euclid40"]
+    perm = np.random.RandomState(9).permutation(case.n).astype(np.int32)
+    for kernel in (0, 1):
+        _check(case, _run(emu_lib, case, kernel=kernel, rank_scatter=1), rank_scatter=True)
+        r = _run(emu_lib, case, kernel=kernel, order=perm)
+        _check(case, r)                                                     # any visiting order: identical records
+
+
+def test_pipe_survives_push_list_overflow(emu_lib, cases):
+    """The persistent kernel must keep its handshakes going when the push list is full (the host then splits the round)."""
+    case = cases["euclid40"]
+    r = _run(emu_lib, case, kernel=1, capacity=len(case.expected) // 3)
+    assert r["overflow"] == 1
+
+
+def test_cases_are_not_trivial(emu_lib, cases):
+    for name, case in cases.items():
+        r = _run(emu_lib, case, kernel=1, grid=2)
+        assert r["n_batches"] >= 12 and r["n_out"] >= 2000 and r["n_active"] > case.n // 4, (name, r["n_batches"], r["n_out"], r["n_active"])
+        print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
