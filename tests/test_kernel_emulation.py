@@ -53,11 +53,13 @@ def emu_lib(tmp_path_factory):
     pipe_defs = _between(pipe, "#define JP_CWARPS", "__device__ __forceinline__ void mbar_arrive", "k_join_pipe's constants")
     pipe = pipe_defs + _between(pipe, "// ------------------------------------------------------------------------------------------------ descriptor prepass",
                     "// ------------------------------------------------------------------------------------------------ host", "k_jp_meta / k_join_pipe")
-    kernels = batch + "\n" + pipe
+    cand = open(os.path.join(CSRC, "k_cand.cu")).read()
+    cand = _between(cand, "__global__ void k_cand_count", "__global__ void k_rng_table", "the candidate kernels")
+    kernels = batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 2 and "extern __shared__" not in kernels
+    assert n_ext == 4 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -73,6 +75,8 @@ def emu_lib(tmp_path_factory):
     lib.emu_join.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_void_p, f32, i32, i32, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_int, C.c_long, i32, i32, f32, u32, u64, u32, i64]
     lib.emu_norms.argtypes = [f32, C.c_long, C.c_int, f32]
+    u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+    lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32]
     return lib
 
 
@@ -186,3 +190,39 @@ def test_cases_are_not_trivial(emu_lib, cases):
         r = _run(emu_lib, case, kernel=1, grid=2)
         assert r["n_batches"] >= 12 and r["n_out"] >= 2000 and r["n_active"] > case.n // 4, (name, r["n_batches"], r["n_out"], r["n_active"])
         print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
+
+
+@pytest.mark.parametrize("skip", [0, 1])
+def test_candidate_kernels_and_cand_skip(emu_lib, skip):
+    """k_cand_count / k_cand_fill / k_cand_select* under the emulator against the oracle's new_build_candidates, over three
+    iterations of a small build (hub vertices with > 32 reverse edges included).  skip=0 is the hardware-verified schedule
+    (all rows must match); skip=1 = NND_CAND_SKIP: rows WITH new candidates must match exactly, the others must come out
+    empty, and the sampled-flag clearing must be identical."""
+    from sklearn.utils import check_random_state
+    from oracle import nnd_oracle as orc
+    n, d, k = 900, 20, 10
+    X = latent(n, d, 8)
+    rs = check_random_state(2)
+    rng_state = rs.randint(orc.INT32_MIN, orc.INT32_MAX, 3).astype(np.int64)
+    la, _ = orc.make_forest(X, k, 3, None, rs, False, 200, "level")
+    heap = orc.make_heap(n, k)
+    orc.init_rp_tree(X, "euclidean", heap, la); orc.init_random(X, "euclidean", heap, rng_state)
+    saw_inactive = saw_hub = False
+    for it in range(4):
+        ind = heap[0].copy(); flags_emu = heap[2].copy()
+        indeg = np.bincount(ind[ind >= 0], minlength=n)
+        saw_hub |= bool((indeg > 32).any())
+        en = np.empty((n, k), np.int32); eo = np.empty((n, k), np.int32)
+        emu_lib.emu_cand(ind, flags_emu, n, k, k, 8, rng_state, skip, en, eo)
+        newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)         # also clears the sampled flags of `heap`
+        assert np.array_equal(en, newc)
+        has_new = (newc >= 0).any(1)
+        saw_inactive |= bool((~has_new).any())
+        assert np.array_equal(eo[has_new], oldc[has_new])
+        if skip:
+            assert np.all(eo[~has_new] == -1)
+        else:
+            assert np.array_equal(eo, oldc)
+        assert np.array_equal(flags_emu, heap[2])
+        orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
+    assert saw_hub and saw_inactive
