@@ -146,6 +146,10 @@ __global__ void __launch_bounds__(JP_THREADS) k_join_pipe(JoinBatchParams P, con
             mbar_wait(&mfull[q], (uint32_t)((i / JP_NM) & 1));
             const JpRec &M = meta[q];
             const int nunits = M.hdr[0], mem = M.hdr[2], totphys = M.hdr[3];
+            // every lane has read the header before lane 0 may run ahead: the consumers release an EMPTY batch without
+            // waiting for anything this warp does, so its ring slot could otherwise be refilled (two iterations from
+            // now) under a lane that has not looked yet (found by the CPU emulation, tests/test_kernel_emulation.py)
+            __syncwarp();
             if (nunits <= 0) continue;
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const int s = (int)(it % NST); const uint32_t n = it / NST;

@@ -12,6 +12,7 @@
 // -ffp-contract=off), so results are bit-comparable with the oracle.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <barrier>
 #include <cmath>
 #include <condition_variable>
@@ -62,7 +63,7 @@ struct MBar {
         tx += expect; --pending; maybe_complete();
     }
     void complete_tx(long n) { std::lock_guard<std::mutex> g(m); tx -= n; maybe_complete(); }
-    void wait(unsigned parity) { std::unique_lock<std::mutex> g(m); cv.wait(g, [&] { return (phase & 1u) != parity; }); }
+    void wait(unsigned parity);
 };
 struct Warp { std::barrier<> bar{32}; uint64_t slot[32]; };
 struct Copy { void *dst; const void *src; size_t bytes; MBar *bar; };
@@ -103,6 +104,21 @@ struct Block {
 };
 static Block *g_block = nullptr;
 static thread_local int t_tid = 0;
+// a wait that lasts 30 s is a deadlock: print who waits on what, then abort (the test fails instead of hanging)
+inline void MBar::wait(unsigned parity) {
+    std::unique_lock<std::mutex> g(m);
+    for (int spins = 0; !cv.wait_for(g, std::chrono::seconds(1), [&] { return (phase & 1u) != parity; }); ++spins) {
+        if (spins < 30) continue;
+        long off = -1;
+        for (auto &kv : g_block->bars) if (kv.second.get() == this) off = (long)((const unsigned char *)kv.first - g_block->smem);
+        fprintf(stderr, "emu: DEADLOCK block %u thread %d waits parity %u on mbarrier@smem+%ld (count %d pending %d tx %ld phase %u)\n",
+                blockIdx.x, t_tid, parity, off, count, pending, tx, phase);
+        for (auto &kv : g_block->bars)
+            fprintf(stderr, "     bar@%ld count %d pending %d tx %ld phase %u\n", (long)((const unsigned char *)kv.first - g_block->smem),
+                    kv.second->count, kv.second->pending, kv.second->tx, kv.second->phase);
+        abort();
+    }
+}
 static inline Warp &warp() { return *g_block->warps[t_tid >> 5]; }
 static inline int lane() { return t_tid & 31; }
 static inline unsigned char *dyn_smem() { return g_block->smem; }

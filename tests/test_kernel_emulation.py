@@ -121,7 +121,9 @@ class Case:
 @pytest.fixture(scope="module")
 def cases():
     return {"euclid40": Case(500, 40, 10, "euclidean", 3), "euclid128": Case(300, 128, 15, "euclidean", 4),
-            "cosine72": Case(400, 72, 10, "cosine", 5)}
+            "cosine72": Case(400, 72, 10, "cosine", 5),
+            # C = 30: one row can outweigh a whole batch window, so some windows are EMPTY (descriptor with 0 units)
+            "euclid24_k30": Case(160, 24, 30, "euclidean", 6)}
 
 
 def _run(lib, case, kernel, dk=32, nst=4, grid=3, rank_scatter=0, order=None, capacity=None):
@@ -158,13 +160,14 @@ def _check(case, r, rank_scatter=False):
     assert r["rows"] == mem                                                 # profile counter: rows gathered
 
 
-@pytest.mark.parametrize("name", ["euclid40", "euclid128", "cosine72"])
+@pytest.mark.parametrize("name", ["euclid40", "euclid128", "cosine72", "euclid24_k30"])
 def test_emulator_reproduces_the_hardware_verified_kernel(emu_lib, cases, name):
     _check(cases[name], _run(emu_lib, cases[name], kernel=0))
 
 
 @pytest.mark.parametrize("name,dk,nst,grid", [("euclid40", 32, 4, 3), ("euclid40", 32, 2, 1), ("euclid40", 64, 2, 5), ("euclid128", 32, 3, 2),
-                                             ("euclid128", 128, 2, 4), ("cosine72", 32, 4, 2), ("cosine72", 64, 2, 3)])
+                                             ("euclid128", 128, 2, 4), ("cosine72", 32, 4, 2), ("cosine72", 64, 2, 3),
+                                             ("euclid24_k30", 32, 4, 3), ("euclid24_k30", 32, 2, 200)])
 def test_k_join_pipe_equals_oracle(emu_lib, cases, name, dk, nst, grid):
     _check(cases[name], _run(emu_lib, cases[name], kernel=1, dk=dk, nst=nst, grid=grid))
 
