@@ -123,7 +123,9 @@ def cases():
     return {"euclid40": Case(500, 40, 10, "euclidean", 3), "euclid128": Case(300, 128, 15, "euclidean", 4),
             "cosine72": Case(400, 72, 10, "cosine", 5),
             # C = 30: one row can outweigh a whole batch window, so some windows are EMPTY (descriptor with 0 units)
-            "euclid24_k30": Case(160, 24, 30, "euclidean", 6)}
+            "euclid24_k30": Case(160, 24, 30, "euclidean", 6),
+            "euclid16_tiny": Case(60, 16, 4, "euclidean", 7),        # one d-chunk, 4 candidates, a handful of batches
+            "cosine8": Case(120, 7, 6, "cosine", 8)}                 # padded rows (d = 7 -> ld = 8), 32-byte bulk copies
 
 
 def _run(lib, case, kernel, dk=32, nst=4, grid=3, rank_scatter=0, order=None, capacity=None):
@@ -167,7 +169,8 @@ def test_emulator_reproduces_the_hardware_verified_kernel(emu_lib, cases, name):
 
 @pytest.mark.parametrize("name,dk,nst,grid", [("euclid40", 32, 4, 3), ("euclid40", 32, 2, 1), ("euclid40", 64, 2, 5), ("euclid128", 32, 3, 2),
                                              ("euclid128", 128, 2, 4), ("cosine72", 32, 4, 2), ("cosine72", 64, 2, 3),
-                                             ("euclid24_k30", 32, 4, 3), ("euclid24_k30", 32, 2, 200)])
+                                             ("euclid24_k30", 32, 4, 3), ("euclid24_k30", 32, 2, 200),
+                                             ("euclid16_tiny", 32, 4, 8), ("euclid16_tiny", 64, 2, 1), ("cosine8", 32, 3, 2)])
 def test_k_join_pipe_equals_oracle(emu_lib, cases, name, dk, nst, grid):
     _check(cases[name], _run(emu_lib, cases[name], kernel=1, dk=dk, nst=nst, grid=grid))
 
@@ -191,7 +194,8 @@ def test_pipe_survives_push_list_overflow(emu_lib, cases):
 def test_cases_are_not_trivial(emu_lib, cases):
     for name, case in cases.items():
         r = _run(emu_lib, case, kernel=1, grid=2)
-        assert r["n_batches"] >= 12 and r["n_out"] >= 2000 and r["n_active"] > case.n // 4, (name, r["n_batches"], r["n_out"], r["n_active"])
+        if case.n >= 150:
+            assert r["n_batches"] >= 12 and r["n_out"] >= 2000 and r["n_active"] > case.n // 4, (name, r["n_batches"], r["n_out"], r["n_active"])
         print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
 
 
