@@ -2,9 +2,10 @@
 diversify_prob = 1 -- the defaults).
 
 GPU (libnnd_b200.so): the hub search tree (rp_trees.py:1233 make_hub_tree) and both diversification passes
-(all the distance work).  Host: the sparse-matrix bookkeeping, done with the very scipy calls the reference makes
-(coo -> csr, eliminate_zeros, transpose, maximum, setdiag, degree prune, leaf-order permutation) and the pre-order
-flattening of the tree (rp_trees.py:2926-3049 convert_tree_format).
+(all the distance work).  Host: the sparse-matrix bookkeeping (`search_graph_bookkeeping`: the reference's coo -> csr,
+transpose, maximum, setdiag, degree prune, leaf-order permutation, restated without per-row Python loops) and the
+pre-order flattening of the tree (`flatten_hub_tree`, rp_trees.py:2926-3049 convert_tree_format), both tested against
+the reference's structures in the CPU suite (tests/test_prepare_host.py).
 """
 import ctypes as C
 
@@ -41,39 +42,49 @@ def build_hub_tree(eng, ng_idx_t, leaf_size, angular, max_depth):
     start = n_start[:n_nodes].cpu().numpy(); size = n_size[:n_nodes].cpu().numpy()
     left = n_left[:n_nodes].cpu().numpy(); right = n_right[:n_nodes].cpu().numpy(); hrow = n_hrow[:n_nodes].cpu().numpy()
     hyp = n_hyper[: nh.value, :d].cpu().numpy(); off = n_off[: nh.value].cpu().numpy()
-    # pre-order numbering (rp_trees.py:2926-2961): left child = me + 1, right child = me + 1 + |left subtree|
+    hyperplanes, offsets, children = flatten_hub_tree(start, size, left, right, hrow, hyp, off, d)
+    return hyperplanes, offsets, children, indices.cpu().numpy()
+
+
+def flatten_hub_tree(start, size, left, right, hrow, hyp, off, d):
+    """Node table of nnd_hub_tree_build (nodes numbered level by level, parents before children; left/right = -1 for a
+    leaf, hrow = row of the node's hyperplane) -> the reference's flat pre-order arrays (rp_trees.py:2926-3049
+    convert_tree_format): node `me` has children me + 1 and me + 1 + |left subtree|, a leaf stores (-start, -end) of its
+    slice of `indices`.  Level-synchronous like the build: subtree sizes bottom-up, pre-order numbers top-down, one
+    vectorised step per tree level instead of a Python visit per node."""
+    n_nodes = len(start)
+    left = np.asarray(left, np.int64); right = np.asarray(right, np.int64)
+    inner = left >= 0
+    depth = np.zeros(n_nodes, np.int64)
+    levels = [np.array([0], np.int64)]
+    while True:                                        # children of level L form level L + 1
+        cur = levels[-1]; cur = cur[inner[cur]]
+        if cur.size == 0:
+            break
+        nxt = np.concatenate([left[cur], right[cur]])
+        depth[nxt] = len(levels)
+        levels.append(nxt)
     sub = np.ones(n_nodes, np.int64)
-    order = []
-    stack = [0]
-    while stack:                       # children are created after their parent, so ids ascend with depth
-        v = stack.pop(); order.append(v)
-        if left[v] >= 0:
-            stack.append(right[v]); stack.append(left[v])
-    for v in reversed(order):
-        if left[v] >= 0:
-            sub[v] = 1 + sub[left[v]] + sub[right[v]]
+    for lv in reversed(levels):
+        v = lv[inner[lv]]
+        sub[v] = 1 + sub[left[v]] + sub[right[v]]
     num = np.zeros(n_nodes, np.int64)
-    for v in order:                    # `order` is a pre-order walk
-        if left[v] >= 0:
-            num[left[v]] = num[v] + 1
-            num[right[v]] = num[v] + 1 + sub[left[v]]
+    for lv in levels:
+        v = lv[inner[lv]]
+        num[left[v]] = num[v] + 1
+        num[right[v]] = num[v] + 1 + sub[left[v]]
     hyperplanes = np.zeros((n_nodes, d), np.float32); offsets = np.zeros(n_nodes, np.float32)
     children = np.full((n_nodes, 2), -1, np.int32)
-    for v in order:
-        me = num[v]
-        if left[v] >= 0:
-            hyperplanes[me] = hyp[hrow[v]]; offsets[me] = off[hrow[v]]
-            children[me, 0] = num[left[v]]; children[me, 1] = num[right[v]]
-        else:
-            children[me, 0] = -start[v]; children[me, 1] = -(start[v] + size[v])
-    return hyperplanes, offsets, children, indices.cpu().numpy()
+    vi = np.flatnonzero(inner); vl = np.flatnonzero(~inner)
+    hyperplanes[num[vi]] = np.asarray(hyp)[np.asarray(hrow)[vi], :d]; offsets[num[vi]] = np.asarray(off)[np.asarray(hrow)[vi]]
+    children[num[vi], 0] = num[left[vi]]; children[num[vi], 1] = num[right[vi]]
+    children[num[vl], 0] = -np.asarray(start)[vl]; children[num[vl], 1] = -(np.asarray(start)[vl] + np.asarray(size)[vl])
+    return hyperplanes, offsets, children
 
 
 def prepare_search_structures(eng, metric, ng_idx_t, ng_dist_t, n_neighbors, angular, leaf_size=None,
                               pruning_degree_multiplier=1.5, max_depth=200):
     """ng_idx_t / ng_dist_t: the deheap-sorted graph on the device with RAW (alternative-metric) distances."""
-    import scipy.sparse as sp
-    n, k = eng.N, ng_idx_t.shape[1]
     search_leaf_size = leaf_size if leaf_size is not None else 30                              # :1341-1345
     hyperplanes, offsets, children, tree_idx = build_hub_tree(eng, ng_idx_t, search_leaf_size, angular, max_depth)
     di_t = ng_idx_t.clone(); dd_t = ng_dist_t.clone()
@@ -85,37 +96,59 @@ def prepare_search_structures(eng, metric, ng_idx_t, ng_dist_t, n_neighbors, ang
     di2_t = di_t.clone(); dd2_t = dd_t.clone()
     check(lib.nnd_diversify(eng._ctx, C.byref(P), _p(di2_t), _p(dd2_t), eng._st()))
     eng.stream.synchronize()
-    di = di_t.cpu().numpy(); dd = dd_t.cpu().numpy()
-    g = sp.coo_array((n, n), dtype=np.float32)                                                  # :1521-1537
-    g.row = np.repeat(np.arange(n, dtype=np.int32), k); g.col = di.ravel(); g.data = dd.ravel()
-    g = g.tocsr()
-    g.data[g.indices == -1] = 0.0
-    g.eliminate_zeros()
-    min_distance = np.min(g.data)                                                               # :1539
-    di2 = di2_t.cpu().numpy()
-    if not np.array_equal(di2, di):                                                             # entries the second pass dropped
-        keep = np.zeros(g.data.shape[0], bool)
-        for i in np.where((di2 != di).any(1))[0]:
-            cols = g.indices[g.indptr[i]: g.indptr[i + 1]]
-            keep_i = np.isin(cols, di2[i][di2[i] >= 0])
-            g.data[g.indptr[i]: g.indptr[i + 1]][~keep_i] = 0.0
-        g.eliminate_zeros()
+    di = di_t.cpu().numpy(); dd = dd_t.cpu().numpy(); di2 = di2_t.cpu().numpy()
+    S = search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_multiplier)
+    S.update(hyperplanes=hyperplanes, offsets=offsets, children=children)
+    return S
+
+
+def search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_multiplier=1.5):
+    """The sparse-matrix part of _init_search_graph (pynndescent_.py:1521-1651) on the host, from the two diversification
+    passes' outputs: `di`, `dd` = forward-diversified rows (-1 holes, zero distances already FLOAT32_EPS, :1526), `di2` = the
+    same rows after the second (CSR) pass -- a subset of `di` with the same distances.
+
+    Same result as the reference's scipy sequence (coo -> csr, eliminate_zeros, transpose, maximum, setdiag(0), degree
+    prune, != 0, leaf-order permutation), restated so that nothing loops over rows in Python and no sparsity-changing
+    scipy call is used where a mask does (`setdiag` alone cost more than everything else together at 1M points):
+    the first-pass matrix only contributes `min_distance` (:1539), the symmetrised matrix is built straight from the
+    second-pass survivors, the diagonal and the degree prune are masks on the CSR arrays.
+    """
+    import scipy.sparse as sp
+    n, k = di.shape
+    min_distance = np.min(dd[di >= 0])                                                           # :1539 (first-pass graph)
+    keep = di2 >= 0
+    indptr = np.zeros(n + 1, np.int64); np.cumsum(keep.sum(1), out=indptr[1:])                 # rows are already grouped and
+    g = sp.csr_array((dd[keep], di2[keep], indptr), shape=(n, n))                              # duplicate-free: CSR as is
+    g.eliminate_zeros()                                                                         # :1521-1537 + :1552-1587
     rev = g.transpose().tocsr()
     rev.sort_indices(); g.sort_indices()
     g = g.maximum(rev).tocsr()                                                                  # :1601
-    g.setdiag(0.0); g.eliminate_zeros()
+    row_of = np.repeat(np.arange(n, dtype=np.int32), np.diff(g.indptr))
+    g.data[g.indices == row_of] = 0.0                                                           # :1605 setdiag(0)
+    g.eliminate_zeros()
     max_degree = int(np.round(pruning_degree_multiplier * n_neighbors))                         # :1608-1611, :728-760
     deg = np.diff(g.indptr)
-    for i in np.where(deg > max_degree)[0]:
-        row = g.data[g.indptr[i]: g.indptr[i + 1]]
-        cut = np.sort(row)[max_degree]
-        row[row > cut] = 0.0
-    g.eliminate_zeros()
-    g = (g != 0).astype(np.uint8)                                                               # :1613
+    hub = np.flatnonzero(deg > max_degree)
+    if hub.size:
+        # degree_prune: in every row with more than max_degree entries, zero what is larger than the (max_degree+1)-th
+        # smallest weight (ties with it stay) -- all hub rows at once: sort their entries by (row, weight)
+        seg = np.zeros(n, bool); seg[hub] = True
+        sel = np.flatnonzero(seg[np.repeat(np.arange(n, dtype=np.int32), deg)])
+        r = np.repeat(np.arange(n, dtype=np.int32), deg)[sel]; w = g.data[sel]
+        order = np.lexsort((w, r))
+        first = np.searchsorted(r[order], hub)                                                  # start of every hub row in `order`
+        cut = np.empty(n, np.float32); cut[hub] = w[order][first + max_degree]
+        g.data[sel[w > cut[r]]] = 0.0
+        g.eliminate_zeros()
     vertex_order = tree_idx                                                                     # :1630
-    g = g[vertex_order, :].tocsc()[:, vertex_order].tocsr(); g.sort_indices()                   # :1631-1634
-    tree_order = np.argsort(vertex_order)
-    new_tree_idx = tree_idx[tree_order].astype(np.int32)                                        # :763-771
-    return dict(indptr=g.indptr.astype(np.int32), indices=g.indices.astype(np.int32), hyperplanes=hyperplanes, offsets=offsets,
-                children=children, tree_indices=new_tree_idx, vertex_order=vertex_order.astype(np.int32),
-                min_distance=np.float32(min_distance))
+    # :1613 + :1631-1634  B[a, b] = (g[vo[a], vo[b]] != 0): new row a is old row vo[a] with its columns renamed by vo^-1
+    inv = np.empty(n, np.int32); inv[vertex_order] = np.arange(n, dtype=np.int32)
+    deg = np.diff(g.indptr)[vertex_order]
+    new_indptr = np.zeros(n + 1, np.int64); np.cumsum(deg, out=new_indptr[1:])
+    it = np.int32 if g.indptr[-1] < 2 ** 31 - 1 else np.int64
+    src = np.repeat((g.indptr[:-1][vertex_order] - new_indptr[:-1]).astype(it), deg) + np.arange(new_indptr[-1], dtype=it)
+    h = sp.csr_array((np.ones(src.shape[0], np.uint8), inv[g.indices[src]], new_indptr), shape=(n, n))
+    h.sort_indices()
+    new_tree_idx = tree_idx[np.argsort(vertex_order)].astype(np.int32)                          # :763-771
+    return dict(indptr=h.indptr.astype(np.int32), indices=h.indices.astype(np.int32), tree_indices=new_tree_idx,
+                vertex_order=np.asarray(vertex_order, np.int32), min_distance=np.float32(min_distance))
