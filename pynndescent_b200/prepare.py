@@ -8,6 +8,7 @@ pre-order flattening of the tree (`flatten_hub_tree`, rp_trees.py:2926-3049 conv
 the reference's structures in the CPU suite (tests/test_prepare_host.py).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -43,7 +44,7 @@ def build_hub_tree(eng, ng_idx_t, leaf_size, angular, max_depth):
     left = n_left[:n_nodes].cpu().numpy(); right = n_right[:n_nodes].cpu().numpy(); hrow = n_hrow[:n_nodes].cpu().numpy()
     hyp = n_hyper[: nh.value, :d].cpu().numpy(); off = n_off[: nh.value].cpu().numpy()
     hyperplanes, offsets, children = flatten_hub_tree(start, size, left, right, hrow, hyp, off, d)
-    return hyperplanes, offsets, children, indices.cpu().numpy()
+    return hyperplanes, offsets, children, indices.cpu().numpy(), indices
 
 
 def flatten_hub_tree(start, size, left, right, hrow, hyp, off, d):
@@ -86,7 +87,7 @@ def prepare_search_structures(eng, metric, ng_idx_t, ng_dist_t, n_neighbors, ang
                               pruning_degree_multiplier=1.5, max_depth=200):
     """ng_idx_t / ng_dist_t: the deheap-sorted graph on the device with RAW (alternative-metric) distances."""
     search_leaf_size = leaf_size if leaf_size is not None else 30                              # :1341-1345
-    hyperplanes, offsets, children, tree_idx = build_hub_tree(eng, ng_idx_t, search_leaf_size, angular, max_depth)
+    hyperplanes, offsets, children, tree_idx, tree_idx_t = build_hub_tree(eng, ng_idx_t, search_leaf_size, angular, max_depth)
     di_t = ng_idx_t.clone(); dd_t = ng_dist_t.clone()
     P = eng.problem()
     check(lib.nnd_diversify(eng._ctx, C.byref(P), _p(di_t), _p(dd_t), eng._st()))            # :1502-1519
@@ -95,11 +96,33 @@ def prepare_search_structures(eng, metric, ng_idx_t, ng_dist_t, n_neighbors, ang
     dd_t[dd_t == 0.0] = float(FLOAT32_EPS)
     di2_t = di_t.clone(); dd2_t = dd_t.clone()
     check(lib.nnd_diversify(eng._ctx, C.byref(P), _p(di2_t), _p(dd2_t), eng._st()))
-    eng.stream.synchronize()
-    di = di_t.cpu().numpy(); dd = dd_t.cpu().numpy(); di2 = di2_t.cpu().numpy()
-    S = search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_multiplier)
+    if os.environ.get("NND_PREPARE_GPU", "") == "1":     # experimental (k_search_graph.cu): the bookkeeping on the device
+        S = search_graph_device(eng, di_t, dd_t, di2_t, tree_idx_t, tree_idx, n_neighbors, pruning_degree_multiplier)
+    else:
+        eng.stream.synchronize()
+        di = di_t.cpu().numpy(); dd = dd_t.cpu().numpy(); di2 = di2_t.cpu().numpy()
+        S = search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_multiplier)
     S.update(hyperplanes=hyperplanes, offsets=offsets, children=children)
     return S
+
+
+def search_graph_device(eng, di_t, dd_t, di2_t, vertex_order_t, vertex_order, n_neighbors, pruning_degree_multiplier=1.5):
+    """search_graph_bookkeeping on the device (nnd_search_graph_build): only the finished CSR comes back to the host."""
+    n, k = di_t.shape
+    nb = C.c_size_t()
+    check(lib.nnd_search_graph_workspace_bytes(n, k, C.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=eng.device)
+    cap = 2 * n * k
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=eng.device)
+    indices = torch.empty(cap, dtype=torch.int32, device=eng.device)
+    nnz = C.c_int64(); md = C.c_float()
+    max_degree = int(np.round(pruning_degree_multiplier * n_neighbors))
+    check(lib.nnd_search_graph_build(eng._ctx, _p(di_t), _p(di2_t), _p(dd_t), n, k, _p(vertex_order_t), max_degree, _p(indptr),
+                                     _p(indices), cap, C.byref(nnz), C.byref(md), _p(ws), nb.value, eng._st()))
+    eng.stream.synchronize()
+    return dict(indptr=indptr.cpu().numpy(), indices=indices[: nnz.value].cpu().numpy(),
+                tree_indices=np.arange(n, dtype=np.int32),                      # :763-771 resort_tree_indices of a permutation
+                vertex_order=np.asarray(vertex_order, np.int32), min_distance=np.float32(md.value))
 
 
 def search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_multiplier=1.5):

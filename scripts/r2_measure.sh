@@ -13,6 +13,10 @@ if [ "$what" = all ] || [ "$what" = tests ]; then
   run timeout 900 python -m pytest tests -m gpu -x -q -n 4 --deselect tests/test_sharded_gpu.py \
       --ignore tests/test_update.py --ignore tests/test_transformer.py --ignore tests/test_zfull_size_gpu.py
   run timeout 600 python -m pytest tests/test_update.py tests/test_transformer.py tests/test_zfull_size_gpu.py -m gpu -q
+  # prepare() with the device-side search-graph bookkeeping (k_search_graph.cu): same structure / query tests, then timing
+  NND_PREPARE_GPU=1 run timeout 600 python -m pytest tests/test_gpu_query.py -m gpu -q
+  run timeout 600 python scripts/query_bench.py 1000000 128 15 100000
+  NND_PREPARE_GPU=1 run timeout 600 python scripts/query_bench.py 1000000 128 15 100000
 fi
 if [ "$what" = all ] || [ "$what" = ab ]; then
   # schedule experiments: bit-equality + timing, small first (a wrong kernel shows up in seconds), then the bench size

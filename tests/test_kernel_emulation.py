@@ -55,7 +55,10 @@ def emu_lib(tmp_path_factory):
                     "// ------------------------------------------------------------------------------------------------ host", "k_jp_meta / k_join_pipe")
     cand = open(os.path.join(CSRC, "k_cand.cu")).read()
     cand = _between(cand, "__global__ void k_cand_count", "__global__ void k_rng_table", "the candidate kernels")
-    kernels = batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand
+    sg = open(os.path.join(CSRC, "k_search_graph.cu")).read()
+    sg = _between(sg, "#define SG_WARPS", "// ------------------------------------------------------------------------------------------------ host",
+                  "the search-graph kernels")
+    kernels = batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
@@ -77,6 +80,8 @@ def emu_lib(tmp_path_factory):
     lib.emu_norms.argtypes = [f32, C.c_long, C.c_int, f32]
     u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
     lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32]
+    lib.emu_search_graph.argtypes = [i32, i32, f32, C.c_long, C.c_int, i32, C.c_int, i32, i32, f32]
+    lib.emu_search_graph.restype = C.c_long
     return lib
 
 
@@ -233,3 +238,53 @@ def test_candidate_kernels_and_cand_skip(emu_lib, skip):
         assert np.array_equal(flags_emu, heap[2])
         orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
     assert saw_hub and saw_inactive
+
+
+def _sg_emulate(emu_lib, di, dd, di2, vertex_order, max_degree):
+    n, k = di.shape
+    indptr = np.zeros(n + 1, np.int32); indices = np.zeros(2 * n * k + 8, np.int32); md = np.zeros(1, np.float32)
+    nnz = emu_lib.emu_search_graph(np.ascontiguousarray(di, np.int32), np.ascontiguousarray(di2, np.int32), np.ascontiguousarray(dd, np.float32),
+                                   n, k, np.ascontiguousarray(vertex_order, np.int32), max_degree, indptr, indices, md)
+    return indptr, indices[:nnz], md[0]
+
+
+@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24", "query_jaccard_2k40"])
+def test_search_graph_kernels_match_reference_structures(emu_lib, name):
+    """k_search_graph.cu under the emulator, on the two diversification passes of the reference's own graphs: the CSR must be
+    the reference's search graph (query goldens) -- same check as tests/test_prepare_host.py makes for the host restatement."""
+    from oracle import nnd_oracle as orc
+    from conftest import load_golden
+    from test_prepare_host import _diversify_passes
+    G = load_golden(name)
+    di, dd, di2 = _diversify_passes(orc, G)
+    indptr, indices, md = _sg_emulate(emu_lib, di, dd, di2, G["vertex_order"], int(np.round(1.5 * int(G["n_neighbors"]))))
+    assert np.array_equal(indptr, G["indptr"]) and np.array_equal(indices, G["indices"])
+    assert np.float32(md) == np.float32(G["min_distance"])
+
+
+def test_search_graph_kernels_hubs_ties_and_big_rows(emu_lib):
+    """Rows beyond SG_CAP entries (sorted in global scratch), weight ties at the degree cut, rows with only reverse edges,
+    empty rows, self loops -- against the host restatement."""
+    from pynndescent_b200.prepare import search_graph_bookkeeping
+    rs = np.random.RandomState(4)
+    n, k, nn = 1500, 12, 6
+    di = np.full((n, k), -1, np.int32); dd = np.full((n, k), np.inf, np.float32)
+    for i in range(n):
+        if i % 7 == 3:
+            continue                                          # rows without forward edges
+        m = rs.randint(1, k + 1)
+        nb = rs.choice(n, m, replace=False)
+        nb[: (2 * m) // 3] = rs.choice(3, (2 * m) // 3)        # vertices 0..2 collect > 256 reverse edges each
+        nb = np.array(list(dict.fromkeys(int(v) for v in nb)), np.int32)
+        if rs.random_sample() < 0.1 and i not in nb:
+            nb[-1] = i                                        # a self loop (dropped with the diagonal)
+        w = np.sort(np.round(rs.random_sample(len(nb)), 1).astype(np.float32) + np.float32(0.1))
+        di[i, : len(nb)] = nb; dd[i, : len(nb)] = w
+    di2 = di.copy()
+    drop = (rs.random_sample(di.shape) < 0.1) & (di >= 0); di2[drop] = -1      # second-pass drops (holes inside rows)
+    vo = rs.permutation(n).astype(np.int32)
+    S = search_graph_bookkeeping(di, dd, di2, vo, nn)
+    indptr, indices, md = _sg_emulate(emu_lib, di, dd, di2, vo, int(np.round(1.5 * nn)))
+    rev_deg = np.bincount(di2[di2 >= 0], minlength=n)
+    assert rev_deg.max() > 300 and (np.diff(S["indptr"]) == 0).any()
+    assert np.array_equal(indptr, S["indptr"]) and np.array_equal(indices, S["indices"]) and np.float32(md) == S["min_distance"]
