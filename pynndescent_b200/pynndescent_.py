@@ -158,20 +158,43 @@ class NNDescent:
             if c_hist and c_hist[-1] <= delta * n_neighbors * data.shape[0]:
                 print("\tStopping threshold met -- exiting after", iters, "iterations")
         self.n_iters_run, self.c_hist, self.join_stats = iters, c_hist, stats
-        t0 = time.perf_counter()
-        self._neighbor_graph = eng.to_host(idx_t, dist_t)
-        self.timings["d2h"] = time.perf_counter() - t0
-        if np.any(self._neighbor_graph[0] < 0):                                             # :1262-1267
+        self._set_graph(idx_t, dist_t)
+
+    # ---- the kNN graph stays on the device; host copies are made when somebody asks for them
+    def _set_graph(self, idx_t, dist_t):
+        self.__dict__.pop("_neighbor_graph", None)
+        self._graph_dev = (idx_t, dist_t)
+        if bool((idx_t < 0).any()):                                                          # :1262-1267
             warn("Failed to correctly find n_neighbors for some samples."
                  " Results may be less than ideal. Try re-running with"
                  " different parameters.")
 
+    def __getattr__(self, name):
+        # `_neighbor_graph` (the reference's attribute: host (indices, distances), used by update() and persistence) is
+        # fetched from the device on first use and cached; an explicitly assigned value shadows this
+        if name == "_neighbor_graph":
+            dev = self.__dict__.get("_graph_dev")
+            if dev is not None:
+                g = self.__dict__["_engine"].to_host(*dev)
+                self.__dict__["_neighbor_graph"] = g
+                return g
+        raise AttributeError(f"{type(self).__name__!r} object has no attribute {name!r}")
+
     @property
     def neighbor_graph(self):
-        """pynndescent_.py:2145-2158: (indices copy, corrected distances)."""
+        """pynndescent_.py:2145-2158: (indices copy, corrected distances).  Every access returns arrays the caller owns:
+        a fresh device -> host copy (one PCIe transfer into pinned staging, no second host-side memcpy), or copies of the
+        cached host graph when one exists."""
+        cached = self.__dict__.get("_neighbor_graph")
+        if cached is not None:
+            hi, hd, own = cached[0].copy(), cached[1], False
+        elif self.__dict__.get("_graph_dev") is not None:
+            (hi, hd), own = self._engine.to_host(*self._graph_dev), True
+        else:
+            raise AttributeError("'NNDescent' object has no attribute '_neighbor_graph'")      # compress_index() dropped it
         if self._distance_correction is not None:
-            return self._neighbor_graph[0].copy(), self._distance_correction(self._neighbor_graph[1])
-        return self._neighbor_graph[0].copy(), self._neighbor_graph[1].copy()
+            return hi, self._distance_correction(hd)
+        return hi, (hd if own else hd.copy())
 
     def update(self, xs_fresh=None, xs_updated=None, updated_indices=None, leaf_array=None):
         """pynndescent_.py:2381-2553 (dense): append `xs_fresh`, replace rows `updated_indices` by `xs_updated`, then
@@ -255,7 +278,7 @@ class NNDescent:
         idx_t, dist_t = eng.deheap_sort(a["dev_correction"])
         self.n_iters_run, self.c_hist, self.join_stats = iters, c_hist, stats
         self._raw_data = data
-        self._neighbor_graph = eng.to_host(idx_t, dist_t)
+        self._set_graph(idx_t, dist_t)
         self.timings["update"] = time.perf_counter() - t0
         if getattr(self, "_search_gpu", None) is not None:                                        # :2539-2553
             self._search_gpu = None
@@ -268,8 +291,8 @@ class NNDescent:
         import gc
         self.prepare()
         self.compressed = True
-        if hasattr(self, "_neighbor_graph"):
-            del self._neighbor_graph
+        self.__dict__.pop("_neighbor_graph", None)
+        self.__dict__.pop("_graph_dev", None)
         gc.collect()
 
     def prepare(self):
