@@ -104,11 +104,11 @@ struct Block {
 };
 static Block *g_block = nullptr;
 static thread_local int t_tid = 0;
-// a wait that lasts 30 s is a deadlock: print who waits on what, then abort (the test fails instead of hanging)
+// a wait that lasts 4 minutes is a deadlock: print who waits on what, then abort (the test fails instead of hanging)
 inline void MBar::wait(unsigned parity) {
     std::unique_lock<std::mutex> g(m);
     for (int spins = 0; !cv.wait_for(g, std::chrono::seconds(1), [&] { return (phase & 1u) != parity; }); ++spins) {
-        if (spins < 30) continue;
+        if (spins < 240) continue;     // generous: the suite may share a loaded machine with other emulations
         long off = -1;
         for (auto &kv : g_block->bars) if (kv.second.get() == this) off = (long)((const unsigned char *)kv.first - g_block->smem);
         fprintf(stderr, "emu: DEADLOCK block %u thread %d waits parity %u on mbarrier@smem+%ld (count %d pending %d tx %ld phase %u)\n",

@@ -22,8 +22,8 @@ import pytest
 
 from conftest import ROOT, latent
 
-# a deadlocked emulation must fail, not hang the suite (mbarrier waits abort after 30 s on their own; plain barriers cannot)
-pytestmark = pytest.mark.timeout(900, method="thread")
+# a deadlocked emulation must fail, not hang the suite (mbarrier waits abort after 4 minutes on their own; plain barriers cannot)
+pytestmark = pytest.mark.timeout(1500, method="thread")
 
 CSRC = os.path.join(ROOT, "pynndescent_b200", "csrc")
 EMU = os.path.join(ROOT, "tests", "emu")
