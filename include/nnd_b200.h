@@ -232,11 +232,12 @@ NND_API int nnd_diversify(nnd_ctx *ctx, const nnd_problem *P, int32_t *ind, floa
 
 /* The sparse-matrix part of _init_search_graph on the device (pynndescent_.py:1521-1651: G = max(G, G^T) of the twice
  * diversified graph, setdiag(0), degree_prune :728-760, != 0, rows and columns permuted to leaf order :1629-1634).
- * di / di2 = the rows after the first / second diversification pass (int32[N,k], -1 holes), dd = their distances (zeros
- * already FLOAT32_EPS, :1526), vertex_order = the hub tree's leaf order.  Outputs the CSR of the search graph
+ * (di, dd) / (di2, dd2) = the rows after the first / second diversification pass (int32 / f32 [N,k], -1 holes anywhere;
+ * each pass packs its own survivors, so the two pairs are NOT position-aligned; zero distances already FLOAT32_EPS, :1526),
+ * vertex_order = the hub tree's leaf order.  Outputs the CSR of the search graph
  * (indptr int32[N+1], sorted indices; capacity 2*N*k entries is always enough), its size and min_distance (:1539).      */
 NND_API int nnd_search_graph_workspace_bytes(int64_t N, int32_t k, size_t *bytes);
-NND_API int nnd_search_graph_build(nnd_ctx *ctx, const int32_t *di, const int32_t *di2, const float *dd, int64_t N, int32_t k,
+NND_API int nnd_search_graph_build(nnd_ctx *ctx, const int32_t *di, const float *dd, const int32_t *di2, const float *dd2, int64_t N, int32_t k,
                                    const int32_t *vertex_order, int32_t max_degree, int32_t *indptr_out, int32_t *indices_out,
                                    int64_t capacity, int64_t *nnz_host, float *min_distance_host, void *ws, size_t ws_bytes,
                                    void *stream);

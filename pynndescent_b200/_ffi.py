@@ -77,7 +77,7 @@ SIGNATURES = {
                                      _i64, _pi32, _pi32, _vp, _sz, _vp]),
     "nnd_diversify": (C.c_int, [_vp, _PP, _vp, _vp, _vp]),
     "nnd_search_graph_workspace_bytes": (C.c_int, [_i64, _i32, _psz]),
-    "nnd_search_graph_build": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i64, _pi64, C.POINTER(C.c_float), _vp,
+    "nnd_search_graph_build": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _i64, _pi64, C.POINTER(C.c_float), _vp,
                                         _sz, _vp]),
     "nnd_rng_stream": (C.c_int, [_vp, _pi64, _i64, _i64, _i32, _vp, _vp]),
     "nnd_rng_advance_host": (C.c_int, [_vp, _pi64, _i64]),

@@ -175,12 +175,12 @@ extern "C" int nnd_search_graph_workspace_bytes(int64_t N, int32_t k, size_t *by
     *bytes = need + 4096;
     return NND_OK;
 }
-extern "C" int nnd_search_graph_build(nnd_ctx *ctx, const int32_t *di, const int32_t *di2, const float *dd, int64_t N, int32_t k,
+extern "C" int nnd_search_graph_build(nnd_ctx *ctx, const int32_t *di, const float *dd, const int32_t *di2, const float *dd2, int64_t N, int32_t k,
                                       const int32_t *vertex_order, int32_t max_degree, int32_t *indptr_out, int32_t *indices_out,
                                       int64_t capacity, int64_t *nnz_host, float *min_distance_host, void *ws, size_t ws_bytes,
                                       void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    NND_CHECK(ctx && di && di2 && dd && vertex_order && indptr_out && indices_out && nnz_host && min_distance_host && N > 0 && k > 0 &&
+    NND_CHECK(ctx && di && di2 && dd && dd2 && vertex_order && indptr_out && indices_out && nnz_host && min_distance_host && N > 0 && k > 0 &&
                   max_degree >= 0, NND_ERR_INVALID, "nnd_search_graph_build: bad args");
     NND_CHECK((double)N * k * 4 < 4.0e9, NND_ERR_UNSUPPORTED, "nnd_search_graph_build: N*k too large for 32-bit offsets");
     SgWs W;
@@ -193,10 +193,10 @@ extern "C" int nnd_search_graph_build(nnd_ctx *ctx, const int32_t *di, const int
     k_sg_inv<<<gn, 256, 0, st>>>(vertex_order, N, W.inv); NND_LAUNCH(ctx);
     k_sg_indeg<<<ge, 256, 0, st>>>(di2, k, N, W.indeg); NND_LAUNCH(ctx);
     NND_TRY(nnd_exclusive_scan_u32(ctx, W.indeg, W.roff, N, W.scan_tmp, st));
-    k_sg_fill<<<ge, 256, 0, st>>>(di2, dd, k, N, W.roff, W.cursor, W.rev); NND_LAUNCH(ctx);
+    k_sg_fill<<<ge, 256, 0, st>>>(di2, dd2, k, N, W.roff, W.cursor, W.rev); NND_LAUNCH(ctx);
     k_sg_sizes<<<gn, 256, 0, st>>>(di2, k, N, W.indeg, W.m, W.pad); NND_LAUNCH(ctx);
     NND_TRY(nnd_exclusive_scan_u32(ctx, W.pad, W.soff, N, W.scan_tmp, st));
-    k_sg_rows<<<(unsigned)cdiv(N, SG_WARPS), SG_WARPS * 32, 0, st>>>(di2, dd, k, N, W.indeg, W.roff, W.rev, W.m, W.soff, W.scratch, W.inv,
+    k_sg_rows<<<(unsigned)cdiv(N, SG_WARPS), SG_WARPS * 32, 0, st>>>(di2, dd2, k, N, W.indeg, W.roff, W.rev, W.m, W.soff, W.scratch, W.inv,
                                                                     max_degree, W.cnt_new);
     NND_LAUNCH(ctx);
     NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt_new, W.indptr, N, W.scan_tmp, st));

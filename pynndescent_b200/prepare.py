@@ -97,16 +97,16 @@ def prepare_search_structures(eng, metric, ng_idx_t, ng_dist_t, n_neighbors, ang
     di2_t = di_t.clone(); dd2_t = dd_t.clone()
     check(lib.nnd_diversify(eng._ctx, C.byref(P), _p(di2_t), _p(dd2_t), eng._st()))
     if os.environ.get("NND_PREPARE_GPU", "") == "1":     # experimental (k_search_graph.cu): the bookkeeping on the device
-        S = search_graph_device(eng, di_t, dd_t, di2_t, tree_idx_t, tree_idx, n_neighbors, pruning_degree_multiplier)
+        S = search_graph_device(eng, di_t, dd_t, di2_t, dd2_t, tree_idx_t, tree_idx, n_neighbors, pruning_degree_multiplier)
     else:
         eng.stream.synchronize()
-        di = di_t.cpu().numpy(); dd = dd_t.cpu().numpy(); di2 = di2_t.cpu().numpy()
-        S = search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_multiplier)
+        S = search_graph_bookkeeping(di_t.cpu().numpy(), dd_t.cpu().numpy(), di2_t.cpu().numpy(), dd2_t.cpu().numpy(), tree_idx,
+                                     n_neighbors, pruning_degree_multiplier)
     S.update(hyperplanes=hyperplanes, offsets=offsets, children=children)
     return S
 
 
-def search_graph_device(eng, di_t, dd_t, di2_t, vertex_order_t, vertex_order, n_neighbors, pruning_degree_multiplier=1.5):
+def search_graph_device(eng, di_t, dd_t, di2_t, dd2_t, vertex_order_t, vertex_order, n_neighbors, pruning_degree_multiplier=1.5):
     """search_graph_bookkeeping on the device (nnd_search_graph_build): only the finished CSR comes back to the host."""
     n, k = di_t.shape
     nb = C.c_size_t()
@@ -117,7 +117,7 @@ def search_graph_device(eng, di_t, dd_t, di2_t, vertex_order_t, vertex_order, n_
     indices = torch.empty(cap, dtype=torch.int32, device=eng.device)
     nnz = C.c_int64(); md = C.c_float()
     max_degree = int(np.round(pruning_degree_multiplier * n_neighbors))
-    check(lib.nnd_search_graph_build(eng._ctx, _p(di_t), _p(di2_t), _p(dd_t), n, k, _p(vertex_order_t), max_degree, _p(indptr),
+    check(lib.nnd_search_graph_build(eng._ctx, _p(di_t), _p(dd_t), _p(di2_t), _p(dd2_t), n, k, _p(vertex_order_t), max_degree, _p(indptr),
                                      _p(indices), cap, C.byref(nnz), C.byref(md), _p(ws), nb.value, eng._st()))
     eng.stream.synchronize()
     return dict(indptr=indptr.cpu().numpy(), indices=indices[: nnz.value].cpu().numpy(),
@@ -125,10 +125,11 @@ def search_graph_device(eng, di_t, dd_t, di2_t, vertex_order_t, vertex_order, n_
                 vertex_order=np.asarray(vertex_order, np.int32), min_distance=np.float32(md.value))
 
 
-def search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_multiplier=1.5):
+def search_graph_bookkeeping(di, dd, di2, dd2, tree_idx, n_neighbors, pruning_degree_multiplier=1.5):
     """The sparse-matrix part of _init_search_graph (pynndescent_.py:1521-1651) on the host, from the two diversification
-    passes' outputs: `di`, `dd` = forward-diversified rows (-1 holes, zero distances already FLOAT32_EPS, :1526), `di2` = the
-    same rows after the second (CSR) pass -- a subset of `di` with the same distances.
+    passes' outputs: (`di`, `dd`) = forward-diversified rows (-1 holes, zero distances already FLOAT32_EPS, :1526) and
+    (`di2`, `dd2`) = the same rows after the second (CSR) pass: a subset of the first pass's entries with the same distances,
+    but PACKED by the pass itself, so the two pairs are not position-aligned.
 
     Same result as the reference's scipy sequence (coo -> csr, eliminate_zeros, transpose, maximum, setdiag(0), degree
     prune, != 0, leaf-order permutation), restated so that nothing loops over rows in Python and no sparsity-changing
@@ -141,7 +142,7 @@ def search_graph_bookkeeping(di, dd, di2, tree_idx, n_neighbors, pruning_degree_
     min_distance = np.min(dd[di >= 0])                                                           # :1539 (first-pass graph)
     keep = di2 >= 0
     indptr = np.zeros(n + 1, np.int64); np.cumsum(keep.sum(1), out=indptr[1:])                 # rows are already grouped and
-    g = sp.csr_array((dd[keep], di2[keep], indptr), shape=(n, n))                              # duplicate-free: CSR as is
+    g = sp.csr_array((dd2[keep], di2[keep], indptr), shape=(n, n))                             # duplicate-free: CSR as is
     g.eliminate_zeros()                                                                         # :1521-1537 + :1552-1587
     rev = g.transpose().tocsr()
     rev.sort_indices(); g.sort_indices()

@@ -83,7 +83,7 @@ def emu_lib(tmp_path_factory):
     lib.emu_norms.argtypes = [f32, C.c_long, C.c_int, f32]
     u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
     lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32]
-    lib.emu_search_graph.argtypes = [i32, i32, f32, C.c_long, C.c_int, i32, C.c_int, i32, i32, f32]
+    lib.emu_search_graph.argtypes = [i32, f32, i32, f32, C.c_long, C.c_int, i32, C.c_int, i32, i32, f32]
     lib.emu_search_graph.restype = C.c_long
     return lib
 
@@ -243,11 +243,11 @@ def test_candidate_kernels_and_cand_skip(emu_lib, skip):
     assert saw_hub and saw_inactive
 
 
-def _sg_emulate(emu_lib, di, dd, di2, vertex_order, max_degree):
+def _sg_emulate(emu_lib, di, dd, di2, dd2, vertex_order, max_degree):
     n, k = di.shape
     indptr = np.zeros(n + 1, np.int32); indices = np.zeros(2 * n * k + 8, np.int32); md = np.zeros(1, np.float32)
-    nnz = emu_lib.emu_search_graph(np.ascontiguousarray(di, np.int32), np.ascontiguousarray(di2, np.int32), np.ascontiguousarray(dd, np.float32),
-                                   n, k, np.ascontiguousarray(vertex_order, np.int32), max_degree, indptr, indices, md)
+    nnz = emu_lib.emu_search_graph(np.ascontiguousarray(di, np.int32), np.ascontiguousarray(dd, np.float32), np.ascontiguousarray(di2, np.int32),
+                                   np.ascontiguousarray(dd2, np.float32), n, k, np.ascontiguousarray(vertex_order, np.int32), max_degree, indptr, indices, md)
     return indptr, indices[:nnz], md[0]
 
 
@@ -259,8 +259,8 @@ def test_search_graph_kernels_match_reference_structures(emu_lib, name):
     from conftest import load_golden
     from test_prepare_host import _diversify_passes
     G = load_golden(name)
-    di, dd, di2 = _diversify_passes(orc, G)
-    indptr, indices, md = _sg_emulate(emu_lib, di, dd, di2, G["vertex_order"], int(np.round(1.5 * int(G["n_neighbors"]))))
+    di, dd, di2, dd2 = _diversify_passes(orc, G, packed=True)
+    indptr, indices, md = _sg_emulate(emu_lib, di, dd, di2, dd2, G["vertex_order"], int(np.round(1.5 * int(G["n_neighbors"]))))
     assert np.array_equal(indptr, G["indptr"]) and np.array_equal(indices, G["indices"])
     assert np.float32(md) == np.float32(G["min_distance"])
 
@@ -286,8 +286,13 @@ def test_search_graph_kernels_hubs_ties_and_big_rows(emu_lib):
     di2 = di.copy()
     drop = (rs.random_sample(di.shape) < 0.1) & (di >= 0); di2[drop] = -1      # second-pass drops (holes inside rows)
     vo = rs.permutation(n).astype(np.int32)
-    S = search_graph_bookkeeping(di, dd, di2, vo, nn)
-    indptr, indices, md = _sg_emulate(emu_lib, di, dd, di2, vo, int(np.round(1.5 * nn)))
+    S = search_graph_bookkeeping(di, dd, di2, dd, vo, nn)
+    indptr, indices, md = _sg_emulate(emu_lib, di, dd, di2, dd, vo, int(np.round(1.5 * nn)))
     rev_deg = np.bincount(di2[di2 >= 0], minlength=n)
     assert rev_deg.max() > 300 and (np.diff(S["indptr"]) == 0).any()
+    assert np.array_equal(indptr, S["indptr"]) and np.array_equal(indices, S["indices"]) and np.float32(md) == S["min_distance"]
+    # the layout nnd_diversify really hands over: second-pass survivors packed to the left with their own distances
+    order = np.argsort(di2 < 0, axis=1, kind="stable")
+    pi = np.take_along_axis(di2, order, 1); pd = np.take_along_axis(dd, order, 1); pd[pi < 0] = np.inf
+    indptr, indices, md = _sg_emulate(emu_lib, di, dd, pi, pd, vo, int(np.round(1.5 * nn)))
     assert np.array_equal(indptr, S["indptr"]) and np.array_equal(indices, S["indices"]) and np.float32(md) == S["min_distance"]

@@ -12,7 +12,7 @@ import pytest
 from conftest import QUERY_GOLDENS, load_golden
 
 
-def _diversify_passes(orc, G):
+def _diversify_passes(orc, G, packed=False):
     """(di, dd, di2) exactly as prepare_search_structures obtains them from the GPU: forward diversify, zero -> eps, and the
     second pass restated literally as in the oracle (diversify_csr on the forward rows, pynndescent_.py:1552-1587)."""
     import scipy.sparse as sp
@@ -33,16 +33,22 @@ def _diversify_passes(orc, G):
     dropped = np.zeros(di.shape, bool)
     dropped[col < cnt[:, None]] = gdata == 0.0
     di2[dropped] = -1
-    return di, dd, di2
+    dd2 = dd.copy()
+    if packed:        # what nnd_diversify hands back: every pass packs its own survivors to the left, distances alongside
+        order = np.argsort(di2 < 0, axis=1, kind="stable")
+        di2 = np.take_along_axis(di2, order, 1); dd2 = np.take_along_axis(dd2, order, 1)
+        dd2[di2 < 0] = np.inf
+    return di, dd, di2, dd2
 
 
+@pytest.mark.parametrize("packed", [False, True])
 @pytest.mark.parametrize("name", list(QUERY_GOLDENS))
-def test_search_graph_bookkeeping_matches_reference(name):
+def test_search_graph_bookkeeping_matches_reference(name, packed):
     from oracle import nnd_oracle as orc
     from pynndescent_b200.prepare import search_graph_bookkeeping
     G = load_golden(name)
-    di, dd, di2 = _diversify_passes(orc, G)
-    S = search_graph_bookkeeping(di, dd, di2, np.ascontiguousarray(G["vertex_order"], np.int32), int(G["n_neighbors"]))
+    di, dd, di2, dd2 = _diversify_passes(orc, G, packed)
+    S = search_graph_bookkeeping(di, dd, di2, dd2, np.ascontiguousarray(G["vertex_order"], np.int32), int(G["n_neighbors"]))
     for key in ("indptr", "indices", "tree_indices", "vertex_order"):
         assert S[key].dtype == np.int32 and np.array_equal(S[key], G[key]), key
     assert np.float32(S["min_distance"]) == np.float32(G["min_distance"])
@@ -62,7 +68,7 @@ def test_degree_prune_ties_and_hubs():
         w = np.sort(np.round(rs.random_sample(len(nb)), 1).astype(np.float32) + np.float32(0.1))   # coarse weights -> ties
         di[i, : len(nb)] = nb; dd[i, : len(nb)] = w
     tree_idx = rs.permutation(n).astype(np.int32)
-    S = search_graph_bookkeeping(di, dd, di.copy(), tree_idx, nn)
+    S = search_graph_bookkeeping(di, dd, di.copy(), dd.copy(), tree_idx, nn)
     # the reference's own sequence (scipy, row by row)
     import scipy.sparse as sp
     g = sp.coo_array((n, n), dtype=np.float32)
@@ -78,6 +84,28 @@ def test_degree_prune_ties_and_hubs():
     g = (g != 0).astype(np.uint8)
     g = g[tree_idx, :].tocsc()[:, tree_idx].tocsr(); g.sort_indices()
     assert np.array_equal(S["indptr"], g.indptr) and np.array_equal(S["indices"], g.indices)
+
+
+def test_second_pass_survivors_need_not_be_position_aligned():
+    """nnd_diversify packs its survivors, so (di2, dd2) is a re-packed subset of (di, dd): same graph either way.  (In all
+    five reference goldens the second pass drops nothing, so only synthetic drops exercise this.)"""
+    from pynndescent_b200.prepare import search_graph_bookkeeping
+    rs = np.random.RandomState(3)
+    n, k = 600, 10
+    di = np.full((n, k), -1, np.int32); dd = np.full((n, k), np.inf, np.float32)
+    for i in range(n):
+        m = rs.randint(2, k + 1)
+        di[i, :m] = rs.choice(np.delete(np.arange(n), i), m, replace=False)
+        dd[i, :m] = np.sort(rs.random_sample(m).astype(np.float32) + np.float32(0.05))
+    di2 = di.copy(); di2[(rs.random_sample(di.shape) < 0.3) & (di >= 0)] = -1
+    order = np.argsort(di2 < 0, axis=1, kind="stable")
+    pi = np.take_along_axis(di2, order, 1); pd = np.take_along_axis(dd, order, 1); pd[pi < 0] = np.inf
+    assert not np.array_equal(pi, di2)
+    vo = rs.permutation(n).astype(np.int32)
+    A = search_graph_bookkeeping(di, dd, di2, dd, vo, 4)
+    B = search_graph_bookkeeping(di, dd, pi, pd, vo, 4)
+    assert np.array_equal(A["indptr"], B["indptr"]) and np.array_equal(A["indices"], B["indices"])
+    assert A["min_distance"] == B["min_distance"] == dd[di >= 0].min()
 
 
 def _flatten_reference(start, size, left, right, hrow, hyp, off, d):
