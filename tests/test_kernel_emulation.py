@@ -82,7 +82,7 @@ def emu_lib(tmp_path_factory):
                              C.c_int, C.c_long, i32, i32, f32, u32, u64, u32, i64]
     lib.emu_norms.argtypes = [f32, C.c_long, C.c_int, f32]
     u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
-    lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32]
+    lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32, C.c_long, C.c_long]
     lib.emu_search_graph.argtypes = [i32, f32, i32, f32, C.c_long, C.c_int, i32, C.c_int, i32, i32, f32]
     lib.emu_search_graph.restype = C.c_long
     return lib
@@ -228,7 +228,7 @@ def test_candidate_kernels_and_cand_skip(emu_lib, skip):
         indeg = np.bincount(ind[ind >= 0], minlength=n)
         saw_hub |= bool((indeg > 32).any())
         en = np.empty((n, k), np.int32); eo = np.empty((n, k), np.int32)
-        emu_lib.emu_cand(ind, flags_emu, n, k, k, 8, rng_state, skip, en, eo)
+        emu_lib.emu_cand(ind, flags_emu, n, k, k, 8, rng_state, skip, en, eo, 0, 2 ** 62)
         newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)         # also clears the sampled flags of `heap`
         assert np.array_equal(en, newc)
         has_new = (newc >= 0).any(1)
@@ -296,3 +296,38 @@ def test_search_graph_kernels_hubs_ties_and_big_rows(emu_lib):
     pi = np.take_along_axis(di2, order, 1); pd = np.take_along_axis(dd, order, 1); pd[pi < 0] = np.inf
     indptr, indices, md = _sg_emulate(emu_lib, di, dd, pi, pd, vo, int(np.round(1.5 * nn)))
     assert np.array_equal(indptr, S["indptr"]) and np.array_equal(indices, S["indices"]) and np.float32(md) == S["min_distance"]
+
+
+@pytest.mark.parametrize("skip", [0, 1])
+def test_candidate_kernels_row_sharded(emu_lib, skip):
+    """The sharded build (nnd_set_row_range): every process samples candidates for its own row range only, from the replicated
+    heap.  Two ranges, each emulated separately, must add up to the oracle's lists (and flag clearing) -- with and without
+    NND_CAND_SKIP."""
+    from sklearn.utils import check_random_state
+    from oracle import nnd_oracle as orc
+    n, d, k = 700, 16, 8
+    X = latent(n, d, 12)
+    rs = check_random_state(4)
+    rng_state = rs.randint(orc.INT32_MIN, orc.INT32_MAX, 3).astype(np.int64)
+    la, _ = orc.make_forest(X, k, 3, None, rs, False, 200, "level")
+    heap = orc.make_heap(n, k)
+    orc.init_rp_tree(X, "euclidean", heap, la); orc.init_random(X, "euclidean", heap, rng_state)
+    for it in range(3):
+        ind = heap[0].copy(); f0 = heap[2].copy()
+        B = n // 2 + 1                                             # utils.py:259 ownership rule for 2 processes
+        parts = []
+        for lo, hi in ((0, B), (B, n)):
+            fl = f0.copy(); en = np.full((n, k), -7, np.int32); eo = np.full((n, k), -7, np.int32)
+            emu_lib.emu_cand(ind, fl, n, k, k, 8, rng_state, skip, en, eo, lo, hi)
+            assert np.all(en[:lo] == -7) and np.all(en[hi:] == -7)   # nothing written outside the own range
+            parts.append((lo, hi, en, eo, fl))
+        newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)
+        has_new = (newc >= 0).any(1)
+        for lo, hi, en, eo, fl in parts:
+            assert np.array_equal(en[lo:hi], newc[lo:hi])
+            sel = has_new[lo:hi]
+            assert np.array_equal(eo[lo:hi][sel], oldc[lo:hi][sel])
+            if not skip:
+                assert np.array_equal(eo[lo:hi], oldc[lo:hi])
+            assert np.array_equal(fl[lo:hi], heap[2][lo:hi]) and np.array_equal(fl[:lo], f0[:lo]) and np.array_equal(fl[hi:], f0[hi:])
+        orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
