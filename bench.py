@@ -251,7 +251,7 @@ def main():
     del eng, idx_t, dist_t, sb
     torch.cuda.empty_cache()
     Xp = torch.from_numpy(X).pin_memory().numpy()
-    NNDescent(Xp, metric, n_neighbors=k, random_state=42, sharded=(world > 1))  # warm allocator
+    NNDescent(Xp, metric, n_neighbors=k, random_state=42, sharded=(world > 1)).neighbor_graph  # warm allocators (device + pinned staging)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = max(1, min(args.steps, 3))
