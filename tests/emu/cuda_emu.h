@@ -53,6 +53,15 @@ struct dim3 { unsigned x = 1, y = 1, z = 1; };
 static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace emu {
+// EMU_CHAOS=<permille>: every synchronisation primitive first sleeps for a random 0-300 us with that probability, so that
+// repeated runs visit very different interleavings of producer lanes, consumer warps and the copy engine
+static inline void chaos() {
+    static const int permille = [] { const char *e = getenv("EMU_CHAOS"); return e ? atoi(e) : 0; }();
+    if (permille <= 0) return;
+    static thread_local unsigned s = (unsigned)std::hash<std::thread::id>()(std::this_thread::get_id()) | 1u;
+    s = s * 1664525u + 1013904223u;
+    if ((int)((s >> 10) % 1000u) < permille) std::this_thread::sleep_for(std::chrono::microseconds((s >> 20) % 300u));
+}
 struct MBar {
     std::mutex m; std::condition_variable cv;
     int count = 0, pending = 0; long tx = 0; unsigned phase = 0;
@@ -89,6 +98,7 @@ struct Block {
                     size_t pick = (lcg >> 8) % q.size();
                     c = q[pick]; q.erase(q.begin() + pick);
                 }
+                chaos();
                 memcpy(c.dst, c.src, c.bytes);
                 c.bar->complete_tx((long)c.bytes);
             }
@@ -154,7 +164,7 @@ static void launch_seq(long grid, int block, F kernel) {
 
 // ---- synchronisation
 static inline void __syncthreads() { emu::g_block->bar.arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp().bar.arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::chaos(); emu::warp().bar.arrive_and_wait(); }
 template <class T, class SEL>
 static inline T emu_exchange(T v, SEL pick) {
     static_assert(sizeof(T) <= 8, "shuffle of a type wider than 8 bytes");
@@ -189,11 +199,12 @@ static inline void mbar_init(uint64_t *bar, uint32_t count) {
     p.reset(new emu::MBar()); p->count = (int)count; p->pending = (int)count;
 }
 static inline void mbar_fence_init() {}
-static inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { emu::g_block->mbar(bar)->arrive((long)bytes); }
-static inline void mbar_arrive(uint64_t *bar) { emu::g_block->mbar(bar)->arrive(0); }
-static inline void mbar_wait(uint64_t *bar, uint32_t parity) { emu::g_block->mbar(bar)->wait(parity); }
+static inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { emu::chaos(); emu::g_block->mbar(bar)->arrive((long)bytes); }
+static inline void mbar_arrive(uint64_t *bar) { emu::chaos(); emu::g_block->mbar(bar)->arrive(0); }
+static inline void mbar_wait(uint64_t *bar, uint32_t parity) { emu::chaos(); emu::g_block->mbar(bar)->wait(parity); emu::chaos(); }
 static inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15) || (bytes & 15)) { fprintf(stderr, "emu: misaligned bulk copy\n"); abort(); }
+    emu::chaos();
     emu::Block *B = emu::g_block;
     emu::MBar *mb = B->mbar(bar);
     { std::lock_guard<std::mutex> g(B->qm); B->q.push_back(emu::Copy{dst, src, bytes, mb}); }
