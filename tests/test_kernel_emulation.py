@@ -61,11 +61,13 @@ def emu_lib(tmp_path_factory):
     sg = open(os.path.join(CSRC, "k_search_graph.cu")).read()
     sg = _between(sg, "#define SG_WARPS", "// ------------------------------------------------------------------------------------------------ host",
                   "the search-graph kernels")
-    kernels = batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg
+    route = _between(desc, "// ------------------------------------------------------------------ routing",
+                     "// ---- thread-per-row apply for rows with few records", "k_scatter / k_scatter_rank / k_apply")
+    kernels = batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg + "\n#define EMU_WITH_APPLY 1\n" + route
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 4 and "extern __shared__" not in kernels
+    assert n_ext == 5 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -85,6 +87,9 @@ def emu_lib(tmp_path_factory):
     lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32, C.c_long, C.c_long]
     lib.emu_search_graph.argtypes = [i32, f32, i32, f32, C.c_long, C.c_int, i32, C.c_int, i32, i32, f32]
     lib.emu_search_graph.restype = C.c_long
+    lib.emu_process_candidates.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_void_p, i32, f32, u8, C.c_int, i32, i32, C.c_int, C.c_void_p,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.emu_process_candidates.restype = C.c_long
     return lib
 
 
@@ -331,3 +336,29 @@ def test_candidate_kernels_row_sharded(emu_lib, skip):
                 assert np.array_equal(eo[lo:hi], oldc[lo:hi])
             assert np.array_equal(fl[lo:hi], heap[2][lo:hi]) and np.array_equal(fl[:lo], f0[:lo]) and np.array_equal(fl[hi:], f0[hi:])
         orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
+
+
+@pytest.mark.parametrize("kernel,rank_scatter,leaf_order", [(0, 0, False), (0, 1, False), (1, 0, False), (1, 1, True)])
+def test_whole_iterations_match_the_oracle_heaps(emu_lib, kernel, rank_scatter, leaf_order):
+    """Three NN-descent iterations: candidates from the oracle, then join -> scatter -> apply under the emulator; after every
+    iteration the heaps (indices, distances, flags, layout) and the accepted-push count must equal the oracle's
+    process_candidates.  (0, 0) is the hardware-verified schedule = emulator check; the others are the switches of DESIGN 10a
+    (k_join_pipe, NND_RANK_SCATTER, a permuted join order)."""
+    from sklearn.utils import check_random_state
+    from oracle import nnd_oracle as orc
+    n, d, k = 450, 24, 10
+    X = latent(n, d, 21)
+    rs = check_random_state(6)
+    rng_state = rs.randint(orc.INT32_MIN, orc.INT32_MAX, 3).astype(np.int64)
+    la, _ = orc.make_forest(X, k, 3, None, rs, False, 200, "level")
+    heap = orc.make_heap(n, k)
+    orc.init_rp_tree(X, "euclidean", heap, la); orc.init_random(X, "euclidean", heap, rng_state)
+    order = np.random.RandomState(1).permutation(n).astype(np.int32) if leaf_order else None
+    for it in range(3):
+        newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)
+        e_idx, e_dist, e_flag = (a.copy() for a in heap)
+        c_emu = emu_lib.emu_process_candidates(np.ascontiguousarray(X), n, d, 0, None, e_idx, e_dist, e_flag, k, newc, oldc, k,
+                                               None if order is None else order.ctypes.data_as(C.c_void_p), kernel, 32, 3, 4, rank_scatter)
+        c_orc, _ = orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
+        assert c_emu == c_orc and c_orc > 0
+        assert np.array_equal(e_idx, heap[0]) and np.array_equal(e_dist, heap[1]) and np.array_equal(e_flag, heap[2])
