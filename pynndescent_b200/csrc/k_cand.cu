@@ -220,6 +220,11 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *i
 // the reverse edges are staged in shared memory (column per thread), the next edge in scan order
 // is found by selection, and checked_heap_push is replayed by the thread on column-layout heaps.
 #define SEL_T 128
+// SMEM_KEYS (NND_CAND_KEYS=1, default off until measured): the selection below reads the key word of every remaining
+// reverse edge once per step -- nrev^2/2 loads per vertex, each a different address per lane, i.e. up to 32 L1 wavefronts
+// per warp load.  Staging the <= 32 key words of the vertex once, column-wise in shared memory ([j][thread]: one
+// conflict-free wavefront per warp load), leaves nrev uncoalesced loads and moves the quadratic part on chip.
+template <bool SMEM_KEYS>
 __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
                                                              const uint32_t *indeg, const uint32_t *revoff,
                                                              const unsigned long long *rev, const float *fprio,
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
     float *npri = (float *)smem_raw + tid;                                         // [C][SEL_T]
     float *opri = npri + (size_t)C * SEL_T;
     int32_t *nind = (int32_t *)(opri + (size_t)C * SEL_T), *oind = nind + (size_t)C * SEL_T;
+    uint32_t *skey = (uint32_t *)(oind + (size_t)C * SEL_T);     // [SEL_SMALL][SEL_T] (SMEM_KEYS only); like the heaps: column `tid`
     if (v >= N || v < lo || v >= hi) return;
     const uint32_t nrev = indeg[v];
     if (nrev > SEL_SMALL) return;  // handled by the warp kernel
@@ -240,6 +246,8 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
     }
     for (int c = 0; c < C; ++c) { npri[c * SEL_T] = CUDART_INF_F; opri[c * SEL_T] = CUDART_INF_F; nind[c * SEL_T] = -1; oind[c * SEL_T] = -1; }
     const unsigned long long *seg = rev + revoff[v];
+    if (SMEM_KEYS)
+        for (uint32_t j = 0; j < nrev; ++j) skey[j * SEL_T] = ((const uint32_t *)seg)[2 * j + 1];
     int jf = 0; uint32_t left = nrev, used = 0;   // bit j of `used`: reverse edge j already consumed
     const unsigned long long fbase = (unsigned long long)v * k;
     for (;;) {
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
                 uint32_t bk = 0xFFFFFFFFu;
                 for (uint32_t j = 0; j < nrev; ++j) {
                     if ((used >> j) & 1u) continue;
-                    uint32_t x = kw[2 * j + 1];
+                    uint32_t x = SMEM_KEYS ? skey[j * SEL_T] : kw[2 * j + 1];
                     if (x < bk) { bk = x; bj = (int)j; }
                 }
                 if (bj >= 0) best = seg[bj];
@@ -361,9 +369,15 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
     size_t smem_small = (size_t)C * SEL_T * 16;
     const int use_small = smem_small <= 200 * 1024;
-    if (use_small) {
-        NND_CUDA(cudaFuncSetAttribute(k_cand_select_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
-        k_cand_select_small<<<(unsigned)cdiv(N, SEL_T), SEL_T, smem_small, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
+    if (use_small && ctx->opt_cand_keys && smem_small + (size_t)SEL_SMALL * SEL_T * 4 <= 200 * 1024) {
+        const size_t sm2 = smem_small + (size_t)SEL_SMALL * SEL_T * 4;
+        NND_CUDA(cudaFuncSetAttribute(k_cand_select_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        k_cand_select_small<true><<<(unsigned)cdiv(N, SEL_T), SEL_T, sm2, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg, W.revoff, W.rev,
+                                                                           W.fprio, new_cand, old_cand, ctx->row_lo, ctx->row_hi, act);
+        NND_LAUNCH(ctx);
+    } else if (use_small) {
+        NND_CUDA(cudaFuncSetAttribute(k_cand_select_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        k_cand_select_small<false><<<(unsigned)cdiv(N, SEL_T), SEL_T, smem_small, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
                                                                             W.revoff, W.rev, W.fprio, new_cand, old_cand, ctx->row_lo, ctx->row_hi, act);
         NND_LAUNCH(ctx);
     }

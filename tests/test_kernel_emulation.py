@@ -84,7 +84,7 @@ def emu_lib(tmp_path_factory):
                              C.c_int, C.c_long, i32, i32, f32, u32, u64, u32, i64]
     lib.emu_norms.argtypes = [f32, C.c_long, C.c_int, f32]
     u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
-    lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32, C.c_long, C.c_long]
+    lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32, C.c_long, C.c_long, C.c_int]
     lib.emu_search_graph.argtypes = [i32, f32, i32, f32, C.c_long, C.c_int, i32, C.c_int, i32, i32, f32]
     lib.emu_search_graph.restype = C.c_long
     lib.emu_process_candidates.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_void_p, i32, f32, u8, C.c_int, i32, i32, C.c_int, C.c_void_p,
@@ -212,11 +212,11 @@ def test_cases_are_not_trivial(emu_lib, cases):
         print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
 
 
-@pytest.mark.parametrize("skip", [0, 1])
-def test_candidate_kernels_and_cand_skip(emu_lib, skip):
+@pytest.mark.parametrize("skip,keys", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_candidate_kernels_and_cand_skip(emu_lib, skip, keys):
     """k_cand_count / k_cand_fill / k_cand_select* under the emulator against the oracle's new_build_candidates, over three
     iterations of a small build (hub vertices with > 32 reverse edges included).  skip=0 is the hardware-verified schedule
-    (all rows must match); skip=1 = NND_CAND_SKIP: rows WITH new candidates must match exactly, the others must come out
+    (all rows must match); keys=1 = NND_CAND_KEYS (reverse-edge key words staged in shared memory); skip=1 = NND_CAND_SKIP: rows WITH new candidates must match exactly, the others must come out
     empty, and the sampled-flag clearing must be identical."""
     from sklearn.utils import check_random_state
     from oracle import nnd_oracle as orc
@@ -233,7 +233,7 @@ def test_candidate_kernels_and_cand_skip(emu_lib, skip):
         indeg = np.bincount(ind[ind >= 0], minlength=n)
         saw_hub |= bool((indeg > 32).any())
         en = np.empty((n, k), np.int32); eo = np.empty((n, k), np.int32)
-        emu_lib.emu_cand(ind, flags_emu, n, k, k, 8, rng_state, skip, en, eo, 0, 2 ** 62)
+        emu_lib.emu_cand(ind, flags_emu, n, k, k, 8, rng_state, skip, en, eo, 0, 2 ** 62, keys)
         newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)         # also clears the sampled flags of `heap`
         assert np.array_equal(en, newc)
         has_new = (newc >= 0).any(1)
@@ -323,7 +323,7 @@ def test_candidate_kernels_row_sharded(emu_lib, skip):
         parts = []
         for lo, hi in ((0, B), (B, n)):
             fl = f0.copy(); en = np.full((n, k), -7, np.int32); eo = np.full((n, k), -7, np.int32)
-            emu_lib.emu_cand(ind, fl, n, k, k, 8, rng_state, skip, en, eo, lo, hi)
+            emu_lib.emu_cand(ind, fl, n, k, k, 8, rng_state, skip, en, eo, lo, hi, skip)
             assert np.all(en[:lo] == -7) and np.all(en[hi:] == -7)   # nothing written outside the own range
             parts.append((lo, hi, en, eo, fl))
         newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)
