@@ -24,7 +24,8 @@ CONFIGS = {
     "leaf+rank": {"NND_JOIN_ORDER": "leaf", "NND_RANK_SCATTER": "1"},
     "candskip": {"NND_CAND_SKIP": "1"},
     "candkeys": {"NND_CAND_KEYS": "1"},
-    "candskip+keys": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "1"},
+    "candtile": {"NND_CAND_KEYS": "2"},
+    "candskip+tile": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2"},
     "pipe": {"NND_JOIN_PIPE": "1"},
     "pipe+rank": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1"},
     "pipe+rank+leaf": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf"},

@@ -67,7 +67,7 @@ def emu_lib(tmp_path_factory):
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 5 and "extern __shared__" not in kernels
+    assert n_ext == 6 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -212,11 +212,11 @@ def test_cases_are_not_trivial(emu_lib, cases):
         print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
 
 
-@pytest.mark.parametrize("skip,keys", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("skip,keys", [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)])
 def test_candidate_kernels_and_cand_skip(emu_lib, skip, keys):
     """k_cand_count / k_cand_fill / k_cand_select* under the emulator against the oracle's new_build_candidates, over three
     iterations of a small build (hub vertices with > 32 reverse edges included).  skip=0 is the hardware-verified schedule
-    (all rows must match); keys=1 = NND_CAND_KEYS (reverse-edge key words staged in shared memory); skip=1 = NND_CAND_SKIP: rows WITH new candidates must match exactly, the others must come out
+    (all rows must match); keys=1 / 2 = NND_CAND_KEYS (reverse-edge key words / the whole tile staged in shared memory); skip=1 = NND_CAND_SKIP: rows WITH new candidates must match exactly, the others must come out
     empty, and the sampled-flag clearing must be identical."""
     from sklearn.utils import check_random_state
     from oracle import nnd_oracle as orc
@@ -323,7 +323,7 @@ def test_candidate_kernels_row_sharded(emu_lib, skip):
         parts = []
         for lo, hi in ((0, B), (B, n)):
             fl = f0.copy(); en = np.full((n, k), -7, np.int32); eo = np.full((n, k), -7, np.int32)
-            emu_lib.emu_cand(ind, fl, n, k, k, 8, rng_state, skip, en, eo, lo, hi, skip)
+            emu_lib.emu_cand(ind, fl, n, k, k, 8, rng_state, skip, en, eo, lo, hi, 2 * skip)
             assert np.all(en[:lo] == -7) and np.all(en[hi:] == -7)   # nothing written outside the own range
             parts.append((lo, hi, en, eo, fl))
         newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)
