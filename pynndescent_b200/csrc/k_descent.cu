@@ -29,7 +29,7 @@
 struct JoinParams {
     const float *X; int64_t N; int d, ld; int metric; const void *aux;
     const float *thr;
-    int mode;  // 0 local join, 1 leaf (routed), 2 leaf fused with apply
+    int mode;  // 0 local join, 1 leaf (routed), 2 leaf fused with apply, 3 leaf: distance matrix only (-> k_leaf_push)
     const int32_t *newc, *oldc; int C; int64_t unit_begin, unit_end;
     const int32_t *leaf_points; const int64_t *leaf_offsets;
     int m_max, slot_stride;
@@ -41,6 +41,8 @@ struct JoinParams {
     // mode 2 (fused leaf join + apply): heaps are updated in place by the leaf's own CTA
     int32_t *heap_idx; float *heap_dist; uint8_t *heap_flag; int k; int d_alias;
     int64_t row_lo, row_hi;   // mode 0: rows outside are skipped (sharded build)
+    // mode 3 (split leaf init, NND_LEAF_SPLIT): the leaf's distance matrix goes to global memory, k_leaf_push applies it
+    float *leaf_D; const uint32_t *leaf_doff;
 };
 
 // compile-time views of a metric CLASS (nnd_metric_class): per-row auxiliaries in shared memory, accumulator type
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     if (nn == 0 || (P.mode != 0 && m < 2)) return;
     for (int j = tid; j < m; j += nthr) {
         int32_t id = ids[j];
-        thr_s[j] = (P.mode == 2) ? CUDART_INF_F : P.thr[id];
+        thr_s[j] = (P.mode >= 2) ? CUDART_INF_F : P.thr[id];
         if (MC_AUX1(METRIC)) n2_s[j] = ((const float *)P.aux)[id];
         if (MC_AUX2(METRIC)) {
             mu_s[2 * j] = ((const double *)P.aux)[2 * (int64_t)id];
@@ -261,6 +263,23 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                 dd[i][u * TILE + v] = r;
             }
         npush += __popc(pm[i]);
+    }
+    if (P.mode == 3) {
+        // ---- split leaf init: the m x m distance matrix of the leaf -> global memory, both triangles, row b contiguous
+        // over a, so that k_leaf_push's thread-per-member reads are coalesced
+        float *Dg = P.leaf_D + P.leaf_doff[unit - P.unit_begin];
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            if (my_ta[i] < 0) continue;
+#pragma unroll
+            for (int u = 0; u < TILE; ++u)
+#pragma unroll
+                for (int v = 0; v < TILE; ++v) {
+                    int a = my_ta[i] * TILE + u, b = my_tb[i] * TILE + v;
+                    if (a < nn && b < m && b > a) { Dg[(size_t)a * m + b] = dd[i][u * TILE + v]; Dg[(size_t)b * m + a] = dd[i][u * TILE + v]; }
+                }
+        }
+        return;
     }
     if (P.mode == 2) {
         // ---- fused apply: distance matrix -> smem, then ONE THREAD PER MEMBER replays its pushes.
@@ -781,6 +800,73 @@ __global__ void k_leaf_bound(const int64_t *leaf_offsets, int64_t n_leaves, uint
     bound[i] = m * (m - (m > 0));
 }
 
+// ------------------------------------------------------------------ split leaf init (NND_LEAF_SPLIT, default off)
+// The fused leaf kernel keeps a 42 KB row buffer per CTA alive while ONE THREAD PER MEMBER replays the pushes: 4 CTAs per SM,
+// two busy warps each, long dependent shared-memory chains (ncu_leaf_r01.txt: 16 % of the warp slots active, issue 29 %).
+// Split: k_join mode 3 only produces the leaf's distance matrix (global, 4 m^2 bytes per leaf), and k_leaf_push replays the
+// pushes with nothing but the heap columns in shared memory (9k bytes per member): 1.5k resident threads per SM instead of
+// ~170.  Same pushes in the same order (the other members in ascending leaf position), so the heaps are identical.
+__global__ void k_leaf_prep(const int64_t *leaf_offsets, int64_t l0, int64_t l1, int64_t pos0, uint32_t *dsz, int32_t *pos2leaf) {
+    int64_t l = l0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= l1) return;
+    const int64_t o0 = leaf_offsets[l], o1 = leaf_offsets[l + 1];
+    const uint32_t m = (uint32_t)(o1 - o0);
+    dsz[l - l0] = m * m;
+    for (int64_t p = o0; p < o1; ++p) pos2leaf[p - pos0] = (int32_t)(l - l0);
+}
+#define LP_T 128
+__global__ void __launch_bounds__(LP_T) k_leaf_push(const int32_t *leaf_points, const int64_t *leaf_offsets, int64_t l0, int64_t pos0,
+                                                    int64_t npos, const int32_t *pos2leaf, const uint32_t *doff, const float *D,
+                                                    int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    float *hpri = (float *)smem_raw;                                   // [k][LP_T]
+    int32_t *hind = (int32_t *)(hpri + (size_t)k * LP_T);
+    uint8_t *hflg = (uint8_t *)(hind + (size_t)k * LP_T);
+    int32_t *s_row = (int32_t *)(smem_raw + (((size_t)k * LP_T * 9 + 15) & ~size_t(15)));   // [LP_T] heap row of every thread's member
+    const int64_t p0 = (int64_t)blockIdx.x * LP_T, p = p0 + tid;
+    const int nth = (int)min((int64_t)LP_T, npos - p0);
+    s_row[tid] = p < npos ? leaf_points[pos0 + p] : -1;
+    __syncthreads();
+    for (int e = tid; e < nth * k; e += LP_T) {            // the tile's heap rows (a gather by point id), 15 lanes per row
+        const int r = e / k, j = e - r * k; const int64_t row = s_row[r];
+        hpri[j * LP_T + r] = heap_dist[row * k + j]; hind[j * LP_T + r] = heap_idx[row * k + j]; hflg[j * LP_T + r] = heap_flag[row * k + j];
+    }
+    __syncthreads();
+    if (p < npos) {
+        const int l = pos2leaf[p];
+        const int64_t o0 = leaf_offsets[l0 + l];
+        const int m = (int)(leaf_offsets[l0 + l + 1] - o0), a = (int)(pos0 + p - o0);
+        const float *Dl = D + doff[l];
+        float *pri = hpri + tid; int32_t *ind = hind + tid; uint8_t *flg = hflg + tid;
+        for (int b = 0; b < m; ++b) {
+            if (b == a) continue;
+            const float pr = Dl[(size_t)b * m + a];
+            if (pr >= pri[0]) continue;
+            const int32_t nb = leaf_points[o0 + b];
+            bool dup = false;
+            for (int j = 0; j < k; ++j) dup |= (ind[j * LP_T] == nb);
+            if (dup) continue;
+            int i = 0, i_swap;
+            for (;;) {
+                int ic1 = 2 * i + 1, ic2 = ic1 + 1;
+                if (ic1 >= k) break;
+                else if (ic2 >= k) { if (pri[ic1 * LP_T] > pr) i_swap = ic1; else break; }
+                else if (pri[ic1 * LP_T] >= pri[ic2 * LP_T]) { if (pr < pri[ic1 * LP_T]) i_swap = ic1; else break; }
+                else { if (pr < pri[ic2 * LP_T]) i_swap = ic2; else break; }
+                pri[i * LP_T] = pri[i_swap * LP_T]; ind[i * LP_T] = ind[i_swap * LP_T]; flg[i * LP_T] = flg[i_swap * LP_T];
+                i = i_swap;
+            }
+            pri[i * LP_T] = pr; ind[i * LP_T] = nb; flg[i * LP_T] = 1;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nth * k; e += LP_T) {
+        const int r = e / k, j = e - r * k; const int64_t row = s_row[r];
+        heap_dist[row * k + j] = hpri[j * LP_T + r]; heap_idx[row * k + j] = hind[j * LP_T + r]; heap_flag[row * k + j] = hflg[j * LP_T + r];
+    }
+}
+
 // ------------------------------------------------------------------ host orchestration
 struct DescentWs {
     float *thr; uint32_t *cnt, *off, *bound, *bound_scan, *scan_tmp;
@@ -1080,11 +1166,27 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
             J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
             J.mode = 2; J.leaf_points = leaf_points; J.leaf_offsets = leaf_offsets; J.m_max = mm; J.slot_stride = mm;
             J.heap_idx = P->heap_idx; J.heap_dist = P->heap_dist; J.heap_flag = P->heap_flag; J.k = P->k; J.d_alias = al;
+            // NND_LEAF_SPLIT: distance matrices to global memory (k_join mode 3), pushes by k_leaf_push.  Scratch comes from
+            // arrays of the routing workspace that the fused path never touches; fall back to the fused kernel if it is short.
+            const size_t lp_smem = (((size_t)P->k * LP_T * 9 + 15) & ~size_t(15)) + (size_t)LP_T * 4;
+            bool split = ctx->opt_leaf_split && push_capacity >= N + 16 && (size_t)push_capacity * 2 * sizeof(Rec16) >= (size_t)N * mm * 4 &&
+                         (double)N * mm < 4.0e9 && lp_smem <= 200 * 1024;
+            if (split) NND_CUDA(cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
             NND_CUDA(cudaEventRecord(ctx->ev0, st));
             for (size_t t = 0; t + 1 < tree_cut.size(); ++t) {
                 J.unit_begin = tree_cut[t]; J.unit_end = tree_cut[t + 1];
-                NND_TRY(launch_join(ctx, J, J.unit_end - J.unit_begin, st));
+                if (!split) { NND_TRY(launch_join(ctx, J, J.unit_end - J.unit_begin, st)); continue; }
+                const int64_t l0 = tree_cut[t], l1 = tree_cut[t + 1], nl = l1 - l0, pos0 = offs[l0], npos = offs[l1] - pos0;
+                uint32_t *dsz = W.l_pos, *doff = (uint32_t *)W.l_oth; int32_t *pos2leaf = W.l_tgt; float *D = (float *)W.rec;
+                k_leaf_prep<<<(unsigned)cdiv(nl, 128), 128, 0, st>>>(leaf_offsets, l0, l1, pos0, dsz, pos2leaf); NND_LAUNCH(ctx);
+                NND_TRY(nnd_exclusive_scan_u32(ctx, dsz, doff, nl, W.scan_tmp, st));
+                JoinParams J3 = J; J3.mode = 3; J3.leaf_D = D; J3.leaf_doff = doff;
+                NND_TRY(launch_join(ctx, J3, nl, st));
+                k_leaf_push<<<(unsigned)cdiv(npos, LP_T), LP_T, lp_smem, st>>>(leaf_points, leaf_offsets, l0, pos0, npos, pos2leaf, doff, D,
+                                                                            P->heap_idx, P->heap_dist, P->heap_flag, P->k);
+                NND_LAUNCH(ctx);
             }
+            NND_CUDA(cudaGetLastError());
             NND_CUDA(cudaEventRecord(ctx->ev1, st));
             NND_CUDA(cudaStreamSynchronize(st));
             float ms = 0.f;

@@ -8,7 +8,7 @@ with it, and prints for each: bit-equality of (indices, distances, per-iteration
 schedule, build ms, the local-join kernel ms (CUDA events inside the library) and stage timings.
 
 This is the first thing to run in a round that has GPU time: the kernels behind NND_JOIN_PIPE / NND_RANK_SCATTER /
-NND_JOIN_ORDER / NND_CAND_SKIP were written after round 1's GPU budget was spent and have only been compiled (see k_join_pipe.cu).
+NND_JOIN_ORDER / NND_CAND_SKIP / NND_CAND_KEYS / NND_LEAF_SPLIT were written after round 1's GPU budget was spent and have only been compiled (see k_join_pipe.cu).
 """
 import json
 import os
@@ -22,6 +22,7 @@ CONFIGS = {
     "rank": {"NND_RANK_SCATTER": "1"},
     "leaf": {"NND_JOIN_ORDER": "leaf"},
     "leaf+rank": {"NND_JOIN_ORDER": "leaf", "NND_RANK_SCATTER": "1"},
+    "leafsplit": {"NND_LEAF_SPLIT": "1"},
     "candskip": {"NND_CAND_SKIP": "1"},
     "candkeys": {"NND_CAND_KEYS": "1"},
     "candtile": {"NND_CAND_KEYS": "2"},
@@ -29,7 +30,7 @@ CONFIGS = {
     "pipe": {"NND_JOIN_PIPE": "1"},
     "pipe+rank": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1"},
     "pipe+rank+leaf": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf"},
-    "all": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf", "NND_CAND_SKIP": "1", "NND_CAND_KEYS": "1"},
+    "all": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf", "NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2", "NND_LEAF_SPLIT": "1"},
     "pipe-s3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "3"},
     "pipe-s2c3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "2", "NND_PIPE_CTAS": "3"},
     "pipe-s6": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "6"},

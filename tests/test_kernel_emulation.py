@@ -63,11 +63,16 @@ def emu_lib(tmp_path_factory):
                   "the search-graph kernels")
     route = _between(desc, "// ------------------------------------------------------------------ routing",
                      "// ---- thread-per-row apply for rows with few records", "k_scatter / k_scatter_rank / k_apply")
-    kernels = batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg + "\n#define EMU_WITH_APPLY 1\n" + route
+    join = _between(desc, "#define DK 128", "// =====================================================================================================\n// k_join_batch:",
+                    "JoinParams / k_join")
+    leaf = _between(desc, "// ------------------------------------------------------------------ split leaf init",
+                    "// ------------------------------------------------------------------ host orchestration", "k_leaf_prep / k_leaf_push")
+    kernels = (join + "\n" + batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
+               "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf)
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 6 and "extern __shared__" not in kernels
+    assert n_ext == 8 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -90,6 +95,7 @@ def emu_lib(tmp_path_factory):
     lib.emu_process_candidates.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_void_p, i32, f32, u8, C.c_int, i32, i32, C.c_int, C.c_void_p,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.emu_process_candidates.restype = C.c_long
+    lib.emu_leaf_init.argtypes = [f32, C.c_long, C.c_int, C.c_int, i32, i64, C.c_long, C.c_int, i32, f32, u8, C.c_int, C.c_int]
     return lib
 
 
@@ -362,3 +368,28 @@ def test_whole_iterations_match_the_oracle_heaps(emu_lib, kernel, rank_scatter, 
         c_orc, _ = orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
         assert c_emu == c_orc and c_orc > 0
         assert np.array_equal(e_idx, heap[0]) and np.array_equal(e_dist, heap[1]) and np.array_equal(e_flag, heap[2])
+
+
+@pytest.mark.parametrize("split", [0, 1])
+def test_leaf_init_fused_and_split(emu_lib, split):
+    """init_rp_tree (pynndescent_.py:116-185): the fused leaf kernel (k_join mode 2 -- the hardware-verified path, so this
+    validates the emulator) and the NND_LEAF_SPLIT pair (k_join mode 3 writes the distance matrices, k_leaf_push replays the
+    pushes) must both leave exactly the oracle's heaps: indices, distance bits, flags, layout -- over a 4-tree forest, i.e.
+    on heaps that are empty for the first tree and partly filled afterwards."""
+    from sklearn.utils import check_random_state
+    from oracle import nnd_oracle as orc
+    n, d, k = 800, 20, 10
+    X = latent(n, d, 31)
+    rs = check_random_state(9)
+    la, _ = orc.make_forest(X, k, 4, 24, rs, False, 200, "level")        # leaf_size 24: ~100 leaves per tree, sizes 2..24
+    heap = orc.make_heap(n, k)
+    orc.init_rp_tree(X, "euclidean", heap, la)
+    sizes = (la >= 0).sum(1)
+    assert la.shape[0] > 100 and sizes.min() >= 1 and sizes.max() <= 24
+    pts = la[la >= 0].astype(np.int32)
+    offs = np.zeros(la.shape[0] + 1, np.int64); np.cumsum(sizes, out=offs[1:])
+    assert offs[-1] == 4 * n
+    e = orc.make_heap(n, k)
+    rc = emu_lib.emu_leaf_init(np.ascontiguousarray(X), n, d, d, pts, offs, la.shape[0], int(sizes.max()), e[0], e[1], e[2], k, split)
+    assert rc == 0
+    assert np.array_equal(e[0], heap[0]) and np.array_equal(e[1], heap[1]) and np.array_equal(e[2], heap[2])
