@@ -467,6 +467,12 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
     size_t smem_small = (size_t)C * SEL_T * 16;
     const int use_small = smem_small <= 200 * 1024;
+    if (ctx->opt_carveout) {   // NND_SMEM_CARVEOUT=1: ask for the largest shared-memory carveout (ncu: select_small ran 3 CTAs/SM)
+        cudaFuncSetAttribute(k_cand_select_small<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_cand_select_small<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_cand_select_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_cand_select, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     if (use_small && ctx->opt_cand_keys == 2 && cand_tile_smem(k, C) <= 200 * 1024) {
         const size_t sm3 = cand_tile_smem(k, C);
         NND_CUDA(cudaFuncSetAttribute(k_cand_select_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));

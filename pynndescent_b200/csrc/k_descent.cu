@@ -1049,6 +1049,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "apply: k=%d too large", P->k);
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->opt_carveout) cudaFuncSetAttribute(k_apply, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     size_t smem_s = (size_t)P->k * APPLY_T * 9 + 16;
     const char *e_small = getenv("NND_APPLY_SMALL");   // experimental: thread-per-row apply (slower on B200 as measured)
     const int use_small = (e_small && e_small[0] == '1') && smem_s <= 64 * 1024;
@@ -1172,6 +1173,7 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
             bool split = ctx->opt_leaf_split && push_capacity >= N + 16 && (size_t)push_capacity * 2 * sizeof(Rec16) >= (size_t)N * mm * 4 &&
                          (double)N * mm < 4.0e9 && lp_smem <= 200 * 1024;
             if (split) NND_CUDA(cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
+            if (split && ctx->opt_carveout) cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             NND_CUDA(cudaEventRecord(ctx->ev0, st));
             for (size_t t = 0; t + 1 < tree_cut.size(); ++t) {
                 J.unit_begin = tree_cut[t]; J.unit_end = tree_cut[t + 1];

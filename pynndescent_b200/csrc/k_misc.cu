@@ -62,6 +62,7 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
         c->opt_cand_skip = env_int("NND_CAND_SKIP", 0);
         c->opt_cand_keys = env_int("NND_CAND_KEYS", 0);
         c->opt_leaf_split = env_int("NND_LEAF_SPLIT", 0);
+        c->opt_carveout = env_int("NND_SMEM_CARVEOUT", 0);
         c->join_order = nullptr; c->join_order_n = 0;
     }
     NND_CUDA(cudaEventCreate(&c->ev0));
