@@ -642,7 +642,8 @@ __global__ void k_scatter_rank(const int32_t *tgt, const int32_t *oth, const flo
 #define APPLY_WARPS 8
 __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag,
                                                             int k, int64_t N, const uint32_t *cnt, const uint32_t *off,
-                                                            Rec16 *rec, unsigned long long *c_total, int skip_small) {
+                                                            Rec16 *rec, unsigned long long *c_total, int skip_small,
+                                                            int short_sort) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * APPLY_WARPS + warp;
@@ -677,8 +678,13 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
             // common case: sort (key, slot) pairs in registers with shuffles -- no shared-memory traffic
             unsigned long long key = lane < kept ? buf[lane].key : ~0ULL;
             int slot = lane;
+            // NND_APPLY_SHORT_SORT: a bitonic network over the first next_pow2(kept) lanes sorts them just as well (the other
+            // lanes hold the maximum key and never mix with them) -- 1-3 stages instead of 15 for the 1-3 records a touched
+            // row typically receives after the first iterations
+            const int top = short_sort ? (int)next_pow2_u32((uint32_t)(kept > 2 ? kept : 2)) : 32;
 #pragma unroll
             for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+                if (k2 > top) break;
 #pragma unroll
                 for (int j = k2 >> 1; j > 0; j >>= 1) {
                     unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
@@ -1060,7 +1066,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
         NND_LAUNCH(ctx);
     }
     k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
-                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1, use_small);
+                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1, use_small, ctx->opt_apply_short);
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
     return NND_OK;
@@ -1477,7 +1483,7 @@ extern "C" int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, 
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_apply<<<(unsigned)cdiv(Nr, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx + lo * P->k, P->heap_dist + lo * P->k,
                                                                             P->heap_flag + lo * P->k, P->k, Nr, W.cnt, W.off, W.rec,
-                                                                            W.dev_scalars + 1, 0);
+                                                                            W.dev_scalars + 1, 0, ctx->opt_apply_short);
     NND_LAUNCH(ctx);
     unsigned long long hc = 0, hbad = 0;
     NND_CUDA(cudaMemcpyAsync(&hc, W.dev_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));
