@@ -734,10 +734,117 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
 }
 
 
+// ---- NND_APPLY_HALF (default off): k_apply for rows with at most APPLY_SMALL records, TWO ROWS PER WARP.  A heap row has k <= 16
+// useful lanes in the duplicate test and one in the sift, and a touched row rarely keeps more than 16 records, so a whole warp
+// per row spends half of its issue slots on idle lanes (ncu: k_apply is issue-bound, 75 % busy).  Each half-warp runs exactly
+// the same algorithm (filter by the initial root, order by emission sequence, replay checked_flagged_heap_push); rows with
+// more records stay with k_apply (skip_small).
+#define APPLY_SMALL 48
+#define AH_ROWS 16   // half-warps (rows) per CTA
+__device__ __forceinline__ int half_heap_push(float *pri, int32_t *ind, uint8_t *flg, int size, float p, int32_t n, uint8_t f, int hl,
+                                              unsigned mask) {
+    if (p >= pri[0]) return 0;
+    bool dup = false;
+    for (int i = hl; i < size; i += 16) dup |= (ind[i] == n);
+    if (__ballot_sync(mask, dup) != 0) return 0;
+    if (hl == 0) {
+        int i = 0, i_swap;
+        for (;;) {
+            int ic1 = 2 * i + 1, ic2 = ic1 + 1;
+            if (ic1 >= size) break;
+            else if (ic2 >= size) { if (pri[ic1] > p) i_swap = ic1; else break; }
+            else if (pri[ic1] >= pri[ic2]) { if (p < pri[ic1]) i_swap = ic1; else break; }
+            else { if (p < pri[ic2]) i_swap = ic2; else break; }
+            pri[i] = pri[i_swap]; ind[i] = ind[i_swap]; flg[i] = flg[i_swap];
+            i = i_swap;
+        }
+        pri[i] = p; ind[i] = n; flg[i] = f;
+    }
+    __syncwarp(mask);
+    return 1;
+}
+__global__ void __launch_bounds__(AH_ROWS * 16) k_apply_half(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int k, int64_t N,
+                                                            const uint32_t *cnt, const uint32_t *off, const Rec16 *rec,
+                                                            unsigned long long *c_total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+    const unsigned mask = 0xFFFFu << (16 * (hw & 1));                 // my half of the warp
+    const int sh = 16 * (hw & 1);
+    const int64_t row = (int64_t)blockIdx.x * AH_ROWS + hw;
+    if (row >= N) return;
+    const uint32_t n = cnt[row];
+    if (n == 0 || n > APPLY_SMALL) return;
+    Rec16 *buf = (Rec16 *)smem_raw + (size_t)hw * 64;                  // up to 48 kept records, padded to 64 for the in-memory sort
+    unsigned char *hp = smem_raw + (size_t)AH_ROWS * 64 * sizeof(Rec16) + (size_t)hw * (((size_t)k * 9 + 15) & ~size_t(15));
+    float *pri = (float *)hp; int32_t *ind = (int32_t *)(pri + k); uint8_t *flg = (uint8_t *)(ind + k);
+    for (int j = hl; j < k; j += 16) { pri[j] = heap_dist[row * k + j]; ind[j] = heap_idx[row * k + j]; flg[j] = heap_flag[row * k + j]; }
+    __syncwarp(mask);
+    const float root0 = pri[0];
+    const Rec16 *seg = rec + off[row];
+    int kept = 0;
+    for (uint32_t b0 = 0; b0 < n; b0 += 16) {      // keep only what can still be accepted (the root only decreases)
+        const uint32_t j = b0 + hl;
+        Rec16 r; r.key = ~0ULL; r.oth = -1; r.d = 0.f;
+        bool keep = false;
+        if (j < n) { r = seg[j]; keep = r.d < root0; }
+        const unsigned mk = (__ballot_sync(mask, keep) >> sh) & 0xFFFFu;
+        if (keep) buf[kept + __popc(mk & ((1u << hl) - 1))] = r;
+        kept += __popc(mk);
+    }
+    if (kept == 0) return;
+    __syncwarp(mask);
+    int c = 0;
+    if (kept <= 16) {
+        unsigned long long key = hl < kept ? buf[hl].key : ~0ULL;
+        int slot = hl;
+        const int top = (int)next_pow2_u32((uint32_t)(kept > 2 ? kept : 2));
+#pragma unroll
+        for (int k2 = 2; k2 <= 16; k2 <<= 1) {
+            if (k2 > top) break;
+#pragma unroll
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(mask, key, j);
+                const int os = __shfl_xor_sync(mask, slot, j);
+                const bool up = ((hl & k2) == 0), lower = ((hl & j) == 0);
+                const bool take = (lower == up) ? (ok < key) : (ok > key);
+                if (take) { key = ok; slot = os; }
+            }
+        }
+        for (int s2 = 0; s2 < kept; ++s2) {
+            const int sl = __shfl_sync(mask, slot, sh + s2);
+            const Rec16 r = buf[sl];
+            c += half_heap_push(pri, ind, flg, k, r.d, r.oth, (uint8_t)1, hl, mask);
+        }
+    } else {
+        const int p2 = (int)next_pow2_u32((uint32_t)kept);             // <= 64
+        for (int j = kept + hl; j < p2; j += 16) { buf[j].key = ~0ULL; buf[j].oth = -1; buf[j].d = CUDART_INF_F; }
+        __syncwarp(mask);
+        for (int k2 = 2; k2 <= p2; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = hl; i < p2; i += 16) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const Rec16 x = buf[i], y = buf[l];
+                        const bool up = ((i & k2) == 0);
+                        if ((x.key > y.key) == up) { buf[i] = y; buf[l] = x; }
+                    }
+                }
+                __syncwarp(mask);
+            }
+        for (int s = 0; s < kept; ++s) {
+            const Rec16 r = buf[s];
+            c += half_heap_push(pri, ind, flg, k, r.d, r.oth, (uint8_t)1, hl, mask);
+        }
+    }
+    if (c > 0) {
+        for (int j = hl; j < k; j += 16) { heap_dist[row * k + j] = pri[j]; heap_idx[row * k + j] = ind[j]; heap_flag[row * k + j] = flg[j]; }
+        if (hl == 0) atomicAdd(c_total, (unsigned long long)c);
+    }
+}
+
 // ---- thread-per-row apply for rows with few records (the common case): column-layout heap in smem, the
 // next record in emission order is found by selection among the records that can still be accepted
 // (d < current root), so no sort is needed.  Rows with more than APPLY_SMALL records go to k_apply.
-#define APPLY_SMALL 48
 #define APPLY_T 128
 __global__ void __launch_bounds__(APPLY_T) k_apply_small(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int k,
                                                          int64_t N, const uint32_t *cnt, const uint32_t *off,
@@ -1058,8 +1165,18 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     if (ctx->opt_carveout) cudaFuncSetAttribute(k_apply, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     size_t smem_s = (size_t)P->k * APPLY_T * 9 + 16;
     const char *e_small = getenv("NND_APPLY_SMALL");   // experimental: thread-per-row apply (slower on B200 as measured)
-    const int use_small = (e_small && e_small[0] == '1') && smem_s <= 64 * 1024;
-    if (use_small) {
+    int use_small = (e_small && e_small[0] == '1') && smem_s <= 64 * 1024;
+    if (ctx->opt_apply_half && !use_small) {            // NND_APPLY_HALF: rows with <= APPLY_SMALL records, two per warp
+        const size_t smem_h = (size_t)AH_ROWS * 64 * sizeof(Rec16) + (size_t)AH_ROWS * (((size_t)P->k * 9 + 15) & ~size_t(15));
+        if (smem_h <= 200 * 1024) {
+            NND_CUDA(cudaFuncSetAttribute(k_apply_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+            k_apply_half<<<(unsigned)cdiv(N, AH_ROWS), AH_ROWS * 16, smem_h, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N, W.cnt, W.off,
+                                                                              W.rec, W.dev_scalars + 1);
+            NND_LAUNCH(ctx);
+            use_small = 2;                              // k_apply below skips the rows handled here
+        }
+    }
+    if (use_small == 1) {
         NND_CUDA(cudaFuncSetAttribute(k_apply_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         k_apply_small<<<(unsigned)cdiv(N, APPLY_T), APPLY_T, smem_s, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N, W.cnt,
                                                                         W.off, W.rec, W.dev_scalars + 1);

@@ -48,6 +48,7 @@ struct nnd_ctx {
     // ---- schedule options (read from the environment by nnd_create; none of them changes any result)
     int opt_join_pipe;        // NND_JOIN_PIPE=1: persistent warp-specialised local join (k_join_pipe.cu) instead of k_join_batch
     int opt_pipe_dk, opt_pipe_stages, opt_pipe_ctas;   // NND_PIPE_DK (32|64), NND_PIPE_STAGES (2..6), NND_PIPE_CTAS (per SM, 0 = max)
+    int opt_apply_half;       // NND_APPLY_HALF=1: rows with <= 48 records are applied two per warp (k_apply_half)
     int opt_apply_short;      // NND_APPLY_SHORT_SORT=1: k_apply sorts only next_pow2(kept) lanes
     int opt_carveout;         // NND_SMEM_CARVEOUT=1: prefer the maximum shared-memory carveout for the occupancy-by-smem kernels
     int opt_leaf_split;       // NND_LEAF_SPLIT=1: leaf init = distance-matrix kernel + thread-per-member push kernel (k_descent.cu)

@@ -23,6 +23,7 @@ CONFIGS = {
     "leaf": {"NND_JOIN_ORDER": "leaf"},
     "leaf+rank": {"NND_JOIN_ORDER": "leaf", "NND_RANK_SCATTER": "1"},
     "applyshort": {"NND_APPLY_SHORT_SORT": "1"},
+    "applyhalf": {"NND_APPLY_HALF": "1"},
     "carveout": {"NND_SMEM_CARVEOUT": "1"},
     "leafsplit": {"NND_LEAF_SPLIT": "1"},
     "leafsplit+carveout": {"NND_LEAF_SPLIT": "1", "NND_SMEM_CARVEOUT": "1"},
@@ -33,7 +34,7 @@ CONFIGS = {
     "pipe": {"NND_JOIN_PIPE": "1"},
     "pipe+rank": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1"},
     "pipe+rank+leaf": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf"},
-    "all": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf", "NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2", "NND_LEAF_SPLIT": "1", "NND_SMEM_CARVEOUT": "1", "NND_APPLY_SHORT_SORT": "1"},
+    "all": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf", "NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2", "NND_LEAF_SPLIT": "1", "NND_SMEM_CARVEOUT": "1", "NND_APPLY_SHORT_SORT": "1", "NND_APPLY_HALF": "1"},
     "pipe-s3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "3"},
     "pipe-s2c3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "2", "NND_PIPE_CTAS": "3"},
     "pipe-s6": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "6"},

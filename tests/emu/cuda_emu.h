@@ -74,7 +74,16 @@ struct MBar {
     void complete_tx(long n) { std::lock_guard<std::mutex> g(m); tx -= n; maybe_complete(); }
     void wait(unsigned parity);
 };
-struct Warp { std::barrier<> bar{32}; uint64_t slot[32]; };
+struct Warp {
+    std::barrier<> bar{32}; std::barrier<> hbar0{16}, hbar1{16}; uint64_t slot[32];
+    // full-warp masks and the two half-warp masks are supported (k_apply_half runs two heap rows per warp)
+    std::barrier<> &group(unsigned mask) {
+        if (mask == 0xffffffffu) return bar;
+        if (mask == 0x0000ffffu) return hbar0;
+        if (mask == 0xffff0000u) return hbar1;
+        fprintf(stderr, "emu: unsupported lane mask %08x\n", mask); abort();
+    }
+};
 struct Copy { void *dst; const void *src; size_t bytes; MBar *bar; };
 struct Block {
     int nthreads;
@@ -164,30 +173,32 @@ static void launch_seq(long grid, int block, F kernel) {
 
 // ---- synchronisation
 static inline void __syncthreads() { emu::g_block->bar.arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::chaos(); emu::warp().bar.arrive_and_wait(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::chaos(); emu::warp().group(mask).arrive_and_wait(); }
 template <class T, class SEL>
-static inline T emu_exchange(T v, SEL pick) {
+static inline T emu_exchange(unsigned mask, T v, SEL pick) {
     static_assert(sizeof(T) <= 8, "shuffle of a type wider than 8 bytes");
     emu::Warp &w = emu::warp();
+    std::barrier<> &b = w.group(mask);
     uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
     w.slot[emu::lane()] = raw;
-    w.bar.arrive_and_wait();
+    b.arrive_and_wait();
     int src = pick(emu::lane());
     T r = v;
-    if (src >= 0 && src < 32) { uint64_t x = w.slot[src]; memcpy(&r, &x, sizeof(T)); }
-    w.bar.arrive_and_wait();
+    if (src >= 0 && src < 32 && ((mask >> src) & 1u)) { uint64_t x = w.slot[src]; memcpy(&r, &x, sizeof(T)); }
+    b.arrive_and_wait();
     return r;
 }
-template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, [=](int) { return src & 31; }); }
-template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_exchange(v, [=](int l) { return l - d; }); }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, [=](int l) { return l ^ m; }); }
-static inline unsigned __ballot_sync(unsigned, int pred) {
+template <class T> static inline T __shfl_sync(unsigned m, T v, int src) { return emu_exchange(m, v, [=](int) { return src & 31; }); }
+template <class T> static inline T __shfl_up_sync(unsigned m, T v, int d) { return emu_exchange(m, v, [=](int l) { return l - d; }); }
+template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int x) { return emu_exchange(m, v, [=](int l) { return l ^ x; }); }
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
     emu::Warp &w = emu::warp();
+    std::barrier<> &b = w.group(mask);
     w.slot[emu::lane()] = pred ? 1u : 0u;
-    w.bar.arrive_and_wait();
+    b.arrive_and_wait();
     unsigned r = 0;
-    for (int i = 0; i < 32; ++i) r |= (unsigned)(w.slot[i] & 1u) << i;
-    w.bar.arrive_and_wait();
+    for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) r |= (unsigned)(w.slot[i] & 1u) << i;
+    b.arrive_and_wait();
     return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }

@@ -72,7 +72,7 @@ def emu_lib(tmp_path_factory):
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 8 and "extern __shared__" not in kernels
+    assert n_ext == 9 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -345,12 +345,12 @@ def test_candidate_kernels_row_sharded(emu_lib, skip):
 
 
 @pytest.mark.parametrize("kernel,rank_scatter,leaf_order,short_sort", [(0, 0, False, 0), (0, 1, False, 0), (1, 0, False, 0), (1, 1, True, 1),
-                                                                       (0, 0, False, 1)])
+                                                                       (0, 0, False, 1), (0, 0, False, 2), (1, 1, True, 3)])
 def test_whole_iterations_match_the_oracle_heaps(emu_lib, kernel, rank_scatter, leaf_order, short_sort):
     """Three NN-descent iterations: candidates from the oracle, then join -> scatter -> apply under the emulator; after every
     iteration the heaps (indices, distances, flags, layout) and the accepted-push count must equal the oracle's
     process_candidates.  (0, 0) is the hardware-verified schedule = emulator check; the others are the switches of DESIGN 10a
-    (k_join_pipe, NND_RANK_SCATTER, a permuted join order)."""
+    (k_join_pipe, NND_RANK_SCATTER, a permuted join order; short_sort bit 0 = NND_APPLY_SHORT_SORT, bit 1 = NND_APPLY_HALF)."""
     from sklearn.utils import check_random_state
     from oracle import nnd_oracle as orc
     n, d, k = 450, 24, 10
