@@ -1598,9 +1598,19 @@ extern "C" int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, 
     k_rec_scatter<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, W.l_pos, (unsigned long long)n, W.off, W.rec, lo); NND_LAUNCH(ctx);
     size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int skip_small = 0;
+    const size_t smem_h = (size_t)AH_ROWS * 64 * sizeof(Rec16) + (size_t)AH_ROWS * (((size_t)P->k * 9 + 15) & ~size_t(15));
+    if (ctx->opt_apply_half && smem_h <= 200 * 1024) {   // NND_APPLY_HALF: rows with <= APPLY_SMALL records, two per warp
+        NND_CUDA(cudaFuncSetAttribute(k_apply_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        k_apply_half<<<(unsigned)cdiv(Nr, AH_ROWS), AH_ROWS * 16, smem_h, st>>>(P->heap_idx + lo * P->k, P->heap_dist + lo * P->k,
+                                                                           P->heap_flag + lo * P->k, P->k, Nr, W.cnt, W.off, W.rec,
+                                                                           W.dev_scalars + 1);
+        NND_LAUNCH(ctx);
+        skip_small = 2;
+    }
     k_apply<<<(unsigned)cdiv(Nr, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx + lo * P->k, P->heap_dist + lo * P->k,
                                                                             P->heap_flag + lo * P->k, P->k, Nr, W.cnt, W.off, W.rec,
-                                                                            W.dev_scalars + 1, 0, ctx->opt_apply_short);
+                                                                            W.dev_scalars + 1, skip_small, ctx->opt_apply_short);
     NND_LAUNCH(ctx);
     unsigned long long hc = 0, hbad = 0;
     NND_CUDA(cudaMemcpyAsync(&hc, W.dev_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));
