@@ -59,3 +59,22 @@ def test_pipe_protocol_simulation():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "pipe_protocol_sim.py"), "400"], capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_ab_harness_switch_names_exist():
+    """scripts/r2_ab.py A/Bs the schedule switches by environment variable: a misspelt name would silently compare the default
+    with itself.  Every name it sets must be read by the library (csrc) or the host package."""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location("r2_ab", os.path.join(ROOT, "scripts", "r2_ab.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    names = {k for cfg in mod.CONFIGS.values() for k in cfg}
+    assert names and all(n.startswith("NND_") for n in names)
+    src = ""
+    for base in ("pynndescent_b200/csrc", "pynndescent_b200"):
+        d = os.path.join(ROOT, base)
+        for f in os.listdir(d):
+            if f.endswith((".cu", ".cuh", ".py")):
+                src += open(os.path.join(d, f)).read()
+    read = set(re.findall(r'"(NND_[A-Z0-9_]+)"', src))
+    assert names <= read, sorted(names - read)
