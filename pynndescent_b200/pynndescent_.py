@@ -308,9 +308,13 @@ class NNDescent:
                                       leaf_size=self.leaf_size, pruning_degree_multiplier=self.pruning_degree_multiplier,
                                       max_depth=self.max_rptree_depth)
         self._search_structures = S
-        data_reordered = np.ascontiguousarray(self._raw_data[S["vertex_order"], :])                 # :1639-1641
-        self.load_search_structures(data_reordered, S["indptr"], S["indices"], S["hyperplanes"], S["offsets"], S["children"],
-                                    S["tree_indices"], S["vertex_order"], S["min_distance"])
+        # :1639-1641 data re-ordered to leaf order -- gathered on the device from the matrix that is already there
+        import torch
+        from .search import SearchIndexGPU
+        vo_t = torch.from_numpy(np.ascontiguousarray(S["vertex_order"], np.int64)).to(eng.device)
+        self._search_gpu = SearchIndexGPU(None, self.metric, S["indptr"], S["indices"], S["hyperplanes"], S["offsets"], S["children"],
+                                          S["tree_indices"], S["vertex_order"], S["min_distance"], self.n_neighbors,
+                                          self.search_rng_state, data_device=eng.X.index_select(0, vo_t).contiguous(), dim=eng.d)
 
     def load_search_structures(self, data_reordered, indptr, indices, hyperplanes, offsets, children, tree_indices,
                                vertex_order, min_distance, search_rng_state=None):

@@ -20,20 +20,33 @@ def _dev(a, dtype, device):
 
 class SearchIndexGPU:
     def __init__(self, data_reordered, metric, indptr, indices, hyperplanes, offsets, children, tree_indices, vertex_order,
-                 min_distance, n_neighbors, search_rng_state, device=None):
+                 min_distance, n_neighbors, search_rng_state, device=None, data_device=None, dim=None):
+        """`data_reordered`: host matrix in leaf order (pynndescent_.py:1639-1641) -- or, from prepare(), `data_device`: the same
+        matrix already on the GPU as float32[N, ld] (rows padded to a multiple of 4 floats with zeros) with `dim` = d, so that
+        the 4*N*d bytes neither get gathered on the host nor cross PCIe a second time."""
         if not torch.cuda.is_available():
             raise RuntimeError("pynndescent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.metric = metric
         self.metric_id, self.dev_correction, self.host_correction, _ = pynnd_dist.resolve(metric)
-        data = np.ascontiguousarray(data_reordered, np.float32)
-        self.N, self.d = data.shape
-        self.ld = (self.d + 3) // 4 * 4
+        if data_device is not None:
+            self.device = data_device.device
+            self.N, self.ld = int(data_device.shape[0]), int(data_device.shape[1])
+            self.d = int(dim)
+            if self.ld != (self.d + 3) // 4 * 4 or data_device.dtype != torch.float32 or not data_device.is_contiguous():
+                raise ValueError("data_device must be a contiguous float32[N, ld] tensor with ld = d rounded up to 4")
+        else:
+            self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+            data = np.ascontiguousarray(data_reordered, np.float32)
+            self.N, self.d = data.shape
+            self.ld = (self.d + 3) // 4 * 4
         self._ctx = C.c_void_p()
         check(lib.nnd_create(C.byref(self._ctx), self.device.index or 0))
         self.stream = torch.cuda.current_stream(self.device)
-        self.X = torch.zeros((self.N, self.ld), dtype=torch.float32, device=self.device)
-        self.X[:, : self.d].copy_(torch.from_numpy(data))
+        if data_device is not None:
+            self.X = data_device
+        else:
+            self.X = torch.zeros((self.N, self.ld), dtype=torch.float32, device=self.device)
+            self.X[:, : self.d].copy_(torch.from_numpy(data))
         nb = C.c_size_t()
         check(lib.nnd_metric_aux_bytes(self.metric_id, self.N, C.byref(nb)))
         self.aux = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
