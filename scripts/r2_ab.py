@@ -118,6 +118,35 @@ def main():
               f"bit-equal idx/dist/c: {same[0]}/{same[1]}/{same[2]}  stages {r['stage_ms']}", flush=True)
         r.update({"config": name, "status": "ok", "equal_to_default": all(same)})
         rows.append(r)
+    # ---- compose the winners: every switch set that is bit-equal and at least 1 % faster than the default on its own goes
+    # into one combined configuration, which is then run like the others
+    by = {r["config"]: r for r in rows if r.get("status") == "ok"}
+    if "default" in by and "auto" not in opts.get("skip", ""):
+        t0 = by["default"]["build_ms"]
+        combined = {}
+        for name, r in by.items():
+            if name in ("default", "all") or not r.get("equal_to_default") or r["build_ms"] > 0.99 * t0:
+                continue
+            if any(kk in combined and combined[kk] != vv for kk, vv in CONFIGS[name].items()):
+                continue                                     # conflicting values of a tuning knob: keep the first (faster rows come first below)
+            combined.update(CONFIGS[name])
+        if combined:
+            CONFIGS["auto-combined"] = combined
+            env = {kk: vv for kk, vv in os.environ.items() if not kk.startswith("NND_")}; env.update(combined)
+            out = os.path.join(ROOT, "gpurun_out", "ab_auto-combined.json")
+            try:
+                p = subprocess.run([sys.executable, os.path.abspath(__file__), "child", str(n), str(d), str(k), metric, str(reps), out],
+                                   env=env, timeout=tmo, capture_output=True, text=True)
+                if p.returncode == 0 and os.path.exists(out):
+                    r = json.load(open(out))
+                    same = r["idx_sha"] == by["default"]["idx_sha"] and r["dist_sha"] == by["default"]["dist_sha"] and r["c_hist"] == by["default"]["c_hist"]
+                    print(f"auto-combined {combined}\n                 build {r['build_ms']:8.1f} ms (default {t0:.1f})  join {r['join_ms']:7.2f} ms  leaf {r['leaf_ms']:6.2f} ms  "
+                          f"bit-equal: {same}  stages {r['stage_ms']}", flush=True)
+                    r.update({"config": "auto-combined", "env": combined, "status": "ok", "equal_to_default": same}); rows.append(r)
+                else:
+                    print("auto-combined FAILED:", p.stderr.strip()[-400:], flush=True)
+            except subprocess.TimeoutExpired:
+                print("auto-combined TIMEOUT", flush=True)
     json.dump({"n": n, "d": d, "k": k, "metric": metric, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", "ab_summary.json"), "w"), indent=1)
 
 
