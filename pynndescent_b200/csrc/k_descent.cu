@@ -1285,7 +1285,12 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
         int mm = max_leaf < 4 ? 4 : max_leaf, al = 0;
         size_t smem = join_smem_bytes(mm, P->metric) + fused_extra_bytes(mm, P->k, &al) + 32;
         const char *force_routed = getenv("NND_LEAF_ROUTED");  // test switch: exercise the routed leaf path
-        if (partition && smem <= 200 * 1024 && !(force_routed && force_routed[0] == '1')) {
+        // NND_LEAF_SPLIT also serves leaves too large for the fused kernel (cfg5: leaf_size 150, k = 30 needs 216 KB fused):
+        // the distance-matrix kernel only needs the row buffer
+        const size_t lp_smem0 = (((size_t)P->k * LP_T * 9 + 15) & ~size_t(15)) + (size_t)LP_T * 4;
+        const bool split_ok = ctx->opt_leaf_split && push_capacity >= N + 16 && (size_t)push_capacity * 2 * sizeof(Rec16) >= (size_t)N * mm * 4 &&
+                              (double)N * mm < 4.0e9 && lp_smem0 <= 200 * 1024 && join_smem_bytes(mm, P->metric) + 64 <= 200 * 1024;
+        if (partition && (smem <= 200 * 1024 || split_ok) && !(force_routed && force_routed[0] == '1')) {
             JoinParams J; memset(&J, 0, sizeof(J));
             J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
             J.mode = 2; J.leaf_points = leaf_points; J.leaf_offsets = leaf_offsets; J.m_max = mm; J.slot_stride = mm;
@@ -1293,8 +1298,7 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
             // NND_LEAF_SPLIT: distance matrices to global memory (k_join mode 3), pushes by k_leaf_push.  Scratch comes from
             // arrays of the routing workspace that the fused path never touches; fall back to the fused kernel if it is short.
             const size_t lp_smem = (((size_t)P->k * LP_T * 9 + 15) & ~size_t(15)) + (size_t)LP_T * 4;
-            bool split = ctx->opt_leaf_split && push_capacity >= N + 16 && (size_t)push_capacity * 2 * sizeof(Rec16) >= (size_t)N * mm * 4 &&
-                         (double)N * mm < 4.0e9 && lp_smem <= 200 * 1024;
+            const bool split = split_ok;
             if (split) NND_CUDA(cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
             if (split && ctx->opt_carveout) cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             NND_CUDA(cudaEventRecord(ctx->ev0, st));
