@@ -36,6 +36,8 @@ if [ "$what" = all ] || [ "$what" = cfg5 ]; then
   # BASELINE.json configs[4]: 1M x 784 correlation k=30 build + query() of 100k held-out points
   run timeout 1500 python scripts/query_bench.py 1000000 784 30 100000 correlation
   run timeout 1200 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline
+  # leaf_size 150 / k = 30 does not fit the fused leaf kernel (routed path); the split leaf init does
+  NND_LEAF_SPLIT=1 run timeout 1200 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline
 fi
 if [ "$what" = all ] || [ "$what" = ncu ]; then
   # launch list of one warm build (shares), then --set full of the join kernels (default and experimental)
