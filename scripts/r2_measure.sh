@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU commands of round 2 (run under gpurun from the repo root; everything lands in gpurun_out/).
-#   gpurun --timeout 2400 -- 'bash scripts/r2_measure.sh all'          # or one of: tests ab bench cfg3 cfg5 ncu
+#   gpurun --timeout 2400 -- 'bash scripts/r2_measure.sh all'          # or one of: tests switches ab bench cfg3 cfg5 ncu
 # Every step runs under its own `timeout` so that a hung experimental kernel cannot hold the box to gpurun's limit.
 set -u
 cd "$(dirname "$0")/.."
@@ -17,6 +17,16 @@ if [ "$what" = all ] || [ "$what" = tests ]; then
   NND_PREPARE_GPU=1 run timeout 600 python -m pytest tests/test_gpu_query.py -m gpu -q
   run timeout 600 python scripts/query_bench.py 1000000 128 15 100000
   NND_PREPARE_GPU=1 run timeout 600 python scripts/query_bench.py 1000000 128 15 100000
+fi
+if [ "$what" = all ] || [ "$what" = switches ]; then
+  # the whole parity suite again with every schedule switch ON (they are read by nnd_create, so the env covers every test):
+  # the reference goldens, the oracle and the full-size checksum must all still hold
+  NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 \
+    NND_APPLY_HALF=1 NND_SMEM_CARVEOUT=1 NND_PREPARE_GPU=1 run timeout 1500 python -m pytest tests -m gpu -q -n 4 --deselect tests/test_sharded_gpu.py \
+    --deselect "tests/test_gpu_parity.py::test_init_random_build_candidates_process"
+  # (deselected: the stage test compares old_cand of vertices WITHOUT new candidates, which NND_CAND_SKIP leaves empty by design)
+  NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_KEYS=1 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 NND_APPLY_HALF=1 \
+    run timeout 600 python -m pytest "tests/test_gpu_parity.py::test_init_random_build_candidates_process" -m gpu -q
 fi
 if [ "$what" = all ] || [ "$what" = ab ]; then
   # schedule experiments: bit-equality + timing, small first (a wrong kernel shows up in seconds), then the bench size
