@@ -191,6 +191,12 @@ NND_API int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, con
 /* fused leaf join + apply on leaves [l0,l1) of one tree (disjoint point sets) */
 NND_API int nnd_leaf_fused_range(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets,
                                  int64_t l0, int64_t l1, int32_t max_leaf, void *stream);
+/* the same, through the split leaf init (distance-matrix kernel + thread-per-member push kernel; NND_LEAF_SPLIT) when that is
+ * enabled and its scratch fits the routing workspace `ws`, else through the fused kernel.  pos0 / npos = position range of the
+ * leaves [l0,l1) in leaf_points (leaf_offsets[l0], leaf_offsets[l1] - leaf_offsets[l0]; the caller has them on the host).  */
+NND_API int nnd_leaf_range(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets, int64_t l0,
+                           int64_t l1, int64_t pos0, int64_t npos, int32_t max_leaf, int64_t push_capacity, void *ws, size_t ws_bytes,
+                           void *stream);
 /* pack (unpack=0) / unpack (unpack=1) the heap rows listed in `rows` (NULL = rows 0..n-1) */
 NND_API int nnd_heap_pack_rows(nnd_ctx *ctx, const nnd_problem *P, const int32_t *rows, int64_t n, int32_t *out_idx,
                                float *out_dist, uint8_t *out_flag, int32_t unpack, void *stream);

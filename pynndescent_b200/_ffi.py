@@ -69,6 +69,7 @@ SIGNATURES = {
     "nnd_push_export": (C.c_int, [_vp, _PP, _i32, _i64, _vp, _sz, _i64, _i64, _i32, _vp, _pi64, _vp]),
     "nnd_apply_records": (C.c_int, [_vp, _PP, _i32, _vp, _i64, _i64, _vp, _sz, _pi64, _vp]),
     "nnd_leaf_fused_range": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "nnd_leaf_range": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _i64, _vp, _sz, _vp]),
     "nnd_heap_pack_rows": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "nnd_query_workspace_bytes": (C.c_int, [_i64, _i64, _i32, _psz]),
     "nnd_query": (C.c_int, [_vp, C.POINTER(SearchIndex), _vp, _i64, _i32, C.c_double, _pi64, _vp, _vp, _vp, _sz, _pi64, _vp]),

@@ -1249,6 +1249,31 @@ static int plan_blocks(nnd_ctx *ctx, const uint32_t *d_bound, int64_t n_units, D
     return NND_OK;
 }
 
+// split leaf init of leaves [l0,l1) (one tree, or a rank's share of one): positions [pos0, pos0 + npos) of leaf_points
+static int leaf_split_launch(nnd_ctx *ctx, const nnd_problem *P, const JoinParams &J, int64_t l0, int64_t l1, int64_t pos0, int64_t npos,
+                             DescentWs &W, cudaStream_t st) {
+    const int64_t nl = l1 - l0;
+    if (nl <= 0 || npos <= 0) return NND_OK;
+    const size_t lp_smem = (((size_t)P->k * LP_T * 9 + 15) & ~size_t(15)) + (size_t)LP_T * 4;
+    NND_CUDA(cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
+    if (ctx->opt_carveout) cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    uint32_t *dsz = W.l_pos, *doff = (uint32_t *)W.l_oth; int32_t *pos2leaf = W.l_tgt; float *D = (float *)W.rec;
+    k_leaf_prep<<<(unsigned)cdiv(nl, 128), 128, 0, st>>>(J.leaf_offsets, l0, l1, pos0, dsz, pos2leaf); NND_LAUNCH(ctx);
+    NND_TRY(nnd_exclusive_scan_u32(ctx, dsz, doff, nl, W.scan_tmp, st));
+    JoinParams J3 = J; J3.mode = 3; J3.leaf_D = D; J3.leaf_doff = doff; J3.unit_begin = l0; J3.unit_end = l1;
+    NND_TRY(launch_join(ctx, J3, nl, st));
+    k_leaf_push<<<(unsigned)cdiv(npos, LP_T), LP_T, lp_smem, st>>>(J.leaf_points, J.leaf_offsets, l0, pos0, npos, pos2leaf, doff, D, P->heap_idx,
+                                                                P->heap_dist, P->heap_flag, P->k);
+    NND_LAUNCH(ctx);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+static bool leaf_split_fits(const nnd_ctx *ctx, const nnd_problem *P, int mm, int64_t push_capacity) {
+    const size_t lp_smem = (((size_t)P->k * LP_T * 9 + 15) & ~size_t(15)) + (size_t)LP_T * 4;
+    return ctx->opt_leaf_split && push_capacity >= P->N + 16 && (size_t)push_capacity * 2 * sizeof(Rec16) >= (size_t)P->N * mm * 4 &&
+           (double)P->N * mm < 4.0e9 && lp_smem <= 200 * 1024 && join_smem_bytes(mm, P->metric) + 64 <= 200 * 1024;
+}
+
 extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets,
                              const int64_t *leaf_offsets_host, int64_t n_leaves, int32_t max_leaf, int64_t push_capacity,
                              void *ws, size_t ws_bytes, int64_t *n_pushes_host, void *stream) {
@@ -1287,9 +1312,7 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
         const char *force_routed = getenv("NND_LEAF_ROUTED");  // test switch: exercise the routed leaf path
         // NND_LEAF_SPLIT also serves leaves too large for the fused kernel (cfg5: leaf_size 150, k = 30 needs 216 KB fused):
         // the distance-matrix kernel only needs the row buffer
-        const size_t lp_smem0 = (((size_t)P->k * LP_T * 9 + 15) & ~size_t(15)) + (size_t)LP_T * 4;
-        const bool split_ok = ctx->opt_leaf_split && push_capacity >= N + 16 && (size_t)push_capacity * 2 * sizeof(Rec16) >= (size_t)N * mm * 4 &&
-                              (double)N * mm < 4.0e9 && lp_smem0 <= 200 * 1024 && join_smem_bytes(mm, P->metric) + 64 <= 200 * 1024;
+        const bool split_ok = leaf_split_fits(ctx, P, mm, push_capacity);
         if (partition && (smem <= 200 * 1024 || split_ok) && !(force_routed && force_routed[0] == '1')) {
             JoinParams J; memset(&J, 0, sizeof(J));
             J.X = P->X; J.N = N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
@@ -1297,23 +1320,12 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
             J.heap_idx = P->heap_idx; J.heap_dist = P->heap_dist; J.heap_flag = P->heap_flag; J.k = P->k; J.d_alias = al;
             // NND_LEAF_SPLIT: distance matrices to global memory (k_join mode 3), pushes by k_leaf_push.  Scratch comes from
             // arrays of the routing workspace that the fused path never touches; fall back to the fused kernel if it is short.
-            const size_t lp_smem = (((size_t)P->k * LP_T * 9 + 15) & ~size_t(15)) + (size_t)LP_T * 4;
             const bool split = split_ok;
-            if (split) NND_CUDA(cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
-            if (split && ctx->opt_carveout) cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             NND_CUDA(cudaEventRecord(ctx->ev0, st));
             for (size_t t = 0; t + 1 < tree_cut.size(); ++t) {
                 J.unit_begin = tree_cut[t]; J.unit_end = tree_cut[t + 1];
                 if (!split) { NND_TRY(launch_join(ctx, J, J.unit_end - J.unit_begin, st)); continue; }
-                const int64_t l0 = tree_cut[t], l1 = tree_cut[t + 1], nl = l1 - l0, pos0 = offs[l0], npos = offs[l1] - pos0;
-                uint32_t *dsz = W.l_pos, *doff = (uint32_t *)W.l_oth; int32_t *pos2leaf = W.l_tgt; float *D = (float *)W.rec;
-                k_leaf_prep<<<(unsigned)cdiv(nl, 128), 128, 0, st>>>(leaf_offsets, l0, l1, pos0, dsz, pos2leaf); NND_LAUNCH(ctx);
-                NND_TRY(nnd_exclusive_scan_u32(ctx, dsz, doff, nl, W.scan_tmp, st));
-                JoinParams J3 = J; J3.mode = 3; J3.leaf_D = D; J3.leaf_doff = doff;
-                NND_TRY(launch_join(ctx, J3, nl, st));
-                k_leaf_push<<<(unsigned)cdiv(npos, LP_T), LP_T, lp_smem, st>>>(leaf_points, leaf_offsets, l0, pos0, npos, pos2leaf, doff, D,
-                                                                            P->heap_idx, P->heap_dist, P->heap_flag, P->k);
-                NND_LAUNCH(ctx);
+                NND_TRY(leaf_split_launch(ctx, P, J, tree_cut[t], tree_cut[t + 1], offs[tree_cut[t]], offs[tree_cut[t + 1]] - offs[tree_cut[t]], W, st));
             }
             NND_CUDA(cudaGetLastError());
             NND_CUDA(cudaEventRecord(ctx->ev1, st));
@@ -1642,6 +1654,25 @@ extern "C" int nnd_leaf_fused_range(nnd_ctx *ctx, const nnd_problem *P, const in
     J.heap_idx = P->heap_idx; J.heap_dist = P->heap_dist; J.heap_flag = P->heap_flag; J.k = P->k; J.d_alias = al;
     J.unit_begin = l0; J.unit_end = l1;
     return launch_join(ctx, J, l1 - l0, st);
+}
+
+// the same leaves through the split leaf init (NND_LEAF_SPLIT; k_join mode 3 + k_leaf_push) when it is enabled and its scratch
+// fits the routing workspace, else through the fused kernel.  pos0 / npos = the position range of the leaves in leaf_points
+// (the caller knows the offsets on the host).
+extern "C" int nnd_leaf_range(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets, int64_t l0,
+                              int64_t l1, int64_t pos0, int64_t npos, int32_t max_leaf, int64_t push_capacity, void *ws, size_t ws_bytes,
+                              void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && leaf_points && leaf_offsets && l0 >= 0 && l1 >= l0 && pos0 >= 0 && npos >= 0, NND_ERR_INVALID, "nnd_leaf_range: bad args");
+    const int mm = max_leaf < 4 ? 4 : max_leaf;
+    DescentWs W;
+    if (!ws || carve_descent_ws(ws, ws_bytes, P->N, P->k, 1, 1, push_capacity, &W, nullptr) != NND_OK || !leaf_split_fits(ctx, P, mm, push_capacity))
+        return nnd_leaf_fused_range(ctx, P, leaf_points, leaf_offsets, l0, l1, max_leaf, stream);
+    JoinParams J; memset(&J, 0, sizeof(J));
+    J.X = P->X; J.N = P->N; J.d = P->d; J.ld = P->ld; J.metric = P->metric; J.aux = P->aux;
+    J.leaf_points = leaf_points; J.leaf_offsets = leaf_offsets; J.m_max = mm; J.slot_stride = mm;
+    J.heap_idx = P->heap_idx; J.heap_dist = P->heap_dist; J.heap_flag = P->heap_flag; J.k = P->k;
+    return leaf_split_launch(ctx, P, J, l0, l1, pos0, npos, W, st);
 }
 
 // pack / unpack heap rows listed in `rows` (sharded build: exchange of the rows a process has updated)

@@ -330,7 +330,13 @@ class Engine:
                                     C.byref(c), self._st()))
         return int(c.value)
 
-    def leaf_fused_range(self, leaf_points, leaf_offsets, l0, l1, max_leaf):
+    def leaf_fused_range(self, leaf_points, leaf_offsets, l0, l1, max_leaf, pos0=None, npos=None, cap=None):
+        """Leaf join + heap update of leaves [l0,l1) of one tree.  With the position range (pos0, npos) of those leaves and the
+        routing workspace size `cap`, the library may use the split leaf init (NND_LEAF_SPLIT) instead of the fused kernel."""
+        if pos0 is not None and cap is not None and self._ws is not None:
+            check(lib.nnd_leaf_range(self._ctx, C.byref(self.problem()), _ptr(leaf_points), _ptr(leaf_offsets), int(l0), int(l1), int(pos0),
+                                     int(npos), int(max_leaf), int(cap), _ptr(self._ws), self._ws.numel(), self._st()))
+            return
         check(lib.nnd_leaf_fused_range(self._ctx, C.byref(self.problem()), _ptr(leaf_points), _ptr(leaf_offsets), int(l0), int(l1),
                                        int(max_leaf), self._st()))
 

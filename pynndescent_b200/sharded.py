@@ -100,7 +100,8 @@ class ShardedBuilder:
             cuts, p0 = plan[t]
             pts = pts_all[t]; offs = offs_all[obase[t]: obase[t + 1]]
             try:
-                e.leaf_fused_range(pts, offs, cuts[self.rank], cuts[self.rank + 1], max_leaf)
+                e.leaf_fused_range(pts, offs, cuts[self.rank], cuts[self.rank + 1], max_leaf, pos0=p0[self.rank],
+                                   npos=p0[self.rank + 1] - p0[self.rank], cap=cap)
             except NotImplementedError:
                 fused_ok = False
                 break
