@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU commands of round 2 (run under gpurun from the repo root; everything lands in gpurun_out/).
-#   gpurun --timeout 2400 -- 'bash scripts/r2_measure.sh all'          # or one of: tests switches ab bench cfg3 cfg5 ncu
+#   gpurun --timeout 2400 -- 'bash scripts/r2_measure.sh all'          # or one of: tests switches ab bench cfg3 cfg5 ncu | sharded (2 GPUs)
 # Every step runs under its own `timeout` so that a hung experimental kernel cannot hold the box to gpurun's limit.
 set -u
 cd "$(dirname "$0")/.."
@@ -57,5 +57,14 @@ if [ "$what" = all ] || [ "$what" = ncu ]; then
       python scripts/one_build.py 1000000 128 15 euclidean 2
   NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 run timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_join_pipe -s 17 -c 2 \
       -o gpurun_out/join_pipe_r02 -f python scripts/one_build.py 1000000 128 15 euclidean 2
+fi
+if [ "$what" = sharded ]; then
+  # needs `gpurun --gpus 2 -- bash scripts/r2_measure.sh sharded`: the sharded build == the single-GPU build, default schedule and
+  # with every switch on (leaf-order join, split leaf init through nnd_leaf_range, candidate skip, half-warp replay ...)
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29581"
+  run timeout 900 $TR scripts/sharded_check.py
+  NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 \
+    NND_APPLY_HALF=1 NND_SMEM_CARVEOUT=1 run timeout 900 $TR scripts/sharded_check.py
+  run timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline
 fi
 tail -n 60 gpurun_out/r2.log
