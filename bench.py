@@ -307,7 +307,8 @@ def main():
                                  "all-to-all-v of half-updates + all-gather of owners' heap rows per iteration; "
                                  "%.1f MB/step/rank exchanged" % (n_per, comm_bytes / 1e6 / max(args.steps + args.warmup, 1)))
                    if world > 1 else "single GPU",
-                   "l2": "inputs (X = %.0f MB) exceed the 126 MB L2; no explicit flush" % (n * ld * 4 / 1e6)},
+                   "l2": "inputs (X = %.0f MB) exceed the 126 MB L2; no explicit flush" % (n * ld * 4 / 1e6),
+                   "schedule_switches": {kk: vv for kk, vv in sorted(os.environ.items()) if kk.startswith("NND_") and not kk.startswith("NND_BENCH")}},
         "recall_at_k": rec,
         "e2e": {"value": e2e, "unit": "edges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(n * d * 4) * world,
                 "d2h_bytes_per_step": int(n * k * 8),
