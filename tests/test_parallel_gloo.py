@@ -140,3 +140,91 @@ def test_sharded_exchange_protocol_gloo(tmp_path):
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
     assert line[1] == "OK", out.stdout[-2000:]
+
+
+LEAF_WORKER = r'''
+"""ShardedBuilder.forest_and_leaf_init over gloo with an oracle-backed engine: trees built by their owner rank, leaves broadcast,
+every tree's leaves split among the ranks, updated heap rows exchanged.  Afterwards EVERY rank must hold exactly the heap the
+oracle's init_rp_tree produces from the whole forest -- and every leaf_fused_range call must carry the position range of its
+leaves (what nnd_leaf_range needs for the split leaf init)."""
+import os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+dist.init_process_group("gloo")
+from conftest import latent
+from oracle import nnd_oracle as orc
+from pynndescent_b200.sharded import ShardedBuilder
+r, w = dist.get_rank(), dist.get_world_size()
+N, K, LEAF, NT = 600, 8, 20, 5
+X = latent(N, 12, 2)
+states = np.random.RandomState(7).randint(-2 ** 31 + 1, 2 ** 31 - 1, size=(NT, 3)).astype(np.int64)
+
+
+def csr(la):
+    sizes = (la >= 0).sum(1)
+    offs = np.zeros(la.shape[0] + 1, np.int64); np.cumsum(sizes, out=offs[1:])
+    return la[la >= 0].astype(np.int32), offs, int(sizes.max())
+
+
+class OracleShardEngine:
+    def __init__(self):
+        self.N, self.k, self.device = N, K, torch.device("cpu")
+        self.heap_idx = self.heap_dist = self.heap_flag = None
+        self.calls = []
+    def set_join_order(self, perm): pass
+    def forest(self, tree_states, leaf_size, angular, max_depth):
+        la = orc.forest_leaf_array(X, np.ascontiguousarray(tree_states, np.int64), leaf_size, angular, max_depth, "level")
+        pts, offs, ml = csr(la)
+        return torch.from_numpy(pts), torch.from_numpy(offs), la.shape[0], ml
+    def leaf_fused_range(self, pts, offs, l0, l1, max_leaf, pos0=None, npos=None, cap=None):
+        o = offs.numpy(); p = pts.numpy()
+        assert pos0 == int(o[l0]) and npos == int(o[l1] - o[l0]) and cap is not None
+        self.calls.append((l0, l1))
+        if l1 == l0: return
+        la = np.full((l1 - l0, max_leaf), -1, np.int32)
+        for i, l in enumerate(range(l0, l1)):
+            m = p[o[l]: o[l + 1]]; la[i, : len(m)] = m
+        heap = (self.heap_idx.numpy(), self.heap_dist.numpy(), self.heap_flag.numpy())
+        orc.init_rp_tree(X, "euclidean", heap, la)
+    def heap_pack_rows(self, rows, n, oi, od, of, unpack):
+        if n == 0: return
+        idx = rows[:n].long()
+        if not unpack:
+            oi[:n] = self.heap_idx[idx]; od[:n] = self.heap_dist[idx]; of[:n] = self.heap_flag[idx]
+        else:
+            self.heap_idx[idx] = oi[:n]; self.heap_dist[idx] = od[:n]; self.heap_flag[idx] = of[:n]
+
+
+e = OracleShardEngine()
+sb = ShardedBuilder(e)
+hi, hd, hf = orc.make_heap(N, K)
+e.heap_idx.copy_(torch.from_numpy(hi)); e.heap_dist.copy_(torch.from_numpy(hd)); e.heap_flag.copy_(torch.from_numpy(hf))
+sb.forest_and_leaf_init(states, LEAF, False, 200, 1 << 20)
+ref = orc.make_heap(N, K)
+orc.init_rp_tree(X, "euclidean", ref, orc.forest_leaf_array(X, states, LEAF, False, 200, "level"))
+ok = (np.array_equal(e.heap_idx.numpy(), ref[0]) and np.array_equal(e.heap_dist.numpy(), ref[1]) and np.array_equal(e.heap_flag.numpy(), ref[2])
+      and len(e.calls) == NT)
+flags = [None] * w
+dist.all_gather_object(flags, bool(ok))
+if r == 0:
+    print("RESULT", "OK" if all(flags) else "BAD", flags, flush=True)
+dist.destroy_process_group()
+'''
+
+
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_forest_and_leaf_init_gloo(tmp_path, world):
+    """world_size 2 and 3 (5 trees: uneven tree ownership) over gloo: the sharded forest + leaf-init protocol end to end on an
+    oracle-backed engine."""
+    script = tmp_path / "leaf_worker.py"
+    script.write_text(LEAF_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    assert line[1] == "OK", out.stdout[-2000:]
