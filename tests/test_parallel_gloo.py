@@ -228,3 +228,145 @@ def test_sharded_forest_and_leaf_init_gloo(tmp_path, world):
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
     assert line[1] == "OK", out.stdout[-2000:]
+
+
+BUILD_WORKER = r'''
+"""The WHOLE sharded build (ShardedBuilder.build: forest, leaf init, init_random, NN-descent with the all-to-all exchange of
+half-updates, heap all-gathers, termination) over gloo, every engine primitive executed by the oracle.  The graph must be
+identical to the single-process oracle build -- for any world size (the property tests/test_sharded_gpu.py checks on GPUs)."""
+import os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+dist.init_process_group("gloo")
+from conftest import latent
+from oracle import nnd_oracle as orc
+from pynndescent_b200.sharded import ShardedBuilder
+r, w = dist.get_rank(), dist.get_world_size()
+N, D, K, LEAF, NT, T = 500, 10, 6, 16, 4, 8
+X = latent(N, D, 4)
+rs = np.random.RandomState(11)
+rng_state = rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, 3).astype(np.int64)
+states = rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, size=(NT, 3)).astype(np.int64)
+
+
+def csr(la):
+    sizes = (la >= 0).sum(1)
+    offs = np.zeros(la.shape[0] + 1, np.int64); np.cumsum(sizes, out=offs[1:])
+    return la[la >= 0].astype(np.int32), offs, int(sizes.max())
+
+
+class OracleShardEngine:
+    def __init__(self):
+        self.N, self.k, self.device = N, K, torch.device("cpu")
+        self.heap_idx = self.heap_dist = self.heap_flag = None
+        self.lo, self.hi = 0, N
+        self._ws = None
+        self.stream = type("S", (), {"synchronize": lambda self: None})()
+    def heap(self): return (self.heap_idx.numpy(), self.heap_dist.numpy(), self.heap_flag.numpy())
+    def default_push_capacity(self): return 1 << 20
+    def workspace(self, C_, T_, cap): return None
+    def set_join_order(self, perm): pass
+    def make_heap(self):
+        a, b, c = orc.make_heap(N, K)
+        self.heap_idx.copy_(torch.from_numpy(a)); self.heap_dist.copy_(torch.from_numpy(b)); self.heap_flag.copy_(torch.from_numpy(c))
+    def forest(self, tree_states, leaf_size, angular, max_depth):
+        la = orc.forest_leaf_array(X, np.ascontiguousarray(tree_states, np.int64), leaf_size, angular, max_depth, "level")
+        pts, offs, ml = csr(la)
+        return torch.from_numpy(pts), torch.from_numpy(offs), la.shape[0], ml
+    def leaf_fused_range(self, pts, offs, l0, l1, max_leaf, pos0=None, npos=None, cap=None):
+        if l1 == l0: return
+        o = offs.numpy(); p = pts.numpy()
+        la = np.full((l1 - l0, max_leaf), -1, np.int32)
+        for i, l in enumerate(range(l0, l1)):
+            m = p[o[l]: o[l + 1]]; la[i, : len(m)] = m
+        orc.init_rp_tree(X, "euclidean", self.heap(), la)
+    def heap_pack_rows(self, rows, n, oi, od, of, unpack):
+        if n == 0: return
+        idx = rows[:n].long()
+        if not unpack:
+            oi[:n] = self.heap_idx[idx]; od[:n] = self.heap_dist[idx]; of[:n] = self.heap_flag[idx]
+        else:
+            self.heap_idx[idx] = oi[:n]; self.heap_dist[idx] = od[:n]; self.heap_flag[idx] = of[:n]
+    def init_random(self, rng): orc.init_random(X, "euclidean", self.heap(), rng)
+    def set_row_range(self, lo, hi): self.lo, self.hi = lo, min(hi, N)
+    def build_candidates(self, C_, rng, T_, tables_valid=False):
+        # the oracle samples for every vertex and clears the sampled flags everywhere; the rows this rank does not own are
+        # overwritten by their owners' copies at the end of the iteration (all-gather), exactly like on the GPUs
+        return orc.new_build_candidates(self.heap(), C_, np.ascontiguousarray(rng, np.int64), T_)
+    def join_prepare(self, newc, oldc, cap):
+        self.newc, self.oldc = newc, oldc
+        return 1
+    def join_emit_round(self, C_, cap, rnd):
+        if rnd > 0: return 0
+        thr = self.heap()[1][:, 0].copy()
+        stride = 2 * C_
+        recs = []
+        for i in range(self.lo, self.hi):                      # own rows only; emission keys as in k_join / k_join_batch
+            nw = self.newc[i][self.newc[i] >= 0]; ol = self.oldc[i][self.oldc[i] >= 0]
+            mem = np.concatenate([nw, ol])
+            for a in range(len(nw)):
+                for b in range(a, len(mem)):
+                    p, q = int(mem[a]), int(mem[b])
+                    dd = np.float32(orc.dist("euclidean", X[p], X[q]))
+                    base = (i << 20) | ((a * stride + b) << 1)
+                    if dd < thr[p]: recs.append((p, q, dd, base))
+                    if b != a and dd < thr[q]: recs.append((q, p, dd, base | 1))
+        self.cur = recs
+        return len(recs)
+    def push_export(self, C_, cap, n, B, world):
+        if n == 0: return torch.zeros(24, dtype=torch.uint8), [0] * world
+        recs = sorted(self.cur, key=lambda t: min(t[0] // B, world - 1))          # grouped by owner, any order inside
+        rec = np.zeros((n, 6), np.int32)
+        rec[:, 0] = [t[0] for t in recs]; rec[:, 1] = [t[1] for t in recs]
+        rec[:, 2] = np.array([t[2] for t in recs], np.float32).view(np.int32)
+        seq = np.array([t[3] for t in recs], np.int64); rec[:, 4:6] = seq.view(np.int32).reshape(n, 2)
+        counts = [int(sum(1 for t in recs if min(t[0] // B, world - 1) == o)) for o in range(world)]
+        return torch.from_numpy(rec).view(torch.uint8).reshape(-1), counts
+    def apply_records(self, C_, cap, buf, n):
+        rec = buf[: n * 24].view(torch.int32).view(n, 6).numpy()
+        seq = np.ascontiguousarray(rec[:, 4:6]).view(np.int64).ravel()
+        hi_, hd_, hf_ = self.heap()
+        c = 0
+        for j in np.lexsort((seq, rec[:, 0])):                  # per target row in ascending emission sequence
+            t = int(rec[j, 0]); assert self.lo <= t < self.hi
+            c += orc.lib().orc_checked_flagged_heap_push(hd_[t], hi_[t], hf_[t], K, float(rec[j, 2:3].view(np.float32)[0]), int(rec[j, 1]), 1)
+        return c
+    def deheap_sort(self, correction):
+        a, b, _ = self.heap()
+        orc.deheap_sort(a, b)
+        return self.heap_idx, torch.from_numpy(np.sqrt(b) if correction == 1 else b.copy())
+
+
+e = OracleShardEngine()
+sb = ShardedBuilder(e)
+idx_t, dist_t, iters, c_hist = sb.build(rng_state.copy(), states, LEAF, False, K, T, 8, 0.001, 1)
+# single-process oracle with the same seeds (forest scheme "level" from the same tree states)
+la = orc.forest_leaf_array(X, states, LEAF, False, 200, "level")
+ref = orc.make_heap(N, K)
+orc.init_rp_tree(X, "euclidean", ref, la)
+rng2 = rng_state.copy()
+orc.init_random(X, "euclidean", ref, rng2)
+ch = np.zeros(8, np.int64)
+it2 = orc.lib().orc_nn_descent_internal(X, N, D, 0, ref[0], ref[1], ref[2], K, K, rng2, T, 8, 0.001, 16384, ch)
+orc.deheap_sort(ref[0], ref[1])
+ok = (np.array_equal(idx_t.numpy(), ref[0]) and np.array_equal(dist_t.numpy(), np.sqrt(ref[1])) and iters == it2
+      and list(c_hist) == [int(c) for c in ch[:it2]])
+flags = [None] * w
+dist.all_gather_object(flags, bool(ok))
+if r == 0:
+    print("RESULT", "OK" if all(flags) else "BAD", flags, iters, it2, list(c_hist), [int(c) for c in ch[:it2]], flush=True)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_whole_sharded_build_equals_single_process_oracle_gloo(tmp_path, world):
+    script = tmp_path / "build_worker.py"
+    script.write_text(BUILD_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    assert line[1] == "OK", out.stdout[-2000:]
