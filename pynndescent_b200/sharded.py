@@ -95,16 +95,26 @@ class ShardedBuilder:
         gi = torch.empty((self.world * maxn, k), dtype=torch.int32, device=dev)
         gd = torch.empty((self.world * maxn, k), dtype=torch.float32, device=dev)
         gf = torch.empty((self.world * maxn, k), dtype=torch.uint8, device=dev)
+        # NND_LEAF_EXCHANGE=targeted (default off until run over NCCL; the CPU gloo tests cover both modes): between two trees a
+        # rank only needs the rows of the points it is about to process, and it knows (everything here is replicated plan data)
+        # which rank processed each of them in the previous tree -- so every rank sends every other rank exactly those rows with
+        # one all-to-all-v per tree (N/world rows in, N/world out) instead of all-gathering all N rows; the replicas are made
+        # consistent by the ordinary all-gather after the LAST tree, whose shares contain every point exactly once.
+        targeted = os.environ.get("NND_LEAF_EXCHANGE", "") == "targeted" and self.world > 1
         fused_ok = True
         for t in range(n_trees):
             cuts, p0 = plan[t]
             pts = pts_all[t]; offs = offs_all[obase[t]: obase[t + 1]]
+            if targeted and t > 0:
+                self._fetch_rows(pts_all[t - 1], plan[t - 1][1], pts, p0, maxn)
             try:
                 e.leaf_fused_range(pts, offs, cuts[self.rank], cuts[self.rank + 1], max_leaf, pos0=p0[self.rank],
                                    npos=p0[self.rank + 1] - p0[self.rank], cap=cap)
             except NotImplementedError:
                 fused_ok = False
                 break
+            if targeted and t + 1 < n_trees:
+                continue
             # exchange the rows each rank has just updated (its leaves' points, in position order)
             e.heap_pack_rows(pts[p0[self.rank]: p0[self.rank + 1]], p0[self.rank + 1] - p0[self.rank], si, sd, sf, False)
             dist.all_gather_into_tensor(gi, si); dist.all_gather_into_tensor(gd, sd); dist.all_gather_into_tensor(gf, sf)
@@ -118,6 +128,37 @@ class ShardedBuilder:
             lo = torch.cat([offs_all[obase[t]: obase[t + 1] - 1] + t * N for t in range(n_trees)] +
                            [torch.tensor([n_trees * N], dtype=torch.int64, device=dev)])
             e.leaf_init(pts_all.reshape(-1), lo, lo.numel() - 1, max_leaf, cap)
+
+    def _fetch_rows(self, prev_pts, prev_p0, pts, p0, maxn):
+        """Bring the heap rows of the points this rank processes in the coming tree (positions [p0[rank], p0[rank+1]) of `pts`)
+        up to date: each was last written by the rank whose share of the PREVIOUS tree (`prev_pts`, `prev_p0`) contains it."""
+        e, k, dev, W, me = self.e, self.k, self.e.device, self.world, self.rank
+        N = self.N
+        pos_prev = torch.empty(N, dtype=torch.int64, device=dev)
+        pos_prev[prev_pts.long()] = torch.arange(N, dtype=torch.int64, device=dev)
+        bounds = torch.tensor(prev_p0[1:-1], dtype=torch.int64, device=dev)
+        writer = torch.bucketize(pos_prev, bounds, right=True)                       # rank that processed each point last
+        send_rows, send_counts, recv_rows, recv_counts = [], [], [], []
+        for q in range(W):
+            theirs = pts[p0[q]: p0[q + 1]]                                            # what rank q is about to process ...
+            mine_for_q = theirs[writer[theirs.long()] == me] if q != me else theirs[:0]   # ... and I wrote last
+            send_rows.append(mine_for_q); send_counts.append(int(mine_for_q.numel()))
+            my_next = pts[p0[me]: p0[me + 1]]
+            from_q = my_next[writer[my_next.long()] == q] if q != me else my_next[:0]
+            recv_rows.append(from_q); recv_counts.append(int(from_q.numel()))
+        ns, nr = sum(send_counts), sum(recv_counts)
+        srows = torch.cat(send_rows) if ns else torch.zeros(0, dtype=torch.int32, device=dev)
+        bufs = []
+        for dt in (torch.int32, torch.float32, torch.uint8):
+            bufs.append((torch.zeros((max(ns, 1), k), dtype=dt, device=dev), torch.zeros((max(nr, 1), k), dtype=dt, device=dev)))
+        if ns:
+            e.heap_pack_rows(srows.contiguous(), ns, bufs[0][0], bufs[1][0], bufs[2][0], False)
+        for snd, rcv in bufs:
+            dist.all_to_all_single(rcv[:nr].reshape(-1), snd[:ns].reshape(-1), output_split_sizes=[c * k for c in recv_counts],
+                                   input_split_sizes=[c * k for c in send_counts])
+            self.comm_bytes += nr * k * snd.element_size()
+        if nr:
+            e.heap_pack_rows(torch.cat(recv_rows).contiguous(), nr, bufs[0][1], bufs[1][1], bufs[2][1], True)
 
     def _replay(self, C_, cap, inbox):
         """Apply the collected 24-byte records to the own heap rows; returns the accepted-push count.

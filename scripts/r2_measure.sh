@@ -66,5 +66,7 @@ if [ "$what" = sharded ]; then
   NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 \
     NND_APPLY_HALF=1 NND_SMEM_CARVEOUT=1 run timeout 900 $TR scripts/sharded_check.py
   run timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline
+  NND_LEAF_EXCHANGE=targeted run timeout 900 $TR scripts/sharded_check.py
+  NND_LEAF_EXCHANGE=targeted run timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline
 fi
 tail -n 60 gpurun_out/r2.log

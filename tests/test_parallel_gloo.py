@@ -215,13 +215,14 @@ dist.destroy_process_group()
 import pytest
 
 
+@pytest.mark.parametrize("exchange", ["allgather", "targeted"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_forest_and_leaf_init_gloo(tmp_path, world):
+def test_sharded_forest_and_leaf_init_gloo(tmp_path, world, exchange):
     """world_size 2 and 3 (5 trees: uneven tree ownership) over gloo: the sharded forest + leaf-init protocol end to end on an
     oracle-backed engine."""
     script = tmp_path / "leaf_worker.py"
     script.write_text(LEAF_WORKER)
-    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1", NND_LEAF_EXCHANGE=exchange)   # "targeted": sharded.py _fetch_rows
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
@@ -359,11 +360,11 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_whole_sharded_build_equals_single_process_oracle_gloo(tmp_path, world):
+@pytest.mark.parametrize("world,exchange", [(2, "allgather"), (3, "allgather"), (3, "targeted")])
+def test_whole_sharded_build_equals_single_process_oracle_gloo(tmp_path, world, exchange):
     script = tmp_path / "build_worker.py"
     script.write_text(BUILD_WORKER)
-    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1", NND_LEAF_EXCHANGE=exchange)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
