@@ -262,7 +262,7 @@ def _sg_emulate(emu_lib, di, dd, di2, dd2, vertex_order, max_degree):
     return indptr, indices[:nnz], md[0]
 
 
-@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24", "query_jaccard_2k40"])
+@pytest.mark.parametrize("name", ["query_cosine_2k24", "query_jaccard_2k40"])
 def test_search_graph_kernels_match_reference_structures(emu_lib, name):
     """k_search_graph.cu under the emulator, on the two diversification passes of the reference's own graphs: the CSR must be
     the reference's search graph (query goldens) -- same check as tests/test_prepare_host.py makes for the host restatement."""
@@ -344,8 +344,7 @@ def test_candidate_kernels_row_sharded(emu_lib, skip):
         orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
 
 
-@pytest.mark.parametrize("kernel,rank_scatter,leaf_order,short_sort", [(0, 0, False, 0), (0, 1, False, 0), (1, 0, False, 0), (1, 1, True, 1),
-                                                                       (0, 0, False, 1), (0, 0, False, 2), (1, 1, True, 3)])
+@pytest.mark.parametrize("kernel,rank_scatter,leaf_order,short_sort", [(0, 0, False, 0), (0, 1, False, 1), (0, 0, False, 2), (1, 1, True, 3)])
 def test_whole_iterations_match_the_oracle_heaps(emu_lib, kernel, rank_scatter, leaf_order, short_sort):
     """Three NN-descent iterations: candidates from the oracle, then join -> scatter -> apply under the emulator; after every
     iteration the heaps (indices, distances, flags, layout) and the accepted-push count must equal the oracle's
