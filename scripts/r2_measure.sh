@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU commands of round 2 (run under gpurun from the repo root; everything lands in gpurun_out/).
-#   gpurun --timeout 2400 -- 'bash scripts/r2_measure.sh all'          # or one of: tests switches ab bench cfg3 cfg5 ncu | sharded (2 GPUs)
+#   gpurun --timeout 2400 -- 'bash scripts/r2_measure.sh all'          # or one of: tests switches sanitize ab bench cfg3 cfg5 ncu | sharded (2 GPUs)
 # Every step runs under its own `timeout` so that a hung experimental kernel cannot hold the box to gpurun's limit.
 set -u
 cd "$(dirname "$0")/.."
@@ -27,6 +27,15 @@ if [ "$what" = all ] || [ "$what" = switches ]; then
   # (deselected: the stage test compares old_cand of vertices WITHOUT new candidates, which NND_CAND_SKIP leaves empty by design)
   NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_KEYS=1 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 NND_APPLY_HALF=1 \
     run timeout 600 python -m pytest "tests/test_gpu_parity.py::test_init_random_build_candidates_process" -m gpu -q
+fi
+if [ "$what" = all ] || [ "$what" = sanitize ]; then
+  # compute-sanitizer over one small build with every switch on: out-of-bounds / misaligned accesses (memcheck) and
+  # shared-memory hazards (racecheck; mbarrier-ordered accesses may be reported conservatively -- read, do not gate on it)
+  ALLSW="NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 NND_APPLY_HALF=1 NND_PREPARE_GPU=1"
+  run timeout 900 env $ALLSW compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/memcheck_all.log python scripts/one_build.py 6000 40 10 euclidean 1
+  run timeout 900 env $ALLSW compute-sanitizer --tool racecheck --log-file gpurun_out/racecheck_all.log python scripts/one_build.py 3000 40 10 euclidean 1
+  run timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/memcheck_default.log python scripts/one_build.py 6000 40 10 euclidean 1
+  tail -n 5 gpurun_out/memcheck_all.log gpurun_out/racecheck_all.log gpurun_out/memcheck_default.log >> gpurun_out/r2.log 2>&1
 fi
 if [ "$what" = all ] || [ "$what" = ab ]; then
   # schedule experiments: bit-equality + timing, small first (a wrong kernel shows up in seconds), then the bench size
