@@ -60,3 +60,31 @@ def test_cfg2_full_size_properties_and_determinism():
     gi2, gd2 = idx2.neighbor_graph
     assert idx2.n_iters_run == iters and list(idx2.c_hist) == c_hist
     assert np.array_equal(gi, gi2) and np.array_equal(gd, gd2)
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg5"])
+def test_full_size_checksum_of_the_other_configs(name):
+    """BASELINE.json configs[2] (2M x 256 float32 cosine k=15: angular trees, alternative_cosine + correction) and configs[4]
+    (1M x 784 correlation k=30: f64 accumulation, leaves of up to 150 points, C = 30): the whole graph equals the CPU oracle's,
+    bit for bit (fixtures: tests/golden/make_full_size_checksum.py cfg3 | cfg5)."""
+    import hashlib
+    import json
+    import os
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from conftest import GOLDEN
+    from pynndescent_b200 import NNDescent
+    path = os.path.join(GOLDEN, name + "_full_oracle.json")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated (minutes of oracle time): python tests/golden/make_full_size_checksum.py " + name)
+    g = json.load(open(path))
+    X = latent(g["n"], g["d"], 0)
+    idx = NNDescent(X, g["metric"], n_neighbors=g["k"], random_state=g["random_state"])
+    gi, gd = idx.neighbor_graph
+    assert gi.shape == (g["n"], g["k"]) and str(np.asarray(gd).dtype) == g["dist_dtype"]
+    assert idx.n_iters_run == g["iters"] and [int(c) for c in idx.c_hist] == g["c_hist"]
+    for r, row in g["rows"].items():
+        assert gi[int(r)].tolist() == row["idx"] and [float(v) for v in gd[int(r)]] == row["dist"]
+    assert hashlib.sha256(np.ascontiguousarray(gi, np.int32).tobytes()).hexdigest() == g["idx_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(gd).tobytes()).hexdigest() == g["dist_sha256"]
+    assert np.all(np.diff(gd, axis=1) >= 0) and (gi[:, 0] == np.arange(g["n"])).mean() >= 0.9999
