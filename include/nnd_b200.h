@@ -63,7 +63,10 @@ extern "C" {
 #define NND_METRIC_SOKALSNEATH 14
 #define NND_METRIC_YULE 15
 #define NND_METRIC_ALT_HELLINGER 16 /* distances.py:1387-1416 alternative_hellinger (correction sqrt(1 - 2^-d)) */
-#define NND_METRIC_MAX 16
+/* distances.py:759-790 alternative_inner_product (inner_product): 1 / <x, y>, FLOAT32_MAX when <x, y> <= 0; the same f32 dot
+ * accumulation as NND_METRIC_ALT_DOT (one kernel class), no normalisation, correction -1 / d (distances.py:842-853) */
+#define NND_METRIC_ALT_INNER 17
+#define NND_METRIC_MAX 17
 
 #define NND_CORRECT_NONE 0
 #define NND_CORRECT_SQRT 1   /* distances.py:2171       np.sqrt                         */

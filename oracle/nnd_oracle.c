@@ -35,7 +35,7 @@ enum { ORC_SQEUCLIDEAN = 0, ORC_ALT_COSINE = 1, ORC_ALT_DOT = 2, ORC_CORRELATION
        /* SURVEY 8f-2 */
        ORC_MANHATTAN = 4, ORC_CHEBYSHEV = 5, ORC_CANBERRA = 6, ORC_HAMMING = 7, ORC_ALT_JACCARD = 8, ORC_DICE = 9,
        ORC_MATCHING = 10, ORC_KULSINSKI = 11, ORC_ROGERSTANIMOTO = 12, ORC_RUSSELLRAO = 13, ORC_SOKALSNEATH = 14,
-       ORC_YULE = 15, ORC_ALT_HELLINGER = 16 };
+       ORC_YULE = 15, ORC_ALT_HELLINGER = 16, ORC_ALT_INNER = 17 };
 
 /* ------------------------------------------------------------------ RNG ---- */
 /* utils.py:17-40 tau_rand_int.  State words are int64 and are NOT confined to 32
@@ -122,6 +122,12 @@ static inline float d_alt_dot(const float *x, const float *y, int d) {
     float dot = seq_dot(x, y, d);
     if (dot <= 0.0f) return FLT_MAX;
     return (float)(-det_log2((double)dot));
+}
+/* distances.py:759-790 alternative_inner_product: `result` is a float32 local; 1.0 / result is formed in f64 and returned as f4 */
+static inline float d_alt_inner(const float *x, const float *y, int d) {
+    float dot = seq_dot(x, y, d);
+    if (dot <= 0.0f) return FLT_MAX;
+    return (float)(1.0 / (double)dot);
 }
 /* distances.py:1283-1320 correlation (f64 accumulators as in the reference) */
 static inline double seq_mean(const float *x, int d) {
@@ -224,6 +230,7 @@ static inline float dist_fn(int metric, const float *x, const float *y, int d) {
     case ORC_CANBERRA: return d_canberra(x, y, d);
     case ORC_HAMMING: return d_hamming(x, y, d);
     case ORC_ALT_HELLINGER: return d_alt_hellinger(x, y, d);
+    case ORC_ALT_INNER: return d_alt_inner(x, y, d);
     default: return d_binary(metric, x, y, d);
     }
 }

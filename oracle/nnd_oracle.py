@@ -22,7 +22,9 @@ METRIC_IDS = {"sqeuclidean": 0, "euclidean": 0, "l2": 0, "cosine": 1, "dot": 2, 
               "manhattan": 4, "taxicab": 4, "l1": 4, "chebyshev": 5, "linfinity": 5, "linfty": 5, "linf": 5,
               "canberra": 6, "hamming": 7, "jaccard": 8, "dice": 9, "matching": 10, "kulsinski": 11,
               "rogerstanimoto": 12, "sokalmichener": 12, "russellrao": 13, "sokalsneath": 14, "yule": 15,
-              "hellinger": 16}
+              "hellinger": 16,
+              # alternative_inner_product (distances.py:759-790); true_angular computes in alternative_cosine (distances.py:2181-2184)
+              "inner_product": 17, "true_angular": 1}
 ANGULAR_METRICS = ("cosine", "dot", "correlation", "dice", "jaccard", "hellinger", "hamming")
 INT32_MIN = np.iinfo(np.int32).min + 1
 INT32_MAX = np.iinfo(np.int32).max - 1
@@ -271,6 +273,11 @@ def correction(metric, d):
         return 1.0 - np.power(2.0, -d.astype(np.float64))
     if metric == "hellinger":                             # correct_alternative_hellinger: sqrt(1 - 2^-d)
         return np.sqrt(1.0 - np.power(2.0, -d.astype(np.float64)))
+    if metric == "true_angular":                          # true_angular_from_alt_cosine (distances.py:1273-1280)
+        return 1.0 - np.arccos(np.power(2.0, -d.astype(np.float64))) / np.pi
+    if metric == "inner_product":                         # correct_alternative_inner_product (distances.py:841-853)
+        d64 = d.astype(np.float64)
+        return np.where(d >= np.finfo(np.float32).max, 0.0, -1.0 / np.where(d64 == 0.0, 1.0, d64))
     return d.copy()
 
 

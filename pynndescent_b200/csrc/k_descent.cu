@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                 if (valid) {
                     if (METRIC == NND_METRIC_SQEUCLIDEAN) r = (float)acc[i][u * TILE + v];
                     else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine((float)acc[i][u * TILE + v], n2_s[a], n2_s[b]);
-                    else if (METRIC == NND_METRIC_ALT_DOT) r = finish_alt_dot((float)acc[i][u * TILE + v]);
+                    else if (METRIC == NND_METRIC_ALT_DOT) r = finish_alt_dot((float)acc[i][u * TILE + v], P.metric);
                     else if (METRIC == NND_METRIC_CORRELATION) r = finish_correlation((double)acc[i][u * TILE + v], mu_s[2 * a + 1], mu_s[2 * b + 1]);
                     else if (METRIC == NND_METRIC_ALT_JACCARD) r = finish_binary(P.metric, (float)acc[i][u * TILE + v], n2_s[a], n2_s[b], P.d);
                     else if (METRIC == NND_METRIC_ALT_HELLINGER) r = finish_alt_hellinger((float)acc[i][u * TILE + v], n2_s[a], n2_s[b]);
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
                 if (valid) {
                     if (METRIC == NND_METRIC_SQEUCLIDEAN) r = acc[qa * TILE + qb];
                     else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine(acc[qa * TILE + qb], n2_s[uo + a], n2_s[uo + b]);
-                    else r = finish_alt_dot(acc[qa * TILE + qb]);
+                    else r = finish_alt_dot(acc[qa * TILE + qb], P.metric);
                     if (r < thr_s[uo + a]) pm |= 1u << (2 * (qa * TILE + qb));
                     if (b != a && r < thr_s[uo + b]) pm |= 2u << (2 * (qa * TILE + qb));
                 }
@@ -1088,7 +1088,8 @@ static int launch_join(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaS
     switch (P.metric) {
     case NND_METRIC_SQEUCLIDEAN: return launch_join_m<NND_METRIC_SQEUCLIDEAN>(ctx, P, n_units, st);
     case NND_METRIC_ALT_COSINE: return launch_join_m<NND_METRIC_ALT_COSINE>(ctx, P, n_units, st);
-    case NND_METRIC_ALT_DOT: return launch_join_m<NND_METRIC_ALT_DOT>(ctx, P, n_units, st);
+    case NND_METRIC_ALT_DOT:
+    case NND_METRIC_ALT_INNER: return launch_join_m<NND_METRIC_ALT_DOT>(ctx, P, n_units, st);   // one class, P.metric picks the tail
     case NND_METRIC_CORRELATION: return launch_join_m<NND_METRIC_CORRELATION>(ctx, P, n_units, st);
     case NND_METRIC_MANHATTAN: return launch_join_m<NND_METRIC_MANHATTAN>(ctx, P, n_units, st);
     case NND_METRIC_CHEBYSHEV: return launch_join_m<NND_METRIC_CHEBYSHEV>(ctx, P, n_units, st);
@@ -1380,8 +1381,9 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
     J.mode = 0; J.newc = new_cand; J.oldc = old_cand; J.C = C; J.m_max = 2 * C < 4 ? 4 : 2 * C; J.slot_stride = 2 * C;
     J.row_lo = ctx->row_lo; J.row_hi = ctx->row_hi;
     const char *force_old = getenv("NND_JOIN_UNBATCHED");
-    // the batched kernel is instantiated for the three f32 dot/difference metrics; everything else runs the generic join
-    PL.batched = P->metric <= NND_METRIC_ALT_DOT && 2 * C <= 60 && !(force_old && force_old[0] == '1');
+    // the batched kernel is instantiated for the three f32 dot/difference classes (inner_product shares dot's); everything else
+    // runs the generic join
+    PL.batched = nnd_metric_class(P->metric) <= NND_METRIC_ALT_DOT && 2 * C <= 60 && !(force_old && force_old[0] == '1');
     if (PL.batched) {
         // ---- batched path: compact the active rows and their members, cut batches by weight, one CTA per batch
         const int maxphys = ((2 * C + 3) >> 2) << 2;

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(JP_THREADS) k_join_pipe(JoinBatchParams P, con
                         if (valid) {
                             if (METRIC == NND_METRIC_SQEUCLIDEAN) r = acc[qa * TILE + qb];
                             else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine(acc[qa * TILE + qb], M.n2[uo + a], M.n2[uo + b]);
-                            else r = finish_alt_dot(acc[qa * TILE + qb]);
+                            else r = finish_alt_dot(acc[qa * TILE + qb], P.metric);
                             if (r < M.thr[uo + a]) pm |= 1u << (2 * (qa * TILE + qb));
                             if (b != a && r < M.thr[uo + b]) pm |= 2u << (2 * (qa * TILE + qb));
                         }

@@ -64,10 +64,10 @@ __device__ __forceinline__ float query_distance(const QueryParams &P, const floa
             dp = __fma_rn(sx, sy, dp);
         }
         return finish_correlation(dp, nq2, mu[2 * (int64_t)c + 1]);
-    } else if (P.metric == NND_METRIC_ALT_COSINE || P.metric == NND_METRIC_ALT_DOT) {
+    } else if (P.metric == NND_METRIC_ALT_COSINE || P.metric == NND_METRIC_ALT_DOT || P.metric == NND_METRIC_ALT_INNER) {
         float acc = 0.0f;
         for (int e = 0; e < P.d; ++e) acc = __fmaf_rn(q[e], y[e], acc);
-        if (P.metric == NND_METRIC_ALT_DOT) return finish_alt_dot(acc);
+        if (P.metric != NND_METRIC_ALT_COSINE) return finish_alt_dot(acc, P.metric);
         return finish_alt_cosine(acc, qn2, ((const float *)P.aux)[c]);
     }
     // SURVEY 8f-2 metrics: the same per-element steps and tails as the join (nnd_common.cuh); the query-side

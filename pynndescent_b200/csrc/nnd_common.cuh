@@ -118,8 +118,11 @@ __device__ __forceinline__ float finish_alt_cosine(float dot, float nx, float ny
     return (float)det_log2((double)r);
 }
 // distances.py:665-701 tail of alternative_dot
-__device__ __forceinline__ float finish_alt_dot(float dot) {
+// ... and of alternative_inner_product (distances.py:759-790; same class, `metric` picks the tail): 1.0 / result with an f32
+// `result` -- the reference's f64 quotient rounded to f32 equals the f32 quotient (53 >= 2*24+2 bits: double rounding is innocuous)
+__device__ __forceinline__ float finish_alt_dot(float dot, int metric) {
     if (dot <= 0.0f) return NND_FLT_MAX;
+    if (metric == NND_METRIC_ALT_INNER) return __fdiv_rn(1.0f, dot);
     return (float)(-det_log2((double)dot));
 }
 // distances.py:1283-1320 tail of correlation given the centred dot and squared norms (f64)
@@ -132,6 +135,7 @@ __device__ __forceinline__ float finish_correlation(double dp, double nx, double
 // ---- SURVEY 8f-2 metrics ---------------------------------------------------------------------------------
 // metric class = which per-element accumulation a kernel instantiation runs; the binary family shares one
 __host__ __device__ __forceinline__ int nnd_metric_class(int metric) {
+    if (metric == NND_METRIC_ALT_INNER) return NND_METRIC_ALT_DOT;      // same dot accumulation, another tail
     return (metric >= NND_METRIC_ALT_JACCARD && metric <= NND_METRIC_YULE) ? NND_METRIC_ALT_JACCARD : metric;
 }
 // classes whose accumulator is f64 (the reference accumulates these in a float64 `result`)
@@ -203,10 +207,10 @@ __device__ __forceinline__ float pair_distance_seq(const float *__restrict__ x, 
         float acc = 0.0f;
         for (int e = 0; e < d; ++e) { float df = __fsub_rn(x[e], y[e]); acc = __fmaf_rn(df, df, acc); }
         return acc;
-    } else if (metric == NND_METRIC_ALT_COSINE || metric == NND_METRIC_ALT_DOT) {
+    } else if (metric == NND_METRIC_ALT_COSINE || metric == NND_METRIC_ALT_DOT || metric == NND_METRIC_ALT_INNER) {
         float acc = 0.0f;
         for (int e = 0; e < d; ++e) acc = __fmaf_rn(x[e], y[e], acc);
-        if (metric == NND_METRIC_ALT_DOT) return finish_alt_dot(acc);
+        if (metric != NND_METRIC_ALT_COSINE) return finish_alt_dot(acc, metric);
         const float *n2 = (const float *)aux;
         return finish_alt_cosine(acc, n2[ix], n2[iy]);
     } else if (metric == NND_METRIC_CORRELATION) {

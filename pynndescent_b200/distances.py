@@ -12,7 +12,7 @@ NND_METRIC_SQEUCLIDEAN, NND_METRIC_ALT_COSINE, NND_METRIC_ALT_DOT, NND_METRIC_CO
 # SURVEY 8f-2 (include/nnd_b200.h)
 (NND_METRIC_MANHATTAN, NND_METRIC_CHEBYSHEV, NND_METRIC_CANBERRA, NND_METRIC_HAMMING, NND_METRIC_ALT_JACCARD,
  NND_METRIC_DICE, NND_METRIC_MATCHING, NND_METRIC_KULSINSKI, NND_METRIC_ROGERSTANIMOTO, NND_METRIC_RUSSELLRAO,
- NND_METRIC_SOKALSNEATH, NND_METRIC_YULE, NND_METRIC_ALT_HELLINGER) = range(4, 17)
+ NND_METRIC_SOKALSNEATH, NND_METRIC_YULE, NND_METRIC_ALT_HELLINGER, NND_METRIC_ALT_INNER) = range(4, 18)
 NND_CORRECT_NONE, NND_CORRECT_SQRT = 0, 1
 
 
@@ -24,6 +24,18 @@ def correct_alternative_cosine(d):
 def correct_alternative_hellinger(d):
     """distances.py:1419-1426: sqrt(1 - 2^-d)."""
     return np.sqrt(1.0 - np.power(2.0, -np.asarray(d).astype(np.float64)))
+
+
+def true_angular_from_alt_cosine(d):
+    """distances.py:1273-1280: 1 - arccos(2^-d) / pi."""
+    return 1.0 - np.arccos(np.power(2.0, -np.asarray(d).astype(np.float64))) / np.pi
+
+
+def correct_alternative_inner_product(d):
+    """distances.py:841-853: -1 / d, and 0 for the FLOAT32_MAX sentinel (non-positive inner product)."""
+    d = np.asarray(d)
+    d64 = d.astype(np.float64)
+    return np.where(d >= np.finfo(np.float32).max, 0.0, -1.0 / np.where(d64 == 0.0, 1.0, d64))
 
 
 # correct_alternative_jaccard (distances.py:329-336) is the same map as correct_alternative_cosine
@@ -57,6 +69,10 @@ gpu_distances = {
     "sokalsneath": (NND_METRIC_SOKALSNEATH, NND_CORRECT_NONE, None, False),
     "yule": (NND_METRIC_YULE, NND_CORRECT_NONE, None, False),
     "hellinger": (NND_METRIC_ALT_HELLINGER, NND_CORRECT_NONE, correct_alternative_hellinger, True),
+    # fast_distance_alternatives (distances.py:2176-2184); neither name is in the angular-tree list (pynndescent_.py:1074-1085)
+    # and only "dot" normalises the data (:1101-1103)
+    "inner_product": (NND_METRIC_ALT_INNER, NND_CORRECT_NONE, correct_alternative_inner_product, False),
+    "true_angular": (NND_METRIC_ALT_COSINE, NND_CORRECT_NONE, true_angular_from_alt_cosine, False),
 }
 
 # every key of the reference's named_distances (distances.py:2103-2162)

@@ -21,6 +21,10 @@ GOLDEN_CASES = {
     "binary_jaccard_1200x40": "jaccard",
     "cat_hamming_1200x30": "hamming",
     "nonneg_hellinger_1200x24": "hellinger",
+    # fast_distance_alternatives without a kernel class of their own (tests/golden/make_golden_metrics2.py): inner_product = the dot
+    # accumulation with a 1/x tail (mixed-sign data: half the pairs carry the FLOAT32_MAX sentinel), true_angular = alternative_cosine
+    "latent_inner_1500x20": "inner_product",
+    "latent_trueang_1500x20": "true_angular",
 }
 
 # Goldens whose RP forest cannot be re-derived bit-exactly by ANY independent implementation: integer / binary

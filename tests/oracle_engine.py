@@ -11,7 +11,7 @@ import torch
 from oracle import nnd_oracle as orc
 
 ID_TO_NAME = {0: "sqeuclidean", 1: "cosine", 2: "dot", 3: "correlation", 4: "manhattan", 5: "chebyshev", 6: "canberra",
-              7: "hamming", 8: "jaccard", 16: "hellinger"}
+              7: "hamming", 8: "jaccard", 16: "hellinger", 17: "inner_product"}
 
 
 class OracleEngine:

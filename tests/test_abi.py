@@ -3,6 +3,8 @@ import os
 import re
 import subprocess
 
+import numpy as np
+
 from conftest import ROOT
 
 
@@ -44,6 +46,13 @@ def test_metric_registry_matches_reference_names():
     assert dist.resolve("linf")[0] == dist.NND_METRIC_CHEBYSHEV and dist.resolve("sokalmichener")[0] == dist.NND_METRIC_ROGERSTANIMOTO
     assert [dist.resolve(m)[3] for m in ("jaccard", "dice", "hellinger", "hamming", "manhattan", "yule")] == [True] * 4 + [False] * 2
     assert dist.resolve("jaccard")[2] is not None and dist.resolve("hellinger")[2] is not None and dist.resolve("dice")[2] is None
+    # fast_distance_alternatives (distances.py:2176-2184): inner_product has its own tail in the dot kernel class, true_angular
+    # is the alternative_cosine kernel under another correction; neither uses angular trees
+    assert dist.resolve("inner_product")[0] == dist.NND_METRIC_ALT_INNER == 17
+    assert dist.resolve("true_angular")[0] == dist.NND_METRIC_ALT_COSINE
+    assert dist.resolve("inner_product")[3] is False and dist.resolve("true_angular")[3] is False
+    assert dist.resolve("inner_product")[2](np.array([0.5, 3.4028235e38], np.float32)).tolist() == [-2.0, 0.0]
+    assert dist.resolve("true_angular")[2](np.array([0.0, 1.0], np.float32)).tolist() == [1.0, 1.0 - np.arccos(0.5) / np.pi]
     with pytest.raises(NotImplementedError):
         dist.resolve("minkowski")          # needs metric_kwds
     with pytest.raises(NotImplementedError):

@@ -74,7 +74,7 @@ def test_rng_stream_matches_reference_kat_and_oracle(torch_cuda, oracle):
     assert np.array_equal(eng.rng_advance(s, 100000), ref)
 
 
-@pytest.mark.parametrize("metric", ["euclidean", "cosine", "dot", "correlation"])
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "dot", "correlation", "inner_product", "true_angular"])
 @pytest.mark.parametrize("d", [3, 16, 37, 128, 200])
 def test_pair_distances_bit_exact_vs_oracle(torch_cuda, oracle, metric, d):
     rs = np.random.RandomState(d)
@@ -98,6 +98,26 @@ def test_distance_kat_vs_reference(torch_cuda):
         big = R > 1e30
         assert np.array_equal(big, got > 1e30)
         np.testing.assert_allclose(got[~big], R[~big], rtol=1e-5, atol=2e-6)
+
+
+def test_inner_product_and_true_angular_kat_vs_reference(torch_cuda):
+    """alternative_inner_product / alternative_cosine matrices of the reference's numba functions (kat_metrics2.npz): same
+    sentinel positions; the corrected distances = the reference's correction of its own matrix (tolerance on the inner product
+    itself -- 1 / <x, y> amplifies the f32 sum's rounding when the terms cancel)."""
+    from pynndescent_b200 import distances
+    g = load_golden("kat_metrics2")
+    A = g["real_A"]
+    ii, jj = np.meshgrid(np.arange(24), np.arange(24), indexing="ij")
+    for metric in ("inner_product", "true_angular"):
+        eng, _ = _engine(A, metric, 4)
+        got = eng.pair_distances(ii.ravel(), jj.ravel()).reshape(24, 24)
+        R = g[f"dist_{metric}"]
+        big = R > 1e30
+        assert big.any() and np.array_equal(big, got > 1e30) and np.array_equal(got[big], R[big])
+        corr = distances.resolve(metric)[2](got)
+        np.testing.assert_allclose(corr[~big], g[f"corr_{metric}"][~big], rtol=1e-5, atol=2e-5 if metric == "inner_product" else 1e-6)
+        if metric == "inner_product":
+            assert np.array_equal(corr[big], np.zeros(int(big.sum())))
 
 
 # ------------------------------------------------------------------ SURVEY 8f-2 metrics
@@ -132,7 +152,8 @@ def test_more_metrics_pair_distances(torch_cuda, oracle, metric):
                                                ("canberra", 2000, 16, 8, 5), ("hamming", 2000, 30, 10, 6),
                                                ("jaccard", 2500, 40, 10, 7), ("dice", 1500, 40, 10, 8),
                                                ("yule", 1500, 33, 6, 9), ("russellrao", 1200, 40, 10, 10),
-                                               ("hellinger", 2000, 24, 10, 11), ("kulsinski", 1200, 130, 12, 12)])
+                                               ("hellinger", 2000, 24, 10, 11), ("kulsinski", 1200, 130, 12, 12),
+                                               ("inner_product", 2000, 20, 10, 13), ("true_angular", 2000, 24, 10, 14)])
 def test_more_metrics_full_build_bit_exact_vs_oracle(torch_cuda, oracle, metric, n, d, k, seed):
     """Forest (euclidean or angular per pynndescent_.py:1074-1085) + leaf init + descent under the added metrics ==
     the oracle's level-scheme build, indices and distances bit for bit -- binary / categorical data makes almost every

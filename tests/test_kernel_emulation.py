@@ -144,7 +144,10 @@ def cases():
             # C = 30: one row can outweigh a whole batch window, so some windows are EMPTY (descriptor with 0 units)
             "euclid24_k30": Case(160, 24, 30, "euclidean", 6),
             "euclid16_tiny": Case(60, 16, 4, "euclidean", 7),        # one d-chunk, 4 candidates, a handful of batches
-            "cosine8": Case(120, 7, 6, "cosine", 8)}                 # padded rows (d = 7 -> ld = 8), 32-byte bulk copies
+            "cosine8": Case(120, 7, 6, "cosine", 8),                 # padded rows (d = 7 -> ld = 8), 32-byte bulk copies
+            # the dot class with both tails: -log2(dot) and 1/dot (inner_product); mixed-sign rows, so about half of all pairs
+            # carry the FLOAT32_MAX sentinel (never below a finite threshold, below an infinite one)
+            "dot40": Case(400, 40, 10, "dot", 9), "inner40": Case(400, 40, 10, "inner_product", 10)}
 
 
 def _run(lib, case, kernel, dk=32, nst=4, grid=3, rank_scatter=0, order=None, capacity=None):
@@ -156,7 +159,7 @@ def _run(lib, case, kernel, dk=32, nst=4, grid=3, rank_scatter=0, order=None, ca
     tgt = np.zeros(cap, np.int32); oth = np.zeros(cap, np.int32); dd = np.zeros(cap, np.float32)
     pos = np.full(cap, 0xFFFFFFFF, np.uint32); seq = np.zeros(cap, np.uint64); cnt = np.zeros(n + 1, np.uint32)
     info = np.zeros(8, np.int64)
-    rc = lib.emu_join(case.X, n, case.ld, 1 if case.metric == "cosine" else 0, None if aux is None else aux.ctypes.data_as(C.c_void_p),
+    rc = lib.emu_join(case.X, n, case.ld, {"euclidean": 0, "cosine": 1, "dot": 2, "inner_product": 17}[case.metric], None if aux is None else aux.ctypes.data_as(C.c_void_p),
                       case.thr, case.newc, case.oldc, case.C, None if order is None else order.ctypes.data_as(C.c_void_p), kernel, dk, nst,
                       grid, rank_scatter, cap, tgt, oth, dd, pos, seq, cnt, info)
     assert rc == 0
@@ -181,7 +184,7 @@ def _check(case, r, rank_scatter=False):
     assert r["rows"] == mem                                                 # profile counter: rows gathered
 
 
-@pytest.mark.parametrize("name", ["euclid40", "euclid128", "cosine72", "euclid24_k30"])
+@pytest.mark.parametrize("name", ["euclid40", "euclid128", "cosine72", "euclid24_k30", "dot40", "inner40"])
 def test_emulator_reproduces_the_hardware_verified_kernel(emu_lib, cases, name):
     _check(cases[name], _run(emu_lib, cases[name], kernel=0))
 
@@ -189,7 +192,7 @@ def test_emulator_reproduces_the_hardware_verified_kernel(emu_lib, cases, name):
 @pytest.mark.parametrize("name,dk,nst,grid", [("euclid40", 32, 4, 3), ("euclid40", 32, 2, 1), ("euclid128", 32, 3, 2),
                                              ("euclid128", 128, 2, 4), ("cosine72", 64, 2, 3),
                                              ("euclid24_k30", 32, 4, 3), ("euclid24_k30", 32, 2, 200),
-                                             ("euclid16_tiny", 64, 2, 8), ("cosine8", 32, 3, 2)])
+                                             ("euclid16_tiny", 64, 2, 8), ("cosine8", 32, 3, 2), ("inner40", 32, 3, 2)])
 def test_k_join_pipe_equals_oracle(emu_lib, cases, name, dk, nst, grid):
     _check(cases[name], _run(emu_lib, cases[name], kernel=1, dk=dk, nst=nst, grid=grid))
 

@@ -84,6 +84,41 @@ def test_distance_kat_more_metrics(oracle, metric):
         np.testing.assert_allclose(oracle.correction(metric, D[fin]), g[f"corr_{metric}"][fin], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("metric", ["inner_product", "true_angular"])
+def test_distance_kat_alternatives_without_own_class(oracle, metric):
+    """inner_product (alternative_inner_product, distances.py:759-790) and true_angular (alternative_cosine + its own correction,
+    distances.py:2181-2184) vs the reference's numba functions: sentinel positions identical, values within 1e-5, and the
+    corrected distances equal the reference's correction AND its true distance function."""
+    g = load_golden("kat_metrics2")
+    A = g["real_A"]
+    D = np.array([[oracle.dist(metric, A[i], A[j]) for j in range(24)] for i in range(24)], np.float32)
+    R = g[f"dist_{metric}"]
+    big = R > 1e30
+    assert big.any() and np.array_equal(big, D > 1e30) and np.array_equal(D[big], R[big])
+    corr = oracle.correction(metric, D)
+    if metric == "inner_product":
+        # 1 / <x, y> of mixed-sign rows: the f32 sum's error is relative to sum |x_i y_i| (about 25 here), not to a result that
+        # cancellation can make 1e-2 -- so the comparison is on the inner product itself, i.e. on the corrected distance
+        np.testing.assert_allclose(1.0 / D[~big], 1.0 / R[~big], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(corr[~big], g[f"corr_{metric}"][~big], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(corr[~big], g[f"true_{metric}"][~big], rtol=1e-5, atol=2e-5)
+    else:
+        np.testing.assert_allclose(D[~big], R[~big], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(corr[~big], g[f"corr_{metric}"][~big], rtol=1e-5, atol=1e-6)
+        # (the reference's own true_angular(0, 0) is 0.0 while its correction maps alternative_cosine(0, 0) = 0 to 1.0: the graph
+        # path reports the correction, so the zero row is left out of the comparison with the true function)
+        nz = ~big & (np.abs(A).sum(1)[:, None] > 0) & (np.abs(A).sum(1)[None, :] > 0)
+        np.testing.assert_allclose(corr[nz], g[f"true_{metric}"][nz], rtol=2e-4, atol=2e-4)
+    if metric == "inner_product":
+        assert np.array_equal(corr[big], np.zeros(int(big.sum())))          # the sentinel maps to 0.0 (distances.py:851-852)
+        import pynndescent_b200.distances as ours
+        assert np.array_equal(ours.correct_alternative_inner_product(D), corr)
+    else:
+        import pynndescent_b200.distances as ours
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(ours.true_angular_from_alt_cosine(D), corr, equal_nan=True)
+
+
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
 def test_end_to_end_matches_reference(oracle, name):
     """Full build replay: leaf_array, heaps after each init stage, candidates, per-iteration
