@@ -54,6 +54,8 @@ fi
 if [ "$what" = all ] || [ "$what" = cfg5 ]; then
   # BASELINE.json configs[4]: 1M x 784 correlation k=30 build + query() of 100k held-out points
   run timeout 1500 python scripts/query_bench.py 1000000 784 30 100000 correlation
+  # full-size parity of the same build: sha256 of the oracle's 1M x 30 graph (tests/golden/cfg5_full_oracle.json)
+  NND_FULL_CFG5=1 run timeout 1500 python -m pytest "tests/test_zfull_size_gpu.py::test_full_size_checksum_of_the_other_configs[cfg5]" -m gpu -q
   run timeout 1200 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline
   # leaf_size 150 / k = 30 does not fit the fused leaf kernel (routed path); the split leaf init does
   NND_LEAF_SPLIT=1 run timeout 1200 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline

@@ -44,6 +44,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # a GPU test that hangs (a kernel that never returns) must end the run with a failure, not hold the box: pytest-timeout's
+    # thread method terminates the process even when the main thread is blocked inside a CUDA call.  The largest test of the
+    # suite (cfg3 at full size: 2M x 256) needs well under a minute of GPU time plus host-side data generation.
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -75,6 +75,10 @@ def test_full_size_checksum_of_the_other_configs(name):
     from conftest import GOLDEN
     from pynndescent_b200 import NNDescent
     path = os.path.join(GOLDEN, name + "_full_oracle.json")
+    if name == "cfg5" and os.environ.get("NND_FULL_CFG5") != "1":
+        # 1M x 784 correlation k=30 is ~4e9 pair evaluations of 784 f64 fma each on the generic join: minutes of GPU time, and the
+        # configuration has not run at full size on hardware yet -- scripts/r2_measure.sh sets NND_FULL_CFG5=1 and runs it on its own
+        pytest.skip("set NND_FULL_CFG5=1 (minutes of GPU time; first run is scripted in scripts/r2_measure.sh)")
     if not os.path.exists(path):
         pytest.skip("fixture not generated (minutes of oracle time): python tests/golden/make_full_size_checksum.py " + name)
     g = json.load(open(path))
