@@ -78,17 +78,17 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     float *n2_s = nullptr; double *mu_s = nullptr;
     if (MC_AUX1(METRIC)) { n2_s = (float *)cur; cur += (size_t)P.m_max * 4; }
     if (MC_AUX2(METRIC)) {
-        cur = (unsigned char *)(((uintptr_t)cur + 7) & ~uintptr_t(7));
+        cur = smem_align_up(smem_raw, cur, 8);
         mu_s = (double *)cur; cur += (size_t)P.m_max * 16;
     }
     float *hpri = nullptr; int32_t *hind = nullptr; uint8_t *hflg = nullptr; float *dsep = nullptr;
     if (P.mode == 2) {
-        cur = (unsigned char *)(((uintptr_t)cur + 15) & ~uintptr_t(15));
+        cur = smem_align_up(smem_raw, cur, 16);
         hpri = (float *)cur; hind = (int32_t *)(hpri + (size_t)P.k * P.m_max); hflg = (uint8_t *)(hind + (size_t)P.k * P.m_max);
         cur += ((size_t)P.k * P.m_max * 9 + 15) & ~size_t(15);
         if (!P.d_alias) { dsep = (float *)cur; cur += (size_t)P.m_max * (P.m_max | 1) * 4 + 16; }
     }
-    float *rows = (float *)(((uintptr_t)cur + 15) & ~uintptr_t(15));
+    float *rows = (float *)smem_align_up(smem_raw, cur, 16);
     __shared__ int s_nn, s_m;
 
     const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
     int32_t *ids = (int32_t *)(s_utile + JB_MAXU + 1);      // [JB_SCAP]
     float *thr_s = (float *)(ids + JB_SCAP);
     float *n2_s = thr_s + JB_SCAP;                          // cosine only
-    float *rows = (float *)(((uintptr_t)(n2_s + (METRIC == NND_METRIC_ALT_COSINE ? JB_SCAP : 0)) + 15) & ~uintptr_t(15));
+    float *rows = (float *)smem_align_up(smem_raw, (unsigned char *)(n2_s + (METRIC == NND_METRIC_ALT_COSINE ? JB_SCAP : 0)), 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t B = P.batch_begin + blockIdx.x;
     if (B >= P.batch_end) return;

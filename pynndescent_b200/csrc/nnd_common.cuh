@@ -362,6 +362,15 @@ __host__ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t v) {
 #define NND_SEG_SMEM 128
 __host__ __device__ __forceinline__ uint32_t padded_seg(uint32_t n) { return n <= NND_SEG_SMEM ? n : next_pow2_u32(n); }
 
+// Round a pointer into the dynamic shared array up to `a` bytes (a power of two <= the array's declared alignment) WITHOUT an
+// integer round trip: `(T *)(((uintptr_t)p + a - 1) & ~(a - 1))` is an inttoptr, which drops the shared address space -- every
+// access through it becomes a generic LD.E / ST.E with 64-bit address arithmetic (and a long-scoreboard dependency) instead of
+// LDS / STS with an immediate offset.  Same address as the absolute rounding because `base` is aligned to >= a.
+__device__ __forceinline__ unsigned char *smem_align_up(unsigned char *base, unsigned char *p, unsigned a) {
+    const unsigned off = (unsigned)(p - base);
+    return base + ((off + (a - 1u)) & ~(a - 1u));
+}
+
 // ------------------------------------------------------------------ PTX: mbarrier + bulk copy (TMA engine, 1-D)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
