@@ -234,16 +234,19 @@ __global__ void __launch_bounds__(256) k_forest_side128(const float *X, int ld, 
     int32_t my_pos = 0, my_o = 0, my_pt = 0;
     if (lane < cnt) { my_pos = act[i0 + lane]; my_o = seg[my_pos]; my_pt = perm[my_pos]; }
     int cur_o = -1; float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f); float off = 0.f;
-    float4 xq[2];
+    // next row prefetched one entry ahead; two NAMED registers (a dynamically indexed float4[2] lives in local memory: one STL
+    // and one LDL per entry on top of the row itself)
+    float4 xcur, xnext;
     {
         int pt0 = __shfl_sync(0xffffffffu, my_pt, 0);
-        xq[0] = has ? *(const float4 *)(X + (int64_t)pt0 * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xcur = has ? *(const float4 *)(X + (int64_t)pt0 * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    xnext = xcur;
     uint32_t sbits = 0;   // lane 0 collects the side bits of the run
     for (int q = 0; q < cnt; ++q) {
         if (q + 1 < cnt) {
             int ptn = __shfl_sync(0xffffffffu, my_pt, q + 1);
-            xq[(q + 1) & 1] = has ? *(const float4 *)(X + (int64_t)ptn * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xnext = has ? *(const float4 *)(X + (int64_t)ptn * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const int o = __shfl_sync(0xffffffffu, my_o, q);
         if (o != cur_o) {
@@ -251,7 +254,8 @@ __global__ void __launch_bounds__(256) k_forest_side128(const float *X, int ld, 
             h4 = has ? *(const float4 *)(hyper + (size_t)o * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             off = noff[o];
         }
-        const float4 b = xq[q & 1];
+        const float4 b = xcur;
+        xcur = xnext;
         float acc = 0.0f;
         acc = __fmaf_rn(h4.x, b.x, acc); acc = __fmaf_rn(h4.y, b.y, acc); acc = __fmaf_rn(h4.z, b.z, acc); acc = __fmaf_rn(h4.w, b.w, acc);
 #pragma unroll
