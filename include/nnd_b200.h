@@ -167,7 +167,7 @@ NND_API int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int
  * running batches inside one neighbourhood (L2 hits instead of HBM reads).  Schedule switches read from the
  * environment by nnd_create (all default off, none changes a result; csrc/nnd_common.cuh):
  * NND_JOIN_PIPE (+ NND_PIPE_DK, NND_PIPE_STAGES, NND_PIPE_CTAS), NND_RANK_SCATTER, NND_CAND_SKIP, NND_CAND_KEYS,
- * NND_LEAF_SPLIT, NND_APPLY_SHORT_SORT, NND_APPLY_HALF, NND_SMEM_CARVEOUT.                                           */
+ * NND_LEAF_SPLIT, NND_APPLY_SHORT_SORT, NND_APPLY_HALF, NND_SMEM_CARVEOUT, NND_FOREST_PM (+ NND_FOREST_PM_MB).              */
 NND_API int nnd_set_join_order(nnd_ctx *ctx, const int32_t *perm, int64_t n);
 
 /* ---- sharded build (one process per GPU) ----------------------------------------------

@@ -37,6 +37,7 @@ struct ForestWs {
     uint64_t *tree_seed;  // [n_trees]
     int32_t *scalars;     // [0] n_degenerate [1] max_leaf [2] next active count
     int32_t *act[2];      // [TN] active positions (ping-pong, unordered)
+    int32_t *invp;        // [TN] position of point p in tree t at invp[t*N+p], -1 once it sits in a final leaf (NND_FOREST_PM)
     int64_t M_max;
 };
 
@@ -55,6 +56,7 @@ static int carve_forest_ws(void *ws, size_t ws_bytes, int64_t N, int ld, int n_t
     W->tree_first = A.get<int32_t>(n_trees); W->tree_seed = A.get<uint64_t>(n_trees);
     W->scalars = A.get<int32_t>(16);
     for (int i = 0; i < 2; ++i) W->act[i] = A.get<int32_t>(TN);
+    W->invp = A.get<int32_t>(TN);
     // hyperplanes: nodes that split hold > leaf_size points, but leaf_size is not known here;
     // active nodes of one level are disjoint and each has >= 2 points
     W->hyper = A.get<float>((size_t)0);  // sized by forest_hyper_elems() below (needs leaf_size)
@@ -106,7 +108,7 @@ __device__ __forceinline__ uint64_t node_key(uint64_t seed, int level, int64_t o
 
 // ---------------------------------------------------------------- kernels
 __global__ void k_forest_init(int32_t *perm, int32_t *seg, uint8_t *segstart, int32_t *act, int32_t *leaf_points,
-                              uint32_t *flag32, int64_t N, int n_trees, int active) {
+                              uint32_t *flag32, int64_t N, int n_trees, int active, int32_t *invp) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)n_trees * N) return;
     int64_t t = i / N, p = i - t * N;
@@ -116,6 +118,7 @@ __global__ void k_forest_init(int32_t *perm, int32_t *seg, uint8_t *segstart, in
     act[i] = (int32_t)i;
     flag32[i] = 0;
     if (!active) leaf_points[i] = (int32_t)p;
+    if (invp) invp[i] = active ? (int32_t)i : -1;
 }
 
 // one warp per active node: choose the two members, build the hyperplane (rp_trees.py:351-367 / :88-118)
@@ -278,6 +281,65 @@ __global__ void __launch_bounds__(256) k_forest_side128(const float *X, int ld, 
     }
 }
 
+// Point-major variant (NND_FOREST_PM, default off): the position-major passes above read every row of X once PER TREE and level
+// (rows are gathered in each tree's own permuted order and X does not fit the L2: 4*ld*N*n_trees bytes of DRAM traffic per
+// level -- 92 GB per 1M x 128 build with 12 trees).  Here one warp keeps a point's row in registers and walks the point's
+// node in EVERY tree: X is read once per level (12x less DRAM traffic), the per-(tree, point) stream becomes the node's
+// hyperplane, which comes from the L2 while the level's table (M x ld floats) is small -- the host switches back to the
+// position-major kernel when it is not.  Same margin arithmetic (4 fma per lane, xor butterfly, + offset) and the same tie
+// hash as k_forest_side128, so side[] / flag32[] are bit-identical; invp (maintained by k_forest_scatter) supplies
+// position = invp[tree*N + point], -1 for a point that already sits in a final leaf of that tree.  Needs n_trees <= 32.
+#define PM_RUN 8
+__global__ void __launch_bounds__(256) k_forest_side_pm128(const float *X, int ld, int64_t N, int n_trees, int level,
+                                                           const int32_t *invp, const int32_t *seg, const int32_t *nstart,
+                                                           const int32_t *tree_first, const uint64_t *tree_seed, const float *hyper,
+                                                           const float *noff, uint8_t *side, uint32_t *flag32) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t p0 = w * PM_RUN;
+    if (p0 >= N) return;
+    const int cnt = (int)min((int64_t)PM_RUN, N - p0);
+    const bool has = lane * 4 < ld;
+    float4 xcur = has ? *(const float4 *)(X + p0 * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f), xnext = xcur;
+    for (int q = 0; q < cnt; ++q) {
+        const int64_t p = p0 + q;
+        if (q + 1 < cnt) xnext = has ? *(const float4 *)(X + (p + 1) * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // lane t < n_trees: where the point sits in tree t and which active node that is
+        int32_t my_pos = -1, my_o = -1;
+        if (lane < n_trees) { my_pos = invp[(int64_t)lane * N + p]; if (my_pos >= 0) my_o = seg[my_pos]; }
+        unsigned live = __ballot_sync(0xffffffffu, my_pos >= 0);
+        const float4 b = xcur;
+        xcur = xnext;
+        uint32_t sbits = 0;
+        while (live) {
+            const int t = __ffs(live) - 1;
+            live &= live - 1;
+            const int o = __shfl_sync(0xffffffffu, my_o, t);
+            const float4 h4 = has ? *(const float4 *)(hyper + (size_t)o * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float off = noff[o];
+            float acc = 0.0f;
+            acc = __fmaf_rn(h4.x, b.x, acc); acc = __fmaf_rn(h4.y, b.y, acc); acc = __fmaf_rn(h4.z, b.z, acc); acc = __fmaf_rn(h4.w, b.w, acc);
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, sft));
+            const float margin = __fadd_rn(off, acc);
+            uint32_t s;
+            if (fabs((double)margin) < 1e-8) {
+                const int pos = __shfl_sync(0xffffffffu, my_pos, t);
+                const int start = nstart[o];
+                const int tree = (int)(start / N);
+                const uint64_t key = node_key(tree_seed[tree], level, (int64_t)(o - tree_first[tree]));
+                s = (uint32_t)(mix64(key ^ (0x100ULL + (uint64_t)(pos - start))) & 1ULL);
+            } else s = margin > 0 ? 0u : 1u;
+            sbits |= s << t;
+        }
+        if (my_pos >= 0) {
+            const uint32_t s = (sbits >> lane) & 1u;
+            side[my_pos] = (uint8_t)s;
+            flag32[my_pos] = (s == 0);
+        }
+    }
+}
+
 // degenerate nodes (all points on one side): random split (rp_trees.py:395-403)
 __global__ void k_forest_fix_side(int64_t n_act, const int32_t *act, int64_t N, int level, const int32_t *seg,
                                   const int32_t *nstart, const uint8_t *ndegen, const int32_t *tree_first,
@@ -334,7 +396,7 @@ __global__ void k_forest_scatter(int64_t n_act, const int32_t *act, const int32_
                                  const uint8_t *side, const uint32_t *pl, const int32_t *nstart, const int32_t *nsize,
                                  const int32_t *nleft, const uint32_t *nchild_scan, int leaf_size, int depth_left_after,
                                  int32_t *perm2, int32_t *seg2, int32_t *act2, int32_t *n_act2, int32_t *leaf_points,
-                                 uint32_t *flag32) {
+                                 uint32_t *flag32, int32_t *invp, int64_t N) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool alive = false; int32_t np32 = 0;
@@ -355,6 +417,7 @@ __global__ void k_forest_scatter(int64_t n_act, const int32_t *act, const int32_
         const int32_t pt = perm[pos];
         if (child >= 0) { perm2[np] = pt; seg2[np] = child; alive = true; np32 = (int32_t)np; }
         else leaf_points[np] = pt;
+        if (invp) invp[(int64_t)(start / N) * N + pt] = child >= 0 ? (int32_t)np : -1;   // NND_FOREST_PM: point -> next position
         flag32[pos] = 0;  // scan input must be zero outside the (new) active set
     }
     unsigned mk = __ballot_sync(0xffffffffu, alive);
@@ -411,7 +474,10 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
     NND_CUDA(cudaMemcpyAsync(W.tree_seed, seeds.data(), sizeof(uint64_t) * n_trees, cudaMemcpyHostToDevice, st));
     const bool root_active = (N > leaf_size && max_depth > 0);
     const unsigned gpos = (unsigned)cdiv(TN + 1, 256);
-    k_forest_init<<<gpos, 256, 0, st>>>(W.perm[0], W.seg[0], W.segstart, W.act[0], leaf_points, W.flag32, N, n_trees, root_active ? 1 : 0); NND_LAUNCH(ctx);
+    // NND_FOREST_PM: the inverse permutation is maintained (init + scatter) only when the point-major pass can be used at all
+    const bool pm_on = ctx->opt_forest_pm && ld <= 128 && n_trees <= 32;
+    int32_t *invp = pm_on ? W.invp : nullptr;
+    k_forest_init<<<gpos, 256, 0, st>>>(W.perm[0], W.seg[0], W.segstart, W.act[0], leaf_points, W.flag32, N, n_trees, root_active ? 1 : 0, invp); NND_LAUNCH(ctx);
     NND_CUDA(cudaMemsetAsync(W.scalars, 0, sizeof(int32_t) * 16, st));
     int cur = 0;
     int M = 0;
@@ -434,7 +500,11 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
                                                                                  W.nsize[ncur], W.perm[cur], W.tree_first,
                                                                                  W.tree_seed, W.hyper, W.noff);
         NND_LAUNCH(ctx);
-        if (ld <= 128)
+        if (pm_on && (size_t)M * ld * 4 <= (size_t)ctx->opt_forest_pm_mb << 20)
+            k_forest_side_pm128<<<(unsigned)cdiv(cdiv(N, PM_RUN) * 32, 256), 256, 0, st>>>(X, ld, N, n_trees, level, invp, W.seg[cur],
+                                                                                      W.nstart[ncur], W.tree_first, W.tree_seed, W.hyper,
+                                                                                      W.noff, W.side, W.flag32);
+        else if (ld <= 128)
             k_forest_side128<<<(unsigned)cdiv(cdiv(n_act, SIDE_RUN) * 32, 256), 256, 0, st>>>(X, ld, n_act, W.act[cur], N, level,
                                                                                          W.perm[cur], W.seg[cur], W.nstart[ncur],
                                                                                          W.tree_first, W.tree_seed, W.hyper, W.noff,
@@ -471,7 +541,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
         k_forest_scatter<<<(unsigned)cdiv(n_act, 256), 256, 0, st>>>(n_act, W.act[cur], W.perm[cur], W.seg[cur], W.side, W.pl,
                                                                      W.nstart[ncur], W.nsize[ncur], W.nleft, W.nchild_scan, leaf_size,
                                                                      depth_left_after, W.perm[cur ^ 1], W.seg[cur ^ 1], W.act[cur ^ 1],
-                                                                     W.scalars + 2, leaf_points, W.flag32);
+                                                                     W.scalars + 2, leaf_points, W.flag32, invp, N);
         NND_LAUNCH(ctx);
         uint32_t m_next = 0; int32_t a_next = 0;
         NND_CUDA(cudaMemcpyAsync(&m_next, W.nchild_scan + M, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -65,6 +65,8 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
         c->opt_carveout = env_int("NND_SMEM_CARVEOUT", 0);
         c->opt_apply_short = env_int("NND_APPLY_SHORT_SORT", 0);
         c->opt_apply_half = env_int("NND_APPLY_HALF", 0);
+        c->opt_forest_pm = env_int("NND_FOREST_PM", 0);
+        c->opt_forest_pm_mb = env_int("NND_FOREST_PM_MB", 48);
         c->join_order = nullptr; c->join_order_n = 0;
     }
     NND_CUDA(cudaEventCreate(&c->ev0));

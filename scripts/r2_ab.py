@@ -31,10 +31,13 @@ CONFIGS = {
     "candkeys": {"NND_CAND_KEYS": "1"},
     "candtile": {"NND_CAND_KEYS": "2"},
     "candskip+tile": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2"},
+    "forestpm": {"NND_FOREST_PM": "1"},
+    "forestpm16": {"NND_FOREST_PM": "1", "NND_FOREST_PM_MB": "16"},
+    "forestpm96": {"NND_FOREST_PM": "1", "NND_FOREST_PM_MB": "96"},
     "pipe": {"NND_JOIN_PIPE": "1"},
     "pipe+rank": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1"},
     "pipe+rank+leaf": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf"},
-    "all": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf", "NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2", "NND_LEAF_SPLIT": "1", "NND_SMEM_CARVEOUT": "1", "NND_APPLY_SHORT_SORT": "1", "NND_APPLY_HALF": "1"},
+    "all": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf", "NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2", "NND_LEAF_SPLIT": "1", "NND_SMEM_CARVEOUT": "1", "NND_APPLY_SHORT_SORT": "1", "NND_APPLY_HALF": "1", "NND_FOREST_PM": "1"},
     "pipe-s3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "3"},
     "pipe-s2c3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "2", "NND_PIPE_CTAS": "3"},
     "pipe-s6": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "6"},

@@ -22,16 +22,16 @@ if [ "$what" = all ] || [ "$what" = switches ]; then
   # the whole parity suite again with every schedule switch ON (they are read by nnd_create, so the env covers every test):
   # the reference goldens, the oracle and the full-size checksum must all still hold
   NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 \
-    NND_APPLY_HALF=1 NND_SMEM_CARVEOUT=1 NND_PREPARE_GPU=1 run timeout 1500 python -m pytest tests -m gpu -q -n 4 --deselect tests/test_sharded_gpu.py \
+    NND_APPLY_HALF=1 NND_SMEM_CARVEOUT=1 NND_PREPARE_GPU=1 NND_FOREST_PM=1 run timeout 1500 python -m pytest tests -m gpu -q -n 4 --deselect tests/test_sharded_gpu.py \
     --deselect "tests/test_gpu_parity.py::test_init_random_build_candidates_process"
   # (deselected: the stage test compares old_cand of vertices WITHOUT new candidates, which NND_CAND_SKIP leaves empty by design)
-  NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_KEYS=1 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 NND_APPLY_HALF=1 \
+  NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_KEYS=1 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 NND_APPLY_HALF=1 NND_FOREST_PM=1 \
     run timeout 600 python -m pytest "tests/test_gpu_parity.py::test_init_random_build_candidates_process" -m gpu -q
 fi
 if [ "$what" = all ] || [ "$what" = sanitize ]; then
   # compute-sanitizer over one small build with every switch on: out-of-bounds / misaligned accesses (memcheck) and
   # shared-memory hazards (racecheck; mbarrier-ordered accesses may be reported conservatively -- read, do not gate on it)
-  ALLSW="NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 NND_APPLY_HALF=1 NND_PREPARE_GPU=1"
+  ALLSW="NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 NND_APPLY_HALF=1 NND_PREPARE_GPU=1 NND_FOREST_PM=1"
   run timeout 900 env $ALLSW compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/memcheck_all.log python scripts/one_build.py 6000 40 10 euclidean 1
   run timeout 900 env $ALLSW compute-sanitizer --tool racecheck --log-file gpurun_out/racecheck_all.log python scripts/one_build.py 3000 40 10 euclidean 1
   run timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/memcheck_default.log python scripts/one_build.py 6000 40 10 euclidean 1

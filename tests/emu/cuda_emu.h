@@ -232,6 +232,17 @@ static inline unsigned atomicMin(unsigned *p, unsigned v) {
     return old;
 }
 
+static inline int atomicMin(int *p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline int atomicMax(int *p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+
 // ---- arithmetic intrinsics (IEEE round-to-nearest; build with -ffp-contract=off)
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -67,8 +67,12 @@ def emu_lib(tmp_path_factory):
                     "JoinParams / k_join")
     leaf = _between(desc, "// ------------------------------------------------------------------ split leaf init",
                     "// ------------------------------------------------------------------ host orchestration", "k_leaf_prep / k_leaf_push")
+    forest = open(os.path.join(CSRC, "k_forest.cu")).read()
+    forest = _between(forest, "// ---------------------------------------------------------------- canonical warp reductions",
+                      'extern "C" int nnd_forest_build', "the forest kernels")
+    forest = forest.replace("extern __shared__ float s_t[];", "float *s_t = (float *)emu::dyn_smem();")
     kernels = (join + "\n" + batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
-               "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf)
+               "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf + "\n#define EMU_WITH_FOREST 1\n" + forest)
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
@@ -96,6 +100,7 @@ def emu_lib(tmp_path_factory):
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.emu_process_candidates.restype = C.c_long
     lib.emu_leaf_init.argtypes = [f32, C.c_long, C.c_int, C.c_int, i32, i64, C.c_long, C.c_int, i32, f32, u8, C.c_int, C.c_int]
+    lib.emu_forest.argtypes = [f32, C.c_long, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, i32, i64, i64]
     return lib
 
 
@@ -396,3 +401,40 @@ def test_leaf_init_fused_and_split(emu_lib, split):
     rc = emu_lib.emu_leaf_init(np.ascontiguousarray(X), n, d, d, pts, offs, la.shape[0], int(sizes.max()), e[0], e[1], e[2], k, split)
     assert rc == 0
     assert np.array_equal(e[0], heap[0]) and np.array_equal(e[1], heap[1]) and np.array_equal(e[2], heap[2])
+
+
+# ---- RP forest (k_forest.cu): every kernel of the level-synchronous forest under emulation against the oracle's level scheme
+# (the GPU suite's test_forest_bit_exact_vs_oracle_level_scheme, on the CPU), and the point-major hyperplane pass NND_FOREST_PM
+@pytest.mark.parametrize("n,d,angular,trees,leaf,pm,pm_limit", [
+    (260, 20, 0, 3, 16, 0, 0),                 # the hardware-verified position-major pass (k_forest_side128) validates the harness
+    (260, 20, 0, 3, 16, 1, 1 << 30),           # point-major on every level
+    (260, 20, 0, 3, 16, 1, 500),               # point-major while the level's table is <= 500 B (6 nodes), position-major below
+    (200, 128, 1, 2, 12, 1, 1 << 30),          # angular trees, full 128-float rows (every lane holds data)
+    (160, 7, 1, 2, 10, 1, 1 << 30),            # padded rows (ld = 8: lanes 2..31 hold nothing)
+    (120, 130, 0, 2, 10, 1, 1 << 30),          # ld > 128: the switch must leave the generic k_forest_side in charge
+])  # (every emulated CUDA thread is an OS thread: sizes are kept small; 700 x 20 x 5 trees and 500 x 128 angular passed as well)
+def test_forest_kernels_and_point_major_pass(emu_lib, n, d, angular, trees, leaf, pm, pm_limit):
+    from oracle import nnd_oracle as orc
+    X = latent(n, d, 17 + d)
+    if angular:
+        X[3] = 0.0                                                            # a zero row: norm guard of the angular hyperplane
+    X[5] = X[6]                                                               # duplicates: margin ties -> hash coin
+    ld = (d + 3) // 4 * 4
+    Xp = np.zeros((n, ld), np.float32); Xp[:, :d] = X
+    states = np.random.RandomState(3).randint(-2 ** 31 + 1, 2 ** 31 - 1, size=(trees, 3)).astype(np.int64)
+    lp = np.full(trees * n, -7, np.int32); lo = np.zeros(trees * n + 1, np.int64); info = np.zeros(8, np.int64)
+    rc = emu_lib.emu_forest(Xp, n, ld, angular, states, trees, leaf, 200, pm, pm_limit, lp, lo, info)
+    assert rc == 0
+    nl, ml, levels, levels_pm = (int(v) for v in info[:4])
+    want = orc.forest_leaf_array(X, states, leaf, bool(angular), 200, "level")
+    assert nl == want.shape[0] and ml == want.shape[1]
+    got = np.full_like(want, -1)
+    for i in range(nl):
+        got[i, : lo[i + 1] - lo[i]] = lp[lo[i]: lo[i + 1]]
+    assert np.array_equal(got, want)
+    if not pm or ld > 128:
+        assert levels_pm == 0
+    elif pm_limit >= 1 << 30:
+        assert levels_pm == levels > 3
+    else:
+        assert 0 < levels_pm < levels                                         # both kernels took part in this forest
