@@ -15,7 +15,7 @@ def _index(G):
                           G["search_rng_state"])
 
 
-@pytest.mark.parametrize("name", list(QUERY_GOLDENS))
+@pytest.mark.parametrize("name", list(QUERY_GOLDENS[:2]))   # the later goldens: tests/test_xpending_gpu.py
 def test_query_matches_reference(name, oracle):
     G = load_golden(name)
     si = _index(G)
@@ -54,7 +54,7 @@ def test_query_rng_fallback_and_edge_cases(oracle):
     assert np.all(hi[3] == -1)
 
 
-@pytest.mark.parametrize("name", list(QUERY_GOLDENS))
+@pytest.mark.parametrize("name", list(QUERY_GOLDENS[:2]))   # the later goldens: tests/test_xpending_gpu.py
 def test_prepare_matches_reference_structures(name):
     """prepare(): from the reference's kNN graph, the GPU hub tree + diversification + the scipy bookkeeping give
     the reference's search graph, search tree, leaf order and min_distance."""

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 import test_gpu_parity as tp
-from conftest import GOLDEN_CASES_PENDING_GPU, load_golden
+import test_gpu_query as tq
+from conftest import GOLDEN_CASES_PENDING_GPU, QUERY_GOLDENS, load_golden
 from test_gpu_parity import _engine, torch_cuda  # noqa: F401  (fixture)
 
 pytestmark = pytest.mark.gpu
@@ -53,3 +54,10 @@ def test_staged_builds_from_reference_goldens(torch_cuda, oracle, name):
 @pytest.mark.parametrize("metric,n,d,k,seed", [("inner_product", 2000, 20, 10, 13), ("true_angular", 2000, 24, 10, 14)])
 def test_full_build_bit_exact_vs_oracle(torch_cuda, oracle, metric, n, d, k, seed):
     tp.test_more_metrics_full_build_bit_exact_vs_oracle(torch_cuda, oracle, metric, n, d, k, seed)
+
+
+# query / prepare goldens of manhattan, jaccard and hellinger (tests/golden/make_golden_query.py), added after the last hardware run
+@pytest.mark.parametrize("name", list(QUERY_GOLDENS[2:]))
+def test_query_and_prepare_match_reference(name, oracle):
+    tq.test_query_matches_reference(name, oracle)
+    tq.test_prepare_matches_reference_structures(name)
