@@ -407,9 +407,8 @@ def test_leaf_init_fused_and_split(emu_lib, split):
 # (the GPU suite's test_forest_bit_exact_vs_oracle_level_scheme, on the CPU), and the point-major hyperplane pass NND_FOREST_PM
 @pytest.mark.parametrize("n,d,angular,trees,leaf,pm,pm_limit", [
     (260, 20, 0, 3, 16, 0, 0),                 # the hardware-verified position-major pass (k_forest_side128) validates the harness
-    (260, 20, 0, 3, 16, 1, 1 << 30),           # point-major on every level
     (260, 20, 0, 3, 16, 1, 500),               # point-major while the level's table is <= 500 B (6 nodes), position-major below
-    (200, 128, 1, 2, 12, 1, 1 << 30),          # angular trees, full 128-float rows (every lane holds data)
+    (200, 128, 1, 2, 12, 1, 1 << 30),          # point-major on every level; angular trees, full 128-float rows (every lane holds data)
     (160, 7, 1, 2, 10, 1, 1 << 30),            # padded rows (ld = 8: lanes 2..31 hold nothing)
     (120, 130, 0, 2, 10, 1, 1 << 30),          # ld > 128: the switch must leave the generic k_forest_side in charge
 ])  # (every emulated CUDA thread is an OS thread: sizes are kept small; 700 x 20 x 5 trees and 500 x 128 angular passed as well)
