@@ -66,7 +66,12 @@ extern "C" {
 /* distances.py:759-790 alternative_inner_product (inner_product): 1 / <x, y>, FLOAT32_MAX when <x, y> <= 0; the same f32 dot
  * accumulation as NND_METRIC_ALT_DOT (one kernel class), no normalisation, correction -1 / d (distances.py:842-853) */
 #define NND_METRIC_ALT_INNER 17
-#define NND_METRIC_MAX 17
+/* distances.py:138-153 minkowski(x, y, p): float64 result += (f32 |x_i - y_i|) ** p, then result ** (1 / p).  p reaches the
+ * reference's function positionally from metric_kwds.values() (pynndescent_.py:1064-1065, 1294-1302); here the caller stores it
+ * in the first 16 bytes of the metric aux buffer with nnd_metric_set_param (two doubles: p, 1 / p).  x ** p is evaluated by a
+ * deterministic exp2(p * log2 x) (fma chains only), restated in the oracle: f32 results equal the reference's on its KATs */
+#define NND_METRIC_MINKOWSKI 18
+#define NND_METRIC_MAX 18
 
 #define NND_CORRECT_NONE 0
 #define NND_CORRECT_SQRT 1   /* distances.py:2171       np.sqrt                         */
@@ -100,6 +105,10 @@ NND_API int nnd_metric_aux_bytes(int32_t metric, int64_t N, size_t *bytes);
 /* fills aux (per-point squared norms / means) in the canonical summation order */
 NND_API int nnd_metric_prepare(nnd_ctx *ctx, const float *X, int64_t N, int32_t d, int32_t ld, int32_t metric, void *aux,
                        void *stream);
+/* parameter of a metric that takes one -- the reference passes metric_kwds.values() positionally to the distance function
+ * (pynndescent_.py:1064-1065, 1294-1302); NND_METRIC_MINKOWSKI: p > 0 (distances.py:138).  Stored in the first 16 bytes of aux
+ * (every aux buffer has them, nnd_metric_aux_bytes); call after nnd_metric_prepare, before any stage.                        */
+NND_API int nnd_metric_set_param(nnd_ctx *ctx, int32_t metric, void *aux, double value, void *stream);
 /* utils.py:130-158 make_heap: idx=-1, dist=+inf, flag=0 */
 NND_API int nnd_make_heap(nnd_ctx *ctx, int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int64_t N, int32_t k,
                   void *stream);

@@ -35,7 +35,7 @@ enum { ORC_SQEUCLIDEAN = 0, ORC_ALT_COSINE = 1, ORC_ALT_DOT = 2, ORC_CORRELATION
        /* SURVEY 8f-2 */
        ORC_MANHATTAN = 4, ORC_CHEBYSHEV = 5, ORC_CANBERRA = 6, ORC_HAMMING = 7, ORC_ALT_JACCARD = 8, ORC_DICE = 9,
        ORC_MATCHING = 10, ORC_KULSINSKI = 11, ORC_ROGERSTANIMOTO = 12, ORC_RUSSELLRAO = 13, ORC_SOKALSNEATH = 14,
-       ORC_YULE = 15, ORC_ALT_HELLINGER = 16, ORC_ALT_INNER = 17 };
+       ORC_YULE = 15, ORC_ALT_HELLINGER = 16, ORC_ALT_INNER = 17, ORC_MINKOWSKI = 18 };
 
 /* ------------------------------------------------------------------ RNG ---- */
 /* utils.py:17-40 tau_rand_int.  State words are int64 and are NOT confined to 32
@@ -93,6 +93,38 @@ static double det_log2(double x) {
     return fma(ln_m, 1.4426950408889634, (double)e);
 }
 ORC_API double orc_det_log2(double x) { return det_log2(x); }
+/* deterministic 2^z in double (same contract): z = n + f, |f| <= 1/2, 2^f = exp(f ln 2) by a degree-13 Horner chain of fma
+ * (|f ln 2| <= 0.3466: the first dropped term is 0.3466^14 / 14! = 4e-18), scaled by 2^n through the exponent bits */
+static double det_exp2(double z) {
+    if (z > 1023.0) return INFINITY;
+    if (z < -1021.0) return 0.0;
+    double n = nearbyint(z);
+    double g = (z - n) * 0.6931471805599453;
+    double q = 1.0 / 6227020800.0;
+    q = fma(q, g, 1.0 / 479001600.0);
+    q = fma(q, g, 1.0 / 39916800.0);
+    q = fma(q, g, 1.0 / 3628800.0);
+    q = fma(q, g, 1.0 / 362880.0);
+    q = fma(q, g, 1.0 / 40320.0);
+    q = fma(q, g, 1.0 / 5040.0);
+    q = fma(q, g, 1.0 / 720.0);
+    q = fma(q, g, 1.0 / 120.0);
+    q = fma(q, g, 1.0 / 24.0);
+    q = fma(q, g, 1.0 / 6.0);
+    q = fma(q, g, 0.5);
+    q = fma(q, g, 1.0);
+    q = fma(q, g, 1.0);
+    union { double d; uint64_t u; } s;
+    s.u = (uint64_t)((int64_t)n + 1023) << 52;
+    return q * s.d;
+}
+/* x^y for x >= 0, y > 0 (what minkowski needs): 0^y = 0, else 2^(y log2 x) */
+static double det_pow(double x, double y) { return x > 0.0 ? det_exp2(y * det_log2(x)) : 0.0; }
+ORC_API double orc_det_pow(double x, double y) { return det_pow(x, y); }
+/* parameter of the metrics that take one (distances.py:138-153 minkowski: p); the oracle is test infrastructure, a process-wide
+ * setting is enough */
+static double g_metric_param = 2.0;
+ORC_API void orc_set_metric_param(double v) { g_metric_param = v; }
 
 /* distances.py:63-91 squared_euclidean (canonical order: sequential fma chain) */
 static inline float d_sqeuclid(const float *x, const float *y, int d) {
@@ -128,6 +160,13 @@ static inline float d_alt_inner(const float *x, const float *y, int d) {
     float dot = seq_dot(x, y, d);
     if (dot <= 0.0f) return FLT_MAX;
     return (float)(1.0 / (double)dot);
+}
+/* distances.py:138-153 minkowski: result (float64) += (f32 |x_i - y_i|) ** p, then result ** (1 / p) */
+static inline float d_minkowski(const float *x, const float *y, int d) {
+    const double p = g_metric_param;
+    double acc = 0.0;
+    for (int e = 0; e < d; ++e) acc += det_pow((double)fabsf(x[e] - y[e]), p);
+    return (float)det_pow(acc, 1.0 / p);
 }
 /* distances.py:1283-1320 correlation (f64 accumulators as in the reference) */
 static inline double seq_mean(const float *x, int d) {
@@ -231,6 +270,7 @@ static inline float dist_fn(int metric, const float *x, const float *y, int d) {
     case ORC_HAMMING: return d_hamming(x, y, d);
     case ORC_ALT_HELLINGER: return d_alt_hellinger(x, y, d);
     case ORC_ALT_INNER: return d_alt_inner(x, y, d);
+    case ORC_MINKOWSKI: return d_minkowski(x, y, d);
     default: return d_binary(metric, x, y, d);
     }
 }

@@ -24,7 +24,9 @@ METRIC_IDS = {"sqeuclidean": 0, "euclidean": 0, "l2": 0, "cosine": 1, "dot": 2, 
               "rogerstanimoto": 12, "sokalmichener": 12, "russellrao": 13, "sokalsneath": 14, "yule": 15,
               "hellinger": 16,
               # alternative_inner_product (distances.py:759-790); true_angular computes in alternative_cosine (distances.py:2181-2184)
-              "inner_product": 17, "true_angular": 1}
+              "inner_product": 17, "true_angular": 1,
+              # distances.py:138-153 minkowski(x, y, p): p is process-wide state of the oracle (set_metric_param)
+              "minkowski": 18}
 ANGULAR_METRICS = ("cosine", "dot", "correlation", "dice", "jaccard", "hellinger", "hamming")
 INT32_MIN = np.iinfo(np.int32).min + 1
 INT32_MAX = np.iinfo(np.int32).max - 1
@@ -91,6 +93,8 @@ def lib():
     L.orc_diversify_csr.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _f32p, C.c_int, C.c_int]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
+    L.orc_set_metric_param.argtypes = [C.c_double]
+    L.orc_set_metric_param.restype = None
     _LIB = L
     return L
 
@@ -102,6 +106,16 @@ def tau_rand_int(state):
 
 def tau_rand(state):
     return float(lib().orc_tau_rand(state))
+
+
+def set_metric_param(metric, metric_kwds=None):
+    """metric_kwds.values() are passed positionally to the distance function (pynndescent_.py:1064-1065, 1294-1302); the only
+    parametrised metric restated here is minkowski (p, default 2: distances.py:138)."""
+    if metric == "minkowski":
+        vals = list((metric_kwds or {}).values())
+        lib().orc_set_metric_param(float(vals[0]) if vals else 2.0)
+    elif metric_kwds:
+        raise NotImplementedError("metric_kwds of " + metric)
 
 
 def dist(metric, x, y):
@@ -291,8 +305,10 @@ class OracleNNDescent:
 
     def __init__(self, data, metric="euclidean", n_neighbors=30, n_trees=None, leaf_size=None, random_state=None,
                  max_candidates=None, n_iters=None, delta=0.001, tree_init=True, max_rptree_depth=200, n_threads=8,
-                 forest="dfs", leaf_array=None, keep_stages=False, block_size=16384, init_graph=None, init_dist=None):
+                 forest="dfs", leaf_array=None, keep_stages=False, block_size=16384, init_graph=None, init_dist=None,
+                 metric_kwds=None):
         from sklearn.utils import check_random_state
+        set_metric_param(metric, metric_kwds)
         data = np.ascontiguousarray(data, np.float32)
         n = data.shape[0]
         if n_trees is None:

@@ -48,7 +48,7 @@ struct JoinParams {
 // compile-time views of a metric CLASS (nnd_metric_class): per-row auxiliaries in shared memory, accumulator type
 #define MC_AUX1(M) ((M) == NND_METRIC_ALT_COSINE || (M) == NND_METRIC_ALT_JACCARD || (M) == NND_METRIC_ALT_HELLINGER)
 #define MC_AUX2(M) ((M) == NND_METRIC_CORRELATION)
-#define MC_F64(M) ((M) == NND_METRIC_CORRELATION || (M) == NND_METRIC_MANHATTAN || (M) == NND_METRIC_CANBERRA)
+#define MC_F64(M) ((M) == NND_METRIC_CORRELATION || (M) == NND_METRIC_MANHATTAN || (M) == NND_METRIC_CANBERRA || (M) == NND_METRIC_MINKOWSKI)
 
 static size_t join_smem_bytes(int m_max, int metric) {
     size_t b = 16;                       // mbarrier
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
     }
 
     typedef typename std::conditional<MC_F64(METRIC), double, float>::type acc_t;
+    const double mk_p = METRIC == NND_METRIC_MINKOWSKI ? ((const double *)P.aux)[0] : 0.0;   // distances.py:138 p (nnd_metric_set_param)
     acc_t acc[TPT][TILE * TILE];
 #pragma unroll
     for (int i = 0; i < TPT; ++i)
@@ -222,6 +223,8 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                                 }
                             } else if (METRIC == NND_METRIC_ALT_COSINE || METRIC == NND_METRIC_ALT_DOT) {
                                 acc[i][u * TILE + v] = __fmaf_rn(xa, xb, (float)acc[i][u * TILE + v]);
+                            } else if (METRIC == NND_METRIC_MINKOWSKI) {
+                                acc[i][u * TILE + v] = (acc_t)nnd_minkowski_step((double)acc[i][u * TILE + v], xa, xb, mk_p);
                             } else {
                                 acc[i][u * TILE + v] = nnd_metric_step<METRIC, acc_t>(acc[i][u * TILE + v], xa, xb);
                             }
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
                     else if (METRIC == NND_METRIC_ALT_JACCARD) r = finish_binary(P.metric, (float)acc[i][u * TILE + v], n2_s[a], n2_s[b], P.d);
                     else if (METRIC == NND_METRIC_ALT_HELLINGER) r = finish_alt_hellinger((float)acc[i][u * TILE + v], n2_s[a], n2_s[b]);
                     else if (METRIC == NND_METRIC_CHEBYSHEV) r = (float)acc[i][u * TILE + v];
+                    else if (METRIC == NND_METRIC_MINKOWSKI) r = finish_minkowski((double)acc[i][u * TILE + v], ((const double *)P.aux)[1]);
                     else r = finish_plain(METRIC, (double)acc[i][u * TILE + v], P.d);
                     if (r < thr_s[a]) pm[i] |= 1u << (2 * (u * TILE + v));
                     if (b != a && r < thr_s[b]) pm[i] |= 2u << (2 * (u * TILE + v));
@@ -1096,6 +1100,7 @@ static int launch_join(nnd_ctx *ctx, const JoinParams &P, int64_t n_units, cudaS
     case NND_METRIC_CANBERRA: return launch_join_m<NND_METRIC_CANBERRA>(ctx, P, n_units, st);
     case NND_METRIC_HAMMING: return launch_join_m<NND_METRIC_HAMMING>(ctx, P, n_units, st);
     case NND_METRIC_ALT_HELLINGER: return launch_join_m<NND_METRIC_ALT_HELLINGER>(ctx, P, n_units, st);
+    case NND_METRIC_MINKOWSKI: return launch_join_m<NND_METRIC_MINKOWSKI>(ctx, P, n_units, st);
     }
     if (nnd_metric_class(P.metric) == NND_METRIC_ALT_JACCARD) return launch_join_m<NND_METRIC_ALT_JACCARD>(ctx, P, n_units, st);
     nnd_set_error("join: unknown metric %d", P.metric);

@@ -225,6 +225,16 @@ extern "C" int nnd_metric_aux_bytes(int32_t metric, int64_t N, size_t *bytes) {
     *bytes = (kind == 1 ? (size_t)N * 4 : kind == 2 ? (size_t)N * 16 : 0) + 16;
     return NND_OK;
 }
+// distances.py:138 minkowski's p (metric_kwds.values(), pynndescent_.py:1294-1302) -> the first 16 bytes of the aux buffer
+extern "C" int nnd_metric_set_param(nnd_ctx *ctx, int32_t metric, void *aux, double value, void *stream) {
+    NND_CHECK(ctx && aux, NND_ERR_INVALID, "nnd_metric_set_param: bad args");
+    NND_CHECK(metric == NND_METRIC_MINKOWSKI, NND_ERR_UNSUPPORTED, "metric id %d takes no parameter", metric);
+    NND_CHECK(value > 0.0 && value < 1.0e6, NND_ERR_INVALID, "minkowski: p = %g is outside (0, 1e6)", value);
+    const double h[2] = {value, 1.0 / value};
+    NND_CUDA(cudaMemcpyAsync(aux, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    NND_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // h is a stack array
+    return NND_OK;
+}
 __global__ void k_metric_prepare(const float *X, int64_t N, int d, int ld, int metric, void *aux) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;

@@ -73,6 +73,12 @@ __device__ __forceinline__ float query_distance(const QueryParams &P, const floa
     // SURVEY 8f-2 metrics: the same per-element steps and tails as the join (nnd_common.cuh); the query-side
     // auxiliaries arrive in qn2 (non-zero count / l1 norm)
     const int mc = nnd_metric_class(P.metric);
+    if (mc == NND_METRIC_MINKOWSKI) {
+        const double p = ((const double *)P.aux)[0], inv_p = ((const double *)P.aux)[1];
+        double acc = 0.0;
+        for (int e = 0; e < P.d; ++e) acc = nnd_minkowski_step(acc, q[e], y[e], p);
+        return finish_minkowski(acc, inv_p);
+    }
     if (mc == NND_METRIC_MANHATTAN) {
         double acc = 0.0;
         for (int e = 0; e < P.d; ++e) acc = nnd_metric_step<NND_METRIC_MANHATTAN, double>(acc, q[e], y[e]);

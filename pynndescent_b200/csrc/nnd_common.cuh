@@ -109,6 +109,32 @@ __device__ __forceinline__ double det_log2(double x) {
     return __fma_rn(ln_m, 1.4426950408889634, (double)e);
 }
 
+// deterministic 2^z in double (same contract as det_log2; oracle/nnd_oracle.c det_exp2): z = n + f, |f| <= 1/2,
+// 2^f = exp(f ln 2) by a degree-13 Horner chain, scaled by 2^n through the exponent bits
+__device__ __forceinline__ double det_exp2(double z) {
+    if (z > 1023.0) return CUDART_INF;
+    if (z < -1021.0) return 0.0;
+    const double n = rint(z);
+    const double g = __dmul_rn(__dadd_rn(z, -n), 0.6931471805599453);
+    double q = 1.0 / 6227020800.0;
+    q = __fma_rn(q, g, 1.0 / 479001600.0);
+    q = __fma_rn(q, g, 1.0 / 39916800.0);
+    q = __fma_rn(q, g, 1.0 / 3628800.0);
+    q = __fma_rn(q, g, 1.0 / 362880.0);
+    q = __fma_rn(q, g, 1.0 / 40320.0);
+    q = __fma_rn(q, g, 1.0 / 5040.0);
+    q = __fma_rn(q, g, 1.0 / 720.0);
+    q = __fma_rn(q, g, 1.0 / 120.0);
+    q = __fma_rn(q, g, 1.0 / 24.0);
+    q = __fma_rn(q, g, 1.0 / 6.0);
+    q = __fma_rn(q, g, 0.5);
+    q = __fma_rn(q, g, 1.0);
+    q = __fma_rn(q, g, 1.0);
+    return __dmul_rn(q, __longlong_as_double(((long long)n + 1023LL) << 52));
+}
+// x^y for x >= 0, y > 0 (minkowski): 0^y = 0 -- so zero-padded columns contribute nothing -- else 2^(y log2 x)
+__device__ __forceinline__ double det_pow(double x, double y) { return x > 0.0 ? det_exp2(__dmul_rn(y, det_log2(x))) : 0.0; }
+
 #define NND_FLT_MAX 3.402823466e+38f
 
 // distances.py:583-630 tail of alternative_cosine given dot and the two squared norms
@@ -142,7 +168,7 @@ __host__ __device__ __forceinline__ int nnd_metric_class(int metric) {
 }
 // classes whose accumulator is f64 (the reference accumulates these in a float64 `result`)
 __host__ __device__ __forceinline__ bool nnd_metric_acc_f64(int metric) {
-    return metric == NND_METRIC_CORRELATION || metric == NND_METRIC_MANHATTAN || metric == NND_METRIC_CANBERRA;
+    return metric == NND_METRIC_CORRELATION || metric == NND_METRIC_MANHATTAN || metric == NND_METRIC_CANBERRA || metric == NND_METRIC_MINKOWSKI;
 }
 // per-row auxiliary: 0 none, 1 one f32 per row (cosine: squared norm; binary family: non-zero count;
 // hellinger: l1 norm), 2 two f64 per row (correlation: mean, centred squared norm)
@@ -166,6 +192,11 @@ __device__ __forceinline__ ACC nnd_metric_step(ACC acc, float xa, float xb) {
     if (MC == NND_METRIC_ALT_HELLINGER) return (ACC)__fadd_rn((float)acc, __fsqrt_rn(__fmul_rn(xa, xb)));
     return acc;
 }
+// distances.py:138-153 minkowski: one element of the sum (p = first double of the metric aux buffer) and the tail
+__device__ __forceinline__ double nnd_minkowski_step(double acc, float xa, float xb, double p) {
+    return __dadd_rn(acc, det_pow((double)fabsf(__fsub_rn(xa, xb)), p));
+}
+__device__ __forceinline__ float finish_minkowski(double acc, double inv_p) { return (float)det_pow(acc, inv_p); }
 // tails of the binary family from tt = #{both non-zero}, the two non-zero counts and the dimension (all exact
 // small integers; the reference does the final division in float64)
 __device__ __forceinline__ float finish_binary(int metric, float ttf, float nxf, float nyf, int dim) {
@@ -225,6 +256,12 @@ __device__ __forceinline__ float pair_distance_seq(const float *__restrict__ x, 
         return finish_correlation(dp, mu[2 * ix + 1], mu[2 * iy + 1]);
     }
     const int mc = nnd_metric_class(metric);
+    if (mc == NND_METRIC_MINKOWSKI) {
+        const double p = ((const double *)aux)[0], inv_p = ((const double *)aux)[1];
+        double acc = 0.0;
+        for (int e = 0; e < d; ++e) acc = nnd_minkowski_step(acc, x[e], y[e], p);
+        return finish_minkowski(acc, inv_p);
+    }
     if (mc == NND_METRIC_MANHATTAN) {
         double acc = 0.0;
         for (int e = 0; e < d; ++e) acc = nnd_metric_step<NND_METRIC_MANHATTAN, double>(acc, x[e], y[e]);

@@ -12,7 +12,7 @@ NND_METRIC_SQEUCLIDEAN, NND_METRIC_ALT_COSINE, NND_METRIC_ALT_DOT, NND_METRIC_CO
 # SURVEY 8f-2 (include/nnd_b200.h)
 (NND_METRIC_MANHATTAN, NND_METRIC_CHEBYSHEV, NND_METRIC_CANBERRA, NND_METRIC_HAMMING, NND_METRIC_ALT_JACCARD,
  NND_METRIC_DICE, NND_METRIC_MATCHING, NND_METRIC_KULSINSKI, NND_METRIC_ROGERSTANIMOTO, NND_METRIC_RUSSELLRAO,
- NND_METRIC_SOKALSNEATH, NND_METRIC_YULE, NND_METRIC_ALT_HELLINGER, NND_METRIC_ALT_INNER) = range(4, 18)
+ NND_METRIC_SOKALSNEATH, NND_METRIC_YULE, NND_METRIC_ALT_HELLINGER, NND_METRIC_ALT_INNER, NND_METRIC_MINKOWSKI) = range(4, 19)
 NND_CORRECT_NONE, NND_CORRECT_SQRT = 0, 1
 
 
@@ -73,7 +73,29 @@ gpu_distances = {
     # and only "dot" normalises the data (:1101-1103)
     "inner_product": (NND_METRIC_ALT_INNER, NND_CORRECT_NONE, correct_alternative_inner_product, False),
     "true_angular": (NND_METRIC_ALT_COSINE, NND_CORRECT_NONE, true_angular_from_alt_cosine, False),
+    # distances.py:138-153; p comes from metric_kwds (metric_param below), default 2
+    "minkowski": (NND_METRIC_MINKOWSKI, NND_CORRECT_NONE, None, False),
 }
+
+# metrics whose distance function takes one scalar parameter: name -> (keyword, default) of the reference's signature
+parametrised = {"minkowski": ("p", 2.0)}
+
+
+def metric_param(metric, metric_kwds):
+    """pynndescent_.py:1064-1065, 1294-1302: the reference passes tuple(metric_kwds.values()) positionally to the distance function.
+    Returns the scalar the kernels need (None for the metrics without one); keywords a GPU metric cannot take raise -- never a
+    silent drop."""
+    vals = list((metric_kwds or {}).values())
+    if isinstance(metric, str) and metric in parametrised:
+        if len(vals) > 1:
+            raise NotImplementedError(f"metric {metric!r} takes one parameter on the sm_100a path, got {metric_kwds!r}")
+        v = float(vals[0]) if vals else parametrised[metric][1]
+        if not (v > 0.0 and v < 1.0e6):
+            raise ValueError(f"metric {metric!r}: parameter {v!r} is outside (0, 1e6)")
+        return v
+    if vals:
+        raise NotImplementedError(f"metric_kwds {metric_kwds!r} are not supported for metric {metric!r} on the sm_100a path")
+    return None
 
 # every key of the reference's named_distances (distances.py:2103-2162)
 named_distances = (

@@ -27,7 +27,7 @@ def _ptr(t):
 
 
 class Engine:
-    def __init__(self, data, metric_id, n_neighbors, device=None):
+    def __init__(self, data, metric_id, n_neighbors, device=None, metric_param=None):
         if not torch.cuda.is_available():
             raise RuntimeError("pynndescent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -52,6 +52,8 @@ class Engine:
         self.aux = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
         check(lib.nnd_metric_prepare(self._ctx, _ptr(self.X), self.N, self.d, self.ld, self.metric_id, _ptr(self.aux),
                                      self._st()))
+        if metric_param is not None:      # distances.py:138 minkowski's p (metric_kwds.values(), pynndescent_.py:1294-1302)
+            check(lib.nnd_metric_set_param(self._ctx, self.metric_id, _ptr(self.aux), float(metric_param), self._st()))
         self.heap_idx = torch.empty((self.N, self.k), dtype=torch.int32, device=self.device)
         self.heap_dist = torch.empty((self.N, self.k), dtype=torch.float32, device=self.device)
         self.heap_flag = torch.empty((self.N, self.k), dtype=torch.uint8, device=self.device)

@@ -54,7 +54,7 @@ def reference_state(index):
         max_candidates=index.max_candidates, max_rptree_depth=index.max_rptree_depth, n_iters=index.n_iters, delta=index.delta,
         n_jobs=index.n_jobs, compressed=index.compressed, parallel_batch_queries=False, verbose=False, dim=index.dim,
         # derived state
-        _dist_args=tuple(), _is_sparse=False, _input_dtype=np.dtype(np.float32), _angular_trees=bool(index._angular_trees),
+        _dist_args=tuple((index.metric_kwds or {}).values()), _is_sparse=False,      # :1064-1065 _input_dtype=np.dtype(np.float32), _angular_trees=bool(index._angular_trees),
         _bit_trees=False, rng_state=np.asarray(index.rng_state, np.int64), search_rng_state=np.asarray(index.search_rng_state, np.int64),
         _raw_data=np.ascontiguousarray(index._raw_data[vertex_order, :]),                                    # :1639-1641
         _neighbor_graph=(np.asarray(ng_idx, np.int32), np.asarray(ng_dist, np.float32)),

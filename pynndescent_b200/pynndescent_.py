@@ -62,8 +62,6 @@ class NNDescent:
 
         if issparse(data):
             raise NotImplementedError("sparse input is outside the sm_100a hot path (SURVEY.md 2 #13)")
-        if metric_kwds:
-            raise NotImplementedError("metric_kwds are not supported by the GPU metrics")
         if quantization is not None or bit_metric:
             raise NotImplementedError("quantized / bit metrics are outside the sm_100a hot path")
         if init_graph is not None:                                                   # pynndescent_.py:1228-1236
@@ -95,6 +93,7 @@ class NNDescent:
         self.dim = data.shape[1]
 
         metric_id, dev_correction, host_correction, angular = pynnd_dist.resolve(metric)    # :1271-1292
+        metric_param = pynnd_dist.metric_param(metric, metric_kwds)                          # :1064-1065, 1294-1302
         self._distance_correction = host_correction
         self._angular_trees = angular
         # :1054 check_array -- dtype / layout conversion on the host; the NaN/inf scan (sklearn sums the whole
@@ -119,11 +118,11 @@ class NNDescent:
         self.emulated_threads = T
         eff_C = min(60, n_neighbors) if max_candidates is None else max_candidates           # :1135-1138
         self.n_trees_after_update = max(2, int(np.round(self.n_trees / 3)))                  # :1016
-        self._build_args = dict(metric_id=metric_id, dev_correction=dev_correction, eff_C=eff_C, device=device,
+        self._build_args = dict(metric_id=metric_id, metric_param=metric_param, dev_correction=dev_correction, eff_C=eff_C, device=device,
                                 push_capacity=push_capacity, sharded=bool(sharded))
 
         t0 = time.perf_counter()
-        eng = Engine(data, metric_id, n_neighbors, device=device)
+        eng = Engine(data, metric_id, n_neighbors, device=device, metric_param=metric_param)
         self._engine = eng
         if not eng.all_finite():
             raise ValueError("Input contains NaN, infinity or a value too large for dtype('float32').")
@@ -257,7 +256,7 @@ class NNDescent:
         old.close()
         del old
         t0 = time.perf_counter()
-        eng = Engine(data, a["metric_id"], self.n_neighbors, device=a["device"])
+        eng = Engine(data, a["metric_id"], self.n_neighbors, device=a["device"], metric_param=a["metric_param"])
         self._engine = eng
         self.timings = {"h2d_setup": time.perf_counter() - t0}
         cap = a["push_capacity"] or eng.default_push_capacity()
@@ -314,7 +313,8 @@ class NNDescent:
         vo_t = torch.from_numpy(np.ascontiguousarray(S["vertex_order"], np.int64)).to(eng.device)
         self._search_gpu = SearchIndexGPU(None, self.metric, S["indptr"], S["indices"], S["hyperplanes"], S["offsets"], S["children"],
                                           S["tree_indices"], S["vertex_order"], S["min_distance"], self.n_neighbors,
-                                          self.search_rng_state, data_device=eng.X.index_select(0, vo_t).contiguous(), dim=eng.d)
+                                          self.search_rng_state, data_device=eng.X.index_select(0, vo_t).contiguous(), dim=eng.d,
+                                          metric_param=self._build_args["metric_param"])
 
     def load_search_structures(self, data_reordered, indptr, indices, hyperplanes, offsets, children, tree_indices,
                                vertex_order, min_distance, search_rng_state=None):
@@ -323,7 +323,8 @@ class NNDescent:
         from .search import SearchIndexGPU
         self._search_gpu = SearchIndexGPU(data_reordered, self.metric, indptr, indices, hyperplanes, offsets, children,
                                           tree_indices, vertex_order, min_distance, self.n_neighbors,
-                                          self.search_rng_state if search_rng_state is None else search_rng_state)
+                                          self.search_rng_state if search_rng_state is None else search_rng_state,
+                                          metric_param=pynnd_dist.metric_param(self.metric, self.metric_kwds))
         return self
 
     def reference_state(self):

@@ -20,7 +20,7 @@ def _dev(a, dtype, device):
 
 class SearchIndexGPU:
     def __init__(self, data_reordered, metric, indptr, indices, hyperplanes, offsets, children, tree_indices, vertex_order,
-                 min_distance, n_neighbors, search_rng_state, device=None, data_device=None, dim=None):
+                 min_distance, n_neighbors, search_rng_state, device=None, data_device=None, dim=None, metric_param=None):
         """`data_reordered`: host matrix in leaf order (pynndescent_.py:1639-1641) -- or, from prepare(), `data_device`: the same
         matrix already on the GPU as float32[N, ld] (rows padded to a multiple of 4 floats with zeros) with `dim` = d, so that
         the 4*N*d bytes neither get gathered on the host nor cross PCIe a second time."""
@@ -52,6 +52,9 @@ class SearchIndexGPU:
         self.aux = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
         check(lib.nnd_metric_prepare(self._ctx, C.c_void_p(self.X.data_ptr()), self.N, self.d, self.ld, self.metric_id,
                                      C.c_void_p(self.aux.data_ptr()), C.c_void_p(self.stream.cuda_stream)))
+        if metric_param is not None:
+            check(lib.nnd_metric_set_param(self._ctx, self.metric_id, C.c_void_p(self.aux.data_ptr()), float(metric_param),
+                                           C.c_void_p(self.stream.cuda_stream)))
         hp = np.zeros((np.asarray(hyperplanes).shape[0], self.ld), np.float32)
         hp[:, : self.d] = np.asarray(hyperplanes, np.float32)[:, : self.d]
         self.indptr = _dev(indptr, np.int32, self.device); self.indices = _dev(indices, np.int32, self.device)

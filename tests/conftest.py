@@ -25,10 +25,13 @@ GOLDEN_CASES = {
     # accumulation with a 1/x tail (mixed-sign data: half the pairs carry the FLOAT32_MAX sentinel), true_angular = alternative_cosine
     "latent_inner_1500x20": "inner_product",
     "latent_trueang_1500x20": "true_angular",
+    # metric_kwds surface (pynndescent_.py:1064-1065, 1294-1302): minkowski with p = 3 (METRIC_KWDS below)
+    "latent_minkowski3_1500x20": "minkowski",
 }
+METRIC_KWDS = {"latent_minkowski3_1500x20": {"p": 3.0}}
 # goldens whose GPU parity tests have not run on hardware yet: the GPU suite takes them in tests/test_xpending_gpu.py, which sorts
 # after every hardware-verified file, so that `pytest -x` reports the verified tests first
-GOLDEN_CASES_PENDING_GPU = ("latent_inner_1500x20", "latent_trueang_1500x20")
+GOLDEN_CASES_PENDING_GPU = ("latent_inner_1500x20", "latent_trueang_1500x20", "latent_minkowski3_1500x20")
 
 # Goldens whose RP forest cannot be re-derived bit-exactly by ANY independent implementation: integer / binary
 # data under angular trees puts many points exactly on the hyperplane (margin == 0 up to the reference's own

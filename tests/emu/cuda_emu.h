@@ -39,6 +39,7 @@
 #define __align__(n) alignas(n)
 #define __shared__ static
 #define CUDART_INF_F (std::numeric_limits<float>::infinity())
+#define CUDART_INF (std::numeric_limits<double>::infinity())
 
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;

@@ -74,7 +74,7 @@ def kat():
     np.savez_compressed(os.path.join(OUT, "kat.npz"), **out)
 
 
-def staged(name, X, metric, k, seed, n_trees=None, leaf_size=None, n_iters=None):
+def staged(name, X, metric, k, seed, n_trees=None, leaf_size=None, n_iters=None, metric_kwds=None):
     """Replay NNDescent.__init__ (pynndescent_.py:976-1269) stage by stage with the reference's
     own numba functions and dump every intermediate."""
     out = {"X": X, "k": k, "seed": seed, "T": T}
@@ -83,8 +83,8 @@ def staged(name, X, metric, k, seed, n_trees=None, leaf_size=None, n_iters=None)
         n_trees = max(3, min(12, int(round(2.0 * np.log10(n)))))
     if n_iters is None:
         n_iters = max(5, int(round(np.log2(n))))
-    idx = pynndescent.NNDescent(X, metric, n_neighbors=k, random_state=seed, n_trees=n_trees, leaf_size=leaf_size,
-                                n_iters=n_iters)
+    idx = pynndescent.NNDescent(X, metric, metric_kwds=metric_kwds, n_neighbors=k, random_state=seed, n_trees=n_trees,
+                                leaf_size=leaf_size, n_iters=n_iters)
     gi, gd = idx.neighbor_graph
     out["graph_idx"], out["graph_dist"] = gi, gd
     dist = idx._distance_func

@@ -9,6 +9,7 @@ the REAL reference (build container only):
 * latent_inner_1500x20  -- staged build replay (make_golden.staged) for metric="inner_product" on mixed-sign data: about half of
                            all pairs have a non-positive inner product and carry the sentinel distance
 * latent_trueang_1500x20 -- the same for metric="true_angular" (alternative_cosine kernel, euclidean trees, no normalisation)
+* latent_minkowski3_1500x20 -- the same for metric="minkowski", metric_kwds={"p": 3.0}
 """
 import os
 import sys
@@ -32,6 +33,9 @@ def kat():
     out["dist_true_angular"] = np.array([[pd.alternative_cosine(A[i], A[j]) for j in range(24)] for i in range(24)], np.float32)
     out["corr_true_angular"] = pd.true_angular_from_alt_cosine(out["dist_true_angular"])
     out["true_true_angular"] = np.array([[pd.true_angular(A[i], A[j]) for j in range(24)] for i in range(24)], np.float32)
+    # minkowski(x, y, p) (distances.py:138-153; p reaches the function positionally from metric_kwds.values())
+    for p in (0.5, 1.5, 3.0, 4.0):
+        out["dist_minkowski_p%g" % p] = np.array([[pd.minkowski(A[i], A[j], p) for j in range(24)] for i in range(24)], np.float32)
     np.savez_compressed(os.path.join(OUT, "kat_metrics2.npz"), **out)
 
 
@@ -39,3 +43,4 @@ if __name__ == "__main__":
     kat()
     staged("latent_inner_1500x20", latent(1500, 20, 31), "inner_product", 10, 13)
     staged("latent_trueang_1500x20", latent(1500, 20, 32), "true_angular", 10, 14)
+    staged("latent_minkowski3_1500x20", latent(1500, 20, 33), "minkowski", 10, 15, metric_kwds={"p": 3.0})

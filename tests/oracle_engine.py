@@ -11,11 +11,13 @@ import torch
 from oracle import nnd_oracle as orc
 
 ID_TO_NAME = {0: "sqeuclidean", 1: "cosine", 2: "dot", 3: "correlation", 4: "manhattan", 5: "chebyshev", 6: "canberra",
-              7: "hamming", 8: "jaccard", 16: "hellinger", 17: "inner_product"}
+              7: "hamming", 8: "jaccard", 16: "hellinger", 17: "inner_product", 18: "minkowski"}
 
 
 class OracleEngine:
-    def __init__(self, data, metric_id, n_neighbors, device=None):
+    def __init__(self, data, metric_id, n_neighbors, device=None, metric_param=None):
+        if metric_param is not None:
+            orc.lib().orc_set_metric_param(float(metric_param))
         self.X = np.ascontiguousarray(data, np.float32)
         self.N, self.d = self.X.shape
         self.k = int(n_neighbors)

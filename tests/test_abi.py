@@ -53,8 +53,9 @@ def test_metric_registry_matches_reference_names():
     assert dist.resolve("inner_product")[3] is False and dist.resolve("true_angular")[3] is False
     assert dist.resolve("inner_product")[2](np.array([0.5, 3.4028235e38], np.float32)).tolist() == [-2.0, 0.0]
     assert dist.resolve("true_angular")[2](np.array([0.0, 1.0], np.float32)).tolist() == [1.0, 1.0 - np.arccos(0.5) / np.pi]
+    assert dist.resolve("minkowski")[0] == dist.NND_METRIC_MINKOWSKI == 18 and dist.metric_param("minkowski", {"p": 3}) == 3.0
     with pytest.raises(NotImplementedError):
-        dist.resolve("minkowski")          # needs metric_kwds
+        dist.resolve("wminkowski")         # needs a weight vector
     with pytest.raises(NotImplementedError):
         dist.resolve("bit_jaccard")
     with pytest.raises(NotImplementedError):

@@ -8,7 +8,7 @@ the oracle (same defined summation order) and within 1e-5 relative of the refere
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, GOLDEN_CASES_PENDING_GPU, METRIC_KATS, latent, load_golden, metric_data
+from conftest import GOLDEN_CASES, GOLDEN_CASES_PENDING_GPU, METRIC_KATS, METRIC_KWDS, latent, load_golden, metric_data
 
 # (the cases added after the last hardware run are parametrised in tests/test_xpending_gpu.py; see conftest)
 GPU_CASES = [n for n in GOLDEN_CASES if n not in GOLDEN_CASES_PENDING_GPU]
@@ -33,12 +33,13 @@ def torch_cuda():
     return torch
 
 
-def _engine(X, metric, k, normalize_dot=True):
+def _engine(X, metric, k, normalize_dot=True, metric_kwds=None):
+    from pynndescent_b200 import distances
     from pynndescent_b200.engine import Engine
     if metric == "dot" and normalize_dot:
         from sklearn.preprocessing import normalize
         X = normalize(X, norm="l2", copy=True)
-    return Engine(X, METRIC_ID[metric], k), np.ascontiguousarray(X, np.float32)
+    return Engine(X, METRIC_ID[metric], k, metric_param=distances.metric_param(metric, metric_kwds)), np.ascontiguousarray(X, np.float32)
 
 
 def _brute_knn(X, k, rows, metric="euclidean"):
@@ -155,7 +156,8 @@ def test_more_metrics_full_build_bit_exact_vs_oracle(torch_cuda, oracle, metric,
 @pytest.mark.parametrize("name", GPU_CASES)
 def test_leaf_init_from_reference_leaves(torch_cuda, oracle, name):
     G = load_golden(name); metric = GOLDEN_CASES[name]
-    eng, Xh = _engine(G["X"], metric, int(G["k"]))
+    oracle.set_metric_param(metric, METRIC_KWDS.get(name))
+    eng, Xh = _engine(G["X"], metric, int(G["k"]), metric_kwds=METRIC_KWDS.get(name))
     eng.leaf_init_from_array(G["leaf_array"])
     hi, hd, hf = eng.get_heap()
     assert np.array_equal(hi, G["leaf_heap_idx"]) and np.array_equal(hf, G["leaf_heap_flag"])
@@ -181,7 +183,7 @@ def test_leaf_init_from_reference_leaves(torch_cuda, oracle, name):
 def test_init_random_build_candidates_process(torch_cuda, oracle, name):
     G = load_golden(name); metric = GOLDEN_CASES[name]
     k = int(G["k"]); T = int(G["T"]); C = min(60, k)
-    eng, Xh = _engine(G["X"], metric, k)
+    eng, Xh = _engine(G["X"], metric, k, metric_kwds=METRIC_KWDS.get(name))
     eng.set_heap(G["leaf_heap_idx"], G["leaf_heap_dist"], G["leaf_heap_flag"])
     rng = G["rng_state0"].copy()
     eng.init_random(rng)
@@ -209,8 +211,8 @@ def test_end_to_end_with_reference_leaves_matches_reference_graph(torch_cuda, na
     """Same seed, same leaves => the SAME graph as the reference's NNDescent(...) (T=8)."""
     from pynndescent_b200 import NNDescent
     G = load_golden(name); metric = GOLDEN_CASES[name]
-    idx = NNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_jobs=int(G["T"]),
-                    leaf_array=G["leaf_array"])
+    idx = NNDescent(G["X"], metric, metric_kwds=METRIC_KWDS.get(name), n_neighbors=int(G["k"]), random_state=int(G["seed"]),
+                    n_jobs=int(G["T"]), leaf_array=G["leaf_array"])
     gi, gd = idx.neighbor_graph
     assert idx.c_hist == [int(c) for c in G["c_hist"]]
     assert np.array_equal(gi, G["graph_idx"])

@@ -100,6 +100,9 @@ def emu_lib(tmp_path_factory):
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.emu_process_candidates.restype = C.c_long
     lib.emu_leaf_init.argtypes = [f32, C.c_long, C.c_int, C.c_int, i32, i64, C.c_long, C.c_int, i32, f32, u8, C.c_int, C.c_int]
+    lib.emu_leaf_init_metric.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, i64, C.c_long, C.c_int, i32, f32, u8, C.c_int]
+    lib.emu_pair_distances.argtypes = [f32, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, i32, C.c_long, f32]
+    lib.emu_pair_distances.restype = None
     lib.emu_forest.argtypes = [f32, C.c_long, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, i32, i64, i64]
     return lib
 
@@ -401,6 +404,42 @@ def test_leaf_init_fused_and_split(emu_lib, split):
     rc = emu_lib.emu_leaf_init(np.ascontiguousarray(X), n, d, d, pts, offs, la.shape[0], int(sizes.max()), e[0], e[1], e[2], k, split)
     assert rc == 0
     assert np.array_equal(e[0], heap[0]) and np.array_equal(e[1], heap[1]) and np.array_equal(e[2], heap[2])
+
+
+@pytest.mark.parametrize("metric,mid,param", [("inner_product", 17, None), ("minkowski", 18, 3.0), ("minkowski", 18, 1.5)])
+def test_generic_join_and_pair_distances_for_the_metrics_added_last(emu_lib, metric, mid, param):
+    """inner_product (the dot class's second tail, picked by the RUNTIME metric id) and minkowski (p and 1/p from the first 16
+    bytes of aux; x ** p by the deterministic exp2(p log2 x) restated in the oracle) through the source of the generic k_join
+    (fused leaf init: distance phase, filter, per-member pushes) and of pair_distance_seq: heaps and distances equal the oracle's
+    bit for bit."""
+    from sklearn.utils import check_random_state
+    from oracle import nnd_oracle as orc
+    n, d, k = 500, 20, 8
+    X = np.ascontiguousarray(latent(n, d, 37))
+    X[7] = X[8]; X[9] = 0.0
+    orc.set_metric_param(metric, None if param is None else {"p": param})
+    aux = np.zeros(2, np.float64)
+    if param is not None:
+        aux[:] = (param, 1.0 / param)
+    auxp = aux.ctypes.data_as(C.c_void_p)
+    rs = np.random.RandomState(1)
+    a = rs.randint(0, n, 3000).astype(np.int32); b = rs.randint(0, n, 3000).astype(np.int32)
+    got = np.zeros(3000, np.float32)
+    emu_lib.emu_pair_distances(X, d, d, mid, auxp, a, b, 3000, got)
+    want = np.array([orc.dist(metric, X[i], X[j]) for i, j in zip(a, b)], np.float32)
+    assert np.array_equal(got, want)
+    la, _ = orc.make_forest(X, k, 3, 20, check_random_state(5), False, 200, "level")
+    heap = orc.make_heap(n, k)
+    orc.init_rp_tree(X, metric, heap, la)
+    sizes = (la >= 0).sum(1)
+    pts = la[la >= 0].astype(np.int32)
+    offs = np.zeros(la.shape[0] + 1, np.int64); np.cumsum(sizes, out=offs[1:])
+    e = orc.make_heap(n, k)
+    rc = emu_lib.emu_leaf_init_metric(X, n, d, d, mid, auxp, pts, offs, la.shape[0], int(sizes.max()), e[0], e[1], e[2], k)
+    assert rc == 0
+    assert np.array_equal(e[0], heap[0]) and np.array_equal(e[1], heap[1]) and np.array_equal(e[2], heap[2])
+    if metric == "inner_product":
+        assert ((heap[1] > 1e30) & np.isfinite(heap[1])).any()                      # FLOAT32_MAX sentinels took part in the pushes
 
 
 # ---- RP forest (k_forest.cu): every kernel of the level-synchronous forest under emulation against the oracle's level scheme

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import FOREST_FROM_REFERENCE, GOLDEN_CASES, METRIC_KATS, QUERY_GOLDENS, load_golden
+from conftest import FOREST_FROM_REFERENCE, GOLDEN_CASES, METRIC_KATS, METRIC_KWDS, QUERY_GOLDENS, load_golden
 
 
 def test_tau_rand_kat(oracle):
@@ -119,6 +119,19 @@ def test_distance_kat_alternatives_without_own_class(oracle, metric):
             assert np.array_equal(ours.true_angular_from_alt_cosine(D), corr, equal_nan=True)
 
 
+@pytest.mark.parametrize("p", [0.5, 1.5, 3.0, 4.0])
+def test_distance_kat_minkowski(oracle, p):
+    """minkowski(x, y, p) (distances.py:138-153) through the oracle's deterministic x ** p = exp2(p * log2 x): the float32 results
+    are the reference's own bits on the KAT matrix (zero row, duplicates), for p below and above 1."""
+    g = load_golden("kat_metrics2")
+    A = g["real_A"]
+    oracle.set_metric_param("minkowski", {"p": p})
+    D = np.array([[oracle.dist("minkowski", A[i], A[j]) for j in range(24)] for i in range(24)], np.float32)
+    R = g["dist_minkowski_p%g" % p]
+    np.testing.assert_allclose(D, R, rtol=2e-7, atol=0)
+    assert (D == R).mean() > 0.99 and np.all(np.diag(D) == 0)
+
+
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
 def test_end_to_end_matches_reference(oracle, name):
     """Full build replay: leaf_array, heaps after each init stage, candidates, per-iteration
@@ -128,7 +141,7 @@ def test_end_to_end_matches_reference(oracle, name):
     metric = GOLDEN_CASES[name]
     inject = G["leaf_array"] if name in FOREST_FROM_REFERENCE else None      # see conftest.FOREST_FROM_REFERENCE
     o = oracle.OracleNNDescent(G["X"], metric, n_neighbors=int(G["k"]), random_state=int(G["seed"]), n_threads=int(G["T"]),
-                               keep_stages=True, leaf_array=inject)
+                               keep_stages=True, leaf_array=inject, metric_kwds=METRIC_KWDS.get(name))
     assert np.array_equal(o.leaf_array, G["leaf_array"])
     assert np.array_equal(o.heap_after_leaf[0], G["leaf_heap_idx"])
     assert np.array_equal(o.heap_after_leaf[2], G["leaf_heap_flag"])

@@ -61,3 +61,44 @@ def test_full_build_bit_exact_vs_oracle(torch_cuda, oracle, metric, n, d, k, see
 def test_query_and_prepare_match_reference(name, oracle):
     tq.test_query_matches_reference(name, oracle)
     tq.test_prepare_matches_reference_structures(name)
+
+
+# ---- minkowski / the metric_kwds surface (NND_METRIC_MINKOWSKI; p through nnd_metric_set_param)
+@pytest.mark.parametrize("p", [0.5, 1.5, 3.0, 4.0])
+def test_minkowski_pair_distances(torch_cuda, oracle, p):
+    """bit-exact vs the oracle on three widths (padded and unpadded rows), and the reference's own float32 values on its KAT matrix"""
+    kw = {"p": p}
+    oracle.set_metric_param("minkowski", kw)
+    for d in (5, 37, 130):
+        rs = np.random.RandomState(d)
+        X = rs.standard_normal((64, d)).astype(np.float32)
+        X[5] = 0.0; X[6] = X[7]
+        eng, Xh = _engine(X, "minkowski", 4, metric_kwds=kw)
+        a = rs.randint(0, 64, 400).astype(np.int32); b = rs.randint(0, 64, 400).astype(np.int32)
+        want = np.array([oracle.dist("minkowski", Xh[i], Xh[j]) for i, j in zip(a, b)], np.float32)
+        assert np.array_equal(eng.pair_distances(a, b), want)
+    g = load_golden("kat_metrics2")
+    A = g["real_A"]
+    ii, jj = np.meshgrid(np.arange(24), np.arange(24), indexing="ij")
+    eng, _ = _engine(A, "minkowski", 4, metric_kwds=kw)
+    got = eng.pair_distances(ii.ravel(), jj.ravel()).reshape(24, 24)
+    np.testing.assert_allclose(got, g["dist_minkowski_p%g" % p], rtol=2e-7, atol=0)
+
+
+@pytest.mark.parametrize("p,n,d,k,seed", [(3.0, 2000, 20, 10, 15), (1.5, 1500, 130, 8, 16), (2.0, 1500, 16, 10, 17)])
+def test_minkowski_full_build_and_query_bit_exact_vs_oracle(torch_cuda, oracle, p, n, d, k, seed):
+    from conftest import latent
+    from pynndescent_b200 import NNDescent
+    X = latent(n, d, seed)
+    kw = None if p == 2.0 else {"p": p}                                      # p = 2 is the reference's default (distances.py:138)
+    idx = NNDescent(X, "minkowski", metric_kwds=kw, n_neighbors=k, random_state=seed)
+    gi, gd = idx.neighbor_graph
+    o = oracle.OracleNNDescent(X, "minkowski", n_neighbors=k, random_state=seed, n_threads=8, forest="level", metric_kwds=kw)
+    oi, od = o.neighbor_graph
+    assert idx.c_hist == [int(c) for c in o.c_hist[: o.n_iters_run]]
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    Q = latent(64, d, seed + 100)
+    qi, qd = idx.query(Q, k=5)
+    exact = (np.abs(Q[:, None, :].astype(np.float64) - X[qi].astype(np.float64)) ** p).sum(-1) ** (1.0 / p)
+    np.testing.assert_allclose(qd, exact, rtol=1e-5, atol=1e-6)             # the reported distances are the true ones
+    assert np.all(np.diff(qd, axis=1) >= 0)
