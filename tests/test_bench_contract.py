@@ -1,0 +1,34 @@
+"""bench.py's reference arm (`--impl reference`: the CPU implementation of the path on the host cores) runs without a GPU: its JSON
+line carries the keys the driver reads, rank 0 alone prints it."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def _run(extra_env=None):
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "2",
+                          "--warmup", "1", "--gpus", "1"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_arm_json_line():
+    lines = _run()
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "kNN-graph build edges/sec" and j["unit"] == "edges/s"
+    assert j["higher_is_better"] is True and j["steps"] == 2 and j["warmup"] == 1 and j["n_gpus"] == 1 and j["vs_baseline"] is None
+    assert j["value"] > 0 and abs(j["value"] - 1000 * 10 / (j["ms_per_step"] * 1e-3)) < 1e-6 * j["value"]
+    assert j["config"]["workload"].startswith("1kx16") and j["dtype"] == "f32" and "synthetic" in j["data"]
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    assert _run({"RANK": "1", "WORLD_SIZE": "2"}) == []
