@@ -62,6 +62,22 @@ def test_metric_registry_matches_reference_names():
         dist.resolve(lambda a, b: 0.0)
 
 
+def test_host_only_entry_points_without_a_gpu():
+    """The sizing / registry entry points are host code: they answer without a device (no compute call is made here)."""
+    import ctypes as C
+    from pynndescent_b200 import _ffi, distances as dist
+    nb = C.c_size_t()
+    for mid, per_row in ((dist.NND_METRIC_SQEUCLIDEAN, 0), (dist.NND_METRIC_ALT_COSINE, 4), (dist.NND_METRIC_CORRELATION, 16),
+                         (dist.NND_METRIC_ALT_INNER, 0), (dist.NND_METRIC_MINKOWSKI, 0)):
+        assert _ffi.lib.nnd_metric_aux_bytes(mid, 1000, C.byref(nb)) == 0
+        assert nb.value == 1000 * per_row + 16          # the 16 bytes every aux buffer has hold minkowski's (p, 1/p)
+    assert _ffi.lib.nnd_metric_aux_bytes(19, 1000, C.byref(nb)) != 0
+    assert b"unknown metric" in _ffi.lib.nnd_last_error()
+    fb = C.c_size_t()
+    assert _ffi.lib.nnd_forest_workspace_bytes(100000, 128, 12, C.byref(fb)) == 0
+    assert fb.value > 12 * 100000 * 4 * 8               # perm, seg, act (x2 each), flags, scan, invp ... per (tree, point)
+
+
 def test_sm100a_sass_has_bulk_copy():
     """The join kernel stages rows with the TMA engine's bulk copy: SASS must show UBLKCP."""
     so = os.path.join(ROOT, "pynndescent_b200", "libnnd_b200.so")
