@@ -23,59 +23,51 @@ class PyNNDescentTransformer(BaseEstimator, TransformerMixin):
                  search_epsilon=0.1, pruning_degree_multiplier=1.5, diversify_prob=1.0, n_search_trees=1, tree_init=True,
                  random_state=None, n_jobs=None, low_memory=True, max_candidates=None, n_iters=None,
                  early_termination_value=0.001, parallel_batch_queries=False, verbose=False):
-        self.n_neighbors = n_neighbors
-        self.metric = metric
-        self.metric_kwds = metric_kwds
-        self.n_trees = n_trees
-        self.leaf_size = leaf_size
-        self.search_epsilon = search_epsilon
-        self.pruning_degree_multiplier = pruning_degree_multiplier
-        self.diversify_prob = diversify_prob
-        self.n_search_trees = n_search_trees
-        self.tree_init = tree_init
-        self.random_state = random_state
-        self.low_memory = low_memory
-        self.max_candidates = max_candidates
-        self.n_iters = n_iters
-        self.early_termination_value = early_termination_value
-        self.n_jobs = n_jobs
-        self.parallel_batch_queries = parallel_batch_queries
-        self.verbose = verbose
+        # sklearn's estimator contract: every constructor argument is stored verbatim under its own name (get_params / clone)
+        given = dict(locals())
+        given.pop("self")
+        for name, value in given.items():
+            setattr(self, name, value)
+
+    # transformer keyword -> NNDescent keyword, where the two differ (pynndescent_.py:2772-2797)
+    _RENAMED = {"early_termination_value": "delta"}
+    _NOT_FORWARDED = ("n_neighbors", "search_epsilon", "metric_kwds")
 
     def fit(self, X, compress_index=True):
-        """pynndescent_.py:2747-2799.  `compress_index` is accepted for signature parity; the device index has no
-        compressed form (nothing is dropped, query() keeps working either way)."""
+        """pynndescent_.py:2747-2799.  The index is built with one neighbour more than asked for: sklearn does not count a point
+        as its own neighbour (:2767-2769).  `compress_index` is accepted for signature parity; the device index has no compressed
+        form (nothing is dropped, query() keeps working either way)."""
         self.n_samples_fit = X.shape[0]
-        metric_kwds = {} if self.metric_kwds is None else self.metric_kwds
         if self.verbose:
             print(_ts(), "Creating index")
-        effective_n_neighbors = self.n_neighbors + 1
-        self.index_ = NNDescent(
-            X, metric=self.metric, metric_kwds=metric_kwds, n_neighbors=effective_n_neighbors, n_trees=self.n_trees,
-            leaf_size=self.leaf_size, pruning_degree_multiplier=self.pruning_degree_multiplier,
-            diversify_prob=self.diversify_prob, n_search_trees=self.n_search_trees, tree_init=self.tree_init,
-            random_state=self.random_state, low_memory=self.low_memory, max_candidates=self.max_candidates,
-            n_iters=self.n_iters, delta=self.early_termination_value, n_jobs=self.n_jobs, compressed=compress_index,
-            parallel_batch_queries=self.parallel_batch_queries, verbose=self.verbose)
+        kw = {self._RENAMED.get(name, name): value for name, value in self.get_params(deep=False).items()
+              if name not in self._NOT_FORWARDED}
+        self.index_ = NNDescent(X, n_neighbors=self.n_neighbors + 1, metric_kwds=dict(self.metric_kwds or {}),
+                                compressed=compress_index, **kw)
         return self
 
+    def _as_neighbor_matrix(self, indices, distances, n_rows):
+        """(n_rows, n_samples_fit) CSR with Xt[i, indices[i, j]] = distances[i, j].  Like the reference (:2822-2833) the triplets
+        are ATTACHED to an empty float32 COO container: scipy still believes the (empty) container to be in canonical form, so
+        tocsr() neither sorts the columns nor merges entries and every row keeps its ascending-distance order -- building the COO
+        from (data, (row, col)) would sort each row by column instead."""
+        m = coo_array((n_rows, self.n_samples_fit), dtype=np.float32)
+        m.data, m.col = distances.ravel(), indices.ravel()
+        m.row = np.repeat(np.arange(indices.shape[0], dtype=np.int32), indices.shape[1])
+        return m.tocsr()
+
     def transform(self, X, y=None):
-        """pynndescent_.py:2801-2833: CSR (n_samples_transform, n_samples_fit), Xt[i, j] = distance of neighbour j."""
+        """pynndescent_.py:2801-2833: `X=None` returns the fitted points' own graph, otherwise query() answers."""
         if X is None:
-            n_samples_transform = self.n_samples_fit
             indices, distances = self.index_.neighbor_graph
+            n_rows = self.n_samples_fit
         else:
-            n_samples_transform = X.shape[0]
             indices, distances = self.index_.query(X, k=self.n_neighbors, epsilon=self.search_epsilon)
+            n_rows = X.shape[0]
         if self.verbose:
             print(_ts(), "Constructing neighbor matrix")
-        result = coo_array((n_samples_transform, self.n_samples_fit), dtype=np.float32)
-        result.row = np.repeat(np.arange(indices.shape[0], dtype=np.int32), indices.shape[1])
-        result.col = indices.ravel()
-        result.data = distances.ravel()
-        return result.tocsr()
+        return self._as_neighbor_matrix(indices, distances, n_rows)
 
     def fit_transform(self, X, y=None, **fit_params):
         """pynndescent_.py:2835-2863 (the diagonal is always explicit: every point is its own first neighbour)."""
-        self.fit(X, compress_index=False)
-        return self.transform(X=None)
+        return self.fit(X, compress_index=False).transform(X=None)
