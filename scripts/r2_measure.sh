@@ -68,6 +68,11 @@ if [ "$what" = all ] || [ "$what" = ncu ]; then
       python scripts/one_build.py 1000000 128 15 euclidean 2
   NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 run timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_join_pipe -s 17 -c 2 \
       -o gpurun_out/join_pipe_r02 -f python scripts/one_build.py 1000000 128 15 euclidean 2
+  # the forest's hyperplane pass, position-major (default) and point-major: dram__bytes per level is the number to compare
+  run timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_forest_side -s 40 -c 6 -o gpurun_out/forest_side_r02 -f \
+      python scripts/one_build.py 1000000 128 15 euclidean 2
+  NND_FOREST_PM=1 run timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_forest_side -s 40 -c 6 \
+      -o gpurun_out/forest_side_pm_r02 -f python scripts/one_build.py 1000000 128 15 euclidean 2
 fi
 if [ "$what" = sharded ]; then
   # needs `gpurun --gpus 2 -- bash scripts/r2_measure.sh sharded`: the sharded build == the single-GPU build, default schedule and
@@ -75,7 +80,7 @@ if [ "$what" = sharded ]; then
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29581"
   run timeout 900 $TR scripts/sharded_check.py
   NND_JOIN_PIPE=1 NND_RANK_SCATTER=1 NND_JOIN_ORDER=leaf NND_CAND_SKIP=1 NND_CAND_KEYS=2 NND_LEAF_SPLIT=1 NND_APPLY_SHORT_SORT=1 \
-    NND_APPLY_HALF=1 NND_SMEM_CARVEOUT=1 run timeout 900 $TR scripts/sharded_check.py
+    NND_APPLY_HALF=1 NND_SMEM_CARVEOUT=1 NND_FOREST_PM=1 run timeout 900 $TR scripts/sharded_check.py
   run timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline
   NND_LEAF_EXCHANGE=targeted run timeout 900 $TR scripts/sharded_check.py
   NND_LEAF_EXCHANGE=targeted run timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline
