@@ -71,12 +71,15 @@ def emu_lib(tmp_path_factory):
     forest = _between(forest, "// ---------------------------------------------------------------- canonical warp reductions",
                       'extern "C" int nnd_forest_build', "the forest kernels")
     forest = forest.replace("extern __shared__ float s_t[];", "float *s_t = (float *)emu::dyn_smem();")
+    query = open(os.path.join(CSRC, "k_query.cu")).read()
+    query = _between(query, "struct Seed {", 'extern "C" int nnd_query_workspace_bytes', "the query kernels")
     kernels = (join + "\n" + batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
-               "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf + "\n#define EMU_WITH_FOREST 1\n" + forest)
+               "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf + "\n#define EMU_WITH_FOREST 1\n" + forest +
+               "\n#define EMU_WITH_QUERY 1\n" + query)
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 9 and "extern __shared__" not in kernels
+    assert n_ext == 11 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -103,6 +106,8 @@ def emu_lib(tmp_path_factory):
     lib.emu_leaf_init_metric.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, i64, C.c_long, C.c_int, i32, f32, u8, C.c_int]
     lib.emu_pair_distances.argtypes = [f32, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, i32, C.c_long, f32]
     lib.emu_pair_distances.restype = None
+    lib.emu_query.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, i32, f32, f32, i32, i32, f32, C.c_long, C.c_int, C.c_double,
+                              C.c_float, C.c_int, C.c_int, i64, i32, f32, i64]
     lib.emu_forest.argtypes = [f32, C.c_long, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, i32, i64, i64]
     return lib
 
@@ -477,3 +482,92 @@ def test_forest_kernels_and_point_major_pass(emu_lib, n, d, angular, trees, leaf
         assert levels_pm == levels > 3
     else:
         assert 0 < levels_pm < levels                                         # both kernels took part in this forest
+
+
+# ---- query graph walk (k_query.cu) under emulation: the reference's own query() answers on its prepared structures, and the
+# oracle's search bit for bit -- also for the metrics added after the last hardware run
+def _pad(a, ld):
+    out = np.zeros((a.shape[0], ld), np.float32); out[:, : a.shape[1]] = a
+    return out
+
+
+def _query_aux(emu_lib, metric, data_p, d):
+    from oracle import nnd_oracle as orc
+    n = data_p.shape[0]
+    if metric == "cosine":
+        aux = np.zeros(n, np.float32); emu_lib.emu_norms(data_p, n, data_p.shape[1], aux)
+        return aux
+    if metric == "jaccard":
+        return (data_p != 0).sum(1).astype(np.float32)
+    if metric == "minkowski":
+        return None
+    return np.zeros(4, np.float32)
+
+
+def _emu_query(emu_lib, G, metric, mid, Q, k, eps, aux_override=None, n_neighbors=None):
+    d = G["data"].shape[1]; ld = (d + 3) // 4 * 4
+    data_p = _pad(np.asarray(G["data"], np.float32), ld)
+    aux = aux_override if aux_override is not None else _query_aux(emu_lib, metric, data_p, d)
+    hi = np.full((Q.shape[0], k), -7, np.int32); hd = np.zeros((Q.shape[0], k), np.float32); st = np.zeros(4, np.int64)
+    rc = emu_lib.emu_query(data_p, data_p.shape[0], d, ld, mid, aux.ctypes.data_as(C.c_void_p), np.ascontiguousarray(G["indptr"], np.int32),
+                           np.ascontiguousarray(G["indices"], np.int32), _pad(np.asarray(G["hyperplanes"], np.float32)[:, :d], ld),
+                           np.ascontiguousarray(G["offsets"], np.float32), np.ascontiguousarray(G["children"], np.int32),
+                           np.ascontiguousarray(G["tree_indices"], np.int32), _pad(np.asarray(Q, np.float32), ld), Q.shape[0], k, eps,
+                           float(G["min_distance"]), int(G["n_neighbors"]) if n_neighbors is None else n_neighbors, int(metric in ("cosine", "dot")),
+                           np.ascontiguousarray(G["search_rng_state"], np.int64), hi, hd, st)
+    assert rc == 0
+    return hi, hd, st
+
+
+@pytest.mark.parametrize("name,mid", [("query_euclid_3k32", 0), ("query_cosine_2k24", 1), ("query_manhattan_2k20", 4), ("query_jaccard_2k40", 8)])
+def test_query_walk_matches_reference_answers(emu_lib, name, mid):
+    from conftest import load_golden
+    from oracle import nnd_oracle as orc
+    G = load_golden(name); metric = str(G["metric"])
+    Q = G["Q"][:48]
+    k, eps = int(G["k_query"]), float(G["epsilon"])
+    hi, hd, st = _emu_query(emu_lib, G, metric, mid, Q, k, eps)
+    oi, od = orc.search(G["data"], metric, G["indptr"], G["indices"], G["hyperplanes"], G["offsets"], G["children"], G["tree_indices"], Q, k,
+                        eps, float(G["min_distance"]), int(G["n_neighbors"]), G["search_rng_state"])
+    assert np.array_equal(hi, oi) and np.array_equal(hd, od)                    # raw result heaps: the oracle's, bit for bit
+    si, sd = orc.deheap_sort(hi.copy(), hd.copy())
+    assert np.array_equal(G["vertex_order"][si], G["out_idx"][:48])             # ... and the reference's query() answers
+    np.testing.assert_allclose(orc.correction(metric, sd), G["out_dist"][:48], rtol=1e-5, atol=1e-6)
+    assert st[0] > 0
+
+
+@pytest.mark.parametrize("metric,mid,param", [("inner_product", 17, None), ("minkowski", 18, 3.0)])
+def test_query_walk_for_the_metrics_added_last(emu_lib, metric, mid, param):
+    """The euclidean golden's search structures walked under inner_product / minkowski: whatever the graph was built for, kernel and
+    oracle must agree on every visited vertex and distance (the structures are inputs; the metric only enters query_distance)."""
+    from conftest import load_golden
+    from oracle import nnd_oracle as orc
+    G = load_golden("query_euclid_3k32")
+    orc.set_metric_param(metric, None if param is None else {"p": param})
+    aux = np.zeros(2, np.float64)
+    if param is not None:
+        aux[:] = (param, 1.0 / param)
+    Q = G["Q"][:32]
+    hi, hd, st = _emu_query(emu_lib, G, metric, mid, Q, 10, 0.15, aux_override=aux)
+    oi, od = orc.search(G["data"], metric, G["indptr"], G["indices"], G["hyperplanes"], G["offsets"], G["children"], G["tree_indices"], Q, 10,
+                        0.15, float(G["min_distance"]), int(G["n_neighbors"]), G["search_rng_state"])
+    assert np.array_equal(hi, oi) and np.array_equal(hd, od)
+
+
+def test_query_walk_rng_replay_pass(emu_lib):
+    """min(k, n_neighbors) = 40 is larger than any search-tree leaf (<= 30 points): every query needs random seeds (pynndescent_.py
+    :1835-1847), i.e. the shared rng stream -- pass 1 flags them all, pass 2
+    (k_query_seq: one warp, query order, global seed heap and visited bitmap) replays them with the real stream; a zero query under
+    cosine stays unfilled.  Raw heaps equal the oracle's."""
+    from conftest import load_golden
+    from oracle import nnd_oracle as orc
+    G = load_golden("query_cosine_2k24")
+    Q = G["Q"][:12].copy()
+    Q[3] = 0.0
+    hi, hd, st = _emu_query(emu_lib, G, "cosine", 1, Q, 40, 0.2, n_neighbors=40)
+    oi, od = orc.search(G["data"], "cosine", G["indptr"], G["indices"], G["hyperplanes"], G["offsets"], G["children"], G["tree_indices"], Q, 40,
+                        0.2, float(G["min_distance"]), 40, G["search_rng_state"])
+    assert st[2] >= 11                                                          # (almost) every query went through the replay pass
+    keep = np.arange(12) != 3
+    assert np.array_equal(hi[keep], oi[keep]) and np.array_equal(hd[keep], od[keep])
+    assert np.all(oi[3] == -1)
