@@ -73,13 +73,18 @@ def emu_lib(tmp_path_factory):
     forest = forest.replace("extern __shared__ float s_t[];", "float *s_t = (float *)emu::dyn_smem();")
     query = open(os.path.join(CSRC, "k_query.cu")).read()
     query = _between(query, "struct Seed {", 'extern "C" int nnd_query_workspace_bytes', "the query kernels")
+    misc = open(os.path.join(CSRC, "k_misc.cu")).read()
+    misc = (_between(misc, "// ------------------------------------------------------------------ init_random", "int nnd_rng_table_launch", "k_init_random") +
+            _between(misc, "// ------------------------------------------------------------------ deheap_sort", 'extern "C" int nnd_deheap_sort', "k_deheap_sort"))
+    prep = open(os.path.join(CSRC, "k_prepare.cu")).read()
+    misc += _between(prep, "// ------------------------------------------------------------------ diversification", 'extern "C" int nnd_diversify', "k_diversify")
     kernels = (join + "\n" + batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
                "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf + "\n#define EMU_WITH_FOREST 1\n" + forest +
-               "\n#define EMU_WITH_QUERY 1\n" + query)
+               "\n#define EMU_WITH_QUERY 1\n" + query + "\n#define EMU_WITH_MISC 1\n" + misc)
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 11 and "extern __shared__" not in kernels
+    assert n_ext == 14 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -108,6 +113,12 @@ def emu_lib(tmp_path_factory):
     lib.emu_pair_distances.restype = None
     lib.emu_query.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, i32, f32, f32, i32, i32, f32, C.c_long, C.c_int, C.c_double,
                               C.c_float, C.c_int, C.c_int, i64, i32, f32, i64]
+    lib.emu_init_random.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, f32, u8, C.c_int, i64]
+    lib.emu_init_random.restype = C.c_long
+    lib.emu_deheap_sort.argtypes = [i32, f32, C.c_long, C.c_int, C.c_int, f32]
+    lib.emu_deheap_sort.restype = None
+    lib.emu_diversify.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, f32, C.c_int]
+    lib.emu_diversify.restype = None
     lib.emu_forest.argtypes = [f32, C.c_long, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, i32, i64, i64]
     return lib
 
@@ -571,3 +582,42 @@ def test_query_walk_rng_replay_pass(emu_lib):
     keep = np.arange(12) != 3
     assert np.array_equal(hi[keep], oi[keep]) and np.array_equal(hd[keep], od[keep])
     assert np.all(oi[3] == -1)
+
+
+# ---- init_random, deheap_sort, diversify (the kernels around the descent loop that evaluate pair distances one by one)
+@pytest.mark.parametrize("metric,mid,param", [("euclidean", 0, None), ("inner_product", 17, None), ("minkowski", 18, 3.0)])
+def test_init_random_deheap_sort_and_diversify(emu_lib, metric, mid, param):
+    """init_random (pynndescent_.py:188-203: rows the leaves left short draw from the ONE sequential rng stream), deheap_sort
+    (utils.py:189-218) and the forward diversification (pynndescent_.py:369-403) under emulation: heaps, rng state, sorted graph and
+    pruned rows equal the oracle's bit for bit."""
+    from sklearn.utils import check_random_state
+    from oracle import nnd_oracle as orc
+    n, d, k = 400, 20, 12
+    X = np.ascontiguousarray(latent(n, d, 41))
+    orc.set_metric_param(metric, None if param is None else {"p": param})
+    aux = np.zeros(2, np.float64)
+    if param is not None:
+        aux[:] = (param, 1.0 / param)
+    auxp = aux.ctypes.data_as(C.c_void_p)
+    rs = check_random_state(11)
+    rng0 = rs.randint(orc.INT32_MIN, orc.INT32_MAX, 3).astype(np.int64)
+    la, _ = orc.make_forest(X, k, 2, 8, rs, False, 200, "level")          # tiny leaves: most rows stay short after the leaf init
+    heap = orc.make_heap(n, k)
+    orc.init_rp_tree(X, metric, heap, la)
+    e = tuple(a.copy() for a in heap)
+    rng_o, rng_e = rng0.copy(), rng0.copy()
+    orc.init_random(X, metric, heap, rng_o)
+    total = emu_lib.emu_init_random(X, n, d, d, mid, auxp, e[0], e[1], e[2], k, rng_e)
+    assert total > n                                                          # more than one draw per row on average
+    assert np.array_equal(rng_e, rng_o)
+    assert np.array_equal(e[0], heap[0]) and np.array_equal(e[1], heap[1]) and np.array_equal(e[2], heap[2])
+    si, sd = orc.deheap_sort(heap[0].copy(), heap[1].copy())
+    out = np.zeros_like(e[1])
+    emu_lib.emu_deheap_sort(e[0], e[1], n, k, 0, out)
+    assert np.array_equal(e[0], si) and np.array_equal(out, sd) and np.array_equal(e[1], sd)
+    oi, od = si.copy(), sd.copy()
+    orc.lib().orc_diversify(oi, od, n, k, X, d, orc.METRIC_IDS[metric])
+    gi, gd = si.copy(), sd.copy()
+    emu_lib.emu_diversify(X, n, d, d, mid, auxp, gi, gd, k)
+    assert (oi < 0).sum() > (si < 0).sum()                                   # the pass pruned something
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
