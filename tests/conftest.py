@@ -56,7 +56,7 @@ def pytest_collection_modifyitems(config, items):
     # suite (cfg3 at full size: 2M x 256) needs well under a minute of GPU time plus host-side data generation.
     for item in items:
         if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
-            item.add_marker(pytest.mark.timeout(900, method="thread"))
+            item.add_marker(pytest.mark.timeout(1500, method="thread"))   # > the 900 s the sharded test gives its own subprocess
 
 
 def load_golden(name):
