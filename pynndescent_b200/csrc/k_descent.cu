@@ -1208,7 +1208,10 @@ static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st)
     int64_t nb = JB.batch_end - JB.batch_begin;
     if (nb <= 0) return NND_OK;
     static int dk_sel = -1;
-    if (dk_sel < 0) { const char *e = getenv("NND_JB_DK"); dk_sel = e ? atoi(e) : 32; if (dk_sel != 32 && dk_sel != 64 && dk_sel != 128) dk_sel = 32; }
+    // NND_JB_DK: floats per staged chunk (default 32 = the measured configuration).  16 halves the row buffers (2 x 176 x 80 B);
+    // the kernel is then register-bound (93 x 128) at 5 CTAs per SM instead of shared-memory-bound at 4 -- 20 warps to hide the
+    // gather latency -- at the price of twice as many chunk barriers
+    if (dk_sel < 0) { const char *e = getenv("NND_JB_DK"); dk_sel = e ? atoi(e) : 32; if (dk_sel != 16 && dk_sel != 32 && dk_sel != 64 && dk_sel != 128) dk_sel = 32; }
     const int dk = dk_sel;
     size_t smem = join_batch_smem(JB.metric, dk, JB.ld);
     dim3 grid((unsigned)nb);
@@ -1217,7 +1220,7 @@ static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st)
         NND_CUDA(cudaFuncSetAttribute(k_join_batch<M_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_join_batch<M_, D_><<<grid, JB_THREADS, smem, st>>>(JB);                                                     \
     } while (0)
-#define LBM(M_) do { if (dk == 32) LB(M_, 32); else if (dk == 64) LB(M_, 64); else LB(M_, 128); } while (0)
+#define LBM(M_) do { if (dk == 32) LB(M_, 32); else if (dk == 16) LB(M_, 16); else if (dk == 64) LB(M_, 64); else LB(M_, 128); } while (0)
     if (JB.metric == NND_METRIC_SQEUCLIDEAN) LBM(NND_METRIC_SQEUCLIDEAN);
     else if (JB.metric == NND_METRIC_ALT_COSINE) LBM(NND_METRIC_ALT_COSINE);
     else LBM(NND_METRIC_ALT_DOT);

@@ -31,6 +31,8 @@ CONFIGS = {
     "candkeys": {"NND_CAND_KEYS": "1"},
     "candtile": {"NND_CAND_KEYS": "2"},
     "candskip+tile": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2"},
+    "jbdk16": {"NND_JB_DK": "16"},
+    "jbdk64": {"NND_JB_DK": "64"},
     "forestpm": {"NND_FOREST_PM": "1"},
     "forestpm16": {"NND_FOREST_PM": "1", "NND_FOREST_PM_MB": "16"},
     "forestpm96": {"NND_FOREST_PM": "1", "NND_FOREST_PM_MB": "96"},

@@ -213,6 +213,13 @@ def test_emulator_reproduces_the_hardware_verified_kernel(emu_lib, cases, name):
     _check(cases[name], _run(emu_lib, cases[name], kernel=0))
 
 
+@pytest.mark.parametrize("name", ["euclid128", "cosine72", "cosine8"])
+def test_batched_join_with_16_float_chunks(emu_lib, cases, name):
+    """NND_JB_DK=16 (default 32): the same kernel with half-size staged chunks -- 8 chunks for d = 128, a short last chunk for
+    d = 72, a single 8-float chunk for the padded d = 7 rows."""
+    _check(cases[name], _run(emu_lib, cases[name], kernel=0, dk=16))
+
+
 @pytest.mark.parametrize("name,dk,nst,grid", [("euclid40", 32, 4, 3), ("euclid40", 32, 2, 1), ("euclid128", 32, 3, 2),
                                              ("euclid128", 128, 2, 4), ("cosine72", 64, 2, 3),
                                              ("euclid24_k30", 32, 4, 3), ("euclid24_k30", 32, 2, 200),
