@@ -40,6 +40,8 @@
 #define __shared__ static
 #define CUDART_INF_F (std::numeric_limits<float>::infinity())
 #define CUDART_INF (std::numeric_limits<double>::infinity())
+#define CUDART_NAN_F (std::numeric_limits<float>::quiet_NaN())
+using std::isnan;
 
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;

@@ -78,9 +78,13 @@ def emu_lib(tmp_path_factory):
             _between(misc, "// ------------------------------------------------------------------ deheap_sort", 'extern "C" int nnd_deheap_sort', "k_deheap_sort"))
     prep = open(os.path.join(CSRC, "k_prepare.cu")).read()
     misc += _between(prep, "// ------------------------------------------------------------------ diversification", 'extern "C" int nnd_diversify', "k_diversify")
+    hub = _between(prep, "// ------------------------------------------------------------------ canonical warp reductions (as in k_forest.cu)",
+                   'extern "C" int nnd_hub_tree_workspace_bytes', "the hub-tree kernels")
+    hub = hub.replace("extern __shared__ float s_t[];", "float *s_t = (float *)emu::dyn_smem();")
     kernels = (join + "\n" + batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
                "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf + "\n#define EMU_WITH_FOREST 1\n" + forest +
-               "\n#define EMU_WITH_QUERY 1\n" + query + "\n#define EMU_WITH_MISC 1\n" + misc)
+               "\n#define EMU_WITH_QUERY 1\n" + query + "\n#define EMU_WITH_MISC 1\n" + misc +
+               "\n#define EMU_WITH_HUB 1\n" + hub)
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
@@ -119,6 +123,7 @@ def emu_lib(tmp_path_factory):
     lib.emu_deheap_sort.restype = None
     lib.emu_diversify.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, i32, f32, C.c_int]
     lib.emu_diversify.restype = None
+    lib.emu_hub_tree.argtypes = [f32, C.c_long, C.c_int, C.c_int, i32, C.c_int, C.c_int, C.c_int, i32, i32, i32, i32, i32, i32, f32, f32, C.c_long, i32]
     lib.emu_forest.argtypes = [f32, C.c_long, C.c_int, C.c_int, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, i32, i64, i64]
     return lib
 
@@ -628,3 +633,35 @@ def test_init_random_deheap_sort_and_diversify(emu_lib, metric, mid, param):
     emu_lib.emu_diversify(X, n, d, d, mid, auxp, gi, gd, k)
     assert (oi < 0).sum() > (si < 0).sum()                                   # the pass pruned something
     assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+# ---- hub search tree (k_prepare.cu k_hub_*) + the host flattening: the REFERENCE's flat search tree from its own kNN graph
+@pytest.mark.skipif(os.environ.get("NND_SLOW_EMU") != "1", reason="2.5-4 minutes per golden (k_hub_side visits all N points on every one "
+                    "of ~40 levels, one OS thread per emulated CUDA thread); run with NND_SLOW_EMU=1 -- all three passed when written")
+@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24", "query_jaccard_2k40"])
+def test_hub_tree_kernels_reproduce_the_reference_search_tree(emu_lib, name):
+    """make_hub_tree (rp_trees.py:714-1309) level by level under emulation, then prepare.flatten_hub_tree: hyperplanes, offsets,
+    children and leaf order are the reference's own arrays (goldens of make_golden_query.py) -- euclidean splits, angular splits,
+    and binary data under angular splits, where most margins are ties."""
+    from conftest import load_golden
+    from oracle import nnd_oracle as orc
+    G = load_golden(name); metric = str(G["metric"])
+    X = np.asarray(G["X"], np.float32)
+    n, d = X.shape; ld = (d + 3) // 4 * 4
+    Xp = _pad(X, ld)
+    ng = np.ascontiguousarray(G["ng_idx"], np.int32)
+    ncap = 2 * n + 16; hyper_cap = n // 8 + 64
+    indices = np.zeros(n, np.int32)
+    ns, nz, nl, nr, nh = (np.zeros(ncap, np.int32) for _ in range(5))
+    hyp = np.zeros((hyper_cap, ld), np.float32); off = np.zeros(hyper_cap, np.float32); counts = np.zeros(4, np.int32)
+    rc = emu_lib.emu_hub_tree(Xp, n, ld, int(metric in orc.ANGULAR_METRICS), ng, ng.shape[1], 30, 200, indices, ns, nz, nl, nr, nh, hyp, off,
+                              hyper_cap, counts)
+    assert rc == 0 and counts[2] == 0
+    n_nodes, n_hyper = int(counts[0]), int(counts[1])
+    assert np.array_equal(indices, G["vertex_order"])                            # leaf order = the reference's tree.indices
+    from pynndescent_b200.prepare import flatten_hub_tree                        # the product's host-side flattening
+    hyperplanes, offsets, children = flatten_hub_tree(ns[:n_nodes], nz[:n_nodes], nl[:n_nodes], nr[:n_nodes], nh[:n_nodes], hyp[:n_hyper, :d],
+                                                      off[:n_hyper], d)
+    assert np.array_equal(children, G["children"])
+    np.testing.assert_allclose(hyperplanes, G["hyperplanes"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(offsets, G["offsets"], rtol=1e-5, atol=1e-6)
