@@ -473,11 +473,11 @@ def test_generic_join_and_pair_distances_for_the_metrics_added_last(emu_lib, met
 # ---- RP forest (k_forest.cu): every kernel of the level-synchronous forest under emulation against the oracle's level scheme
 # (the GPU suite's test_forest_bit_exact_vs_oracle_level_scheme, on the CPU), and the point-major hyperplane pass NND_FOREST_PM
 @pytest.mark.parametrize("n,d,angular,trees,leaf,pm,pm_limit", [
-    (260, 20, 0, 3, 16, 0, 0),                 # the hardware-verified position-major pass (k_forest_side128) validates the harness
-    (260, 20, 0, 3, 16, 1, 500),               # point-major while the level's table is <= 500 B (6 nodes), position-major below
+    (200, 20, 0, 3, 16, 0, 0),                 # the hardware-verified position-major pass (k_forest_side128) validates the harness
+    (200, 20, 0, 3, 16, 1, 500),               # point-major while the level's table is <= 500 B (6 nodes), position-major below
     (200, 128, 1, 2, 12, 1, 1 << 30),          # point-major on every level; angular trees, full 128-float rows (every lane holds data)
     (160, 7, 1, 2, 10, 1, 1 << 30),            # padded rows (ld = 8: lanes 2..31 hold nothing)
-    (130, 16, 0, 12, 10, 1, 1 << 30),          # the default forest size: 12 trees = 12 lanes look positions up
+    (90, 16, 0, 12, 10, 1, 1 << 30),           # the default forest size: 12 trees = 12 lanes look positions up
     (120, 130, 0, 2, 10, 1, 1 << 30),          # ld > 128: the switch must leave the generic k_forest_side in charge
 ])  # (every emulated CUDA thread is an OS thread: sizes are kept small; 700 x 20 x 5 trees and 500 x 128 angular passed as well)
 def test_forest_kernels_and_point_major_pass(emu_lib, n, d, angular, trees, leaf, pm, pm_limit):
