@@ -52,6 +52,25 @@ class OracleEngine:
     def heap(self):
         return (self.heap_idx.numpy(), self.heap_dist.numpy(), self.heap_flag.numpy())
 
+    def pair_distances(self, a, b):
+        return np.array([orc.dist(self.metric, self.X[i], self.X[j]) for i, j in zip(a, b)], np.float32)
+
+    def get_heap(self):
+        return tuple(a.copy() for a in self.heap)
+
+    def set_heap(self, idx, dist, flag):
+        hi, hd, hf = self.heap
+        hi[...] = idx; hd[...] = dist; hf[...] = flag
+
+    def build_candidates(self, max_candidates, rng_state, n_threads, tables_valid=False):
+        # (the engine's rng_state argument is advanced in place, like nnd_build_candidates')
+        newc, oldc = orc.new_build_candidates(self.heap, int(max_candidates), rng_state, int(n_threads))
+        return torch.from_numpy(newc), torch.from_numpy(oldc)
+
+    def process_candidates(self, newc, oldc, push_capacity=None):
+        c, em = orc.process_candidates(self.X, self.metric, self.heap, np.ascontiguousarray(newc.numpy()), np.ascontiguousarray(oldc.numpy()), 8)
+        return c, [0, 0, em, 0]
+
     # ---- stages
     def make_heap(self):
         hi, hd, hf = orc.make_heap(self.N, self.k)
