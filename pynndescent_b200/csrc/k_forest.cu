@@ -287,41 +287,62 @@ __global__ void __launch_bounds__(256) k_forest_side128(const float *X, int ld, 
 // node in EVERY tree: X is read once per level (12x less DRAM traffic), the per-(tree, point) stream becomes the node's
 // hyperplane, which comes from the L2 while the level's table (M x ld floats) is small -- the host switches back to the
 // position-major kernel when it is not.  Same margin arithmetic (4 fma per lane, xor butterfly, + offset) and the same tie
-// hash as k_forest_side128, so side[] / flag32[] are bit-identical; invp (maintained by k_forest_scatter) supplies
-// position = invp[tree*N + point], -1 for a point that already sits in a final leaf of that tree.  Needs n_trees <= 32.
+// hash as k_forest_side128 / k_forest_side, so side[] / flag32[] are bit-identical; invp (maintained by k_forest_scatter) supplies
+// position = invp[tree*N + point], -1 for a point that already sits in a final leaf of that tree.  Needs n_trees <= 32 and
+// ld <= 1024 (rows of up to eight 128-float chunks in registers: 2M x 256 and 1M x 784 gather 370 and 560 GB per build otherwise).
 #define PM_RUN 8
-__global__ void __launch_bounds__(256) k_forest_side_pm128(const float *X, int ld, int64_t N, int n_trees, int level,
-                                                           const int32_t *invp, const int32_t *seg, const int32_t *nstart,
-                                                           const int32_t *tree_first, const uint64_t *tree_seed, const float *hyper,
-                                                           const float *noff, uint8_t *side, uint32_t *flag32) {
+// NCH = number of 128-float chunks a row spans (ld <= 128 * NCH); lane l holds floats [128 ch + 4 l, 128 ch + 4 l + 4) of chunk
+// ch -- the very elements warp_lane_dot / k_forest_side give it, accumulated in the same order (chunk by chunk, 4 fma each).
+template <int NCH>
+__global__ void __launch_bounds__(256) k_forest_side_pm(const float *X, int ld, int64_t N, int n_trees, int level,
+                                                        const int32_t *invp, const int32_t *seg, const int32_t *nstart,
+                                                        const int32_t *tree_first, const uint64_t *tree_seed, const float *hyper,
+                                                        const float *noff, uint8_t *side, uint32_t *flag32) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t p0 = w * PM_RUN;
     if (p0 >= N) return;
     const int cnt = (int)min((int64_t)PM_RUN, N - p0);
-    const bool has = lane * 4 < ld;
-    float4 xcur = has ? *(const float4 *)(X + p0 * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f), xnext = xcur;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 xcur[NCH], xnext[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const int c = ch * 128 + lane * 4;
+        xcur[ch] = c < ld ? *(const float4 *)(X + p0 * ld + c) : zero4;
+        xnext[ch] = xcur[ch];
+    }
     for (int q = 0; q < cnt; ++q) {
         const int64_t p = p0 + q;
-        if (q + 1 < cnt) xnext = has ? *(const float4 *)(X + (p + 1) * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q + 1 < cnt) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) { const int c = ch * 128 + lane * 4; xnext[ch] = c < ld ? *(const float4 *)(X + (p + 1) * ld + c) : zero4; }
+        }
         // lane t < n_trees: where the point sits in tree t and which active node that is
         int32_t my_pos = -1, my_o = -1;
         if (lane < n_trees) { my_pos = invp[(int64_t)lane * N + p]; if (my_pos >= 0) my_o = seg[my_pos]; }
         unsigned live = __ballot_sync(0xffffffffu, my_pos >= 0);
-        const float4 b = xcur;
-        xcur = xnext;
+        float4 b[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) { b[ch] = xcur[ch]; xcur[ch] = xnext[ch]; }
         uint32_t sbits = 0;
         while (live) {
             const int t = __ffs(live) - 1;
             live &= live - 1;
             const int o = __shfl_sync(0xffffffffu, my_o, t);
-            const float4 h4 = has ? *(const float4 *)(hyper + (size_t)o * ld + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float off = noff[o];
+            const float *hrow = hyper + (size_t)o * ld;
             float acc = 0.0f;
-            acc = __fmaf_rn(h4.x, b.x, acc); acc = __fmaf_rn(h4.y, b.y, acc); acc = __fmaf_rn(h4.z, b.z, acc); acc = __fmaf_rn(h4.w, b.w, acc);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c = ch * 128 + lane * 4;
+                if (c < ld) {
+                    const float4 h4 = *(const float4 *)(hrow + c);
+                    acc = __fmaf_rn(h4.x, b[ch].x, acc); acc = __fmaf_rn(h4.y, b[ch].y, acc);
+                    acc = __fmaf_rn(h4.z, b[ch].z, acc); acc = __fmaf_rn(h4.w, b[ch].w, acc);
+                }
+            }
 #pragma unroll
             for (int sft = 16; sft >= 1; sft >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, sft));
-            const float margin = __fadd_rn(off, acc);
+            const float margin = __fadd_rn(noff[o], acc);
             uint32_t s;
             if (fabs((double)margin) < 1e-8) {
                 const int pos = __shfl_sync(0xffffffffu, my_pos, t);
@@ -475,7 +496,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
     const bool root_active = (N > leaf_size && max_depth > 0);
     const unsigned gpos = (unsigned)cdiv(TN + 1, 256);
     // NND_FOREST_PM: the inverse permutation is maintained (init + scatter) only when the point-major pass can be used at all
-    const bool pm_on = ctx->opt_forest_pm && ld <= 128 && n_trees <= 32;
+    const bool pm_on = ctx->opt_forest_pm && ld <= 1024 && n_trees <= 32;
     int32_t *invp = pm_on ? W.invp : nullptr;
     k_forest_init<<<gpos, 256, 0, st>>>(W.perm[0], W.seg[0], W.segstart, W.act[0], leaf_points, W.flag32, N, n_trees, root_active ? 1 : 0, invp); NND_LAUNCH(ctx);
     NND_CUDA(cudaMemsetAsync(W.scalars, 0, sizeof(int32_t) * 16, st));
@@ -500,11 +521,13 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
                                                                                  W.nsize[ncur], W.perm[cur], W.tree_first,
                                                                                  W.tree_seed, W.hyper, W.noff);
         NND_LAUNCH(ctx);
-        if (pm_on && (size_t)M * ld * 4 <= (size_t)ctx->opt_forest_pm_mb << 20)
-            k_forest_side_pm128<<<(unsigned)cdiv(cdiv(N, PM_RUN) * 32, 256), 256, 0, st>>>(X, ld, N, n_trees, level, invp, W.seg[cur],
-                                                                                      W.nstart[ncur], W.tree_first, W.tree_seed, W.hyper,
-                                                                                      W.noff, W.side, W.flag32);
-        else if (ld <= 128)
+        if (pm_on && (size_t)M * ld * 4 <= (size_t)ctx->opt_forest_pm_mb << 20) {
+            const unsigned g = (unsigned)cdiv(cdiv(N, PM_RUN) * 32, 256);
+#define PMK(NCH_) k_forest_side_pm<NCH_><<<g, 256, 0, st>>>(X, ld, N, n_trees, level, invp, W.seg[cur], W.nstart[ncur], W.tree_first, \
+                                                          W.tree_seed, W.hyper, W.noff, W.side, W.flag32)
+            if (ld <= 128) PMK(1); else if (ld <= 256) PMK(2); else if (ld <= 512) PMK(4); else PMK(8);
+#undef PMK
+        } else if (ld <= 128)
             k_forest_side128<<<(unsigned)cdiv(cdiv(n_act, SIDE_RUN) * 32, 256), 256, 0, st>>>(X, ld, n_act, W.act[cur], N, level,
                                                                                          W.perm[cur], W.seg[cur], W.nstart[ncur],
                                                                                          W.tree_first, W.tree_seed, W.hyper, W.noff,

@@ -478,7 +478,10 @@ def test_generic_join_and_pair_distances_for_the_metrics_added_last(emu_lib, met
     (200, 128, 1, 2, 12, 1, 1 << 30),          # point-major on every level; angular trees, full 128-float rows (every lane holds data)
     (160, 7, 1, 2, 10, 1, 1 << 30),            # padded rows (ld = 8: lanes 2..31 hold nothing)
     (90, 16, 0, 12, 10, 1, 1 << 30),           # the default forest size: 12 trees = 12 lanes look positions up
-    (120, 130, 0, 2, 10, 1, 1 << 30),          # ld > 128: the switch must leave the generic k_forest_side in charge
+    (120, 130, 0, 2, 10, 1, 1 << 30),          # ld = 132: two-chunk rows, only lane 0 holds data of the second chunk
+    (100, 300, 1, 2, 10, 1, 1 << 30),          # ld = 300: four-chunk instantiation, angular
+    (90, 784, 0, 2, 10, 1, 10000),             # ld = 784 (cfg5 rows): eight-chunk instantiation on the shallow levels, k_forest_side below
+    (100, 1030, 0, 2, 10, 1, 1 << 30),         # ld > 1024: the switch must leave the generic k_forest_side in charge
 ])  # (every emulated CUDA thread is an OS thread: sizes are kept small; 700 x 20 x 5 trees and 500 x 128 angular passed as well)
 def test_forest_kernels_and_point_major_pass(emu_lib, n, d, angular, trees, leaf, pm, pm_limit):
     from oracle import nnd_oracle as orc
@@ -499,7 +502,7 @@ def test_forest_kernels_and_point_major_pass(emu_lib, n, d, angular, trees, leaf
     for i in range(nl):
         got[i, : lo[i + 1] - lo[i]] = lp[lo[i]: lo[i + 1]]
     assert np.array_equal(got, want)
-    if not pm or ld > 128:
+    if not pm or ld > 1024:
         assert levels_pm == 0
     elif pm_limit >= 1 << 30:
         assert levels_pm == levels > 3
