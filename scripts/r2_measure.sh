@@ -40,7 +40,7 @@ fi
 if [ "$what" = all ] || [ "$what" = ab ]; then
   # schedule experiments: bit-equality + timing, small first (a wrong kernel shows up in seconds), then the bench size
   run timeout 900 python scripts/r2_ab.py 100000 128 15 euclidean --reps=1 --timeout=120
-  run timeout 900 python scripts/r2_ab.py 60000 256 15 cosine --reps=1 --timeout=120 --configs=default,rank,leaf,pipe,pipe+rank+leaf
+  run timeout 900 python scripts/r2_ab.py 60000 256 15 cosine --reps=1 --timeout=120 --configs=default,rank,leaf,pipe,pipe+rank+leaf,forestpm,jbdk16
   cp gpurun_out/ab_summary.json gpurun_out/ab_summary_small.json 2>/dev/null
   run timeout 1500 python scripts/r2_ab.py 1000000 128 15 euclidean --reps=2 --timeout=200
 fi
