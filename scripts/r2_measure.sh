@@ -50,6 +50,8 @@ if [ "$what" = all ] || [ "$what" = bench ]; then
 fi
 if [ "$what" = all ] || [ "$what" = cfg3 ]; then
   run timeout 900 python bench.py --workload cfg3 --steps 3 --warmup 2 --no-cpu-baseline
+  # 1 KB rows: the position-major forest passes gather 370 GB per build here
+  NND_FOREST_PM=1 run timeout 900 python bench.py --workload cfg3 --steps 3 --warmup 2 --no-cpu-baseline
 fi
 if [ "$what" = all ] || [ "$what" = cfg5 ]; then
   # BASELINE.json configs[4]: 1M x 784 correlation k=30 build + query() of 100k held-out points
@@ -59,6 +61,7 @@ if [ "$what" = all ] || [ "$what" = cfg5 ]; then
   run timeout 1200 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline
   # leaf_size 150 / k = 30 does not fit the fused leaf kernel (routed path); the split leaf init does
   NND_LEAF_SPLIT=1 run timeout 1200 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline
+  NND_LEAF_SPLIT=1 NND_FOREST_PM=1 run timeout 1200 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline
 fi
 if [ "$what" = all ] || [ "$what" = ncu ]; then
   # launch list of one warm build (shares), then --set full of the join kernels (default and experimental)
