@@ -49,12 +49,16 @@ def reference_state(index):
         n_trees=index.n_trees, n_trees_after_update=max(2, int(np.round(index.n_trees / 3))), n_neighbors=index.n_neighbors,
         metric=index.metric, metric_kwds=index.metric_kwds, bit_metric=False, angular_trees=False, leaf_size=index.leaf_size,
         prune_degree_multiplier=index.pruning_degree_multiplier, diversify_prob=1.0, diversify_method="standard",
-        degree_prune_aggressiveness=1.0, n_search_trees=1, search_tree_leaf_size=None, max_search_tree_depth=None,
+        degree_prune_aggressiveness=1.0, n_search_trees=1, search_tree_leaf_size=getattr(index, "search_tree_leaf_size", None),
+        max_search_tree_depth=getattr(index, "max_search_tree_depth", None),
         quantization=None, tree_init=index.tree_init, random_state=index.random_state, low_memory=index.low_memory,
         max_candidates=index.max_candidates, max_rptree_depth=index.max_rptree_depth, n_iters=index.n_iters, delta=index.delta,
         n_jobs=index.n_jobs, compressed=index.compressed, parallel_batch_queries=False, verbose=False, dim=index.dim,
         # derived state
-        _dist_args=tuple((index.metric_kwds or {}).values()), _is_sparse=False,      # :1064-1065 _input_dtype=np.dtype(np.float32), _angular_trees=bool(index._angular_trees),
+        # :1064-1065, 1057, 1074-1090; _distance_correction is preset to None (:1296) -- the reference's __setstate__ /
+        # _set_distance_func only overwrites it for metrics that have a fast alternative
+        _dist_args=tuple((index.metric_kwds or {}).values()), _is_sparse=False,
+        _input_dtype=np.dtype(np.float32), _angular_trees=bool(index._angular_trees), _distance_correction=None,
         _bit_trees=False, rng_state=np.asarray(index.rng_state, np.int64), search_rng_state=np.asarray(index.search_rng_state, np.int64),
         _raw_data=np.ascontiguousarray(index._raw_data[vertex_order, :]),                                    # :1639-1641
         _neighbor_graph=(np.asarray(ng_idx, np.int32), np.asarray(ng_dist, np.float32)),

@@ -71,6 +71,17 @@ class NNDescent:
                 raise ValueError("The shapes of init graph and init distances do not match!")
             if sharded:
                 raise NotImplementedError("init_graph with the sharded build")
+        # keywords of prepare() whose non-default values select code that is not built here (pynndescent_.py:1462-1587):
+        # never a silent drop.  `angular_trees` only matters for callable metrics in the reference (:1091-1095), which
+        # raise here anyway; `parallel_batch_queries` / `degree_prune_aggressiveness` (degree_aware only) change no result.
+        if diversify_prob != 1.0:
+            raise NotImplementedError("diversify_prob != 1.0 (randomised diversification) is outside the sm_100a hot path")
+        if diversify_method != "standard":
+            raise NotImplementedError("diversify_method=%r (only 'standard' is built)" % (diversify_method,))
+        if n_search_trees != 1:
+            raise NotImplementedError("n_search_trees != 1")
+        if leaf_array is not None and sharded:
+            raise NotImplementedError("leaf_array together with the sharded build")
         if n_trees is None:
             n_trees = max(3, min(12, int(round(2.0 * np.log10(data.shape[0])))))      # pynndescent_.py:1009-1010
         if n_iters is None:
@@ -81,6 +92,14 @@ class NNDescent:
         self.metric_kwds = metric_kwds
         self.leaf_size = leaf_size
         self.pruning_degree_multiplier = pruning_degree_multiplier
+        self.angular_trees = angular_trees
+        self.diversify_prob = diversify_prob
+        self.diversify_method = diversify_method
+        self.degree_prune_aggressiveness = degree_prune_aggressiveness
+        self.n_search_trees = n_search_trees
+        self.search_tree_leaf_size = search_tree_leaf_size
+        self.max_search_tree_depth = max_search_tree_depth
+        self.parallel_batch_queries = parallel_batch_queries
         self.max_candidates = max_candidates
         self.max_rptree_depth = max_rptree_depth
         self.n_iters = n_iters
@@ -301,11 +320,17 @@ class NNDescent:
             return
         if self.pruning_degree_multiplier is None:
             raise ValueError("pruning_degree_multiplier must be a number")
+        if not self.tree_init:
+            # the reference then searches WITHOUT a tree (_search_forest = [], pynndescent_.py:1373-1374): not built here
+            raise NotImplementedError("prepare() / query() of an index built with tree_init=False (tree-less search)")
         from .prepare import prepare_search_structures
         eng = self._engine
+        # :1341-1351 dedicated search-tree parameters win over the construction ones
+        search_leaf_size = self.search_tree_leaf_size if self.search_tree_leaf_size is not None else self.leaf_size
+        search_depth = self.max_search_tree_depth if self.max_search_tree_depth is not None else self.max_rptree_depth
         S = prepare_search_structures(eng, self.metric, eng.heap_idx, eng.heap_dist, self.n_neighbors, self._angular_trees,
-                                      leaf_size=self.leaf_size, pruning_degree_multiplier=self.pruning_degree_multiplier,
-                                      max_depth=self.max_rptree_depth)
+                                      leaf_size=search_leaf_size, pruning_degree_multiplier=self.pruning_degree_multiplier,
+                                      max_depth=search_depth)
         self._search_structures = S
         # :1639-1641 data re-ordered to leaf order -- gathered on the device from the matrix that is already there
         import torch

@@ -22,6 +22,11 @@ G = np.load(sys.argv[3])
 qi, qd = obj.query(G["Q"], k=int(G["k_query"]), epsilon=float(G["epsilon"]))
 qi2, qd2 = obj.query(G["Q"], k=5, epsilon=0.3)
 gi, gd = obj.neighbor_graph
+# update() reads _input_dtype / _angular_trees / n_trees_after_update from the unpickled state (pynndescent_.py:2407-2535)
+n0 = gi.shape[0]
+obj.update(xs_fresh=np.ascontiguousarray(G["Q"][:25]))
+ui, ud = obj.neighbor_graph
+assert ui.shape[0] == n0 + 25 and (ui[:, 0] >= 0).all()
 np.savez(sys.argv[4], qi=qi, qd=qd, qi2=qi2, qd2=qd2, gi=gi, gd=gd)
 '''
 
@@ -48,7 +53,7 @@ def _fake_prepared_index(G):
     return o
 
 
-@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24"])
+@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24", "query_manhattan_2k20"])   # the last has no fast alternative
 def test_reference_loads_and_queries_our_pickle(tmp_path, name):
     from oracle import ref_shim
     if not ref_shim.available():
