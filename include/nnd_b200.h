@@ -169,15 +169,9 @@ NND_API int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int
                 int32_t n_iters, double delta, int64_t push_capacity, void *ws, size_t ws_bytes,
                 int32_t *iters_run_host, int64_t *c_hist_host, int64_t *stats_host, void *stream);
 
-/* ---- schedule of the local join (no reference counterpart: the numba path visits rows in ascending order per thread,
- * utils.py:558-658).  `perm` = a permutation of 0..n-1 in DEVICE memory, kept alive by the caller until replaced
- * (NULL / n = 0 restores ascending order).  Half-updates carry their emission sequence (row, pair slot, side), so the
- * visiting order never changes a result; visiting rows in RP-tree leaf order keeps the rows gathered by concurrently
- * running batches inside one neighbourhood (L2 hits instead of HBM reads).  Schedule switches read from the
- * environment by nnd_create (all default off, none changes a result; csrc/nnd_common.cuh):
- * NND_JOIN_PIPE (+ NND_PIPE_DK, NND_PIPE_STAGES, NND_PIPE_CTAS), NND_RANK_SCATTER, NND_CAND_SKIP, NND_CAND_KEYS,
- * NND_LEAF_SPLIT, NND_APPLY_SHORT_SORT, NND_APPLY_HALF, NND_SMEM_CARVEOUT, NND_FOREST_PM (+ NND_FOREST_PM_MB).              */
-NND_API int nnd_set_join_order(nnd_ctx *ctx, const int32_t *perm, int64_t n);
+/* Schedule switches read from the environment by nnd_create (none changes a result; csrc/nnd_common.cuh, DESIGN.md section 10a;
+ * defaults = the winners of the round-2 hardware A/B, profiles/ab_r02_1m_switches.json): NND_RANK_SCATTER, NND_LEAF_SPLIT,
+ * NND_SMEM_CARVEOUT, NND_FOREST_PM (+ NND_FOREST_PM_MB), NND_CAND_SKIP, NND_CAND_KEYS.                                  */
 
 /* ---- sharded build (one process per GPU) ----------------------------------------------
  * Every process holds X and the whole heap; it samples candidates and joins only rows [lo,hi), exchanges the
@@ -276,6 +270,28 @@ NND_API int nnd_pair_distances(nnd_ctx *ctx, const nnd_problem *P, const int32_t
  * launch: out10 = {ms, launches, rows gathered, pairs evaluated, half-updates} for the local join
  * (utils.py:536-658) followed by the same five for the leaf join (pynndescent_.py:73-113).       */
 NND_API int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset);
+/* per-stage device time of the build path: with profiling on (nnd_stage_profile(ctx, 1), or NND_STAGE_PROFILE=1 in the
+ * environment of nnd_create) every stage boundary records a CUDA event on the launching stream; nnd_stage_read waits for
+ * the last one and returns the milliseconds spent in each stage since the last reset: out_ms[NND_STAGE_COUNT], indexed
+ * by NND_ST_*.  (bench.py's stage table; the events cost about a microsecond of host time each.)                      */
+#define NND_ST_OTHER 0        /* time between library calls, small bookkeeping kernels                                   */
+#define NND_ST_FOREST_HYPER 1 /* rp_trees.py:323-420 hyperplanes of a level                                              */
+#define NND_ST_FOREST_SIDE 2  /* margins / sides of a level (the pass that reads X)                                      */
+#define NND_ST_FOREST_PART 3  /* scans, node bookkeeping, stable partition                                               */
+#define NND_ST_LEAF_DIST 4    /* pynndescent_.py:73-113 leaf distance matrices (or the fused leaf kernel)                 */
+#define NND_ST_LEAF_PUSH 5    /* pynndescent_.py:154-185 leaf pushes                                                     */
+#define NND_ST_INIT_RANDOM 6
+#define NND_ST_CAND_FILL 7    /* utils.py:261-306 rng tables, counts, scans, priorities + reverse-edge routing            */
+#define NND_ST_CAND_SELECT 8  /* utils.py:289-318 heap selection, flag clearing                                          */
+#define NND_ST_JOIN_PREP 9    /* batching prepass of the local join                                                      */
+#define NND_ST_JOIN 10        /* utils.py:536-658 the local join kernel                                                  */
+#define NND_ST_SCATTER 11     /* counting sort of the half-updates by target row                                         */
+#define NND_ST_APPLY 12       /* utils.py:661-733 ordered replay of checked_flagged_heap_push                             */
+#define NND_ST_DEHEAP 13      /* utils.py:189-218                                                                        */
+#define NND_ST_EXCHANGE 14    /* sharded build: packing / unpacking of exchanged records and rows                         */
+#define NND_STAGE_COUNT 16
+NND_API int nnd_stage_profile(nnd_ctx *ctx, int32_t enable);
+NND_API int nnd_stage_read(nnd_ctx *ctx, double *out_ms, int32_t reset);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 NND_API int64_t nnd_launch_count(nnd_ctx *ctx);
 

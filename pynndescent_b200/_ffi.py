@@ -64,7 +64,6 @@ SIGNATURES = {
     "nnd_descent": (C.c_int, [_vp, _PP, _i32, _pi64, _i32, _i32, C.c_double, _i64, _vp, _sz, _pi32, _pi64, _pi64, _vp]),
     "nnd_metric_set_param": (C.c_int, [_vp, _i32, _vp, C.c_double, _vp]),
     "nnd_set_row_range": (C.c_int, [_vp, _i64, _i64]),
-    "nnd_set_join_order": (C.c_int, [_vp, _vp, _i64]),
     "nnd_join_prepare": (C.c_int, [_vp, _PP, _i32, _vp, _vp, _i64, _vp, _sz, _pi32, _vp]),
     "nnd_join_emit_round": (C.c_int, [_vp, _PP, _i32, _i64, _vp, _sz, _i32, _pi64, _vp]),
     "nnd_push_export": (C.c_int, [_vp, _PP, _i32, _i64, _vp, _sz, _i64, _i64, _i32, _vp, _pi64, _vp]),
@@ -86,6 +85,8 @@ SIGNATURES = {
     "nnd_pair_distances": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _vp, _vp]),
     "nnd_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), _i32]),
     "nnd_launch_count": (C.c_int64, [_vp]),
+    "nnd_stage_profile": (C.c_int, [_vp, _i32]),
+    "nnd_stage_read": (C.c_int, [_vp, C.POINTER(C.c_double), _i32]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here == ABI drift

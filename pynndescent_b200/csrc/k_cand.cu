@@ -445,6 +445,7 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
               "nnd_build_candidates: workspace too small");
     const int64_t B = N / T + 1;
+    NND_STAGE(ctx, NND_ST_CAND_FILL, st);
     // the T priority streams: constant across iterations (utils.py:262 copies rng_state, never advances it)
     if (!tables_valid) {
         for (int n = 0; n < T; ++n) {
@@ -462,6 +463,7 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     k_cand_fill<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.pre, W.table, W.table_len,
                                                        W.revoff, W.cursor, W.rev, W.fprio, ctx->row_lo, ctx->row_hi, act);
     NND_LAUNCH(ctx);
+    NND_STAGE(ctx, NND_ST_CAND_SELECT, st);
     const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
     size_t smem = (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)SEL_WARPS * hstride;
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
@@ -495,6 +497,7 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     k_cand_select<<<(unsigned)cdiv(N, SEL_WARPS), SEL_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
                                                                              W.revoff, W.rev, W.fprio, new_cand, old_cand, use_small, ctx->row_lo, ctx->row_hi, act);
     NND_LAUNCH(ctx);
+    NND_STAGE(ctx, NND_ST_OTHER, st);
     NND_CUDA(cudaGetLastError());
     return NND_OK;
 }

@@ -390,13 +390,11 @@ __global__ void __launch_bounds__(MAXT) k_join(JoinParams P) {
 // Same arithmetic and the same emission keys as k_join.
 // =====================================================================================================
 // prepass 1: per row -> active flag, physical slots, batching weight
-// `order` (nnd_set_join_order): position p of the scan visits row order[p]; every array written here and consumed by the
-// scans / k_jb_fill is indexed by POSITION, only the candidate lists are indexed by row
 __global__ void k_jb_count(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *flag, uint32_t *phys,
-                           uint32_t *wgt, uint32_t *info, int64_t lo, int64_t hi, const int32_t *order) {
+                           uint32_t *wgt, uint32_t *info, int64_t lo, int64_t hi) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
-    const int64_t i = order ? (int64_t)order[p] : p;
+    const int64_t i = p;
     int nn = 0, no = 0;
     if (i >= lo && i < hi)
         for (int j = 0; j < C; ++j) { nn += newc[i * C + j] >= 0; no += oldc[i * C + j] >= 0; }
@@ -411,11 +409,10 @@ __global__ void k_jb_count(const int32_t *newc, const int32_t *oldc, int C, int6
 // prepass 2: compacted active-row list + member ids in the reference's order (new k asc, then old k asc; holes dropped)
 __global__ void k_jb_fill(const int32_t *newc, const int32_t *oldc, int C, int64_t N, const uint32_t *flag,
                           const uint32_t *pos, const uint32_t *poff, const uint32_t *woff, const uint32_t *info,
-                          int32_t *act_unit, uint32_t *act_info, uint32_t *act_poff, uint32_t *act_woff, int32_t *members,
-                          const int32_t *order) {
+                          int32_t *act_unit, uint32_t *act_info, uint32_t *act_poff, uint32_t *act_woff, int32_t *members) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N || !flag[p]) return;
-    const int64_t i = order ? (int64_t)order[p] : p;
+    const int64_t i = p;
     uint32_t j = pos[p], o = poff[p];
     act_unit[j] = (int32_t)i; act_info[j] = info[p]; act_poff[j] = o; act_woff[j] = woff[p];
     int w = 0;
@@ -996,7 +993,6 @@ struct DescentWs {
     // batched local join prepass
     uint32_t *jb_flag, *jb_phys, *jb_wgt, *jb_info, *jb_pos, *jb_poff, *jb_woff, *act_info, *act_poff, *act_woff;
     int32_t *act_unit, *members, *batch_first;
-    char *jp_meta; size_t jp_meta_bytes;   // k_join_pipe batch descriptors of one routing round
 };
 
 size_t nnd_cand_ws_bytes(int64_t N, int k, int C, int T);
@@ -1029,15 +1025,6 @@ static int carve_descent_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, 
         W->batch_first = A.get<int32_t>((size_t)Nb * (size_t)(mw / psw + 1) + 8);
     }
     W->members = A.get<int32_t>((size_t)Nb * (2 * JB_CMAX + 4));
-    {   // descriptors of ONE routing round: a round holds at most cap / (JB_TCAP*16) batches (build_join_plan) and never more
-        // than there are weight windows
-        int Cc = C < 1 ? 1 : (C > JB_CMAX ? JB_CMAX : C);
-        int mp = ((2 * Cc + 3) >> 2) << 2, mt = (jb_tiles(Cc, 2 * Cc) * 3 + 1) >> 1, mw = mp > mt ? mp : mt;
-        int psw = JB_SCAP - mw; if (psw < 1) psw = 1;
-        int64_t windows = (int64_t)Nb * (mw / psw + 1) + 8, per_round = cap / ((int64_t)JB_TCAP * 16) + 1;
-        W->jp_meta_bytes = join_pipe_meta_bytes(windows < per_round ? windows : per_round);
-        W->jp_meta = A.get<char>(W->jp_meta_bytes);
-    }
     W->cand_bytes = nnd_cand_ws_bytes(N, k, C, T);
     W->cand_base = A.get<char>(W->cand_bytes);
     W->newc = A.get<int32_t>((size_t)Nb * C); W->oldc = A.get<int32_t>((size_t)Nb * C);
@@ -1113,6 +1100,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
                        int64_t cap, unsigned long long *n_pushed, cudaStream_t st, JoinBatchParams *JB = nullptr,
                        bool do_apply = true) {
     const int64_t N = P->N;
+    NND_STAGE(ctx, NND_ST_SCATTER, st);
     k_snapshot_thr<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_dist, P->k, W.thr, N); NND_LAUNCH(ctx);
     NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (N + 1), st));
     NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long), st));  // cursor
@@ -1122,6 +1110,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     J.overflow = (int *)(W.dev_scalars + 4);
     NND_CUDA(cudaMemsetAsync(W.dev_scalars + 5, 0, sizeof(unsigned long long) * 2, st));
     J.stats = W.dev_scalars + 5;
+    NND_STAGE(ctx, NND_ST_JOIN, st);
     NND_CUDA(cudaEventRecord(ctx->ev0, st));
     // schedule options (nnd_ctx): neither changes what is emitted, only how
     const bool rank_scatter = JB && do_apply && ctx->opt_rank_scatter;
@@ -1130,16 +1119,12 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
         JB->out_tgt = W.l_tgt; JB->out_oth = W.l_oth; JB->out_d = W.l_d; JB->out_pos = rank_scatter ? nullptr : W.l_pos; JB->out_seq = W.l_seq;
         JB->tgt_count = W.cnt; JB->cursor = W.dev_scalars; JB->capacity = (unsigned long long)cap;
         JB->overflow = (int *)(W.dev_scalars + 4); JB->stats = W.dev_scalars + 5;
-        if (ctx->opt_join_pipe) {
-            JoinPipeOpts po; po.dk = ctx->opt_pipe_dk; po.stages = ctx->opt_pipe_stages; po.ctas_per_sm = ctx->opt_pipe_ctas;
-            NND_TRY(launch_join_pipe(ctx, *JB, W.jp_meta, W.jp_meta_bytes, po, st));
-        } else {
-            NND_TRY(launch_join_batch(ctx, *JB, st));
-        }
+        NND_TRY(launch_join_batch(ctx, *JB, st));
     } else {
         NND_TRY(launch_join(ctx, J, u1 - u0, st));
     }
     NND_CUDA(cudaEventRecord(ctx->ev1, st));
+    NND_STAGE(ctx, NND_ST_SCATTER, st);
     unsigned long long h[7];
     NND_CUDA(cudaMemcpyAsync(h, W.dev_scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
     NND_CUDA(cudaStreamSynchronize(st));
@@ -1155,6 +1140,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
         double *pf = ctx->prof[J.mode ? 1 : 0];
         pf[0] += ms; pf[1] += 1; pf[2] += (double)h[5]; pf[3] += (double)h[6]; pf[4] += (double)h[0];
         ctx->last_round_rows = h[5]; ctx->last_round_pairs = h[6];
+        if (JB && u1 > u0) { double ppb = (double)h[0] / (double)(u1 - u0); if (ppb > ctx->jb_ppb_max) ctx->jb_ppb_max = ppb; }
     }
     if (h[0] == 0 || !do_apply) return NND_OK;
     NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.cnt, W.off, N, W.scan_tmp, st));  // offsets of power-of-two padded segments
@@ -1165,6 +1151,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
         k_scatter<<<(unsigned)cdiv((int64_t)h[0], 256), 256, 0, st>>>(W.l_tgt, W.l_oth, W.l_d, W.l_pos, W.l_seq, h[0], W.off, W.rec);
     }
     NND_LAUNCH(ctx);
+    NND_STAGE(ctx, NND_ST_APPLY, st);
     size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "apply: k=%d too large", P->k);
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1191,6 +1178,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
                                                                            W.cnt, W.off, W.rec, W.dev_scalars + 1, use_small, ctx->opt_apply_short);
     NND_LAUNCH(ctx);
+    NND_STAGE(ctx, NND_ST_OTHER, st);
     NND_CUDA(cudaGetLastError());
     return NND_OK;
 }
@@ -1207,12 +1195,7 @@ static size_t join_batch_smem(int metric, int dk, int ld) {
 static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st) {
     int64_t nb = JB.batch_end - JB.batch_begin;
     if (nb <= 0) return NND_OK;
-    static int dk_sel = -1;
-    // NND_JB_DK: floats per staged chunk (default 32 = the measured configuration).  16 halves the row buffers (2 x 176 x 80 B);
-    // the kernel is then register-bound (93 x 128) at 5 CTAs per SM instead of shared-memory-bound at 4 -- 20 warps to hide the
-    // gather latency -- at the price of twice as many chunk barriers
-    if (dk_sel < 0) { const char *e = getenv("NND_JB_DK"); dk_sel = e ? atoi(e) : 32; if (dk_sel != 16 && dk_sel != 32 && dk_sel != 64 && dk_sel != 128) dk_sel = 32; }
-    const int dk = dk_sel;
+    const int dk = 32;   // floats per staged chunk (16 / 64 / 128 were measured slower on B200: profiles/ab_r02_1m_switches.json)
     size_t smem = join_batch_smem(JB.metric, dk, JB.ld);
     dim3 grid((unsigned)nb);
 #define LB(M_, D_)                                                                                                   \
@@ -1220,7 +1203,7 @@ static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st)
         NND_CUDA(cudaFuncSetAttribute(k_join_batch<M_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_join_batch<M_, D_><<<grid, JB_THREADS, smem, st>>>(JB);                                                     \
     } while (0)
-#define LBM(M_) do { if (dk == 32) LB(M_, 32); else if (dk == 16) LB(M_, 16); else if (dk == 64) LB(M_, 64); else LB(M_, 128); } while (0)
+#define LBM(M_) LB(M_, 32)
     if (JB.metric == NND_METRIC_SQEUCLIDEAN) LBM(NND_METRIC_SQEUCLIDEAN);
     else if (JB.metric == NND_METRIC_ALT_COSINE) LBM(NND_METRIC_ALT_COSINE);
     else LBM(NND_METRIC_ALT_DOT);
@@ -1267,10 +1250,12 @@ static int leaf_split_launch(nnd_ctx *ctx, const nnd_problem *P, const JoinParam
     NND_CUDA(cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
     if (ctx->opt_carveout) cudaFuncSetAttribute(k_leaf_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     uint32_t *dsz = W.l_pos, *doff = (uint32_t *)W.l_oth; int32_t *pos2leaf = W.l_tgt; float *D = (float *)W.rec;
+    NND_STAGE(ctx, NND_ST_LEAF_DIST, st);
     k_leaf_prep<<<(unsigned)cdiv(nl, 128), 128, 0, st>>>(J.leaf_offsets, l0, l1, pos0, dsz, pos2leaf); NND_LAUNCH(ctx);
     NND_TRY(nnd_exclusive_scan_u32(ctx, dsz, doff, nl, W.scan_tmp, st));
     JoinParams J3 = J; J3.mode = 3; J3.leaf_D = D; J3.leaf_doff = doff; J3.unit_begin = l0; J3.unit_end = l1;
     NND_TRY(launch_join(ctx, J3, nl, st));
+    NND_STAGE(ctx, NND_ST_LEAF_PUSH, st);
     k_leaf_push<<<(unsigned)cdiv(npos, LP_T), LP_T, lp_smem, st>>>(J.leaf_points, J.leaf_offsets, l0, pos0, npos, pos2leaf, doff, D, P->heap_idx,
                                                                 P->heap_dist, P->heap_flag, P->k);
     NND_LAUNCH(ctx);
@@ -1330,6 +1315,7 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
             // NND_LEAF_SPLIT: distance matrices to global memory (k_join mode 3), pushes by k_leaf_push.  Scratch comes from
             // arrays of the routing workspace that the fused path never touches; fall back to the fused kernel if it is short.
             const bool split = split_ok;
+            NND_STAGE(ctx, NND_ST_LEAF_DIST, st);
             NND_CUDA(cudaEventRecord(ctx->ev0, st));
             for (size_t t = 0; t + 1 < tree_cut.size(); ++t) {
                 J.unit_begin = tree_cut[t]; J.unit_end = tree_cut[t + 1];
@@ -1338,6 +1324,7 @@ extern "C" int nnd_leaf_init(nnd_ctx *ctx, const nnd_problem *P, const int32_t *
             }
             NND_CUDA(cudaGetLastError());
             NND_CUDA(cudaEventRecord(ctx->ev1, st));
+            NND_STAGE(ctx, NND_ST_OTHER, st);
             NND_CUDA(cudaStreamSynchronize(st));
             float ms = 0.f;
             NND_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1392,19 +1379,19 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
     // the batched kernel is instantiated for the three f32 dot/difference classes (inner_product shares dot's); everything else
     // runs the generic join
     PL.batched = nnd_metric_class(P->metric) <= NND_METRIC_ALT_DOT && 2 * C <= 60 && !(force_old && force_old[0] == '1');
+    NND_STAGE(ctx, NND_ST_JOIN_PREP, st);
     if (PL.batched) {
         // ---- batched path: compact the active rows and their members, cut batches by weight, one CTA per batch
         const int maxphys = ((2 * C + 3) >> 2) << 2;
         const int maxw_t = (jb_tiles(C, 2 * C) * 3 + 1) >> 1;
         const int maxw = maxphys > maxw_t ? maxphys : maxw_t;
         const uint32_t ps = (uint32_t)(JB_SCAP - maxw);                          // weight window per batch
-        const int32_t *order = (ctx->join_order && ctx->join_order_n == N) ? ctx->join_order : nullptr;
-        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_wgt, W.jb_info, ctx->row_lo, ctx->row_hi, order); NND_LAUNCH(ctx);
+        k_jb_count<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_phys, W.jb_wgt, W.jb_info, ctx->row_lo, ctx->row_hi); NND_LAUNCH(ctx);
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_flag, W.jb_pos, N, W.scan_tmp, st));
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_phys, W.jb_poff, N, W.scan_tmp, st));
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.jb_wgt, W.jb_woff, N, W.scan_tmp, st));
         k_jb_fill<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(new_cand, old_cand, C, N, W.jb_flag, W.jb_pos, W.jb_poff, W.jb_woff, W.jb_info,
-                                                          W.act_unit, W.act_info, W.act_poff, W.act_woff, W.members, order);
+                                                          W.act_unit, W.act_info, W.act_poff, W.act_woff, W.members);
         NND_LAUNCH(ctx);
         uint32_t hh[2];
         NND_CUDA(cudaMemcpyAsync(&hh[0], W.jb_pos + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1421,7 +1408,14 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
             JB.batch_first = W.batch_first; JB.n_active = n_active; JB.n_batches = n_batches; JB.slot_stride = 2 * C;
             // rounds are planned optimistically (16 half-updates per tile slot; the worst case is 32 and the measured
             // average 7); a round that overflows is detected (never silent) and split by the caller
-            const int64_t per_batch = (int64_t)JB_TCAP * 16;
+            // ... and from the second iteration of a build on by the measured emission of the previous iteration's rounds
+            // (half-updates per batch, x1.3: emission falls from iteration to iteration): fewer, fuller rounds
+            int64_t per_batch = (int64_t)JB_TCAP * 16;
+            if (ctx->jb_ppb_max > 0.0) {
+                int64_t est = (int64_t)(ctx->jb_ppb_max * 1.3) + 64;
+                if (est < per_batch) per_batch = est;
+            }
+            ctx->jb_ppb_max = 0.0;
             NND_CHECK(per_batch <= push_capacity, NND_ERR_OVERFLOW, "push_capacity %lld too small for one batch (%lld)",
                       (long long)push_capacity, (long long)per_batch);
             const int64_t bpb = push_capacity / per_batch;

@@ -498,6 +498,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
     // NND_FOREST_PM: the inverse permutation is maintained (init + scatter) only when the point-major pass can be used at all
     const bool pm_on = ctx->opt_forest_pm && ld <= 1024 && n_trees <= 32;
     int32_t *invp = pm_on ? W.invp : nullptr;
+    NND_STAGE(ctx, NND_ST_FOREST_PART, st);
     k_forest_init<<<gpos, 256, 0, st>>>(W.perm[0], W.seg[0], W.segstart, W.act[0], leaf_points, W.flag32, N, n_trees, root_active ? 1 : 0, invp); NND_LAUNCH(ctx);
     NND_CUDA(cudaMemsetAsync(W.scalars, 0, sizeof(int32_t) * 16, st));
     int cur = 0;
@@ -517,10 +518,12 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
         NND_CHECK(M <= hyper_nodes, NND_ERR_OVERFLOW, "forest: %d active nodes exceed the hyperplane pool", M);
         const int depth_left_after = max_depth - (level + 1);
         const int hw = 4;
+        NND_STAGE(ctx, NND_ST_FOREST_HYPER, st);
         k_forest_hyper<<<(unsigned)cdiv(M, hw), hw * 32, (size_t)hw * ld * 4, st>>>(X, ld, N, angular, level, M, W.nstart[ncur],
                                                                                  W.nsize[ncur], W.perm[cur], W.tree_first,
                                                                                  W.tree_seed, W.hyper, W.noff);
         NND_LAUNCH(ctx);
+        NND_STAGE(ctx, NND_ST_FOREST_SIDE, st);
         if (pm_on && (size_t)M * ld * 4 <= (size_t)ctx->opt_forest_pm_mb << 20) {
             const unsigned g = (unsigned)cdiv(cdiv(N, PM_RUN) * 32, 256);
 #define PMK(NCH_) k_forest_side_pm<NCH_><<<g, 256, 0, st>>>(X, ld, N, n_trees, level, invp, W.seg[cur], W.nstart[ncur], W.tree_first, \
@@ -537,6 +540,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
                                                                                        W.seg[cur], W.nstart[ncur], W.tree_first,
                                                                                        W.tree_seed, W.hyper, W.noff, W.side, W.flag32);
         NND_LAUNCH(ctx);
+        NND_STAGE(ctx, NND_ST_FOREST_PART, st);
         NND_TRY(nnd_exclusive_scan_u32(ctx, W.flag32, W.pl, TN, W.scan_tmp, st));
         NND_CUDA(cudaMemsetAsync(W.scalars, 0, sizeof(int32_t), st));
         NND_CUDA(cudaMemsetAsync(W.scalars + 2, 0, sizeof(int32_t), st));
@@ -588,6 +592,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
     NND_CUDA(cudaStreamSynchronize(st));
     *n_leaves_host = (int64_t)nl;
     *max_leaf_host = ml > leaf_size ? ml : leaf_size;
+    NND_STAGE(ctx, NND_ST_OTHER, st);
     NND_CUDA(cudaGetLastError());
     return NND_OK;
 }

@@ -51,24 +51,21 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
     nnd_ctx *c = new nnd_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->launches = 0;
     memset(c->prof, 0, sizeof(c->prof));
-    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr; c->plan_free = nullptr;
+    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr; c->plan_free = nullptr; c->jb_ppb_max = 0.0;
     {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
-        c->opt_join_pipe = env_int("NND_JOIN_PIPE", 0);
-        c->opt_pipe_dk = env_int("NND_PIPE_DK", 32);
-        c->opt_pipe_stages = env_int("NND_PIPE_STAGES", 4);
-        c->opt_pipe_ctas = env_int("NND_PIPE_CTAS", 0);
-        c->opt_rank_scatter = env_int("NND_RANK_SCATTER", 0);
+        c->opt_rank_scatter = env_int("NND_RANK_SCATTER", 1);
         c->opt_cand_skip = env_int("NND_CAND_SKIP", 0);
         c->opt_cand_keys = env_int("NND_CAND_KEYS", 0);
-        c->opt_leaf_split = env_int("NND_LEAF_SPLIT", 0);
-        c->opt_carveout = env_int("NND_SMEM_CARVEOUT", 0);
+        c->opt_leaf_split = env_int("NND_LEAF_SPLIT", 1);
+        c->opt_carveout = env_int("NND_SMEM_CARVEOUT", 1);
         c->opt_apply_short = env_int("NND_APPLY_SHORT_SORT", 0);
         c->opt_apply_half = env_int("NND_APPLY_HALF", 0);
-        c->opt_forest_pm = env_int("NND_FOREST_PM", 0);
-        c->opt_forest_pm_mb = env_int("NND_FOREST_PM_MB", 48);
-        c->join_order = nullptr; c->join_order_n = 0;
+        c->opt_forest_pm = env_int("NND_FOREST_PM", 1);
+        c->opt_forest_pm_mb = env_int("NND_FOREST_PM_MB", 96);
     }
+    c->sp_on = 0; c->sp_n = 0; c->sp_cap = 0; c->sp_ev = nullptr; c->sp_id = nullptr; memset(c->sp_ms, 0, sizeof(c->sp_ms));
+    { const char *e = getenv("NND_STAGE_PROFILE"); if (e && e[0] == '1') c->sp_on = 1; }
     NND_CUDA(cudaEventCreate(&c->ev0));
     NND_CUDA(cudaEventCreate(&c->ev1));
     size_t n = (size_t)3 * NND_JUMP_POW * 64;
@@ -82,6 +79,8 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
 extern "C" int nnd_destroy(nnd_ctx *ctx) {
     if (!ctx) return NND_OK;
     if (ctx->plan && ctx->plan_free) ctx->plan_free(ctx->plan);
+    for (int i = 0; i < ctx->sp_cap; ++i) cudaEventDestroy(ctx->sp_ev[i]);
+    free(ctx->sp_ev); free(ctx->sp_id);
     cudaFree(ctx->d_jump);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -94,13 +93,44 @@ extern "C" int nnd_set_row_range(nnd_ctx *ctx, int64_t lo, int64_t hi) {
     ctx->row_lo = lo; ctx->row_hi = hi;
     return NND_OK;
 }
-// Row visiting order of the batched local join (a permutation of 0..n-1 in device memory that must stay alive until it
-// is replaced; nullptr = ascending row id).  Half-updates carry their emission sequence (row, pair slot, side), so
-// the order in which rows are joined never changes a result -- it only decides which rows are gathered at about the
-// same time (RP-tree leaf order keeps the gathers of concurrently running batches inside one neighbourhood = L2 hits).
-extern "C" int nnd_set_join_order(nnd_ctx *ctx, const int32_t *perm, int64_t n) {
-    NND_CHECK(ctx && n >= 0 && (perm || n == 0), NND_ERR_INVALID, "nnd_set_join_order: bad args");
-    ctx->join_order = n > 0 ? perm : nullptr; ctx->join_order_n = n > 0 ? n : 0;
+// ---- stage profiler: a ring of (event, stage id) marks; the time between two consecutive marks belongs to the earlier mark's stage
+static void stage_resolve(nnd_ctx *ctx) {
+    if (ctx->sp_n < 2) return;
+    cudaEventSynchronize(ctx->sp_ev[ctx->sp_n - 1]);
+    for (int i = 0; i + 1 < ctx->sp_n; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->sp_ev[i], ctx->sp_ev[i + 1]) == cudaSuccess) ctx->sp_ms[ctx->sp_id[i]] += ms;
+    }
+    // the last mark opens an interval that is still running: it becomes the first mark of the next batch
+    std::swap(ctx->sp_ev[0], ctx->sp_ev[ctx->sp_n - 1]);
+    ctx->sp_id[0] = ctx->sp_id[ctx->sp_n - 1];
+    ctx->sp_n = 1;
+}
+void nnd_stage_mark_slow(nnd_ctx *ctx, int id, cudaStream_t st) {
+    if (id < 0 || id >= NND_STAGE_COUNT) id = 0;
+    if (ctx->sp_n > 0 && ctx->sp_id[ctx->sp_n - 1] == id) return;      // same stage continues
+    if (ctx->sp_cap == 0) {
+        ctx->sp_cap = 4096;
+        ctx->sp_ev = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * ctx->sp_cap);
+        ctx->sp_id = (int *)malloc(sizeof(int) * ctx->sp_cap);
+        for (int i = 0; i < ctx->sp_cap; ++i) cudaEventCreate(&ctx->sp_ev[i]);
+    }
+    if (ctx->sp_n == ctx->sp_cap) stage_resolve(ctx);
+    cudaEventRecord(ctx->sp_ev[ctx->sp_n], st);
+    ctx->sp_id[ctx->sp_n] = id;
+    ++ctx->sp_n;
+}
+extern "C" int nnd_stage_profile(nnd_ctx *ctx, int32_t enable) {
+    NND_CHECK(ctx, NND_ERR_INVALID, "nnd_stage_profile: null context");
+    if (!enable && ctx->sp_on) { stage_resolve(ctx); ctx->sp_n = 0; }
+    ctx->sp_on = enable ? 1 : 0;
+    return NND_OK;
+}
+extern "C" int nnd_stage_read(nnd_ctx *ctx, double *out_ms, int32_t reset) {
+    NND_CHECK(ctx && out_ms, NND_ERR_INVALID, "nnd_stage_read: bad args");
+    stage_resolve(ctx);
+    memcpy(out_ms, ctx->sp_ms, sizeof(ctx->sp_ms));
+    if (reset) { memset(ctx->sp_ms, 0, sizeof(ctx->sp_ms)); ctx->sp_n = 0; }
     return NND_OK;
 }
 extern "C" int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset) {
@@ -209,6 +239,7 @@ __global__ void k_make_heap(int32_t *idx, float *dist, uint8_t *flag, int64_t n)
 extern "C" int nnd_make_heap(nnd_ctx *ctx, int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int64_t N, int32_t k,
                              void *stream) {
     NND_CHECK(ctx && heap_idx && heap_dist && heap_flag && N > 0 && k > 0, NND_ERR_INVALID, "nnd_make_heap: bad args");
+    ctx->jb_ppb_max = 0.0;   // a new build: the first local join is planned for the worst case
     k_make_heap<<<(unsigned)cdiv(N * k, 256), 256, 0, (cudaStream_t)stream>>>(heap_idx, heap_dist, heap_flag, N * k);
     NND_LAUNCH(ctx);
     NND_CUDA(cudaGetLastError());
@@ -347,6 +378,7 @@ extern "C" int nnd_init_random(nnd_ctx *ctx, const nnd_problem *P, int64_t *rng_
     uint32_t *need = A.get<uint32_t>(N + 1), *off = A.get<uint32_t>(N + 2);
     uint32_t *tmp = A.get<uint32_t>(nnd_scan_tmp_elems(N + 2));
     NND_CHECK(A.ok, NND_ERR_WORKSPACE, "nnd_init_random: workspace too small");
+    NND_STAGE(ctx, NND_ST_INIT_RANDOM, st);
     k_ir_need<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_idx, k, N, need); NND_LAUNCH(ctx);
     NND_TRY(nnd_exclusive_scan_u32(ctx, need, off, N, tmp, st));
     uint32_t total = 0;
@@ -419,8 +451,10 @@ extern "C" int nnd_deheap_sort(nnd_ctx *ctx, int32_t *idx, float *dist, int64_t 
     size_t smem = (size_t)T * k * 8;
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "deheap_sort: k=%d too large", k);
     NND_CUDA(cudaFuncSetAttribute(k_deheap_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NND_STAGE(ctx, NND_ST_DEHEAP, (cudaStream_t)stream);
     k_deheap_sort<<<(unsigned)cdiv(N, T), T, smem, (cudaStream_t)stream>>>(idx, dist, N, k, correction, out_dist);
     NND_LAUNCH(ctx);
+    NND_STAGE(ctx, NND_ST_OTHER, (cudaStream_t)stream);
     NND_CUDA(cudaGetLastError());
     return NND_OK;
 }

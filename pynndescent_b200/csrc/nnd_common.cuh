@@ -42,12 +42,15 @@ struct nnd_ctx {
     double prof[2][5];
     cudaEvent_t ev0, ev1;
     unsigned long long last_round_rows, last_round_pairs;
+    double jb_ppb_max;        // half-updates per batch of the fullest round since the last plan (0 = unknown): sizes the next plan's rounds
     int64_t row_lo, row_hi;   // sharded build: this process joins / samples candidates only for rows in [row_lo,row_hi)
     void *plan;               // JoinPlan of the sharded round API (k_descent.cu)
     void (*plan_free)(void *);
+    // ---- stage profiler (nnd_stage_profile / nnd_stage_read): events recorded at stage boundaries, resolved lazily
+    int sp_on, sp_n, sp_cap;
+    cudaEvent_t *sp_ev; int *sp_id;
+    double sp_ms[NND_STAGE_COUNT];
     // ---- schedule options (read from the environment by nnd_create; none of them changes any result)
-    int opt_join_pipe;        // NND_JOIN_PIPE=1: persistent warp-specialised local join (k_join_pipe.cu) instead of k_join_batch
-    int opt_pipe_dk, opt_pipe_stages, opt_pipe_ctas;   // NND_PIPE_DK (32|64), NND_PIPE_STAGES (2..6), NND_PIPE_CTAS (per SM, 0 = max)
     int opt_apply_half;       // NND_APPLY_HALF=1: rows with <= 48 records are applied two per warp (k_apply_half)
     int opt_apply_short;      // NND_APPLY_SHORT_SORT=1: k_apply sorts only next_pow2(kept) lanes
     int opt_carveout;         // NND_SMEM_CARVEOUT=1: prefer the maximum shared-memory carveout for the occupancy-by-smem kernels
@@ -57,8 +60,10 @@ struct nnd_ctx {
     int opt_forest_pm;        // NND_FOREST_PM=1: point-major hyperplane pass of the RP forest (k_forest_side_pm<NCH>, k_forest.cu)
     int opt_forest_pm_mb;     // NND_FOREST_PM_MB: ... while the level's hyperplane table is at most this many MB (default 48)
     int opt_rank_scatter;     // NND_RANK_SCATTER=1: joins count targets with fire-and-forget reductions, k_scatter_rank ranks
-    const int32_t *join_order; int64_t join_order_n;   // nnd_set_join_order: row visiting order of the batched local join
 };
+// "from here on the stream's time belongs to stage `id`" (no-op unless profiling is on)
+void nnd_stage_mark_slow(nnd_ctx *ctx, int id, cudaStream_t st);
+#define NND_STAGE(ctx, id, st) do { if ((ctx)->sp_on) nnd_stage_mark_slow((ctx), (id), (st)); } while (0)
 #define NND_JUMP_POW 44
 #define NND_LAUNCH(ctx) ((ctx)->launches++)
 

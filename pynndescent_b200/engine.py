@@ -81,7 +81,8 @@ class Engine:
                        self.heap_idx.data_ptr(), self.heap_dist.data_ptr(), self.heap_flag.data_ptr())
 
     def default_push_capacity(self):
-        return int(min(1 << 28, max(1 << 23, 256 * self.N)))
+        # 56 B of routing workspace per record; 2^29 records (30 GB) keep a 10M-point iteration to a handful of rounds
+        return int(min(1 << 29, max(1 << 23, 256 * self.N)))
 
     def workspace(self, C_, T, cap):
         """One growing scratch buffer shared by all stages (layouts share a common prefix)."""
@@ -263,7 +264,6 @@ class Engine:
                 self.stream.synchronize()
                 t1 = time.perf_counter(); timings[name] = timings.get(name, 0.0) + (t1 - t0); t0 = t1
         self.make_heap()
-        self.set_join_order(None)
         if init_graph is not None:
             # nn_descent :339-350: a supplied graph replaces BOTH the leaf init and init_random
             self.workspace(max(1, max_candidates), n_threads, cap)
@@ -278,9 +278,6 @@ class Engine:
             self.leaf_init_from_array(leaf_array, cap)
         elif tree_rng_states is not None and len(tree_rng_states) > 0:
             lp, lo, n_leaves, max_leaf = self.forest(tree_rng_states, leaf_size, angular, max_depth)
-            if os.environ.get("NND_JOIN_ORDER", "") == "leaf":
-                # schedule only (results are order-independent, include/nnd_b200.h): join rows in the first tree's leaf order
-                self.set_join_order(lp[: self.N].clone())
             lap("forest")
             self.leaf_init(lp, lo, n_leaves, max_leaf, cap)
             del lp, lo
@@ -296,11 +293,6 @@ class Engine:
     # ------------------------------------------------------------------ sharded-build primitives (sharded.py)
     def set_row_range(self, lo, hi):
         check(lib.nnd_set_row_range(self._ctx, int(lo), int(hi)))
-
-    def set_join_order(self, perm):
-        """perm: int32 device tensor holding a permutation of 0..N-1 (kept alive here), or None for ascending rows."""
-        self._join_order = perm
-        check(lib.nnd_set_join_order(self._ctx, _ptr(perm), 0 if perm is None else int(perm.numel())))
 
     def join_prepare(self, newc, oldc, cap):
         C_ = newc.shape[1]
@@ -351,6 +343,18 @@ class Engine:
         check(lib.nnd_profile_read(self._ctx, out, int(bool(reset))))
         keys = ("ms", "launches", "rows", "pairs", "pushes")
         return {"join": dict(zip(keys, list(out)[:5])), "leaf": dict(zip(keys, list(out)[5:]))}
+
+    STAGES = ("other", "forest_hyper", "forest_side", "forest_part", "leaf_dist", "leaf_push", "init_random", "cand_fill",
+              "cand_select", "join_prep", "join", "scatter", "apply", "deheap", "exchange", "spare")
+
+    def stage_profile(self, enable=True):
+        """CUDA-event stage timers inside the library (include/nnd_b200.h NND_ST_*)."""
+        check(lib.nnd_stage_profile(self._ctx, int(bool(enable))))
+
+    def stage_ms(self, reset=True):
+        out = (C.c_double * len(self.STAGES))()
+        check(lib.nnd_stage_read(self._ctx, out, int(bool(reset))))
+        return {n: float(v) for n, v in zip(self.STAGES, out) if n != "spare"}
 
     # ------------------------------------------------------------------ small primitives
     def rng_stream(self, state, start, count, as_float):

@@ -280,7 +280,6 @@ class NNDescent:
         self.timings = {"h2d_setup": time.perf_counter() - t0}
         cap = a["push_capacity"] or eng.default_push_capacity()
         eng.workspace(a["eff_C"], self.emulated_threads, cap)
-        eng.set_join_order(None)
         # :2511-2514 make_heap + init_from_neighbor_graph: the old rows in column order; -1 entries push nothing
         eng.init_from_graph(ns, None, cap)
         eng.heap_flag.zero_()                  # init_from_neighbor_graph pushes with flag 0 (the warm-start replay sets 1)

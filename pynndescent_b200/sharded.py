@@ -79,9 +79,6 @@ class ShardedBuilder:
             dist.broadcast(pts_all[t], src=owner)
             dist.broadcast(ov, src=owner)
         self.comm_bytes += pts_all.numel() * 4 + offs_all.numel() * 8
-        if os.environ.get("NND_JOIN_ORDER", "") == "leaf":
-            # schedule only (include/nnd_b200.h nnd_set_join_order): own rows are joined in the first tree's leaf order
-            e.set_join_order(pts_all[0].clone())
         offs_h = offs_all.cpu().numpy()
         # rank r takes, in every tree, the leaves whose first position lies in [r*N/world, (r+1)*N/world)
         plan = []
@@ -272,7 +269,6 @@ class ShardedBuilder:
                 e.stream.synchronize()
                 t1 = time.perf_counter(); timings[name] = timings.get(name, 0.0) + (t1 - t0); t0 = t1
         e.make_heap()
-        e.set_join_order(None)
         if tree_states is not None and len(tree_states) > 0:
             self.forest_and_leaf_init(np.asarray(tree_states), leaf_size, angular, max_depth, cap)
         lap("forest+leaf_init")

@@ -19,33 +19,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CONFIGS = {
     "default": {},
-    "rank": {"NND_RANK_SCATTER": "1"},
-    "leaf": {"NND_JOIN_ORDER": "leaf"},
-    "leaf+rank": {"NND_JOIN_ORDER": "leaf", "NND_RANK_SCATTER": "1"},
     "applyshort": {"NND_APPLY_SHORT_SORT": "1"},
     "applyhalf": {"NND_APPLY_HALF": "1"},
-    "carveout": {"NND_SMEM_CARVEOUT": "1"},
-    "leafsplit": {"NND_LEAF_SPLIT": "1"},
-    "leafsplit+carveout": {"NND_LEAF_SPLIT": "1", "NND_SMEM_CARVEOUT": "1"},
     "candskip": {"NND_CAND_SKIP": "1"},
     "candkeys": {"NND_CAND_KEYS": "1"},
     "candtile": {"NND_CAND_KEYS": "2"},
     "candskip+tile": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2"},
-    "jbdk16": {"NND_JB_DK": "16"},
-    "jbdk64": {"NND_JB_DK": "64"},
-    "forestpm": {"NND_FOREST_PM": "1"},
-    "forestpm16": {"NND_FOREST_PM": "1", "NND_FOREST_PM_MB": "16"},
-    "forestpm96": {"NND_FOREST_PM": "1", "NND_FOREST_PM_MB": "96"},
-    "pipe": {"NND_JOIN_PIPE": "1"},
-    "pipe+rank": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1"},
-    "pipe+rank+leaf": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf"},
-    "all": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_JOIN_ORDER": "leaf", "NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2", "NND_LEAF_SPLIT": "1", "NND_SMEM_CARVEOUT": "1", "NND_APPLY_SHORT_SORT": "1", "NND_APPLY_HALF": "1", "NND_FOREST_PM": "1"},
-    "pipe-s3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "3"},
-    "pipe-s2c3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "2", "NND_PIPE_CTAS": "3"},
-    "pipe-s6": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_STAGES": "6"},
-    "pipe-dk64s2": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_DK": "64", "NND_PIPE_STAGES": "2"},
-    "pipe-dk128": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_DK": "128"},
-    "pipe-dk64s3": {"NND_JOIN_PIPE": "1", "NND_RANK_SCATTER": "1", "NND_PIPE_DK": "64", "NND_PIPE_STAGES": "3"},
+    "candskip+keys": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "1"},
+    "forestpm48": {"NND_FOREST_PM_MB": "48"},
+    "forestpm200": {"NND_FOREST_PM_MB": "200"},
+    "forestpm1000": {"NND_FOREST_PM_MB": "1000"},
+    "noforestpm": {"NND_FOREST_PM": "0"},
+    "norank": {"NND_RANK_SCATTER": "0"},
+    "noleafsplit": {"NND_LEAF_SPLIT": "0"},
+    "nocarveout": {"NND_SMEM_CARVEOUT": "0"},
+    "round1-defaults": {"NND_RANK_SCATTER": "0", "NND_LEAF_SPLIT": "0", "NND_SMEM_CARVEOUT": "0", "NND_FOREST_PM": "0"},
 }
 
 
@@ -63,23 +51,24 @@ def child(n, d, k, metric, reps, out_path):
     n_trees = max(3, min(12, int(round(2.0 * np.log10(n))))); n_iters = max(5, int(round(np.log2(n))))
     leaf_size = max(60, min(256, 5 * k)); C_ = min(60, k)
     eng = Engine(X, metric_id, k)
+    eng.stage_profile(True)
     res = {}
     for rep in range(reps + 1):            # first build = warm-up
         rs = np.random.RandomState(42)
         rng = rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, 3).astype(np.int64); rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, 3)
         trees = rs.randint(-2 ** 31 + 1, 2 ** 31 - 1, size=(n_trees, 3)).astype(np.int64)
-        eng.profile(reset=True)
+        eng.profile(reset=True); eng.stage_ms(reset=True)
         stage = {}
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         idx_t, dist_t, iters, c_hist, stats = eng.build(rng, trees, leaf_size, angular, C_, 8, n_iters, 0.001, dev_corr, timings=stage)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3
-        prof = eng.profile(reset=True)
+        prof = eng.profile(reset=True); dev = eng.stage_ms(reset=True)
         gi, gd = idx_t.cpu().numpy(), dist_t.cpu().numpy()
         res = {"build_ms": ms, "join_ms": prof["join"]["ms"], "join_launches": prof["join"]["launches"],
                "leaf_ms": prof["leaf"]["ms"], "iters": iters, "c_hist": list(map(int, c_hist)),
-               "stage_ms": {kk: round(vv * 1e3, 2) for kk, vv in stage.items()},
+               "stage_ms": {kk: round(vv * 1e3, 2) for kk, vv in stage.items()}, "dev_ms": {kk: round(vv, 2) for kk, vv in dev.items() if vv > 0.005},
                "idx_sha": hashlib.sha256(gi.tobytes()).hexdigest(), "dist_sha": hashlib.sha256(gd.tobytes()).hexdigest()}
     json.dump(res, open(out_path, "w"))
 
@@ -120,7 +109,7 @@ def main():
             base = base or r
         same = (r["idx_sha"] == base["idx_sha"], r["dist_sha"] == base["dist_sha"], r["c_hist"] == base["c_hist"])
         print(f"{name:16s} build {r['build_ms']:8.1f} ms  join {r['join_ms']:7.2f} ms ({int(r['join_launches'])} launches)  leaf {r['leaf_ms']:6.2f} ms  "
-              f"bit-equal idx/dist/c: {same[0]}/{same[1]}/{same[2]}  stages {r['stage_ms']}", flush=True)
+              f"bit-equal idx/dist/c: {same[0]}/{same[1]}/{same[2]}  stages {r['stage_ms']}\n{'':17s}device events {r.get('dev_ms')}", flush=True)
         r.update({"config": name, "status": "ok", "equal_to_default": all(same)})
         rows.append(r)
     # ---- compose the winners: every switch set that is bit-equal and at least 1 % faster than the default on its own goes

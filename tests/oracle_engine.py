@@ -39,9 +39,6 @@ class OracleEngine:
     def workspace(self, C_, T, cap):
         return None
 
-    def set_join_order(self, perm):
-        assert perm is None
-
     def launch_count(self):
         return 0
 

@@ -52,10 +52,6 @@ def emu_lib(tmp_path_factory):
     desc = open(os.path.join(CSRC, "k_descent.cu")).read()
     batch = _between(desc, "// prepass 1: per row -> active flag", "// ------------------------------------------------------------------ routing",
                      "k_jb_* / k_join_batch")
-    pipe = open(os.path.join(CSRC, "k_join_pipe.cu")).read()
-    pipe_defs = _between(pipe, "#define JP_CWARPS", "__device__ __forceinline__ void mbar_arrive", "k_join_pipe's constants")
-    pipe = pipe_defs + _between(pipe, "// ------------------------------------------------------------------------------------------------ descriptor prepass",
-                    "// ------------------------------------------------------------------------------------------------ host", "k_jp_meta / k_join_pipe")
     cand = open(os.path.join(CSRC, "k_cand.cu")).read()
     cand = _between(cand, "__global__ void k_cand_count", "__global__ void k_rng_table", "the candidate kernels")
     sg = open(os.path.join(CSRC, "k_search_graph.cu")).read()
@@ -81,14 +77,14 @@ def emu_lib(tmp_path_factory):
     hub = _between(prep, "// ------------------------------------------------------------------ canonical warp reductions (as in k_forest.cu)",
                    'extern "C" int nnd_hub_tree_workspace_bytes', "the hub-tree kernels")
     hub = hub.replace("extern __shared__ float s_t[];", "float *s_t = (float *)emu::dyn_smem();")
-    kernels = (join + "\n" + batch + "\n" + pipe + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
+    kernels = (join + "\n" + batch + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
                "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf + "\n#define EMU_WITH_FOREST 1\n" + forest +
                "\n#define EMU_WITH_QUERY 1\n" + query + "\n#define EMU_WITH_MISC 1\n" + misc +
                "\n#define EMU_WITH_HUB 1\n" + hub)
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 14 and "extern __shared__" not in kernels
+    assert n_ext == 13 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -218,40 +214,14 @@ def test_emulator_reproduces_the_hardware_verified_kernel(emu_lib, cases, name):
     _check(cases[name], _run(emu_lib, cases[name], kernel=0))
 
 
-@pytest.mark.parametrize("name", ["euclid128", "cosine72", "cosine8"])
-def test_batched_join_with_16_float_chunks(emu_lib, cases, name):
-    """NND_JB_DK=16 (default 32): the same kernel with half-size staged chunks -- 8 chunks for d = 128, a short last chunk for
-    d = 72, a single 8-float chunk for the padded d = 7 rows."""
-    _check(cases[name], _run(emu_lib, cases[name], kernel=0, dk=16))
-
-
-@pytest.mark.parametrize("name,dk,nst,grid", [("euclid40", 32, 4, 3), ("euclid40", 32, 2, 1), ("euclid128", 32, 3, 2),
-                                             ("euclid128", 128, 2, 4), ("cosine72", 64, 2, 3),
-                                             ("euclid24_k30", 32, 4, 3), ("euclid24_k30", 32, 2, 200),
-                                             ("euclid16_tiny", 64, 2, 8), ("cosine8", 32, 3, 2), ("inner40", 32, 3, 2)])
-def test_k_join_pipe_equals_oracle(emu_lib, cases, name, dk, nst, grid):
-    _check(cases[name], _run(emu_lib, cases[name], kernel=1, dk=dk, nst=nst, grid=grid))
-
-
-def test_rank_scatter_red_path_and_join_order(emu_lib, cases):
+def test_rank_scatter_red_path(emu_lib, cases):
     case = cases["euclid40"]
-    perm = np.random.RandomState(9).permutation(case.n).astype(np.int32)
-    for kernel in (0, 1):
-        _check(case, _run(emu_lib, case, kernel=kernel, rank_scatter=1), rank_scatter=True)
-        r = _run(emu_lib, case, kernel=kernel, order=perm)
-        _check(case, r)                                                     # any visiting order: identical records
-
-
-def test_pipe_survives_push_list_overflow(emu_lib, cases):
-    """The persistent kernel must keep its handshakes going when the push list is full (the host then splits the round)."""
-    case = cases["euclid40"]
-    r = _run(emu_lib, case, kernel=1, capacity=len(case.expected) // 3)
-    assert r["overflow"] == 1
+    _check(case, _run(emu_lib, case, kernel=0, rank_scatter=1), rank_scatter=True)
 
 
 def test_cases_are_not_trivial(emu_lib, cases):
     for name, case in cases.items():
-        r = _run(emu_lib, case, kernel=1, grid=2)
+        r = _run(emu_lib, case, kernel=0, grid=2)
         if case.n >= 150:
             assert r["n_batches"] >= 12 and r["n_out"] >= 2000 and r["n_active"] > case.n // 4, (name, r["n_batches"], r["n_out"], r["n_active"])
         print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
@@ -383,7 +353,7 @@ def test_candidate_kernels_row_sharded(emu_lib, skip):
         orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
 
 
-@pytest.mark.parametrize("kernel,rank_scatter,leaf_order,short_sort", [(0, 0, False, 0), (0, 1, False, 1), (0, 0, False, 2), (1, 1, True, 3)])
+@pytest.mark.parametrize("kernel,rank_scatter,leaf_order,short_sort", [(0, 0, False, 0), (0, 1, False, 1), (0, 0, False, 2), (0, 1, False, 3)])
 def test_whole_iterations_match_the_oracle_heaps(emu_lib, kernel, rank_scatter, leaf_order, short_sort):
     """Three NN-descent iterations: candidates from the oracle, then join -> scatter -> apply under the emulator; after every
     iteration the heaps (indices, distances, flags, layout) and the accepted-push count must equal the oracle's

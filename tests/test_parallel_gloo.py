@@ -171,7 +171,6 @@ class OracleShardEngine:
         self.N, self.k, self.device = N, K, torch.device("cpu")
         self.heap_idx = self.heap_dist = self.heap_flag = None
         self.calls = []
-    def set_join_order(self, perm): pass
     def forest(self, tree_states, leaf_size, angular, max_depth):
         la = orc.forest_leaf_array(X, np.ascontiguousarray(tree_states, np.int64), leaf_size, angular, max_depth, "level")
         pts, offs, ml = csr(la)
@@ -266,7 +265,6 @@ class OracleShardEngine:
     def heap(self): return (self.heap_idx.numpy(), self.heap_dist.numpy(), self.heap_flag.numpy())
     def default_push_capacity(self): return 1 << 20
     def workspace(self, C_, T_, cap): return None
-    def set_join_order(self, perm): pass
     def make_heap(self):
         a, b, c = orc.make_heap(N, K)
         self.heap_idx.copy_(torch.from_numpy(a)); self.heap_dist.copy_(torch.from_numpy(b)); self.heap_flag.copy_(torch.from_numpy(c))
