@@ -177,6 +177,26 @@ NND_API int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int
  * Every process holds X and the whole heap; it samples candidates and joins only rows [lo,hi), exchanges the
  * half-updates with the owners of their target rows and applies what it receives.                            */
 NND_API int nnd_set_row_range(nnd_ctx *ctx, int64_t lo, int64_t hi);
+/* the local join filters with thr[v] = heap_dist[v, 0] of ALL vertices (utils.py:633, pynndescent_.py:246); a process that owns
+ * only a row range of the heap supplies the snapshot itself (N floats in device memory, all-gathered from the owners; NULL =
+ * snapshot the local heap as on one GPU).  Stale / larger thresholds only admit a superset of pushes (utils.py:484 re-checks).  */
+NND_API int nnd_set_thresholds(nnd_ctx *ctx, const float *thr);
+/* new_build_candidates (utils.py:221-320) for the own rows only, in three steps around two collectives of the caller:
+ *  1. nnd_cand_local_counts: out_host[5T + 1 + R] = for every stream n this process's partial prefixes {prR_n(s_n), prV(s_n),
+ *     prV(e_n), prR_n(e_n), total R_n}, then the total of valid edges, then the number of reverse-edge records per owner process;
+ *  2. (caller: all-gather of the tables) nnd_cand_export: glob_host[6T] = per stream {R_s, V_s, V_e, R_e summed over all
+ *     processes, sum of the lower ranks' R_n totals, sum of the lower ranks' valid totals}; forward priorities stay local, one
+ *     12-byte record {target, scan key, priority} per reverse edge goes to the bucket of the target's owner
+ *     (records_out + bucket_off_host[r] records);
+ *  3. (caller: all-to-all-v of the buckets) nnd_cand_import_select: received records -> candidate lists of the own rows, sampled
+ *     flags cleared.  Identical lists to nnd_build_candidates for any number of processes.                               */
+NND_API int nnd_cand_local_counts(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int32_t T, int32_t R, int64_t owner_block, void *ws,
+                          size_t ws_bytes, int64_t *out_host, void *stream);
+NND_API int nnd_cand_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T, int32_t tables_valid,
+                    int32_t R, int64_t owner_block, const int64_t *glob_host, const int64_t *bucket_off_host, void *records_out,
+                    void *ws, size_t ws_bytes, void *stream);
+NND_API int nnd_cand_import_select(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int32_t T, const void *records, int64_t n,
+                           int32_t *new_cand, int32_t *old_cand, void *ws, size_t ws_bytes, void *stream);
 /* prepass of one process_candidates call restricted to the row range; n_rounds_host = routing rounds needed */
 NND_API int nnd_join_prepare(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int32_t *new_cand, const int32_t *old_cand,
                              int64_t push_capacity, void *ws, size_t ws_bytes, int32_t *n_rounds_host, void *stream);

@@ -15,6 +15,7 @@
 //   k_cand_select: one warp per vertex sorts its reverse edges by scan position, merges them with
 //                  its forward edges and replays checked_heap_push in scan order; clears flags
 #include "nnd_common.cuh"
+#include <vector>
 
 struct CandWs {
     uint32_t *cnt;      // [(T+1)*N] per-stream per-row counts; last block = valid counts
@@ -28,6 +29,8 @@ struct CandWs {
     uint32_t *scan_tmp;
     int64_t table_len;
     uint8_t *act;       // [N+1] NND_CAND_SKIP: 1 = the vertex touches a new-flagged edge (= will have new candidates)
+    unsigned long long *scal;   // [4096] small tables of the sharded path: [0,64) record counts / bucket offsets, [64,128) cursors,
+                                // [128,2048) this process's count table, [2048,..) the global count table (u32)
 };
 
 static int64_t cand_table_len(int64_t N, int k) { return N * (int64_t)k; }
@@ -47,6 +50,7 @@ static int carve_cand_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, int
     W->table = A.get<float>((size_t)T * W->table_len);
     W->scan_tmp = A.get<uint32_t>(nnd_scan_tmp_elems((int64_t)(T + 1) * Nb + 2));
     W->act = A.get<uint8_t>(Nb + 1);
+    W->scal = A.get<unsigned long long>(4096);
     if (need) *need = A.off;
     return A.ok ? NND_OK : NND_ERR_WORKSPACE;
 }
@@ -433,37 +437,11 @@ extern "C" int nnd_rng_stream(nnd_ctx *ctx, const int64_t *state_host, int64_t s
     return nnd_rng_table_launch(ctx, state_host, start, count, as_float, out, (cudaStream_t)stream);
 }
 
-extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host,
-                                    int32_t T, int32_t tables_valid, int32_t *new_cand, int32_t *old_cand, void *ws,
-                                    size_t ws_bytes, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    NND_CHECK(ctx && P && rng_state_host && new_cand && old_cand, NND_ERR_INVALID, "nnd_build_candidates: bad args");
-    NND_CHECK(T >= 1 && T <= 256 && C >= 1 && C <= 256, NND_ERR_INVALID, "nnd_build_candidates: T=%d C=%d out of range", T, C);
+// heap selection + flag clearing for the vertices of [ctx->row_lo, ctx->row_hi) from the routed reverse edges (W.rev) and the
+// forward priorities (W.fprio): the tail of nnd_build_candidates, shared with the sharded import path
+static int launch_cand_select(nnd_ctx *ctx, const nnd_problem *P, int32_t C, CandWs &W, int32_t *new_cand, int32_t *old_cand,
+                              uint8_t *act, cudaStream_t st) {
     const int64_t N = P->N; const int k = P->k;
-    NND_CHECK((double)N * k * 2 < 4.0e9, NND_ERR_UNSUPPORTED, "N*k too large for 32-bit edge keys");
-    CandWs W;
-    NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
-              "nnd_build_candidates: workspace too small");
-    const int64_t B = N / T + 1;
-    NND_STAGE(ctx, NND_ST_CAND_FILL, st);
-    // the T priority streams: constant across iterations (utils.py:262 copies rng_state, never advances it)
-    if (!tables_valid) {
-        for (int n = 0; n < T; ++n) {
-            int64_t s[3] = {rng_state_host[0] + n, rng_state_host[1] + n, rng_state_host[2] + n};
-            NND_TRY(nnd_rng_table_launch(ctx, s, 0, W.table_len, 1, W.table + (size_t)n * W.table_len, st));
-        }
-    }
-    NND_CUDA(cudaMemsetAsync(W.indeg, 0, sizeof(uint32_t) * (N + 1), st));
-    NND_CUDA(cudaMemsetAsync(W.cursor, 0, sizeof(uint32_t) * (N + 1), st));
-    uint8_t *act = ctx->opt_cand_skip ? W.act : nullptr;
-    if (act) NND_CUDA(cudaMemsetAsync(act, 0, (size_t)N + 1, st));
-    k_cand_count<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.cnt, W.indeg, act); NND_LAUNCH(ctx);
-    NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
-    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
-    k_cand_fill<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.pre, W.table, W.table_len,
-                                                       W.revoff, W.cursor, W.rev, W.fprio, ctx->row_lo, ctx->row_hi, act);
-    NND_LAUNCH(ctx);
-    NND_STAGE(ctx, NND_ST_CAND_SELECT, st);
     const size_t hstride = ((size_t)C * 16 + 15) & ~size_t(15);
     size_t smem = (size_t)SEL_WARPS * NND_SEG_SMEM * 8 + (size_t)SEL_WARPS * hstride;
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
@@ -497,6 +475,265 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
     k_cand_select<<<(unsigned)cdiv(N, SEL_WARPS), SEL_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
                                                                              W.revoff, W.rev, W.fprio, new_cand, old_cand, use_small, ctx->row_lo, ctx->row_hi, act);
     NND_LAUNCH(ctx);
+    return NND_OK;
+}
+
+extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host,
+                                    int32_t T, int32_t tables_valid, int32_t *new_cand, int32_t *old_cand, void *ws,
+                                    size_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && rng_state_host && new_cand && old_cand, NND_ERR_INVALID, "nnd_build_candidates: bad args");
+    NND_CHECK(T >= 1 && T <= 256 && C >= 1 && C <= 256, NND_ERR_INVALID, "nnd_build_candidates: T=%d C=%d out of range", T, C);
+    const int64_t N = P->N; const int k = P->k;
+    NND_CHECK((double)N * k * 2 < 4.0e9, NND_ERR_UNSUPPORTED, "N*k too large for 32-bit edge keys");
+    CandWs W;
+    NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE,
+              "nnd_build_candidates: workspace too small");
+    const int64_t B = N / T + 1;
+    NND_STAGE(ctx, NND_ST_CAND_FILL, st);
+    // the T priority streams: constant across iterations (utils.py:262 copies rng_state, never advances it)
+    if (!tables_valid) {
+        for (int n = 0; n < T; ++n) {
+            int64_t s[3] = {rng_state_host[0] + n, rng_state_host[1] + n, rng_state_host[2] + n};
+            NND_TRY(nnd_rng_table_launch(ctx, s, 0, W.table_len, 1, W.table + (size_t)n * W.table_len, st));
+        }
+    }
+    NND_CUDA(cudaMemsetAsync(W.indeg, 0, sizeof(uint32_t) * (N + 1), st));
+    NND_CUDA(cudaMemsetAsync(W.cursor, 0, sizeof(uint32_t) * (N + 1), st));
+    uint8_t *act = ctx->opt_cand_skip ? W.act : nullptr;
+    if (act) NND_CUDA(cudaMemsetAsync(act, 0, (size_t)N + 1, st));
+    k_cand_count<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.cnt, W.indeg, act); NND_LAUNCH(ctx);
+    NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
+    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
+    k_cand_fill<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, W.pre, W.table, W.table_len,
+                                                       W.revoff, W.cursor, W.rev, W.fprio, ctx->row_lo, ctx->row_hi, act);
+    NND_LAUNCH(ctx);
+    NND_STAGE(ctx, NND_ST_CAND_SELECT, st);
+    NND_TRY(launch_cand_select(ctx, P, C, W, new_cand, old_cand, act, st));
+    NND_STAGE(ctx, NND_ST_OTHER, st);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+// =====================================================================================================================
+// Row-sharded candidate build (one process per GPU).  A process samples candidates for its own rows
+// [row_lo, row_hi) only and SCANS only its own rows' edges (the reference's threads each scan all N*k edges, utils.py:261-306;
+// so did round 1's sharded build).  What crosses process boundaries:
+//   * a small table of per-stream counts (all-gather by the caller): the draw index of an edge in stream n is the number of
+//     earlier edges, in (row, column) order, that touch R_n -- a prefix over ALL rows, i.e. sum over lower ranks' totals + a local
+//     prefix; the four prefixes at the stream's own range boundaries s_n / e_n are sums over the processes' partial prefixes;
+//   * the reverse-edge proposals (target, scan key, priority) of edges whose target row lives elsewhere (one all-to-all-v).
+// Results are identical to nnd_build_candidates for any number of processes (closed-form draw indices, ordered replay).
+// =====================================================================================================================
+struct __align__(4) CandRec { int32_t tgt; uint32_t key; float prio; };   // 12 bytes on the wire
+
+// per own row: #valid edges, #edges into each R_n (cnt is zero elsewhere: memset by the host), records per destination process
+__global__ void k_cand_count_sh(const int32_t *ind, int k, int64_t N, int T, int64_t B, int64_t lo, int64_t hi, uint32_t *cnt,
+                                int64_t owner_block, int R, unsigned long long *dest_cnt) {
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < hi;
+    const int lane = threadIdx.x & 31;
+    uint32_t valid = 0;
+    if (on)
+        for (int n = 0; n < T; ++n) {
+            const int64_t bs = (int64_t)n * B, be = bs + B;
+            uint32_t c = 0;
+            for (int j = 0; j < k; ++j) { int32_t x = ind[i * k + j]; c += (x >= bs && x < be && x >= 0); }
+            cnt[(size_t)n * N + i] = c;
+        }
+    for (int j = 0; j < k; ++j) {
+        int o = -1;
+        if (on) { const int32_t x = ind[i * k + j]; if (x >= 0) { ++valid; o = (int)(x / owner_block); if (o >= R) o = R - 1; } }
+        const unsigned mk = __match_any_sync(0xffffffffu, o);
+        if (o >= 0 && lane == __ffs(mk) - 1) atomicAdd(&dest_cnt[o], (unsigned long long)__popc(mk));
+    }
+    if (on) cnt[(size_t)T * N + i] = valid;
+}
+
+// out[5n..5n+4] = this process's partial {prR_n(s_n), prV(s_n), prV(e_n), prR_n(e_n), total R_n}; out[5T] = total valid
+__global__ void k_cand_locals(const uint32_t *pre, int64_t N, int T, int64_t B, long long *out) {
+    const int n = threadIdx.x;
+    const uint32_t *PV = pre + (size_t)T * N;
+    const uint32_t baseV = PV[0], endV = pre[(size_t)(T + 1) * N];
+    if (n < T) {
+        const uint32_t *PR = pre + (size_t)n * N;
+        const uint32_t baseR = PR[0], endR = pre[(size_t)(n + 1) * N];
+        const int64_t s = (int64_t)n * B < N ? (int64_t)n * B : N, e = s + B < N ? s + B : N;
+        out[5 * n + 0] = (long long)((s < N ? PR[s] : endR) - baseR);
+        out[5 * n + 1] = (long long)((s < N ? PV[s] : endV) - baseV);
+        out[5 * n + 2] = (long long)((e < N ? PV[e] : endV) - baseV);
+        out[5 * n + 3] = (long long)((e < N ? PR[e] : endR) - baseR);
+        out[5 * n + 4] = (long long)(endR - baseR);
+    }
+    if (n == 0) out[5 * T] = (long long)(endV - baseV);
+}
+
+// glob[6n..6n+5] = {R_s, V_s, V_e, R_e (global), baseR_n, baseV (sums over the lower ranks)}
+__device__ __forceinline__ uint32_t draw_index_sh(const uint32_t *pre, const uint32_t *glob, int64_t N, int T, int64_t B, int n, int64_t i,
+                                                  uint32_t within_valid, uint32_t within_n) {
+    const uint32_t *PR = pre + (size_t)n * N, *PV = pre + (size_t)T * N;
+    const uint32_t *G = glob + 6 * n;
+    const int64_t s = (int64_t)n * B, e = s + B < N ? s + B : N;
+    const uint32_t prR = G[4] + (PR[i] - PR[0]), prV = G[5] + (PV[i] - PV[0]);   // i is an own row: local prefix + lower ranks' totals
+    if (i < s) return prR + within_n;
+    if (i < e) return G[0] + (prV - G[1]) + within_valid;
+    return G[0] + (G[2] - G[1]) + (prR - G[3]) + within_n;
+}
+
+// forward priorities of the own rows + one record per reverse edge, appended to the bucket of the target's owner
+__global__ void k_cand_export(const int32_t *ind, const uint8_t *flags, int k, int64_t N, int T, int64_t B, int64_t lo, int64_t hi,
+                              const uint32_t *pre, const uint32_t *glob, const float *table, int64_t table_len, float *fprio,
+                              int64_t owner_block, int R, const unsigned long long *bucket_off, unsigned long long *bucket_cur,
+                              CandRec *out) {
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < hi;
+    const int lane = threadIdx.x & 31;
+    const int ni = on ? (int)(i / B) : 0;
+    uint32_t wv = 0;
+    for (int j = 0; j < k; ++j) {
+        int o = -1; int32_t x = -1; float pr = 0.f;
+        if (on) {
+            x = ind[i * k + j];
+            if (x < 0) fprio[i * k + j] = 0.f;
+            else {
+                const int nx = (int)(x / B);
+                const uint32_t df = draw_index_sh(pre, glob, N, T, B, ni, i, wv, 0);
+                const float pf = table[(size_t)ni * table_len + df];
+                fprio[i * k + j] = pf;
+                pr = pf;
+                if (nx != ni) {
+                    uint32_t wn = 0;
+                    const int64_t bs = (int64_t)nx * B, be = bs + B;
+                    for (int jj = 0; jj < j; ++jj) { int32_t y = ind[i * k + jj]; wn += (y >= bs && y < be); }
+                    pr = table[(size_t)nx * table_len + draw_index_sh(pre, glob, N, T, B, nx, i, 0, wn)];
+                }
+                o = (int)(x / owner_block); if (o >= R) o = R - 1;
+                ++wv;
+            }
+        }
+        const unsigned mk = __match_any_sync(0xffffffffu, o);
+        const int leader = __ffs(mk) - 1;
+        unsigned long long base = 0;
+        if (o >= 0 && lane == leader) base = atomicAdd(&bucket_cur[o], (unsigned long long)__popc(mk));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (o >= 0) {
+            CandRec r; r.tgt = x; r.key = (uint32_t)(((unsigned long long)(i * k + j) << 1) | (unsigned long long)(flags[i * k + j] != 0)); r.prio = pr;
+            out[bucket_off[o] + base + __popc(mk & ((1u << lane) - 1))] = r;
+        }
+    }
+}
+
+__global__ void k_cand_import_count(const CandRec *in, unsigned long long n, int64_t lo, int64_t hi, uint32_t *indeg, unsigned long long *bad) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t t = in[i].tgt;
+    if (t < lo || t >= hi) { atomicAdd(bad, 1ULL); return; }
+    atomicAdd(&indeg[t], 1u);
+}
+__global__ void k_cand_import_scatter(const CandRec *in, unsigned long long n, int64_t lo, int64_t hi, const uint32_t *revoff, uint32_t *cursor,
+                                      unsigned long long *rev) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CandRec r = in[i];
+    if (r.tgt < lo || r.tgt >= hi) return;
+    const uint32_t slot = atomicAdd(&cursor[r.tgt], 1u);
+    rev[(size_t)revoff[r.tgt] + slot] = ((unsigned long long)r.key << 32) | (unsigned long long)__float_as_uint(r.prio);
+}
+
+static int cand_range(const nnd_ctx *ctx, int64_t N, int64_t *lo, int64_t *hi) {
+    *lo = ctx->row_lo > 0 ? (ctx->row_lo < N ? ctx->row_lo : N) : 0;
+    *hi = ctx->row_hi < N ? (ctx->row_hi > *lo ? ctx->row_hi : *lo) : N;
+    return NND_OK;
+}
+
+extern "C" int nnd_cand_local_counts(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int32_t T, int32_t R, int64_t owner_block,
+                                     void *ws, size_t ws_bytes, int64_t *out_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && out_host && T >= 1 && T <= 256 && R >= 1 && R <= 64 && owner_block > 0, NND_ERR_INVALID, "nnd_cand_local_counts: bad args");
+    const int64_t N = P->N; const int k = P->k;
+    NND_CHECK((double)N * k * 2 < 4.0e9, NND_ERR_UNSUPPORTED, "N*k too large for 32-bit edge keys");
+    CandWs W;
+    NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE, "nnd_cand_local_counts: workspace too small");
+    int64_t lo, hi; cand_range(ctx, N, &lo, &hi);
+    const int64_t B = N / T + 1;
+    NND_STAGE(ctx, NND_ST_CAND_FILL, st);
+    unsigned long long *dest = W.scal;                                         // [R] record counts
+    NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (size_t)(T + 1) * N, st));
+    NND_CUDA(cudaMemsetAsync(dest, 0, sizeof(unsigned long long) * 128, st));
+    if (hi > lo) { k_cand_count_sh<<<(unsigned)cdiv(hi - lo, 128), 128, 0, st>>>(P->heap_idx, k, N, T, B, lo, hi, W.cnt, owner_block, R, dest); NND_LAUNCH(ctx); }
+    NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
+    long long *loc = (long long *)(W.scal + 128);                               // [5T + 1]
+    k_cand_locals<<<1, 256, 0, st>>>(W.pre, N, T, B, loc); NND_LAUNCH(ctx);
+    NND_CUDA(cudaMemcpyAsync(out_host, loc, sizeof(long long) * (5 * T + 1), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaMemcpyAsync(out_host + 5 * T + 1, dest, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    NND_STAGE(ctx, NND_ST_OTHER, st);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+extern "C" int nnd_cand_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T, int32_t tables_valid,
+                               int32_t R, int64_t owner_block, const int64_t *glob_host, const int64_t *bucket_off_host, void *records_out,
+                               void *ws, size_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && rng_state_host && glob_host && bucket_off_host && T >= 1 && T <= 256 && R >= 1 && R <= 64 && owner_block > 0,
+              NND_ERR_INVALID, "nnd_cand_export: bad args");
+    const int64_t N = P->N; const int k = P->k;
+    CandWs W;
+    NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE, "nnd_cand_export: workspace too small");
+    int64_t lo, hi; cand_range(ctx, N, &lo, &hi);
+    const int64_t B = N / T + 1;
+    NND_STAGE(ctx, NND_ST_CAND_FILL, st);
+    if (!tables_valid) {
+        for (int n = 0; n < T; ++n) {
+            int64_t s[3] = {rng_state_host[0] + n, rng_state_host[1] + n, rng_state_host[2] + n};
+            NND_TRY(nnd_rng_table_launch(ctx, s, 0, W.table_len, 1, W.table + (size_t)n * W.table_len, st));
+        }
+    }
+    // upload {glob[6T] as u32, bucket offsets[R], zeroed cursors[R]} into the scalar area
+    unsigned long long *dest = W.scal;
+    std::vector<uint32_t> hg((size_t)6 * T);
+    for (int q = 0; q < 6 * T; ++q) { NND_CHECK(glob_host[q] >= 0 && glob_host[q] < (1LL << 32), NND_ERR_INVALID, "nnd_cand_export: count table out of range"); hg[q] = (uint32_t)glob_host[q]; }
+    std::vector<unsigned long long> hb((size_t)2 * R, 0ULL);
+    for (int r = 0; r < R; ++r) hb[r] = (unsigned long long)bucket_off_host[r];
+    uint32_t *dglob = (uint32_t *)(W.scal + 2048);
+    NND_CUDA(cudaMemcpyAsync(dglob, hg.data(), sizeof(uint32_t) * hg.size(), cudaMemcpyHostToDevice, st));
+    NND_CUDA(cudaMemcpyAsync(dest, hb.data(), sizeof(unsigned long long) * hb.size(), cudaMemcpyHostToDevice, st));
+    NND_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+    if (hi > lo) {
+        NND_CHECK(records_out, NND_ERR_INVALID, "nnd_cand_export: records_out is null");
+        k_cand_export<<<(unsigned)cdiv(hi - lo, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, lo, hi, W.pre, dglob, W.table, W.table_len,
+                                                                W.fprio, owner_block, R, dest, dest + R, (CandRec *)records_out);
+        NND_LAUNCH(ctx);
+    }
+    NND_STAGE(ctx, NND_ST_OTHER, st);
+    NND_CUDA(cudaGetLastError());
+    return NND_OK;
+}
+
+extern "C" int nnd_cand_import_select(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int32_t T, const void *records, int64_t n,
+                                      int32_t *new_cand, int32_t *old_cand, void *ws, size_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NND_CHECK(ctx && P && new_cand && old_cand && n >= 0 && (records || n == 0), NND_ERR_INVALID, "nnd_cand_import_select: bad args");
+    const int64_t N = P->N; const int k = P->k;
+    CandWs W;
+    NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE, "nnd_cand_import_select: workspace too small");
+    NND_CHECK(n <= 2 * N * (int64_t)k, NND_ERR_OVERFLOW, "nnd_cand_import_select: %lld records exceed the reverse-edge scratch", (long long)n);
+    int64_t lo, hi; cand_range(ctx, N, &lo, &hi);
+    NND_STAGE(ctx, NND_ST_CAND_FILL, st);
+    NND_CUDA(cudaMemsetAsync(W.indeg, 0, sizeof(uint32_t) * (N + 1), st));
+    NND_CUDA(cudaMemsetAsync(W.cursor, 0, sizeof(uint32_t) * (N + 1), st));
+    unsigned long long *bad = (unsigned long long *)W.scan_tmp;     // the scan below overwrites it afterwards; read back first
+    NND_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), st));
+    if (n > 0) { k_cand_import_count<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const CandRec *)records, (unsigned long long)n, lo, hi, W.indeg, bad); NND_LAUNCH(ctx); }
+    unsigned long long hbad = 0;
+    NND_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(hbad), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaStreamSynchronize(st));
+    NND_CHECK(hbad == 0, NND_ERR_INVALID, "nnd_cand_import_select: %llu records target rows outside [%lld,%lld)", hbad, (long long)lo, (long long)hi);
+    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
+    if (n > 0) { k_cand_import_scatter<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const CandRec *)records, (unsigned long long)n, lo, hi, W.revoff, W.cursor, W.rev); NND_LAUNCH(ctx); }
+    NND_STAGE(ctx, NND_ST_CAND_SELECT, st);
+    NND_TRY(launch_cand_select(ctx, P, C, W, new_cand, old_cand, nullptr, st));
     NND_STAGE(ctx, NND_ST_OTHER, st);
     NND_CUDA(cudaGetLastError());
     return NND_OK;

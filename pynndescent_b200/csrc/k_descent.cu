@@ -1101,10 +1101,12 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
                        bool do_apply = true) {
     const int64_t N = P->N;
     NND_STAGE(ctx, NND_ST_SCATTER, st);
-    k_snapshot_thr<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_dist, P->k, W.thr, N); NND_LAUNCH(ctx);
+    // sharded build: the snapshot of all N heap roots comes from the caller (all-gathered from the owners, nnd_set_thresholds)
+    const float *thr = ctx->thr_ext ? ctx->thr_ext : W.thr;
+    if (!ctx->thr_ext) { k_snapshot_thr<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(P->heap_dist, P->k, W.thr, N); NND_LAUNCH(ctx); }
     NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (N + 1), st));
     NND_CUDA(cudaMemsetAsync(W.dev_scalars, 0, sizeof(unsigned long long), st));  // cursor
-    J.thr = W.thr; J.unit_begin = u0; J.unit_end = u1;
+    J.thr = thr; J.unit_begin = u0; J.unit_end = u1;
     J.out_tgt = W.l_tgt; J.out_oth = W.l_oth; J.out_d = W.l_d; J.out_pos = W.l_pos; J.out_seq = W.l_seq;
     J.tgt_count = W.cnt; J.cursor = W.dev_scalars; J.capacity = (unsigned long long)cap;
     J.overflow = (int *)(W.dev_scalars + 4);
@@ -1115,7 +1117,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     // schedule options (nnd_ctx): neither changes what is emitted, only how
     const bool rank_scatter = JB && do_apply && ctx->opt_rank_scatter;
     if (JB) {
-        JB->thr = W.thr; JB->batch_begin = u0; JB->batch_end = u1;
+        JB->thr = thr; JB->batch_begin = u0; JB->batch_end = u1;
         JB->out_tgt = W.l_tgt; JB->out_oth = W.l_oth; JB->out_d = W.l_d; JB->out_pos = rank_scatter ? nullptr : W.l_pos; JB->out_seq = W.l_seq;
         JB->tgt_count = W.cnt; JB->cursor = W.dev_scalars; JB->capacity = (unsigned long long)cap;
         JB->overflow = (int *)(W.dev_scalars + 4); JB->stats = W.dev_scalars + 5;

@@ -51,7 +51,7 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
     nnd_ctx *c = new nnd_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->launches = 0;
     memset(c->prof, 0, sizeof(c->prof));
-    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr; c->plan_free = nullptr; c->jb_ppb_max = 0.0;
+    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr; c->plan_free = nullptr; c->jb_ppb_max = 0.0; c->thr_ext = nullptr;
     {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
         c->opt_rank_scatter = env_int("NND_RANK_SCATTER", 1);
@@ -131,6 +131,11 @@ extern "C" int nnd_stage_read(nnd_ctx *ctx, double *out_ms, int32_t reset) {
     stage_resolve(ctx);
     memcpy(out_ms, ctx->sp_ms, sizeof(ctx->sp_ms));
     if (reset) { memset(ctx->sp_ms, 0, sizeof(ctx->sp_ms)); ctx->sp_n = 0; }
+    return NND_OK;
+}
+extern "C" int nnd_set_thresholds(nnd_ctx *ctx, const float *thr) {
+    NND_CHECK(ctx, NND_ERR_INVALID, "nnd_set_thresholds: null context");
+    ctx->thr_ext = thr;
     return NND_OK;
 }
 extern "C" int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset) {

@@ -43,6 +43,7 @@ struct nnd_ctx {
     cudaEvent_t ev0, ev1;
     unsigned long long last_round_rows, last_round_pairs;
     double jb_ppb_max;        // half-updates per batch of the fullest round since the last plan (0 = unknown): sizes the next plan's rounds
+    const float *thr_ext;     // nnd_set_thresholds: heap-root snapshot of all rows supplied by the caller (sharded build), or null
     int64_t row_lo, row_hi;   // sharded build: this process joins / samples candidates only for rows in [row_lo,row_hi)
     void *plan;               // JoinPlan of the sharded round API (k_descent.cu)
     void (*plan_free)(void *);

@@ -207,13 +207,22 @@ class Engine:
                 accepted += self.apply_records(1, cap, sub.view(torch.uint8).reshape(-1), sub.shape[0])
         return accepted
 
-    def build_candidates(self, max_candidates, rng_state, n_threads, tables_valid=False):
+    def _cand_ws(self, max_candidates, n_threads):
+        """Candidate scratch (rng tables included); returns (tensor, bytes, fresh) -- fresh = the tables must be regenerated."""
         nb = C.c_size_t()
         check(lib.nnd_cand_workspace_bytes(self.N, self.k, max_candidates, n_threads, C.byref(nb)))
         key = ("cand", max_candidates, n_threads)
-        if getattr(self, "_cws_key", None) != key:
+        fresh = getattr(self, "_cws_key", None) != key
+        if fresh:
+            self._cws = None
             self._cws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
             self._cws_key = key
+        return self._cws, nb.value, fresh
+
+    def build_candidates(self, max_candidates, rng_state, n_threads, tables_valid=False):
+        _, nbv, fresh = self._cand_ws(max_candidates, n_threads)
+        nb = C.c_size_t(nbv)
+        if fresh:
             tables_valid = False
         newc = torch.empty((self.N, max_candidates), dtype=torch.int32, device=self.device)
         oldc = torch.empty((self.N, max_candidates), dtype=torch.int32, device=self.device)
@@ -293,6 +302,43 @@ class Engine:
     # ------------------------------------------------------------------ sharded-build primitives (sharded.py)
     def set_row_range(self, lo, hi):
         check(lib.nnd_set_row_range(self._ctx, int(lo), int(hi)))
+
+    def set_thresholds(self, thr):
+        """thr: float32 device tensor with the heap roots of ALL rows (kept alive here), or None = snapshot the local heap."""
+        self._thr_ext = thr
+        check(lib.nnd_set_thresholds(self._ctx, _ptr(thr)))
+
+    def cand_local_counts(self, max_candidates, n_threads, world, owner_block):
+        """Step 1 of the row-sharded candidate build: this process's count table, int64[5T + 1 + world]."""
+        ws, nb, fresh = self._cand_ws(max_candidates, n_threads)
+        self._cand_tables_fresh = fresh or getattr(self, "_cand_tables_fresh", False)
+        out = np.zeros(5 * n_threads + 1 + world, np.int64)
+        check(lib.nnd_cand_local_counts(self._ctx, C.byref(self.problem()), int(max_candidates), int(n_threads), int(world),
+                                        int(owner_block), _ptr(ws), nb, out.ctypes.data_as(C.POINTER(C.c_int64)), self._st()))
+        return out
+
+    def cand_export(self, max_candidates, rng_state, n_threads, tables_valid, world, owner_block, glob, bucket_off, n_records):
+        """Step 2: forward priorities of the own rows + 12-byte reverse-edge records grouped by owner process."""
+        ws, nb, fresh = self._cand_ws(max_candidates, n_threads)
+        if fresh or getattr(self, "_cand_tables_fresh", False):
+            tables_valid = False
+        self._cand_tables_fresh = False
+        out = torch.empty(max(int(n_records), 1) * 12, dtype=torch.uint8, device=self.device)
+        st = (C.c_int64 * 3)(*[int(v) for v in rng_state])
+        g = np.ascontiguousarray(glob, np.int64); b = np.ascontiguousarray(bucket_off, np.int64)
+        check(lib.nnd_cand_export(self._ctx, C.byref(self.problem()), int(max_candidates), st, int(n_threads), int(bool(tables_valid)),
+                                  int(world), int(owner_block), g.ctypes.data_as(C.POINTER(C.c_int64)),
+                                  b.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(out), _ptr(ws), nb, self._st()))
+        return out
+
+    def cand_import_select(self, max_candidates, n_threads, records, n):
+        """Step 3: the received records -> (new, old) candidate lists of the own rows; clears the sampled flags."""
+        ws, nb, _ = self._cand_ws(max_candidates, n_threads)
+        newc = torch.empty((self.N, max_candidates), dtype=torch.int32, device=self.device)
+        oldc = torch.empty((self.N, max_candidates), dtype=torch.int32, device=self.device)
+        check(lib.nnd_cand_import_select(self._ctx, C.byref(self.problem()), int(max_candidates), int(n_threads), _ptr(records), int(n),
+                                         _ptr(newc), _ptr(oldc), _ptr(ws), nb, self._st()))
+        return newc, oldc
 
     def join_prepare(self, newc, oldc, cap):
         C_ = newc.shape[1]

@@ -206,6 +206,57 @@ def test_init_random_build_candidates_process(torch_cuda, oracle, name):
         np.testing.assert_allclose(hd[fin], G[f"it{it}_heap_dist"][fin], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("name", ["cfg1_euclid_1k16", "latent_cosine_2k24"])
+def test_row_sharded_candidate_steps_equal_reference_candidates(torch_cuda, name, world):
+    """The three steps of the row-sharded candidate build (nnd_cand_local_counts / nnd_cand_export / nnd_cand_import_select,
+    csrc/k_cand.cu) for `world` simulated processes on ONE GPU -- every process reads only its own rows' edges, the count tables
+    are summed / offset the way sharded.py does it, the 12-byte reverse-edge records are routed by owner -- must reproduce the
+    REFERENCE's new_build_candidates output (utils.py:221-320): candidate lists and cleared flags of both golden iterations."""
+    G = load_golden(name); metric = GOLDEN_CASES[name]
+    k = int(G["k"]); T = int(G["T"]); C = min(60, k)
+    eng, Xh = _engine(G["X"], metric, k)
+    N = eng.N
+    B = N // world + 1
+    ranges = [(min(r * B, N), min((r + 1) * B, N)) for r in range(world)]
+    rng = G["rng_state1"].copy()
+    heaps = [(G["init_heap_idx"], G["init_heap_dist"], G["init_heap_flag"])]
+    if "it0_heap_idx" in G and "it1_new" in G:
+        heaps.append((G["it0_heap_idx"], G["it0_heap_dist"], G["it0_heap_flag"]))
+    for it, (hi_, hd_, hf_) in enumerate(heaps):
+        eng.set_heap(hi_, hd_, hf_)
+        tabs = []
+        for lo, hi in ranges:                                               # step 1 on every "process"
+            eng.set_row_range(lo, hi)
+            tabs.append(eng.cand_local_counts(C, T, world, B))
+        A = np.stack(tabs)
+        sent = []                                                           # [src][dst] -> uint8 records
+        for r, (lo, hi) in enumerate(ranges):                               # step 2
+            eng.set_row_range(lo, hi)
+            assert np.array_equal(eng.cand_local_counts(C, T, world, B), tabs[r])       # (shared scratch: recompute this rank's prefix sums)
+            glob = np.zeros(6 * T, np.int64)
+            for n in range(T):
+                glob[6 * n: 6 * n + 4] = A[:, 5 * n: 5 * n + 4].sum(0)
+                glob[6 * n + 4] = A[:r, 5 * n + 4].sum(); glob[6 * n + 5] = A[:r, 5 * T].sum()
+            cnt = [int(c) for c in A[r, 5 * T + 1:]]
+            boff = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int64)
+            buf = eng.cand_export(C, rng, T, it > 0, world, B, glob, boff, sum(cnt))
+            torch_cuda.cuda.synchronize()
+            sent.append([buf[int(boff[q]) * 12: (int(boff[q]) + cnt[q]) * 12].clone() for q in range(world)])
+        newc = np.full((N, C), -9, np.int32); oldc = np.full((N, C), -9, np.int32)
+        for r, (lo, hi) in enumerate(ranges):                               # step 3
+            eng.set_row_range(lo, hi)
+            rec = torch_cuda.cat([sent[q][r] for q in range(world)])
+            n = rec.numel() // 12
+            assert n == int(A[:, 5 * T + 1 + r].sum())
+            nc, oc = eng.cand_import_select(C, T, rec if n else torch_cuda.zeros(12, dtype=torch_cuda.uint8, device=eng.device), n)
+            torch_cuda.cuda.synchronize()
+            newc[lo:hi] = nc.cpu().numpy()[lo:hi]; oldc[lo:hi] = oc.cpu().numpy()[lo:hi]
+        eng.set_row_range(0, 2 ** 62)
+        assert np.array_equal(newc, G[f"it{it}_new"]) and np.array_equal(oldc, G[f"it{it}_old"])
+        assert np.array_equal(eng.get_heap()[2], G[f"it{it}_flag_after_cand"])
+
+
 @pytest.mark.parametrize("name", GPU_CASES)
 def test_end_to_end_with_reference_leaves_matches_reference_graph(torch_cuda, name):
     """Same seed, same leaves => the SAME graph as the reference's NNDescent(...) (T=8)."""

@@ -8,53 +8,18 @@ import numpy as np
 
 from conftest import ROOT
 
-WORKER = r'''
-import os, sys
-sys.path.insert(0, os.environ["REPO_ROOT"])
-import importlib.util
-spec = importlib.util.spec_from_file_location("parallel", os.path.join(os.environ["REPO_ROOT"], "pynndescent_b200", "parallel.py"))
-par = importlib.util.module_from_spec(spec); spec.loader.exec_module(par)
-import torch.distributed as dist
-dist.init_process_group("gloo")
-r, w = dist.get_rank(), dist.get_world_size()
-lo, hi = par.owner_ranges(1001, w)[r]
-# every rank "builds" its own range; aggregate edges and the slowest time as bench.py does
-edges = par.sum_over_ranks((hi - lo) * 15)
-t = par.max_over_ranks(1.0 + r)
-if r == 0:
-    print("RESULT", int(edges), t, flush=True)
-dist.destroy_process_group()
-'''
-
-
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
 def test_owner_ranges_match_reference_rule():
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("parallel", os.path.join(ROOT, "pynndescent_b200", "parallel.py"))
-    par = importlib.util.module_from_spec(spec); spec.loader.exec_module(par)
+    from pynndescent_b200.sharded import owner_ranges
     for n, w in ((1000, 8), (1001, 2), (17, 4), (10_000_000, 8)):
-        rr = par.owner_ranges(n, w)
+        rr = owner_ranges(n, w)
         assert rr[0][0] == 0 and rr[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(rr, rr[1:]))
         block = n // w + 1                                  # utils.py:259
         assert all(hi - lo <= block for lo, hi in rr)
-        v = np.array([0, n // 2, n - 1])
-        assert np.array_equal(par.owner_of(v, n, w), v // block)
-
-
-def test_world_size_2_gloo_reductions(tmp_path):
-    script = tmp_path / "worker.py"
-    script.write_text(WORKER)
-    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), str(script)]
-    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
-    assert out.returncode == 0, out.stderr[-2000:]
-    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
-    assert int(line[1]) == 1001 * 15 and float(line[2]) == 2.0
 
 
 SHARDED_WORKER = r'''
@@ -78,7 +43,10 @@ class ScriptedEngine:
         self.emitted, self.received, self.it = [], [], 0
         self.lo = self.hi = None
     def set_row_range(self, lo, hi): self.lo, self.hi = lo, hi
-    def build_candidates(self, C_, rng, T, tables_valid=False): return None, None
+    def set_thresholds(self, thr): self.thr = thr
+    def cand_local_counts(self, C_, T, world, B): return np.zeros(5 * T + 1 + world, np.int64)
+    def cand_export(self, C_, rng, T, tables_valid, world, B, glob, boff, n): return torch.zeros(12, dtype=torch.uint8)
+    def cand_import_select(self, C_, T, records, n): return None, None
     def join_prepare(self, newc, oldc, cap):
         self.it += 1
         rs = np.random.RandomState(100 * self.it + r)
@@ -144,7 +112,8 @@ def test_sharded_exchange_protocol_gloo(tmp_path):
 
 LEAF_WORKER = r'''
 """ShardedBuilder.forest_and_leaf_init over gloo with an oracle-backed engine: trees built by their owner rank, leaves broadcast,
-every tree's leaves split among the ranks, updated heap rows exchanged.  Afterwards EVERY rank must hold exactly the heap the
+every tree's leaves split among the ranks, the heap rows of a rank's share fetched from whoever processed them in the previous
+tree, rows sent home after the last tree.  Afterwards every rank must hold, for ITS row range, exactly the heap the
 oracle's init_rp_tree produces from the whole forest -- and every leaf_fused_range call must carry the position range of its
 leaves (what nnd_leaf_range needs for the split leaf init)."""
 import os, sys
@@ -201,8 +170,9 @@ e.heap_idx.copy_(torch.from_numpy(hi)); e.heap_dist.copy_(torch.from_numpy(hd));
 sb.forest_and_leaf_init(states, LEAF, False, 200, 1 << 20)
 ref = orc.make_heap(N, K)
 orc.init_rp_tree(X, "euclidean", ref, orc.forest_leaf_array(X, states, LEAF, False, 200, "level"))
-ok = (np.array_equal(e.heap_idx.numpy(), ref[0]) and np.array_equal(e.heap_dist.numpy(), ref[1]) and np.array_equal(e.heap_flag.numpy(), ref[2])
-      and len(e.calls) == NT)
+lo, hi = sb.lo, sb.hi            # after the sharded leaf init every rank holds the finished rows of ITS range (rows travel home)
+ok = (np.array_equal(e.heap_idx.numpy()[lo:hi], ref[0][lo:hi]) and np.array_equal(e.heap_dist.numpy()[lo:hi], ref[1][lo:hi])
+      and np.array_equal(e.heap_flag.numpy()[lo:hi], ref[2][lo:hi]) and len(e.calls) == NT)
 flags = [None] * w
 dist.all_gather_object(flags, bool(ok))
 if r == 0:
@@ -214,14 +184,13 @@ dist.destroy_process_group()
 import pytest
 
 
-@pytest.mark.parametrize("exchange", ["allgather", "targeted"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_forest_and_leaf_init_gloo(tmp_path, world, exchange):
+def test_sharded_forest_and_leaf_init_gloo(tmp_path, world):
     """world_size 2 and 3 (5 trees: uneven tree ownership) over gloo: the sharded forest + leaf-init protocol end to end on an
     oracle-backed engine."""
     script = tmp_path / "leaf_worker.py"
     script.write_text(LEAF_WORKER)
-    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1", NND_LEAF_EXCHANGE=exchange)   # "targeted": sharded.py _fetch_rows
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
@@ -231,8 +200,9 @@ def test_sharded_forest_and_leaf_init_gloo(tmp_path, world, exchange):
 
 
 BUILD_WORKER = r'''
-"""The WHOLE sharded build (ShardedBuilder.build: forest, leaf init, init_random, NN-descent with the all-to-all exchange of
-half-updates, heap all-gathers, termination) over gloo, every engine primitive executed by the oracle.  The graph must be
+"""The WHOLE sharded build (ShardedBuilder.build: forest, leaf init with travelling heap rows, init_random, NN-descent with the
+row-sharded candidate build (count-table all-gather + all-to-all-v of reverse-edge proposals), threshold all-gather, all-to-all of
+half-updates, termination, final all-gather) over gloo, every engine primitive executed by the oracle on the OWN rows only.  The graph must be
 identical to the single-process oracle build -- for any world size (the property tests/test_sharded_gpu.py checks on GPUs)."""
 import os, sys
 sys.path.insert(0, os.environ["REPO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
@@ -288,16 +258,90 @@ class OracleShardEngine:
             self.heap_idx[idx] = oi[:n]; self.heap_dist[idx] = od[:n]; self.heap_flag[idx] = of[:n]
     def init_random(self, rng): orc.init_random(X, "euclidean", self.heap(), rng)
     def set_row_range(self, lo, hi): self.lo, self.hi = lo, min(hi, N)
-    def build_candidates(self, C_, rng, T_, tables_valid=False):
-        # the oracle samples for every vertex and clears the sampled flags everywhere; the rows this rank does not own are
-        # overwritten by their owners' copies at the end of the iteration (all-gather), exactly like on the GPUs
-        return orc.new_build_candidates(self.heap(), C_, np.ascontiguousarray(rng, np.int64), T_)
+    # ---- the three steps of the row-sharded candidate build (csrc/k_cand.cu nnd_cand_*), restated on the oracle's rng and heap
+    # push: this rank reads ONLY its own rows of the heap (the other rows are stale here, exactly like on the GPUs)
+    def set_thresholds(self, thr): self.thr = None if thr is None else thr.numpy()
+    def _tables(self, rng, T_):
+        if getattr(self, "_tab", None) is None:
+            self._tab = []
+            for n in range(T_):
+                st = (np.asarray(rng, np.int64) + n).copy()                    # utils.py:262 local_rng_state = rng_state + n
+                self._tab.append(np.array([orc.tau_rand(st) for _ in range(N * K + 1)], np.float32))
+        return self._tab
+    def cand_local_counts(self, C_, T_, world, Bown):
+        Bt = N // T_ + 1
+        idx = self.heap()[0]
+        cntR = np.zeros((T_, N), np.int64); valid = np.zeros(N, np.int64); dest = np.zeros(world, np.int64)
+        for i in range(self.lo, self.hi):
+            row = idx[i]; v = row >= 0
+            valid[i] = v.sum()
+            for n in range(T_):
+                cntR[n, i] = ((row >= n * Bt) & (row < (n + 1) * Bt) & v).sum()
+            for x in row[v]:
+                dest[min(int(x) // Bown, world - 1)] += 1
+        self.PR = np.concatenate([np.zeros((T_, 1), np.int64), np.cumsum(cntR, 1)], 1); self.PV = np.concatenate([[0], np.cumsum(valid)])
+        out = np.zeros(5 * T_ + 1 + world, np.int64)
+        for n in range(T_):
+            s = min(n * Bt, N); e_ = min(s + Bt, N)
+            out[5 * n: 5 * n + 5] = [self.PR[n, s], self.PV[s], self.PV[e_], self.PR[n, e_], self.PR[n, N]]
+        out[5 * T_] = self.PV[N]; out[5 * T_ + 1:] = dest
+        return out
+    def cand_export(self, C_, rng, T_, tables_valid, world, Bown, glob, boff, n_rec):
+        Bt = N // T_ + 1
+        tab = self._tables(rng, T_)
+        idx, _, flg = self.heap()
+        def draw(n, i, wv, wn):
+            s = n * Bt; e_ = min(s + Bt, N); G = glob[6 * n: 6 * n + 6]
+            prR = G[4] + self.PR[n, i]; prV = G[5] + self.PV[i]
+            if i < s: return prR + wn
+            if i < e_: return G[0] + (prV - G[1]) + wv
+            return G[0] + (G[2] - G[1]) + (prR - G[3]) + wn
+        self.fprio = np.zeros((N, K), np.float32)
+        buckets = [[] for _ in range(world)]
+        for i in range(self.lo, self.hi):
+            ni = i // Bt; wv = 0
+            for j in range(K):
+                x = int(idx[i, j])
+                if x < 0: continue
+                nx = x // Bt
+                pf = tab[ni][draw(ni, i, wv, 0)]
+                self.fprio[i, j] = pf
+                pr = pf
+                if nx != ni:
+                    wn = int(((idx[i, :j] >= nx * Bt) & (idx[i, :j] < (nx + 1) * Bt)).sum())
+                    pr = tab[nx][draw(nx, i, 0, wn)]
+                buckets[min(x // Bown, world - 1)].append((x, ((i * K + j) << 1) | int(flg[i, j] != 0), pr))
+                wv += 1
+        rec = np.zeros(max(n_rec, 1), np.dtype([("tgt", "<i4"), ("key", "<u4"), ("prio", "<f4")]))
+        for o in range(world):
+            assert (int(boff[o + 1]) if o + 1 < world else n_rec) - int(boff[o]) == len(buckets[o])
+            for q, t in enumerate(buckets[o][::-1]):                # any order inside a bucket
+                rec[int(boff[o]) + q] = t
+        return torch.from_numpy(rec.view(np.uint8).copy())
+    def cand_import_select(self, C_, T_, records, n):
+        rec = records.numpy()[: n * 12].view(np.dtype([("tgt", "<i4"), ("key", "<u4"), ("prio", "<f4")]))
+        idx, _, flg = self.heap()
+        newc = np.full((N, C_), -1, np.int32); oldc = np.full((N, C_), -1, np.int32)
+        by_t = {}
+        for t, key, pr in rec:
+            assert self.lo <= t < self.hi, "reverse-edge record delivered to the wrong owner"
+            by_t.setdefault(int(t), []).append((int(key) >> 1, 1, np.float32(pr), int(key >> 1) // K, int(key) & 1))
+        for v in range(self.lo, self.hi):
+            ev = [(v * K + j, 0, self.fprio[v, j], int(idx[v, j]), int(flg[v, j] != 0)) for j in range(K) if idx[v, j] >= 0] + by_t.get(v, [])
+            ev.sort(key=lambda t: (t[0], t[1]))                       # scan order; the forward edge first on a tie (self edge)
+            hp = {1: (np.full(C_, np.inf, np.float32), newc[v]), 0: (np.full(C_, np.inf, np.float32), oldc[v])}
+            for _, _, pr, cand, isnew in ev:
+                orc.lib().orc_checked_heap_push(hp[isnew][0], hp[isnew][1], C_, float(pr), cand)
+            for j in range(K):                                        # utils.py:311-318
+                if idx[v, j] >= 0 and (newc[v] == idx[v, j]).any():
+                    flg[v, j] = 0
+        return newc, oldc
     def join_prepare(self, newc, oldc, cap):
         self.newc, self.oldc = newc, oldc
         return 1
     def join_emit_round(self, C_, cap, rnd):
         if rnd > 0: return 0
-        thr = self.heap()[1][:, 0].copy()
+        thr = self.thr[:N]                                      # all-gathered from the owners (set_thresholds); local non-own rows are stale
         stride = 2 * C_
         recs = []
         for i in range(self.lo, self.hi):                      # own rows only; emission keys as in k_join / k_join_batch
@@ -358,11 +402,11 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world,exchange", [(2, "allgather"), (3, "allgather"), (3, "targeted")])
-def test_whole_sharded_build_equals_single_process_oracle_gloo(tmp_path, world, exchange):
+@pytest.mark.parametrize("world", [2, 3])
+def test_whole_sharded_build_equals_single_process_oracle_gloo(tmp_path, world):
     script = tmp_path / "build_worker.py"
     script.write_text(BUILD_WORKER)
-    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1", NND_LEAF_EXCHANGE=exchange)
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
