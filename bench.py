@@ -309,6 +309,8 @@ def main():
     prof = eng.profile(reset=True)
     launches = eng.launch_count() - launches0
     gi = idx_t.cpu().numpy(); gd = dist_t.cpu().numpy()
+    if host_corr is not None:          # what NNDescent.neighbor_graph returns (cosine / dot: 1 - 2^-d in float64, distances.py:704-711)
+        gd = host_corr(gd)
 
     # ---- one more build OUTSIDE the timed region with the library's stage timers on (CUDA events at every stage
     # boundary) and host-side stage laps: the stage table of the JSON line

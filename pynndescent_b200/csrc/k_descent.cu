@@ -1197,7 +1197,12 @@ static size_t join_batch_smem(int metric, int dk, int ld) {
 static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st) {
     int64_t nb = JB.batch_end - JB.batch_begin;
     if (nb <= 0) return NND_OK;
-    const int dk = 32;   // floats per staged chunk (16 / 64 / 128 were measured slower on B200: profiles/ab_r02_1m_switches.json)
+    // floats per staged chunk: 32 = the measured default (16 lost the round-2 A/B, profiles/ab_r02_1m_switches.json).
+    // NND_JB_DK=64|128 (experiment): fewer, larger bulk copies per member row -- 128 stages whole 512-byte rows of d = 128 in ONE
+    // copy each (single buffer, 2 CTAs per SM overlap each other's gather) instead of four 128-byte pieces
+    static int dk_sel = -1;
+    if (dk_sel < 0) { const char *e = getenv("NND_JB_DK"); dk_sel = e ? atoi(e) : 32; if (dk_sel != 32 && dk_sel != 64 && dk_sel != 128) dk_sel = 32; }
+    const int dk = dk_sel;
     size_t smem = join_batch_smem(JB.metric, dk, JB.ld);
     dim3 grid((unsigned)nb);
 #define LB(M_, D_)                                                                                                   \
@@ -1205,7 +1210,7 @@ static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st)
         NND_CUDA(cudaFuncSetAttribute(k_join_batch<M_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_join_batch<M_, D_><<<grid, JB_THREADS, smem, st>>>(JB);                                                     \
     } while (0)
-#define LBM(M_) LB(M_, 32)
+#define LBM(M_) do { if (dk == 32) LB(M_, 32); else if (dk == 64) LB(M_, 64); else LB(M_, 128); } while (0)
     if (JB.metric == NND_METRIC_SQEUCLIDEAN) LBM(NND_METRIC_SQEUCLIDEAN);
     else if (JB.metric == NND_METRIC_ALT_COSINE) LBM(NND_METRIC_ALT_COSINE);
     else LBM(NND_METRIC_ALT_DOT);
