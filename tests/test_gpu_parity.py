@@ -196,7 +196,11 @@ def test_init_random_build_candidates_process(torch_cuda, oracle, name):
         newc, oldc = eng.build_candidates(C, rng, T, tables_valid=(it > 0))
         torch_cuda.cuda.synchronize()
         assert np.array_equal(newc.cpu().numpy(), G[f"it{it}_new"])
-        assert np.array_equal(oldc.cpu().numpy(), G[f"it{it}_old"])
+        # the OLD lists of vertices without any new candidate are never read (the local join loops over new candidates only,
+        # utils.py:575-577) and are left empty here instead of being sampled (k_cand.cu `act`, tests/test_schedule_invariants.py)
+        has_new = (G[f"it{it}_new"] >= 0).any(1)
+        oc = oldc.cpu().numpy()
+        assert np.array_equal(oc[has_new], G[f"it{it}_old"][has_new]) and (oc[~has_new] == -1).all()
         assert np.array_equal(eng.get_heap()[2], G[f"it{it}_flag_after_cand"])
         c, stats = eng.process_candidates(newc, oldc)
         assert c == int(G["c_hist"][it])
