@@ -560,6 +560,18 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
         __syncthreads();                                    // everyone done with buffer c&1
         if (c + 2 < nchunks) issue(c + 2);
     }
+    // ---- presence filter: the heap rows (indices) of all members, staged in the row buffers (free now: the chunk loop ends with
+    // a CTA-wide barrier)
+    int32_t *hrow = (int32_t *)rows;                        // [totphys][hk]
+    const int hk = P.heap_idx ? P.k : 0;
+    if (hk) {
+        for (int e = tid; e < totphys * hk; e += JB_THREADS) {
+            const int slot = e / hk, j = e - slot * hk;
+            const int32_t id = ids[slot];
+            hrow[e] = id >= 0 ? P.heap_idx[(int64_t)id * hk + j] : -1;
+        }
+        __syncthreads();
+    }
     // ---- finalise + filter
     uint32_t pm = 0;
     if (u >= 0) {
@@ -574,8 +586,16 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
                     if (METRIC == NND_METRIC_SQEUCLIDEAN) r = acc[qa * TILE + qb];
                     else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine(acc[qa * TILE + qb], n2_s[uo + a], n2_s[uo + b]);
                     else r = finish_alt_dot(acc[qa * TILE + qb], P.metric);
-                    if (r < thr_s[uo + a]) pm |= 1u << (2 * (qa * TILE + qb));
-                    if (b != a && r < thr_s[uo + b]) pm |= 2u << (2 * (qa * TILE + qb));
+                    bool ea = r < thr_s[uo + a], eb = (b != a) && r < thr_s[uo + b];
+                    if (hk && (ea || eb)) {
+                        const int32_t pa = ids[uo + a], pb = ids[uo + b];
+                        const int32_t *ra = hrow + (uo + a) * hk, *rb = hrow + (uo + b) * hk;
+                        bool ina = false, inb = false;
+                        for (int j = 0; j < hk; ++j) { ina |= (ra[j] == pb); inb |= (rb[j] == pa); }
+                        ea = ea && !ina; eb = eb && !inb;
+                    }
+                    if (ea) pm |= 1u << (2 * (qa * TILE + qb));
+                    if (eb) pm |= 2u << (2 * (qa * TILE + qb));
                 }
                 acc[qa * TILE + qb] = r;
             }
@@ -695,11 +715,22 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
                     if (take) { key = ok; slot = os; }
                 }
             }
+            // lane s now owns the s-th record in emission order.  Two filters that cannot change the row (see JoinBatchParams):
+            // a source that already sits in the row as loaded is rejected whenever its turn comes, and of several records with
+            // the same source only the first in emission order can ever be accepted -- both are dropped before the replay.
+            Rec16 mine; mine.key = ~0ULL; mine.oth = -2 - lane; mine.d = 0.f;
+            if (lane < kept) mine = buf[slot];
+            bool live = lane < kept;
+            for (int j = 0; j < k; ++j) live = live && (ind[j] != mine.oth);
+            const unsigned grp = __match_any_sync(0xffffffffu, live ? mine.oth : -2 - lane);
+            live = live && (lane == __ffs(grp) - 1);
+            unsigned lm = __ballot_sync(0xffffffffu, live);
             int c = 0;
-            for (int s2 = 0; s2 < kept; ++s2) {
-                int sl = __shfl_sync(0xffffffffu, slot, s2);
-                Rec16 r = buf[sl];
-                c += warp_heap_push(pri, ind, flg, k, r.d, r.oth, (uint8_t)1, lane);
+            while (lm) {
+                const int s2 = __ffs(lm) - 1; lm &= lm - 1;
+                const float dd = __shfl_sync(0xffffffffu, mine.d, s2);
+                const int32_t oo = __shfl_sync(0xffffffffu, mine.oth, s2);
+                c += warp_heap_push(pri, ind, flg, k, dd, oo, (uint8_t)1, lane);
             }
             if (c > 0) {
                 for (int j = lane; j < k; j += 32) {
@@ -1413,6 +1444,8 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
             JB.X = P->X; JB.N = N; JB.ld = P->ld; JB.metric = P->metric; JB.aux = P->aux;
             JB.act_unit = W.act_unit; JB.act_info = W.act_info; JB.act_poff = W.act_poff; JB.members = W.members;
             JB.batch_first = W.batch_first; JB.n_active = n_active; JB.n_batches = n_batches; JB.slot_stride = 2 * C;
+            // presence filter: k heap indices per member must fit the (single-chunk: one) row buffer of JB_SCAP x (32 + 4) floats
+            if (ctx->opt_presence && P->k <= 32) { JB.heap_idx = P->heap_idx; JB.k = P->k; }
             // rounds are planned optimistically (16 half-updates per tile slot; the worst case is 32 and the measured
             // average 7); a round that overflows is detected (never silent) and split by the caller
             // ... and from the second iteration of a build on by the measured emission of the previous iteration's rounds

@@ -56,6 +56,7 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
         c->opt_rank_scatter = env_int("NND_RANK_SCATTER", 1);
         c->opt_cand_skip = env_int("NND_CAND_SKIP", 1);
+        c->opt_presence = env_int("NND_PRESENCE", 1);
         c->opt_cand_keys = env_int("NND_CAND_KEYS", 0);
         c->opt_leaf_split = env_int("NND_LEAF_SPLIT", 1);
         c->opt_carveout = env_int("NND_SMEM_CARVEOUT", 1);

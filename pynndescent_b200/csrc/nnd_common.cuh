@@ -57,6 +57,7 @@ struct nnd_ctx {
     int opt_carveout;         // NND_SMEM_CARVEOUT=1: prefer the maximum shared-memory carveout for the occupancy-by-smem kernels
     int opt_leaf_split;       // NND_LEAF_SPLIT=1: leaf init = distance-matrix kernel + thread-per-member push kernel (k_descent.cu)
     int opt_cand_keys;        // NND_CAND_KEYS=1: k_cand_select_small stages the reverse-edge key words in shared memory
+    int opt_presence;         // NND_PRESENCE=1 (default): the batched join drops half-updates whose source already sits in the target's heap row
     int opt_cand_skip;        // NND_CAND_SKIP=1: candidates are sampled only for vertices that will have NEW candidates (k_cand.cu)
     int opt_forest_pm;        // NND_FOREST_PM=1: point-major hyperplane pass of the RP forest (k_forest_side_pm<NCH>, k_forest.cu)
     int opt_forest_pm_mb;     // NND_FOREST_PM_MB: ... while the level's hyperplane table is at most this many MB (default 48)

@@ -33,7 +33,12 @@ CONFIGS = {
     "norank": {"NND_RANK_SCATTER": "0"},
     "noleafsplit": {"NND_LEAF_SPLIT": "0"},
     "nocarveout": {"NND_SMEM_CARVEOUT": "0"},
-    "round1-defaults": {"NND_RANK_SCATTER": "0", "NND_LEAF_SPLIT": "0", "NND_SMEM_CARVEOUT": "0", "NND_FOREST_PM": "0"},
+    "round1-defaults": {"NND_RANK_SCATTER": "0", "NND_LEAF_SPLIT": "0", "NND_SMEM_CARVEOUT": "0", "NND_FOREST_PM": "0", "NND_CAND_SKIP": "0",
+                        "NND_APPLY_SHORT_SORT": "0", "NND_PRESENCE": "0"},
+    "nopresence": {"NND_PRESENCE": "0"},
+    "nocandskip": {"NND_CAND_SKIP": "0"},
+    "jbdk64": {"NND_JB_DK": "64"},
+    "jbdk128": {"NND_JB_DK": "128"},
 }
 
 
@@ -46,7 +51,15 @@ def child(n, d, k, metric, reps, out_path):
     from bench import latent
     from pynndescent_b200 import distances as pdist
     from pynndescent_b200.engine import Engine
-    X = latent(n, d, seed=0)
+    cache = "/dev/shm/nnd_ab_%d_%d.npy" % (n, d)          # the generator needs half a minute at 10M points: share it between the children
+    if os.path.exists(cache):
+        X = np.load(cache)
+    else:
+        X = latent(n, d, seed=0)
+        try:
+            np.save(cache, X)
+        except OSError:
+            pass
     metric_id, dev_corr, host_corr, angular = pdist.resolve(metric)
     n_trees = max(3, min(12, int(round(2.0 * np.log10(n))))); n_iters = max(5, int(round(np.log2(n))))
     leaf_size = max(60, min(256, 5 * k)); C_ = min(60, k)

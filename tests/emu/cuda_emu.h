@@ -205,6 +205,17 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+// lanes of `mask` holding the same 32-bit value
+static inline unsigned __match_any_sync(unsigned mask, int v) {
+    emu::Warp &w = emu::warp();
+    std::barrier<> &b = w.group(mask);
+    w.slot[emu::lane()] = (unsigned)v;
+    b.arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if (((mask >> i) & 1u) && w.slot[i] == (unsigned)v) r |= 1u << i;
+    b.arrive_and_wait();
+    return r;
+}
 
 // ---- mbarrier + bulk copy (nnd_common.cuh's PTX wrappers, k_join_pipe.cu's mbar_arrive)
 static inline void mbar_init(uint64_t *bar, uint32_t count) {
