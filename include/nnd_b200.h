@@ -181,20 +181,26 @@ NND_API int nnd_set_row_range(nnd_ctx *ctx, int64_t lo, int64_t hi);
  * only a row range of the heap supplies the snapshot itself (N floats in device memory, all-gathered from the owners; NULL =
  * snapshot the local heap as on one GPU).  Stale / larger thresholds only admit a superset of pushes (utils.py:484 re-checks).  */
 NND_API int nnd_set_thresholds(nnd_ctx *ctx, const float *thr);
+/* The local join and the replay drop half-updates (t <- o, d) whose o already sits in heap row t, and all but the first of
+ * several with the same (t, o): they can never be accepted -- PROVIDED every distance stored in the heap is the metric's own
+ * value for its pair (then an evicted o was the row's maximum with exactly this d, so `d >= root` rejects it, utils.py:484).
+ * A warm start with caller-supplied init_dist (pynndescent_.py:1225-1242 pushes them verbatim) breaks that premise:
+ * trusted = 0 switches both filters off for this context (default 1).                                                  */
+NND_API int nnd_set_heap_trusted(nnd_ctx *ctx, int32_t trusted);
 /* new_build_candidates (utils.py:221-320) for the own rows only, in three steps around two collectives of the caller:
  *  1. nnd_cand_local_counts: out_host[5T + 1 + R] = for every stream n this process's partial prefixes {prR_n(s_n), prV(s_n),
  *     prV(e_n), prR_n(e_n), total R_n}, then the total of valid edges, then the number of reverse-edge records per owner process;
  *  2. (caller: all-gather of the tables) nnd_cand_export: glob_host[6T] = per stream {R_s, V_s, V_e, R_e summed over all
  *     processes, sum of the lower ranks' R_n totals, sum of the lower ranks' valid totals}; forward priorities stay local, one
- *     12-byte record {target, scan key, priority} per reverse edge goes to the bucket of the target's owner
- *     (records_out + bucket_off_host[r] records);
+ *     12-byte record {target, scan key, priority} per reverse edge is appended to records_out, grouped by the target's owner
+ *     process in rank order (step 1's per-owner counts are the segment sizes);
  *  3. (caller: all-to-all-v of the buckets) nnd_cand_import_select: received records -> candidate lists of the own rows, sampled
  *     flags cleared.  Identical lists to nnd_build_candidates for any number of processes.                               */
 NND_API int nnd_cand_local_counts(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int32_t T, int32_t R, int64_t owner_block, void *ws,
                           size_t ws_bytes, int64_t *out_host, void *stream);
 NND_API int nnd_cand_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T, int32_t tables_valid,
-                    int32_t R, int64_t owner_block, const int64_t *glob_host, const int64_t *bucket_off_host, void *records_out,
-                    void *ws, size_t ws_bytes, void *stream);
+                    int32_t R, int64_t owner_block, const int64_t *glob_host, void *records_out, void *ws, size_t ws_bytes,
+                    void *stream);
 NND_API int nnd_cand_import_select(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int32_t T, const void *records, int64_t n,
                            int32_t *new_cand, int32_t *old_cand, void *ws, size_t ws_bytes, void *stream);
 /* prepass of one process_candidates call restricted to the row range; n_rounds_host = routing rounds needed */

@@ -65,8 +65,9 @@ SIGNATURES = {
     "nnd_metric_set_param": (C.c_int, [_vp, _i32, _vp, C.c_double, _vp]),
     "nnd_set_row_range": (C.c_int, [_vp, _i64, _i64]),
     "nnd_set_thresholds": (C.c_int, [_vp, _vp]),
+    "nnd_set_heap_trusted": (C.c_int, [_vp, _i32]),
     "nnd_cand_local_counts": (C.c_int, [_vp, _PP, _i32, _i32, _i32, _i64, _vp, _sz, _pi64, _vp]),
-    "nnd_cand_export": (C.c_int, [_vp, _PP, _i32, _pi64, _i32, _i32, _i32, _i64, _pi64, _pi64, _vp, _vp, _sz, _vp]),
+    "nnd_cand_export": (C.c_int, [_vp, _PP, _i32, _pi64, _i32, _i32, _i32, _i64, _pi64, _vp, _vp, _sz, _vp]),
     "nnd_cand_import_select": (C.c_int, [_vp, _PP, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "nnd_join_prepare": (C.c_int, [_vp, _PP, _i32, _vp, _vp, _i64, _vp, _sz, _pi32, _vp]),
     "nnd_join_emit_round": (C.c_int, [_vp, _PP, _i32, _i64, _vp, _sz, _i32, _pi64, _vp]),

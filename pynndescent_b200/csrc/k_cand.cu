@@ -17,6 +17,7 @@
 #include "nnd_common.cuh"
 #include <vector>
 
+struct CandRec;
 struct CandWs {
     uint32_t *cnt;      // [(T+1)*N] per-stream per-row counts; last block = valid counts
     uint32_t *pre;      // [(T+1)*N + 1] exclusive scan of cnt
@@ -29,8 +30,8 @@ struct CandWs {
     uint32_t *scan_tmp;
     int64_t table_len;
     uint8_t *act;       // [N+1] NND_CAND_SKIP: 1 = the vertex touches a new-flagged edge (= will have new candidates)
-    unsigned long long *scal;   // [4096] small tables of the sharded path: [0,64) record counts / bucket offsets, [64,128) cursors,
-                                // [128,2048) this process's count table, [2048,..) the global count table (u32)
+    unsigned long long *scal;   // [8192] small tables of the partitioned path (layout: SC_* below)
+    struct CandRec *recs;       // [N*k] reverse-edge records of the single-process partitioned build
 };
 
 static int64_t cand_table_len(int64_t N, int k) { return N * (int64_t)k; }
@@ -50,7 +51,8 @@ static int carve_cand_ws(void *ws, size_t ws_bytes, int64_t N, int k, int C, int
     W->table = A.get<float>((size_t)T * W->table_len);
     W->scan_tmp = A.get<uint32_t>(nnd_scan_tmp_elems((int64_t)(T + 1) * Nb + 2));
     W->act = A.get<uint8_t>(Nb + 1);
-    W->scal = A.get<unsigned long long>(4096);
+    W->scal = A.get<unsigned long long>(8192);
+    W->recs = (CandRec *)A.get<char>((size_t)Nb * k * 12);
     if (need) *need = A.off;
     return A.ok ? NND_OK : NND_ERR_WORKSPACE;
 }
@@ -478,6 +480,9 @@ static int launch_cand_select(nnd_ctx *ctx, const nnd_problem *P, int32_t C, Can
     return NND_OK;
 }
 
+struct CandWs;
+int nnd_build_candidates_partitioned(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T, int32_t tables_valid,
+                                     int32_t *new_cand, int32_t *old_cand, CandWs &W, cudaStream_t st);
 extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host,
                                     int32_t T, int32_t tables_valid, int32_t *new_cand, int32_t *old_cand, void *ws,
                                     size_t ws_bytes, void *stream) {
@@ -491,6 +496,13 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
               "nnd_build_candidates: workspace too small");
     const int64_t B = N / T + 1;
     NND_STAGE(ctx, NND_ST_CAND_FILL, st);
+    if (ctx->opt_cand_partition && ctx->row_lo <= 0 && ctx->row_hi >= N) {
+        NND_TRY(nnd_build_candidates_partitioned(ctx, P, C, rng_state_host, T, tables_valid, new_cand, old_cand, W, st));
+        NND_STAGE(ctx, NND_ST_OTHER, st);
+        NND_CUDA(cudaGetLastError());
+        return NND_OK;
+    }
+    // NND_CAND_PARTITION=0: the direct scatter (round-1 path, kept for the A/B)
     // the T priority streams: constant across iterations (utils.py:262 copies rng_state, never advances it)
     if (!tables_valid) {
         for (int n = 0; n < T; ++n) {
@@ -516,24 +528,54 @@ extern "C" int nnd_build_candidates(nnd_ctx *ctx, const nnd_problem *P, int32_t 
 }
 
 // =====================================================================================================================
-// Row-sharded candidate build (one process per GPU).  A process samples candidates for its own rows
-// [row_lo, row_hi) only and SCANS only its own rows' edges (the reference's threads each scan all N*k edges, utils.py:261-306;
-// so did round 1's sharded build).  What crosses process boundaries:
+// Partitioned candidate build (the default on one GPU and the row-sharded build's only path, DESIGN.md sections 6 and 8).
+// A process samples candidates for its own rows [row_lo, row_hi) only and SCANS only its own rows' edges (the reference's
+// threads each scan all N*k edges, utils.py:261-306).  Reverse edges are not scattered straight to their target (at 10M points
+// that is four DRAM-random 4..8-byte accesses per edge: 128 ms per build) but APPENDED to the bucket of the target's range
+// (<= 1024 buckets of ~10k consecutive targets, one sequential write stream each); the import pass then reads the records in
+// memory order, so that the per-target counters, offsets and segments it touches at any time fit the L2.  Buckets are grouped by
+// owner process, so the same records are what crosses NVLink in the sharded build:
 //   * a small table of per-stream counts (all-gather by the caller): the draw index of an edge in stream n is the number of
 //     earlier edges, in (row, column) order, that touch R_n -- a prefix over ALL rows, i.e. sum over lower ranks' totals + a local
 //     prefix; the four prefixes at the stream's own range boundaries s_n / e_n are sums over the processes' partial prefixes;
 //   * the reverse-edge proposals (target, scan key, priority) of edges whose target row lives elsewhere (one all-to-all-v).
-// Results are identical to nnd_build_candidates for any number of processes (closed-form draw indices, ordered replay).
+// Results are identical to the reference's new_build_candidates for any number of processes and buckets (closed-form draw
+// indices, ordered replay).
 // =====================================================================================================================
 struct __align__(4) CandRec { int32_t tgt; uint32_t key; float prio; };   // 12 bytes on the wire
+#define CAND_MAXB 1024
+// scal layout (u64 words): [0,1024) bucket counts, [1024,2048) bucket offsets, [2048,3072) bucket cursors, [3072,3136) totals per
+// owner process, [3136] all records, [4096,4096+5T+1] this process's count table, [6144,..) the global count table (u32)
+#define SC_CNT 0
+#define SC_OFF 1024
+#define SC_CUR 2048
+#define SC_TOT 3072
+#define SC_ALL 3136
+#define SC_LOC 4096
+#define SC_GLOB 6144
 
-// per own row: #valid edges, #edges into each R_n (cnt is zero elsewhere: memset by the host), records per destination process
-__global__ void k_cand_count_sh(const int32_t *ind, int k, int64_t N, int T, int64_t B, int64_t lo, int64_t hi, uint32_t *cnt,
-                                int64_t owner_block, int R, unsigned long long *dest_cnt) {
+struct BucketMap { int64_t owner_block; int R; int nbpr; int64_t bsize; };
+static BucketMap bucket_map(int64_t owner_block, int R) {
+    BucketMap m; m.owner_block = owner_block; m.R = R;
+    m.nbpr = CAND_MAXB / R; if (m.nbpr < 1) m.nbpr = 1;
+    m.bsize = (owner_block + m.nbpr - 1) / m.nbpr; if (m.bsize < 1) m.bsize = 1;
+    return m;
+}
+__device__ __forceinline__ int bucket_of(const BucketMap &m, int32_t x) {
+    int r = (int)(x / m.owner_block); if (r >= m.R) r = m.R - 1;
+    int w = (int)(((int64_t)x - (int64_t)r * m.owner_block) / m.bsize); if (w >= m.nbpr) w = m.nbpr - 1;
+    return r * m.nbpr + w;
+}
+
+// per own row: #valid edges, #edges into each R_n (cnt is zero elsewhere: memset by the host), records per bucket; act[i] = the row
+// has a new-flagged edge (NND_CAND_SKIP; the target side is marked by the import)
+__global__ void k_cand_count_sh(const int32_t *ind, const uint8_t *flags, int k, int64_t N, int T, int64_t B, int64_t lo, int64_t hi,
+                                uint32_t *cnt, BucketMap bm, unsigned long long *bucket_cnt, uint8_t *act) {
     const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = i < hi;
     const int lane = threadIdx.x & 31;
     uint32_t valid = 0;
+    bool anynew = false;
     if (on)
         for (int n = 0; n < T; ++n) {
             const int64_t bs = (int64_t)n * B, be = bs + B;
@@ -543,11 +585,29 @@ __global__ void k_cand_count_sh(const int32_t *ind, int k, int64_t N, int T, int
         }
     for (int j = 0; j < k; ++j) {
         int o = -1;
-        if (on) { const int32_t x = ind[i * k + j]; if (x >= 0) { ++valid; o = (int)(x / owner_block); if (o >= R) o = R - 1; } }
+        if (on) { const int32_t x = ind[i * k + j]; if (x >= 0) { ++valid; o = bucket_of(bm, x); anynew |= flags[i * k + j] != 0; } }
         const unsigned mk = __match_any_sync(0xffffffffu, o);
-        if (o >= 0 && lane == __ffs(mk) - 1) atomicAdd(&dest_cnt[o], (unsigned long long)__popc(mk));
+        if (o >= 0 && lane == __ffs(mk) - 1) atomicAdd(&bucket_cnt[o], (unsigned long long)__popc(mk));
     }
-    if (on) cnt[(size_t)T * N + i] = valid;
+    if (on) { cnt[(size_t)T * N + i] = valid; if (act && anynew) act[i] = 1; }
+}
+
+// one block: exclusive scan of the bucket counts, totals per owner process, cursors cleared
+__global__ void k_cand_bucket_scan(unsigned long long *scal, int nbk, int R, int nbpr) {
+    __shared__ unsigned long long s[CAND_MAXB];
+    const int t = threadIdx.x;
+    const unsigned long long mine = t < nbk ? scal[SC_CNT + t] : 0ULL;
+    s[t] = mine;
+    __syncthreads();
+    for (int o = 1; o < CAND_MAXB; o <<= 1) {
+        unsigned long long v = t >= o ? s[t - o] : 0ULL;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    if (t < nbk) { scal[SC_OFF + t] = s[t] - mine; scal[SC_CUR + t] = 0ULL; }
+    if (t < R) { const int b0 = t * nbpr, b1 = b0 + nbpr - 1; scal[SC_TOT + t] = s[b1] - (b0 > 0 ? s[b0 - 1] : 0ULL); }
+    if (t == 0) scal[SC_ALL] = s[nbk - 1];
 }
 
 // out[5n..5n+4] = this process's partial {prR_n(s_n), prV(s_n), prV(e_n), prR_n(e_n), total R_n}; out[5T] = total valid
@@ -567,6 +627,13 @@ __global__ void k_cand_locals(const uint32_t *pre, int64_t N, int T, int64_t B, 
     }
     if (n == 0) out[5 * T] = (long long)(endV - baseV);
 }
+// one process = all rows: the global table is the local one, the lower ranks' totals are zero
+__global__ void k_cand_glob_single(const long long *loc, int T, uint32_t *glob) {
+    const int n = threadIdx.x;
+    if (n >= T) return;
+    for (int q = 0; q < 4; ++q) glob[6 * n + q] = (uint32_t)loc[5 * n + q];
+    glob[6 * n + 4] = 0u; glob[6 * n + 5] = 0u;
+}
 
 // glob[6n..6n+5] = {R_s, V_s, V_e, R_e (global), baseR_n, baseV (sums over the lower ranks)}
 __device__ __forceinline__ uint32_t draw_index_sh(const uint32_t *pre, const uint32_t *glob, int64_t N, int T, int64_t B, int n, int64_t i,
@@ -580,11 +647,10 @@ __device__ __forceinline__ uint32_t draw_index_sh(const uint32_t *pre, const uin
     return G[0] + (G[2] - G[1]) + (prR - G[3]) + within_n;
 }
 
-// forward priorities of the own rows + one record per reverse edge, appended to the bucket of the target's owner
+// forward priorities of the own rows + one record per reverse edge, appended to the bucket of the target's range
 __global__ void k_cand_export(const int32_t *ind, const uint8_t *flags, int k, int64_t N, int T, int64_t B, int64_t lo, int64_t hi,
                               const uint32_t *pre, const uint32_t *glob, const float *table, int64_t table_len, float *fprio,
-                              int64_t owner_block, int R, const unsigned long long *bucket_off, unsigned long long *bucket_cur,
-                              CandRec *out) {
+                              BucketMap bm, const unsigned long long *bucket_off, unsigned long long *bucket_cur, CandRec *out) {
     const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = i < hi;
     const int lane = threadIdx.x & 31;
@@ -607,7 +673,7 @@ __global__ void k_cand_export(const int32_t *ind, const uint8_t *flags, int k, i
                     for (int jj = 0; jj < j; ++jj) { int32_t y = ind[i * k + jj]; wn += (y >= bs && y < be); }
                     pr = table[(size_t)nx * table_len + draw_index_sh(pre, glob, N, T, B, nx, i, 0, wn)];
                 }
-                o = (int)(x / owner_block); if (o >= R) o = R - 1;
+                o = bucket_of(bm, x);
                 ++wv;
             }
         }
@@ -623,17 +689,20 @@ __global__ void k_cand_export(const int32_t *ind, const uint8_t *flags, int k, i
     }
 }
 
-__global__ void k_cand_import_count(const CandRec *in, unsigned long long n, int64_t lo, int64_t hi, uint32_t *indeg, unsigned long long *bad) {
+// n_dev (optional): the record count lives on the device (single-process path: no host round trip); threads beyond it exit
+__global__ void k_cand_import_count(const CandRec *in, unsigned long long n, const unsigned long long *n_dev, int64_t lo, int64_t hi,
+                                    uint32_t *indeg, uint8_t *act, unsigned long long *bad) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t t = in[i].tgt;
-    if (t < lo || t >= hi) { atomicAdd(bad, 1ULL); return; }
-    atomicAdd(&indeg[t], 1u);
+    if (i >= (n_dev ? *n_dev : n)) return;
+    const CandRec r = in[i];
+    if (r.tgt < lo || r.tgt >= hi) { atomicAdd(bad, 1ULL); return; }
+    atomicAdd(&indeg[r.tgt], 1u);
+    if (act && (r.key & 1u)) act[r.tgt] = 1;
 }
-__global__ void k_cand_import_scatter(const CandRec *in, unsigned long long n, int64_t lo, int64_t hi, const uint32_t *revoff, uint32_t *cursor,
-                                      unsigned long long *rev) {
+__global__ void k_cand_import_scatter(const CandRec *in, unsigned long long n, const unsigned long long *n_dev, int64_t lo, int64_t hi,
+                                      const uint32_t *revoff, uint32_t *cursor, unsigned long long *rev) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (n_dev ? *n_dev : n)) return;
     const CandRec r = in[i];
     if (r.tgt < lo || r.tgt >= hi) return;
     const uint32_t slot = atomicAdd(&cursor[r.tgt], 1u);
@@ -646,6 +715,66 @@ static int cand_range(const nnd_ctx *ctx, int64_t N, int64_t *lo, int64_t *hi) {
     return NND_OK;
 }
 
+// step 1 on the device: counts of the own rows, their prefix sums, bucket offsets, this process's count table (W.scal)
+static int cand_counts_device(nnd_ctx *ctx, const nnd_problem *P, int T, const BucketMap &bm, CandWs &W, int64_t lo, int64_t hi, uint8_t *act,
+                              cudaStream_t st) {
+    const int64_t N = P->N; const int k = P->k;
+    const int64_t B = N / T + 1;
+    NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (size_t)(T + 1) * N, st));
+    NND_CUDA(cudaMemsetAsync(W.scal, 0, sizeof(unsigned long long) * 4096, st));
+    if (act) NND_CUDA(cudaMemsetAsync(act, 0, (size_t)N + 1, st));
+    if (hi > lo) { k_cand_count_sh<<<(unsigned)cdiv(hi - lo, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, lo, hi, W.cnt, bm, W.scal + SC_CNT, act); NND_LAUNCH(ctx); }
+    NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
+    k_cand_bucket_scan<<<1, CAND_MAXB, 0, st>>>(W.scal, bm.R * bm.nbpr, bm.R, bm.nbpr); NND_LAUNCH(ctx);
+    k_cand_locals<<<1, 256, 0, st>>>(W.pre, N, T, B, (long long *)(W.scal + SC_LOC)); NND_LAUNCH(ctx);
+    return NND_OK;
+}
+static int cand_tables(nnd_ctx *ctx, const int64_t *rng_state_host, int T, int tables_valid, CandWs &W, cudaStream_t st) {
+    if (tables_valid) return NND_OK;
+    for (int n = 0; n < T; ++n) {   // the T priority streams: constant across iterations (utils.py:262 copies rng_state, never advances it)
+        int64_t s[3] = {rng_state_host[0] + n, rng_state_host[1] + n, rng_state_host[2] + n};
+        NND_TRY(nnd_rng_table_launch(ctx, s, 0, W.table_len, 1, W.table + (size_t)n * W.table_len, st));
+    }
+    return NND_OK;
+}
+static int cand_import(nnd_ctx *ctx, const nnd_problem *P, int32_t C, CandWs &W, const CandRec *records, int64_t n_max, const unsigned long long *n_dev,
+                       int64_t lo, int64_t hi, uint8_t *act, bool check_bad, int32_t *new_cand, int32_t *old_cand, cudaStream_t st) {
+    const int64_t N = P->N;
+    NND_CUDA(cudaMemsetAsync(W.indeg, 0, sizeof(uint32_t) * (N + 1), st));
+    NND_CUDA(cudaMemsetAsync(W.cursor, 0, sizeof(uint32_t) * (N + 1), st));
+    unsigned long long *bad = W.scal + SC_ALL + 1;
+    NND_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), st));
+    if (n_max > 0) { k_cand_import_count<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(records, (unsigned long long)n_max, n_dev, lo, hi, W.indeg, act, bad); NND_LAUNCH(ctx); }
+    if (check_bad) {
+        unsigned long long hbad = 0;
+        NND_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(hbad), cudaMemcpyDeviceToHost, st));
+        NND_CUDA(cudaStreamSynchronize(st));
+        NND_CHECK(hbad == 0, NND_ERR_INVALID, "candidate import: %llu records target rows outside [%lld,%lld)", hbad, (long long)lo, (long long)hi);
+    }
+    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
+    if (n_max > 0) { k_cand_import_scatter<<<(unsigned)cdiv(n_max, 256), 256, 0, st>>>(records, (unsigned long long)n_max, n_dev, lo, hi, W.revoff, W.cursor, W.rev); NND_LAUNCH(ctx); }
+    NND_STAGE(ctx, NND_ST_CAND_SELECT, st);
+    NND_TRY(launch_cand_select(ctx, P, C, W, new_cand, old_cand, act, st));
+    return NND_OK;
+}
+
+// new_build_candidates on ONE process without a host round trip: counts -> export into range buckets -> import -> selection
+int nnd_build_candidates_partitioned(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T, int32_t tables_valid,
+                                     int32_t *new_cand, int32_t *old_cand, CandWs &W, cudaStream_t st) {
+    const int64_t N = P->N; const int k = P->k;
+    const int64_t B = N / T + 1;
+    const BucketMap bm = bucket_map(N + 1, 1);
+    uint8_t *act = ctx->opt_cand_skip ? W.act : nullptr;
+    NND_TRY(cand_tables(ctx, rng_state_host, T, tables_valid, W, st));
+    NND_TRY(cand_counts_device(ctx, P, T, bm, W, 0, N, act, st));
+    uint32_t *dglob = (uint32_t *)(W.scal + SC_GLOB);
+    k_cand_glob_single<<<1, 256, 0, st>>>((const long long *)(W.scal + SC_LOC), T, dglob); NND_LAUNCH(ctx);
+    k_cand_export<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, 0, N, W.pre, dglob, W.table, W.table_len, W.fprio, bm,
+                                                         W.scal + SC_OFF, W.scal + SC_CUR, W.recs);
+    NND_LAUNCH(ctx);
+    return cand_import(ctx, P, C, W, W.recs, N * (int64_t)k, W.scal + SC_ALL, 0, N, act, false, new_cand, old_cand, st);
+}
+
 extern "C" int nnd_cand_local_counts(nnd_ctx *ctx, const nnd_problem *P, int32_t C, int32_t T, int32_t R, int64_t owner_block,
                                      void *ws, size_t ws_bytes, int64_t *out_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -655,17 +784,10 @@ extern "C" int nnd_cand_local_counts(nnd_ctx *ctx, const nnd_problem *P, int32_t
     CandWs W;
     NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE, "nnd_cand_local_counts: workspace too small");
     int64_t lo, hi; cand_range(ctx, N, &lo, &hi);
-    const int64_t B = N / T + 1;
     NND_STAGE(ctx, NND_ST_CAND_FILL, st);
-    unsigned long long *dest = W.scal;                                         // [R] record counts
-    NND_CUDA(cudaMemsetAsync(W.cnt, 0, sizeof(uint32_t) * (size_t)(T + 1) * N, st));
-    NND_CUDA(cudaMemsetAsync(dest, 0, sizeof(unsigned long long) * 128, st));
-    if (hi > lo) { k_cand_count_sh<<<(unsigned)cdiv(hi - lo, 128), 128, 0, st>>>(P->heap_idx, k, N, T, B, lo, hi, W.cnt, owner_block, R, dest); NND_LAUNCH(ctx); }
-    NND_TRY(nnd_exclusive_scan_u32(ctx, W.cnt, W.pre, (int64_t)(T + 1) * N, W.scan_tmp, st));
-    long long *loc = (long long *)(W.scal + 128);                               // [5T + 1]
-    k_cand_locals<<<1, 256, 0, st>>>(W.pre, N, T, B, loc); NND_LAUNCH(ctx);
-    NND_CUDA(cudaMemcpyAsync(out_host, loc, sizeof(long long) * (5 * T + 1), cudaMemcpyDeviceToHost, st));
-    NND_CUDA(cudaMemcpyAsync(out_host + 5 * T + 1, dest, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, st));
+    NND_TRY(cand_counts_device(ctx, P, T, bucket_map(owner_block, R), W, lo, hi, ctx->opt_cand_skip ? W.act : nullptr, st));
+    NND_CUDA(cudaMemcpyAsync(out_host, W.scal + SC_LOC, sizeof(long long) * (5 * T + 1), cudaMemcpyDeviceToHost, st));
+    NND_CUDA(cudaMemcpyAsync(out_host + 5 * T + 1, W.scal + SC_TOT, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, st));
     NND_CUDA(cudaStreamSynchronize(st));
     NND_STAGE(ctx, NND_ST_OTHER, st);
     NND_CUDA(cudaGetLastError());
@@ -673,37 +795,28 @@ extern "C" int nnd_cand_local_counts(nnd_ctx *ctx, const nnd_problem *P, int32_t
 }
 
 extern "C" int nnd_cand_export(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int64_t *rng_state_host, int32_t T, int32_t tables_valid,
-                               int32_t R, int64_t owner_block, const int64_t *glob_host, const int64_t *bucket_off_host, void *records_out,
-                               void *ws, size_t ws_bytes, void *stream) {
+                               int32_t R, int64_t owner_block, const int64_t *glob_host, void *records_out, void *ws, size_t ws_bytes,
+                               void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    NND_CHECK(ctx && P && rng_state_host && glob_host && bucket_off_host && T >= 1 && T <= 256 && R >= 1 && R <= 64 && owner_block > 0,
-              NND_ERR_INVALID, "nnd_cand_export: bad args");
+    NND_CHECK(ctx && P && rng_state_host && glob_host && T >= 1 && T <= 256 && R >= 1 && R <= 64 && owner_block > 0, NND_ERR_INVALID,
+              "nnd_cand_export: bad args");
     const int64_t N = P->N; const int k = P->k;
     CandWs W;
     NND_CHECK(carve_cand_ws(ws, ws_bytes, N, k, C, T, &W, nullptr) == NND_OK, NND_ERR_WORKSPACE, "nnd_cand_export: workspace too small");
     int64_t lo, hi; cand_range(ctx, N, &lo, &hi);
     const int64_t B = N / T + 1;
     NND_STAGE(ctx, NND_ST_CAND_FILL, st);
-    if (!tables_valid) {
-        for (int n = 0; n < T; ++n) {
-            int64_t s[3] = {rng_state_host[0] + n, rng_state_host[1] + n, rng_state_host[2] + n};
-            NND_TRY(nnd_rng_table_launch(ctx, s, 0, W.table_len, 1, W.table + (size_t)n * W.table_len, st));
-        }
-    }
-    // upload {glob[6T] as u32, bucket offsets[R], zeroed cursors[R]} into the scalar area
-    unsigned long long *dest = W.scal;
+    NND_TRY(cand_tables(ctx, rng_state_host, T, tables_valid, W, st));
     std::vector<uint32_t> hg((size_t)6 * T);
     for (int q = 0; q < 6 * T; ++q) { NND_CHECK(glob_host[q] >= 0 && glob_host[q] < (1LL << 32), NND_ERR_INVALID, "nnd_cand_export: count table out of range"); hg[q] = (uint32_t)glob_host[q]; }
-    std::vector<unsigned long long> hb((size_t)2 * R, 0ULL);
-    for (int r = 0; r < R; ++r) hb[r] = (unsigned long long)bucket_off_host[r];
-    uint32_t *dglob = (uint32_t *)(W.scal + 2048);
+    uint32_t *dglob = (uint32_t *)(W.scal + SC_GLOB);
     NND_CUDA(cudaMemcpyAsync(dglob, hg.data(), sizeof(uint32_t) * hg.size(), cudaMemcpyHostToDevice, st));
-    NND_CUDA(cudaMemcpyAsync(dest, hb.data(), sizeof(unsigned long long) * hb.size(), cudaMemcpyHostToDevice, st));
-    NND_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope
+    NND_CUDA(cudaStreamSynchronize(st));   // the host vector goes out of scope
     if (hi > lo) {
         NND_CHECK(records_out, NND_ERR_INVALID, "nnd_cand_export: records_out is null");
         k_cand_export<<<(unsigned)cdiv(hi - lo, 128), 128, 0, st>>>(P->heap_idx, P->heap_flag, k, N, T, B, lo, hi, W.pre, dglob, W.table, W.table_len,
-                                                                W.fprio, owner_block, R, dest, dest + R, (CandRec *)records_out);
+                                                                W.fprio, bucket_map(owner_block, R), W.scal + SC_OFF, W.scal + SC_CUR,
+                                                                (CandRec *)records_out);
         NND_LAUNCH(ctx);
     }
     NND_STAGE(ctx, NND_ST_OTHER, st);
@@ -721,19 +834,8 @@ extern "C" int nnd_cand_import_select(nnd_ctx *ctx, const nnd_problem *P, int32_
     NND_CHECK(n <= 2 * N * (int64_t)k, NND_ERR_OVERFLOW, "nnd_cand_import_select: %lld records exceed the reverse-edge scratch", (long long)n);
     int64_t lo, hi; cand_range(ctx, N, &lo, &hi);
     NND_STAGE(ctx, NND_ST_CAND_FILL, st);
-    NND_CUDA(cudaMemsetAsync(W.indeg, 0, sizeof(uint32_t) * (N + 1), st));
-    NND_CUDA(cudaMemsetAsync(W.cursor, 0, sizeof(uint32_t) * (N + 1), st));
-    unsigned long long *bad = (unsigned long long *)W.scan_tmp;     // the scan below overwrites it afterwards; read back first
-    NND_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), st));
-    if (n > 0) { k_cand_import_count<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const CandRec *)records, (unsigned long long)n, lo, hi, W.indeg, bad); NND_LAUNCH(ctx); }
-    unsigned long long hbad = 0;
-    NND_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(hbad), cudaMemcpyDeviceToHost, st));
-    NND_CUDA(cudaStreamSynchronize(st));
-    NND_CHECK(hbad == 0, NND_ERR_INVALID, "nnd_cand_import_select: %llu records target rows outside [%lld,%lld)", hbad, (long long)lo, (long long)hi);
-    NND_TRY(nnd_exclusive_scan_u32_padded(ctx, W.indeg, W.revoff, N, W.scan_tmp, st));
-    if (n > 0) { k_cand_import_scatter<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const CandRec *)records, (unsigned long long)n, lo, hi, W.revoff, W.cursor, W.rev); NND_LAUNCH(ctx); }
-    NND_STAGE(ctx, NND_ST_CAND_SELECT, st);
-    NND_TRY(launch_cand_select(ctx, P, C, W, new_cand, old_cand, nullptr, st));
+    // W.act still holds the own rows' marks of step 1 (same scratch); the import adds the targets of new-flagged records
+    NND_TRY(cand_import(ctx, P, C, W, (const CandRec *)records, n, nullptr, lo, hi, ctx->opt_cand_skip ? W.act : nullptr, true, new_cand, old_cand, st));
     NND_STAGE(ctx, NND_ST_OTHER, st);
     NND_CUDA(cudaGetLastError());
     return NND_OK;

@@ -527,6 +527,23 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
     __syncthreads();                                        // ids[] complete, expect_tx posted
     issue(0);
     if (nchunks > 1) issue(1);
+    // presence filter: every thread PREFETCHES its share of the members' heap rows (indices) into registers right behind the first
+    // bulk copies, so that their DRAM latency hides under the chunk loop; they are parked in the row buffers once those are free
+    constexpr int HPRE = (JB_SCAP * 16 + JB_THREADS - 1) / JB_THREADS;          // host: k <= 16
+    int32_t hpre[HPRE];
+    const int hk = P.heap_idx ? P.k : 0;
+    if (hk) {
+        int slot = tid / hk, j = tid - slot * hk;
+        const int dq = JB_THREADS / hk, dr = JB_THREADS - dq * hk;
+#pragma unroll
+        for (int q = 0; q < HPRE; ++q) {
+            int32_t v = -1;
+            if (slot < totphys) { const int32_t id = ids[slot]; if (id >= 0) v = __ldg(P.heap_idx + (int64_t)id * hk + j); }
+            hpre[q] = v;
+            slot += dq; j += dr;
+            if (j >= hk) { j -= hk; ++slot; }
+        }
+    }
     for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
         if (u >= 0) {
@@ -563,13 +580,9 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
     // ---- presence filter: the heap rows (indices) of all members, staged in the row buffers (free now: the chunk loop ends with
     // a CTA-wide barrier)
     int32_t *hrow = (int32_t *)rows;                        // [totphys][hk]
-    const int hk = P.heap_idx ? P.k : 0;
     if (hk) {
-        for (int e = tid; e < totphys * hk; e += JB_THREADS) {
-            const int slot = e / hk, j = e - slot * hk;
-            const int32_t id = ids[slot];
-            hrow[e] = id >= 0 ? P.heap_idx[(int64_t)id * hk + j] : -1;
-        }
+#pragma unroll
+        for (int q = 0; q < HPRE; ++q) { const int e = tid + q * JB_THREADS; if (e < totphys * hk) hrow[e] = hpre[q]; }
         __syncthreads();
     }
     // ---- finalise + filter
@@ -702,7 +715,7 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
             // NND_APPLY_SHORT_SORT: a bitonic network over the first next_pow2(kept) lanes sorts them just as well (the other
             // lanes hold the maximum key and never mix with them) -- 1-3 stages instead of 15 for the 1-3 records a touched
             // row typically receives after the first iterations
-            const int top = short_sort ? (int)next_pow2_u32((uint32_t)(kept > 2 ? kept : 2)) : 32;
+            const int top = (short_sort & 1) ? (int)next_pow2_u32((uint32_t)(kept > 2 ? kept : 2)) : 32;
 #pragma unroll
             for (int k2 = 2; k2 <= 32; k2 <<= 1) {
                 if (k2 > top) break;
@@ -721,9 +734,11 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
             Rec16 mine; mine.key = ~0ULL; mine.oth = -2 - lane; mine.d = 0.f;
             if (lane < kept) mine = buf[slot];
             bool live = lane < kept;
-            for (int j = 0; j < k; ++j) live = live && (ind[j] != mine.oth);
-            const unsigned grp = __match_any_sync(0xffffffffu, live ? mine.oth : -2 - lane);
-            live = live && (lane == __ffs(grp) - 1);
+            if (short_sort & 2) {       // (only while every distance in the row is the metric's own: nnd_set_heap_trusted)
+                for (int j = 0; j < k; ++j) live = live && (ind[j] != mine.oth);
+                const unsigned grp = __match_any_sync(0xffffffffu, live ? mine.oth : -2 - lane);
+                live = live && (lane == __ffs(grp) - 1);
+            }
             unsigned lm = __ballot_sync(0xffffffffu, live);
             int c = 0;
             while (lm) {
@@ -1209,7 +1224,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
         NND_LAUNCH(ctx);
     }
     k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
-                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1, use_small, ctx->opt_apply_short);
+                                                                           W.cnt, W.off, W.rec, W.dev_scalars + 1, use_small, (ctx->opt_apply_short ? 1 : 0) | (ctx->heap_trusted ? 2 : 0));
     NND_LAUNCH(ctx);
     NND_STAGE(ctx, NND_ST_OTHER, st);
     NND_CUDA(cudaGetLastError());
@@ -1228,12 +1243,9 @@ static size_t join_batch_smem(int metric, int dk, int ld) {
 static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st) {
     int64_t nb = JB.batch_end - JB.batch_begin;
     if (nb <= 0) return NND_OK;
-    // floats per staged chunk: 32 = the measured default (16 lost the round-2 A/B, profiles/ab_r02_1m_switches.json).
-    // NND_JB_DK=64|128 (experiment): fewer, larger bulk copies per member row -- 128 stages whole 512-byte rows of d = 128 in ONE
-    // copy each (single buffer, 2 CTAs per SM overlap each other's gather) instead of four 128-byte pieces
-    static int dk_sel = -1;
-    if (dk_sel < 0) { const char *e = getenv("NND_JB_DK"); dk_sel = e ? atoi(e) : 32; if (dk_sel != 32 && dk_sel != 64 && dk_sel != 128) dk_sel = 32; }
-    const int dk = dk_sel;
+    // floats per staged chunk.  16 / 64 / 128 all lost on hardware (1M: profiles/ab_r02_1m_switches.json; 10M: join 513 -> 762 / 732 ms,
+    // profiles/ab_r02_10m_call5.json): smaller chunks double the barriers, larger ones halve the resident CTAs
+    const int dk = 32;
     size_t smem = join_batch_smem(JB.metric, dk, JB.ld);
     dim3 grid((unsigned)nb);
 #define LB(M_, D_)                                                                                                   \
@@ -1241,7 +1253,7 @@ static int launch_join_batch(nnd_ctx *ctx, JoinBatchParams &JB, cudaStream_t st)
         NND_CUDA(cudaFuncSetAttribute(k_join_batch<M_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_join_batch<M_, D_><<<grid, JB_THREADS, smem, st>>>(JB);                                                     \
     } while (0)
-#define LBM(M_) do { if (dk == 32) LB(M_, 32); else if (dk == 64) LB(M_, 64); else LB(M_, 128); } while (0)
+#define LBM(M_) LB(M_, 32)
     if (JB.metric == NND_METRIC_SQEUCLIDEAN) LBM(NND_METRIC_SQEUCLIDEAN);
     else if (JB.metric == NND_METRIC_ALT_COSINE) LBM(NND_METRIC_ALT_COSINE);
     else LBM(NND_METRIC_ALT_DOT);
@@ -1445,7 +1457,7 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
             JB.act_unit = W.act_unit; JB.act_info = W.act_info; JB.act_poff = W.act_poff; JB.members = W.members;
             JB.batch_first = W.batch_first; JB.n_active = n_active; JB.n_batches = n_batches; JB.slot_stride = 2 * C;
             // presence filter: k heap indices per member must fit the (single-chunk: one) row buffer of JB_SCAP x (32 + 4) floats
-            if (ctx->opt_presence && P->k <= 32) { JB.heap_idx = P->heap_idx; JB.k = P->k; }
+            if (ctx->opt_presence && ctx->heap_trusted && P->k <= 16) { JB.heap_idx = P->heap_idx; JB.k = P->k; }
             // rounds are planned optimistically (16 half-updates per tile slot; the worst case is 32 and the measured
             // average 7); a round that overflows is detected (never silent) and split by the caller
             // ... and from the second iteration of a build on by the measured emission of the previous iteration's rounds
@@ -1670,7 +1682,7 @@ extern "C" int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, 
     }
     k_apply<<<(unsigned)cdiv(Nr, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx + lo * P->k, P->heap_dist + lo * P->k,
                                                                             P->heap_flag + lo * P->k, P->k, Nr, W.cnt, W.off, W.rec,
-                                                                            W.dev_scalars + 1, skip_small, ctx->opt_apply_short);
+                                                                            W.dev_scalars + 1, skip_small, (ctx->opt_apply_short ? 1 : 0) | (ctx->heap_trusted ? 2 : 0));
     NND_LAUNCH(ctx);
     unsigned long long hc = 0, hbad = 0;
     NND_CUDA(cudaMemcpyAsync(&hc, W.dev_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));

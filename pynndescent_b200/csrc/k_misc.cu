@@ -51,19 +51,20 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
     nnd_ctx *c = new nnd_ctx();
     c->device = device; c->sm_count = prop.multiProcessorCount; c->launches = 0;
     memset(c->prof, 0, sizeof(c->prof));
-    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr; c->plan_free = nullptr; c->jb_ppb_max = 0.0; c->thr_ext = nullptr;
+    c->row_lo = 0; c->row_hi = INT64_MAX; c->plan = nullptr; c->plan_free = nullptr; c->jb_ppb_max = 0.0; c->thr_ext = nullptr; c->heap_trusted = 1;
     {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
         c->opt_rank_scatter = env_int("NND_RANK_SCATTER", 1);
         c->opt_cand_skip = env_int("NND_CAND_SKIP", 1);
         c->opt_presence = env_int("NND_PRESENCE", 1);
+        c->opt_cand_partition = env_int("NND_CAND_PARTITION", 1);
         c->opt_cand_keys = env_int("NND_CAND_KEYS", 0);
         c->opt_leaf_split = env_int("NND_LEAF_SPLIT", 1);
         c->opt_carveout = env_int("NND_SMEM_CARVEOUT", 1);
         c->opt_apply_short = env_int("NND_APPLY_SHORT_SORT", 1);
         c->opt_apply_half = env_int("NND_APPLY_HALF", 0);
         c->opt_forest_pm = env_int("NND_FOREST_PM", 1);
-        c->opt_forest_pm_mb = env_int("NND_FOREST_PM_MB", 96);
+        c->opt_forest_pm_mb = env_int("NND_FOREST_PM_MB", 4096);   // 10M: 48/96 MB 250 ms, 200+ MB 241 ms (A/B): point-major on every level
     }
     c->sp_on = 0; c->sp_n = 0; c->sp_cap = 0; c->sp_ev = nullptr; c->sp_id = nullptr; memset(c->sp_ms, 0, sizeof(c->sp_ms));
     { const char *e = getenv("NND_STAGE_PROFILE"); if (e && e[0] == '1') c->sp_on = 1; }
@@ -132,6 +133,11 @@ extern "C" int nnd_stage_read(nnd_ctx *ctx, double *out_ms, int32_t reset) {
     stage_resolve(ctx);
     memcpy(out_ms, ctx->sp_ms, sizeof(ctx->sp_ms));
     if (reset) { memset(ctx->sp_ms, 0, sizeof(ctx->sp_ms)); ctx->sp_n = 0; }
+    return NND_OK;
+}
+extern "C" int nnd_set_heap_trusted(nnd_ctx *ctx, int32_t trusted) {
+    NND_CHECK(ctx, NND_ERR_INVALID, "nnd_set_heap_trusted: null context");
+    ctx->heap_trusted = trusted ? 1 : 0;
     return NND_OK;
 }
 extern "C" int nnd_set_thresholds(nnd_ctx *ctx, const float *thr) {

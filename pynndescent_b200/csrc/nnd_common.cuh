@@ -43,6 +43,7 @@ struct nnd_ctx {
     cudaEvent_t ev0, ev1;
     unsigned long long last_round_rows, last_round_pairs;
     double jb_ppb_max;        // half-updates per batch of the fullest round since the last plan (0 = unknown): sizes the next plan's rounds
+    int heap_trusted;         // nnd_set_heap_trusted: every distance in the heap is the metric's own value (enables the presence / duplicate filters)
     const float *thr_ext;     // nnd_set_thresholds: heap-root snapshot of all rows supplied by the caller (sharded build), or null
     int64_t row_lo, row_hi;   // sharded build: this process joins / samples candidates only for rows in [row_lo,row_hi)
     void *plan;               // JoinPlan of the sharded round API (k_descent.cu)
@@ -58,6 +59,7 @@ struct nnd_ctx {
     int opt_leaf_split;       // NND_LEAF_SPLIT=1: leaf init = distance-matrix kernel + thread-per-member push kernel (k_descent.cu)
     int opt_cand_keys;        // NND_CAND_KEYS=1: k_cand_select_small stages the reverse-edge key words in shared memory
     int opt_presence;         // NND_PRESENCE=1 (default): the batched join drops half-updates whose source already sits in the target's heap row
+    int opt_cand_partition;   // NND_CAND_PARTITION=1 (default): reverse edges go through range buckets (sequential appends + L2-local import)
     int opt_cand_skip;        // NND_CAND_SKIP=1: candidates are sampled only for vertices that will have NEW candidates (k_cand.cu)
     int opt_forest_pm;        // NND_FOREST_PM=1: point-major hyperplane pass of the RP forest (k_forest_side_pm<NCH>, k_forest.cu)
     int opt_forest_pm_mb;     // NND_FOREST_PM_MB: ... while the level's hyperplane table is at most this many MB (default 48)

@@ -110,6 +110,7 @@ class Engine:
 
     # ------------------------------------------------------------------ stages
     def make_heap(self):
+        check(lib.nnd_set_heap_trusted(self._ctx, 1))
         check(lib.nnd_make_heap(self._ctx, _ptr(self.heap_idx), _ptr(self.heap_dist), _ptr(self.heap_flag), self.N,
                                 self.k, self._st()))
 
@@ -187,6 +188,9 @@ class Engine:
         n = int(a.numel())
         if n == 0:
             return 0
+        # caller-supplied distances are pushed verbatim like the reference does: the heap then holds values that are not the metric's
+        # own, which is what the presence / duplicate filters of the join and the replay rely on (include/nnd_b200.h)
+        check(lib.nnd_set_heap_trusted(self._ctx, 0 if init_dist is not None else 1))
         if init_dist is None:
             d = torch.empty(n, dtype=torch.float32, device=dev)
             check(lib.nnd_pair_distances(self._ctx, C.byref(self.problem()), _ptr(a), _ptr(b), n, _ptr(d), self._st()))
@@ -317,18 +321,17 @@ class Engine:
                                         int(owner_block), _ptr(ws), nb, out.ctypes.data_as(C.POINTER(C.c_int64)), self._st()))
         return out
 
-    def cand_export(self, max_candidates, rng_state, n_threads, tables_valid, world, owner_block, glob, bucket_off, n_records):
-        """Step 2: forward priorities of the own rows + 12-byte reverse-edge records grouped by owner process."""
+    def cand_export(self, max_candidates, rng_state, n_threads, tables_valid, world, owner_block, glob, n_records):
+        """Step 2: forward priorities of the own rows + 12-byte reverse-edge records grouped by owner process (rank order)."""
         ws, nb, fresh = self._cand_ws(max_candidates, n_threads)
         if fresh or getattr(self, "_cand_tables_fresh", False):
             tables_valid = False
         self._cand_tables_fresh = False
         out = torch.empty(max(int(n_records), 1) * 12, dtype=torch.uint8, device=self.device)
         st = (C.c_int64 * 3)(*[int(v) for v in rng_state])
-        g = np.ascontiguousarray(glob, np.int64); b = np.ascontiguousarray(bucket_off, np.int64)
+        g = np.ascontiguousarray(glob, np.int64)
         check(lib.nnd_cand_export(self._ctx, C.byref(self.problem()), int(max_candidates), st, int(n_threads), int(bool(tables_valid)),
-                                  int(world), int(owner_block), g.ctypes.data_as(C.POINTER(C.c_int64)),
-                                  b.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(out), _ptr(ws), nb, self._st()))
+                                  int(world), int(owner_block), g.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(out), _ptr(ws), nb, self._st()))
         return out
 
     def cand_import_select(self, max_candidates, n_threads, records, n):

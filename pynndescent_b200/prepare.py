@@ -96,7 +96,7 @@ def prepare_search_structures(eng, metric, ng_idx_t, ng_dist_t, n_neighbors, ang
     dd_t[dd_t == 0.0] = float(FLOAT32_EPS)
     di2_t = di_t.clone(); dd2_t = dd_t.clone()
     check(lib.nnd_diversify(eng._ctx, C.byref(P), _p(di2_t), _p(dd2_t), eng._st()))
-    if os.environ.get("NND_PREPARE_GPU", "") == "1":     # experimental (k_search_graph.cu): the bookkeeping on the device
+    if os.environ.get("NND_PREPARE_GPU", "1") != "0":    # default: the bookkeeping on the device (k_search_graph.cu); "0" = host scipy
         S = search_graph_device(eng, di_t, dd_t, di2_t, dd2_t, tree_idx_t, tree_idx, n_neighbors, pruning_degree_multiplier)
     else:
         eng.stream.synchronize()

@@ -206,9 +206,8 @@ class ShardedBuilder:
             glob[6 * n + 5] = A[:me, 5 * T].sum()                                # lower ranks' valid edges
         send_counts = [int(c) for c in A[me, 5 * T + 1:]]
         recv_counts = [int(A[q, 5 * T + 1 + me]) for q in range(W)]
-        boff = np.concatenate([[0], np.cumsum(send_counts)[:-1]]).astype(np.int64)
         ns, nr = sum(send_counts), sum(recv_counts)
-        send = e.cand_export(C_, rng_state, T, tables_valid, W, self.B, glob, boff, ns)
+        send = e.cand_export(C_, rng_state, T, tables_valid, W, self.B, glob, ns)
         recv = torch.empty(max(nr, 1) * 12, dtype=torch.uint8, device=e.device)
         dist.all_to_all_single(recv[: nr * 12], send[: ns * 12], output_split_sizes=[c * 12 for c in recv_counts],
                                input_split_sizes=[c * 12 for c in send_counts])

@@ -37,8 +37,8 @@ CONFIGS = {
                         "NND_APPLY_SHORT_SORT": "0", "NND_PRESENCE": "0"},
     "nopresence": {"NND_PRESENCE": "0"},
     "nocandskip": {"NND_CAND_SKIP": "0"},
-    "jbdk64": {"NND_JB_DK": "64"},
-    "jbdk128": {"NND_JB_DK": "128"},
+    "nocandpartition": {"NND_CAND_PARTITION": "0"},
+    "nopresence+nocandpartition": {"NND_PRESENCE": "0", "NND_CAND_PARTITION": "0"},
 }
 
 

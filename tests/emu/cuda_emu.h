@@ -205,6 +205,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
 // lanes of `mask` holding the same 32-bit value
 static inline unsigned __match_any_sync(unsigned mask, int v) {
     emu::Warp &w = emu::warp();

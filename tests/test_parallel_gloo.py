@@ -45,7 +45,7 @@ class ScriptedEngine:
     def set_row_range(self, lo, hi): self.lo, self.hi = lo, hi
     def set_thresholds(self, thr): self.thr = thr
     def cand_local_counts(self, C_, T, world, B): return np.zeros(5 * T + 1 + world, np.int64)
-    def cand_export(self, C_, rng, T, tables_valid, world, B, glob, boff, n): return torch.zeros(12, dtype=torch.uint8)
+    def cand_export(self, C_, rng, T, tables_valid, world, B, glob, n): return torch.zeros(12, dtype=torch.uint8)
     def cand_import_select(self, C_, T, records, n): return None, None
     def join_prepare(self, newc, oldc, cap):
         self.it += 1
@@ -286,7 +286,7 @@ class OracleShardEngine:
             out[5 * n: 5 * n + 5] = [self.PR[n, s], self.PV[s], self.PV[e_], self.PR[n, e_], self.PR[n, N]]
         out[5 * T_] = self.PV[N]; out[5 * T_ + 1:] = dest
         return out
-    def cand_export(self, C_, rng, T_, tables_valid, world, Bown, glob, boff, n_rec):
+    def cand_export(self, C_, rng, T_, tables_valid, world, Bown, glob, n_rec):
         Bt = N // T_ + 1
         tab = self._tables(rng, T_)
         idx, _, flg = self.heap()
@@ -313,10 +313,11 @@ class OracleShardEngine:
                 buckets[min(x // Bown, world - 1)].append((x, ((i * K + j) << 1) | int(flg[i, j] != 0), pr))
                 wv += 1
         rec = np.zeros(max(n_rec, 1), np.dtype([("tgt", "<i4"), ("key", "<u4"), ("prio", "<f4")]))
-        for o in range(world):
-            assert (int(boff[o + 1]) if o + 1 < world else n_rec) - int(boff[o]) == len(buckets[o])
-            for q, t in enumerate(buckets[o][::-1]):                # any order inside a bucket
-                rec[int(boff[o]) + q] = t
+        assert sum(len(b) for b in buckets) == n_rec
+        q = 0
+        for o in range(world):                                      # grouped by owner process in rank order
+            for t in buckets[o][::-1]:                              # any order inside a group
+                rec[q] = t; q += 1
         return torch.from_numpy(rec.view(np.uint8).copy())
     def cand_import_select(self, C_, T_, records, n):
         rec = records.numpy()[: n * 12].view(np.dtype([("tgt", "<i4"), ("key", "<u4"), ("prio", "<f4")]))
