@@ -38,6 +38,7 @@ CONFIGS = {
     "nopresence": {"NND_PRESENCE": "0"},
     "nocandskip": {"NND_CAND_SKIP": "0"},
     "nocandpartition": {"NND_CAND_PARTITION": "0"},
+    "nopm4": {"NND_FOREST_PM4": "0"},
     "nopresence+nocandpartition": {"NND_PRESENCE": "0", "NND_CAND_PARTITION": "0"},
 }
 
