@@ -15,11 +15,6 @@ struct JoinBatchParams {
     int64_t n_active, n_batches; int64_t batch_begin, batch_end; int slot_stride;
     int32_t *out_tgt, *out_oth; float *out_d; uint32_t *out_pos; unsigned long long *out_seq;
     uint32_t *tgt_count; unsigned long long *cursor; unsigned long long capacity; unsigned long long *stats; int *overflow;
-    // presence filter (optional, null = off): a half-update (t <- o, d) whose o already sits in ANY past state of heap row t can
-    // never be accepted -- while o is in the row the duplicate test rejects it (utils.py:490-492), and once o has been evicted the
-    // root has dropped to at most d (an evicted entry was the row's maximum), so `d >= root` rejects it (utils.py:484).  Measured on
-    // the oracle: 34 % of the emitted half-updates in iteration 0 and 88-95 % in every later iteration.
-    const int32_t *heap_idx; int k;
 };
 
 __host__ __device__ __forceinline__ int jb_tiles(int nn, int m) {

@@ -226,11 +226,6 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_cand_select(const int32_t *i
 // the reverse edges are staged in shared memory (column per thread), the next edge in scan order
 // is found by selection, and checked_heap_push is replayed by the thread on column-layout heaps.
 #define SEL_T 128
-// SMEM_KEYS (NND_CAND_KEYS=1, default off until measured): the selection below reads the key word of every remaining
-// reverse edge once per step -- nrev^2/2 loads per vertex, each a different address per lane, i.e. up to 32 L1 wavefronts
-// per warp load.  Staging the <= 32 key words of the vertex once, column-wise in shared memory ([j][thread]: one
-// conflict-free wavefront per warp load), leaves nrev uncoalesced loads and moves the quadratic part on chip.
-template <bool SMEM_KEYS>
 __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
                                                              const uint32_t *indeg, const uint32_t *revoff,
                                                              const unsigned long long *rev, const float *fprio,
@@ -242,7 +237,6 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
     float *npri = (float *)smem_raw + tid;                                         // [C][SEL_T]
     float *opri = npri + (size_t)C * SEL_T;
     int32_t *nind = (int32_t *)(opri + (size_t)C * SEL_T), *oind = nind + (size_t)C * SEL_T;
-    uint32_t *skey = (uint32_t *)(oind + (size_t)C * SEL_T);     // [SEL_SMALL][SEL_T] (SMEM_KEYS only); like the heaps: column `tid`
     if (v >= N || v < lo || v >= hi) return;
     const uint32_t nrev = indeg[v];
     if (nrev > SEL_SMALL) return;  // handled by the warp kernel
@@ -252,8 +246,6 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
     }
     for (int c = 0; c < C; ++c) { npri[c * SEL_T] = CUDART_INF_F; opri[c * SEL_T] = CUDART_INF_F; nind[c * SEL_T] = -1; oind[c * SEL_T] = -1; }
     const unsigned long long *seg = rev + revoff[v];
-    if (SMEM_KEYS)
-        for (uint32_t j = 0; j < nrev; ++j) skey[j * SEL_T] = ((const uint32_t *)seg)[2 * j + 1];
     int jf = 0; uint32_t left = nrev, used = 0;   // bit j of `used`: reverse edge j already consumed
     const unsigned long long fbase = (unsigned long long)v * k;
     for (;;) {
@@ -267,7 +259,7 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
                 uint32_t bk = 0xFFFFFFFFu;
                 for (uint32_t j = 0; j < nrev; ++j) {
                     if ((used >> j) & 1u) continue;
-                    uint32_t x = SMEM_KEYS ? skey[j * SEL_T] : kw[2 * j + 1];
+                    uint32_t x = kw[2 * j + 1];
                     if (x < bk) { bk = x; bj = (int)j; }
                 }
                 if (bj >= 0) best = seg[bj];
@@ -306,104 +298,6 @@ __global__ void __launch_bounds__(SEL_T) k_cand_select_small(const int32_t *ind,
         if (found) flags[v * k + j] = 0;
     }
     for (int c = 0; c < C; ++c) { newc[v * C + c] = nind[c * SEL_T]; oldc[v * C + c] = oind[c * SEL_T]; }
-}
-
-// ---- NND_CAND_KEYS=2: the same thread-per-vertex selection with EVERYTHING a vertex touches staged in shared memory by
-// coalesced, cooperative loads: the tile's 128 heap rows (indices, forward priorities, flags; rows of consecutive vertices
-// are contiguous in memory), the reverse-edge key words, and the finished candidate lists on the way out.  Per-thread
-// row-wise global accesses cost up to 32 L1 wavefronts per warp instruction; the column layout [j][thread] with a stride
-// of SEL_T + 1 words costs one.  (More shared memory per CTA = fewer resident warps: to be decided by measurement.)
-#define ST_PAD (SEL_T + 1)
-static size_t cand_tile_smem(int k, int C) {
-    return (size_t)ST_PAD * ((size_t)C * 16 + (size_t)SEL_SMALL * 4 + (size_t)k * 8) + (((size_t)k * ST_PAD + 15) & ~size_t(15)) + SEL_T + 64;
-}
-__global__ void __launch_bounds__(SEL_T) k_cand_select_tile(const int32_t *ind, uint8_t *flags, int k, int64_t N, int C,
-                                                            const uint32_t *indeg, const uint32_t *revoff,
-                                                            const unsigned long long *rev, const float *fprio, int32_t *newc,
-                                                            int32_t *oldc, int64_t lo, int64_t hi, const uint8_t *act) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    float *npri_b = (float *)smem_raw, *opri_b = npri_b + (size_t)C * ST_PAD;                       // [C][ST_PAD]
-    int32_t *nind_b = (int32_t *)(opri_b + (size_t)C * ST_PAD), *oind_b = nind_b + (size_t)C * ST_PAD;
-    uint32_t *skey_b = (uint32_t *)(oind_b + (size_t)C * ST_PAD);                                    // [SEL_SMALL][ST_PAD]
-    int32_t *sind_b = (int32_t *)(skey_b + (size_t)SEL_SMALL * ST_PAD);                              // [k][ST_PAD]
-    float *spri_b = (float *)(sind_b + (size_t)k * ST_PAD);
-    uint8_t *sflg_b = (uint8_t *)(spri_b + (size_t)k * ST_PAD);                                      // [k][ST_PAD] bytes
-    uint8_t *s_state = sflg_b + (((size_t)k * ST_PAD + 15) & ~size_t(15));                           // [SEL_T]
-    float *npri = npri_b + tid, *opri = opri_b + tid;
-    int32_t *nind = nind_b + tid, *oind = oind_b + tid;
-    const uint32_t *skey = skey_b + tid; const int32_t *sind = sind_b + tid; const float *spri = spri_b + tid;
-    const uint8_t *sflg = sflg_b + tid;
-    const int64_t v0 = (int64_t)blockIdx.x * SEL_T, v = v0 + tid;
-    const int nrows = (int)min((int64_t)SEL_T, N - v0);
-    for (int e = tid; e < nrows * k; e += SEL_T) {       // the tile's heap rows, coalesced -> column layout
-        const int r = e / k, j = e - r * k;
-        sind_b[j * ST_PAD + r] = ind[v0 * k + e]; spri_b[j * ST_PAD + r] = fprio[v0 * k + e]; sflg_b[j * ST_PAD + r] = flags[v0 * k + e];
-    }
-    // 0 = not this kernel's vertex (other process / hub vertex of k_cand_select), 1 = sample, 2 = no new candidates (empty lists)
-    int state = 0; uint32_t nrev = 0;
-    if (v < N && v >= lo && v < hi) { nrev = indeg[v]; if (nrev <= SEL_SMALL) state = (act && !act[v]) ? 2 : 1; }
-    s_state[tid] = (uint8_t)state;
-    for (int c = 0; c < C; ++c) { npri[c * ST_PAD] = CUDART_INF_F; opri[c * ST_PAD] = CUDART_INF_F; nind[c * ST_PAD] = -1; oind[c * ST_PAD] = -1; }
-    const unsigned long long *seg = rev + (state == 1 ? revoff[v] : 0);
-    if (state == 1)
-        for (uint32_t j = 0; j < nrev; ++j) skey_b[j * ST_PAD + tid] = ((const uint32_t *)seg)[2 * j + 1];
-    __syncthreads();
-    if (state == 1) {
-        int jf = 0; uint32_t left = nrev, used = 0;
-        const unsigned long long fbase = (unsigned long long)v * k;
-        for (;;) {
-            while (jf < k && sind[jf * ST_PAD] < 0) ++jf;
-            const bool hasf = jf < k;
-            unsigned long long best = ~0ULL; int bj = -1;
-            if (left) {
-                uint32_t bk = 0xFFFFFFFFu;
-                for (uint32_t j = 0; j < nrev; ++j) {
-                    if ((used >> j) & 1u) continue;
-                    const uint32_t x = skey[j * ST_PAD];
-                    if (x < bk) { bk = x; bj = (int)j; }
-                }
-                if (bj >= 0) best = seg[bj];
-            }
-            const bool hasr = bj >= 0;
-            if (!hasf && !hasr) break;
-            const bool take_f = hasf && (!hasr || fbase + jf <= (best >> 33));
-            float p; int32_t cand; bool isnew;
-            if (take_f) { p = spri[jf * ST_PAD]; cand = sind[jf * ST_PAD]; isnew = sflg[jf * ST_PAD] != 0; ++jf; }
-            else {
-                used |= 1u << bj; --left;
-                p = __uint_as_float((uint32_t)(best & 0xFFFFFFFFULL)); isnew = (best >> 32) & 1ULL;
-                cand = (int32_t)((best >> 33) / (unsigned long long)k);
-            }
-            float *pri = isnew ? npri : opri; int32_t *idx = isnew ? nind : oind;
-            if (p >= pri[0]) continue;
-            bool dup = false;
-            for (int c = 0; c < C; ++c) dup |= (idx[c * ST_PAD] == cand);
-            if (dup) continue;
-            int i = 0, i_swap;
-            for (;;) {
-                int ic1 = 2 * i + 1, ic2 = ic1 + 1;
-                if (ic1 >= C) break;
-                else if (ic2 >= C) { if (pri[ic1 * ST_PAD] > p) i_swap = ic1; else break; }
-                else if (pri[ic1 * ST_PAD] >= pri[ic2 * ST_PAD]) { if (p < pri[ic1 * ST_PAD]) i_swap = ic1; else break; }
-                else { if (p < pri[ic2 * ST_PAD]) i_swap = ic2; else break; }
-                pri[i * ST_PAD] = pri[i_swap * ST_PAD]; idx[i * ST_PAD] = idx[i_swap * ST_PAD];
-                i = i_swap;
-            }
-            pri[i * ST_PAD] = p; idx[i * ST_PAD] = cand;
-        }
-        for (int j = 0; j < k; ++j) {                      // utils.py:311-318 clear the flags of the sampled new candidates
-            const int32_t x = sind[j * ST_PAD];
-            bool found = false;
-            for (int c = 0; c < C; ++c) found |= (nind[c * ST_PAD] == x);
-            if (found && sflg[j * ST_PAD]) flags[v * k + j] = 0;
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < nrows * C; e += SEL_T) {        // finished lists, coalesced; rows of other kernels are left alone
-        const int r = e / C, c = e - r * C;
-        if (s_state[r]) { newc[v0 * C + e] = nind_b[c * ST_PAD + r]; oldc[v0 * C + e] = oind_b[c * ST_PAD + r]; }
-    }
 }
 
 __global__ void k_rng_table(const uint64_t *jump, long long s0, long long s1, long long s2, int64_t start, int64_t count,
@@ -449,28 +343,14 @@ static int launch_cand_select(nnd_ctx *ctx, const nnd_problem *P, int32_t C, Can
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "cand_select: C=%d too large", C);
     size_t smem_small = (size_t)C * SEL_T * 16;
     const int use_small = smem_small <= 200 * 1024;
-    if (ctx->opt_carveout) {   // NND_SMEM_CARVEOUT=1: ask for the largest shared-memory carveout (ncu: select_small ran 3 CTAs/SM)
-        cudaFuncSetAttribute(k_cand_select_small<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_cand_select_small<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_cand_select_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (ctx->opt_carveout) {   // NND_SMEM_CARVEOUT=1: ask for the largest shared-memory carveout (ncu: select_small ran 3 CTAs/SM without)
+        cudaFuncSetAttribute(k_cand_select_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_cand_select, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    if (use_small && ctx->opt_cand_keys == 2 && cand_tile_smem(k, C) <= 200 * 1024) {
-        const size_t sm3 = cand_tile_smem(k, C);
-        NND_CUDA(cudaFuncSetAttribute(k_cand_select_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
-        k_cand_select_tile<<<(unsigned)cdiv(N, SEL_T), SEL_T, sm3, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg, W.revoff, W.rev, W.fprio,
-                                                                    new_cand, old_cand, ctx->row_lo, ctx->row_hi, act);
-        NND_LAUNCH(ctx);
-    } else if (use_small && ctx->opt_cand_keys && smem_small + (size_t)SEL_SMALL * SEL_T * 4 <= 200 * 1024) {
-        const size_t sm2 = smem_small + (size_t)SEL_SMALL * SEL_T * 4;
-        NND_CUDA(cudaFuncSetAttribute(k_cand_select_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-        k_cand_select_small<true><<<(unsigned)cdiv(N, SEL_T), SEL_T, sm2, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg, W.revoff, W.rev,
-                                                                           W.fprio, new_cand, old_cand, ctx->row_lo, ctx->row_hi, act);
-        NND_LAUNCH(ctx);
-    } else if (use_small) {
-        NND_CUDA(cudaFuncSetAttribute(k_cand_select_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
-        k_cand_select_small<false><<<(unsigned)cdiv(N, SEL_T), SEL_T, smem_small, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg,
-                                                                            W.revoff, W.rev, W.fprio, new_cand, old_cand, ctx->row_lo, ctx->row_hi, act);
+    if (use_small) {
+        NND_CUDA(cudaFuncSetAttribute(k_cand_select_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        k_cand_select_small<<<(unsigned)cdiv(N, SEL_T), SEL_T, smem_small, st>>>(P->heap_idx, P->heap_flag, k, N, C, W.indeg, W.revoff, W.rev, W.fprio,
+                                                                            new_cand, old_cand, ctx->row_lo, ctx->row_hi, act);
         NND_LAUNCH(ctx);
     }
     NND_CUDA(cudaFuncSetAttribute(k_cand_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

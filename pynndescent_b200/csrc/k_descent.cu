@@ -527,23 +527,6 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
     __syncthreads();                                        // ids[] complete, expect_tx posted
     issue(0);
     if (nchunks > 1) issue(1);
-    // presence filter: every thread PREFETCHES its share of the members' heap rows (indices) into registers right behind the first
-    // bulk copies, so that their DRAM latency hides under the chunk loop; they are parked in the row buffers once those are free
-    constexpr int HPRE = (JB_SCAP * 16 + JB_THREADS - 1) / JB_THREADS;          // host: k <= 16
-    int32_t hpre[HPRE];
-    const int hk = P.heap_idx ? P.k : 0;
-    if (hk) {
-        int slot = tid / hk, j = tid - slot * hk;
-        const int dq = JB_THREADS / hk, dr = JB_THREADS - dq * hk;
-#pragma unroll
-        for (int q = 0; q < HPRE; ++q) {
-            int32_t v = -1;
-            if (slot < totphys) { const int32_t id = ids[slot]; if (id >= 0) v = __ldg(P.heap_idx + (int64_t)id * hk + j); }
-            hpre[q] = v;
-            slot += dq; j += dr;
-            if (j >= hk) { j -= hk; ++slot; }
-        }
-    }
     for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
         if (u >= 0) {
@@ -577,14 +560,6 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
         __syncthreads();                                    // everyone done with buffer c&1
         if (c + 2 < nchunks) issue(c + 2);
     }
-    // ---- presence filter: the heap rows (indices) of all members, staged in the row buffers (free now: the chunk loop ends with
-    // a CTA-wide barrier)
-    int32_t *hrow = (int32_t *)rows;                        // [totphys][hk]
-    if (hk) {
-#pragma unroll
-        for (int q = 0; q < HPRE; ++q) { const int e = tid + q * JB_THREADS; if (e < totphys * hk) hrow[e] = hpre[q]; }
-        __syncthreads();
-    }
     // ---- finalise + filter
     uint32_t pm = 0;
     if (u >= 0) {
@@ -599,16 +574,8 @@ __global__ void __launch_bounds__(JB_THREADS) k_join_batch(JoinBatchParams P) {
                     if (METRIC == NND_METRIC_SQEUCLIDEAN) r = acc[qa * TILE + qb];
                     else if (METRIC == NND_METRIC_ALT_COSINE) r = finish_alt_cosine(acc[qa * TILE + qb], n2_s[uo + a], n2_s[uo + b]);
                     else r = finish_alt_dot(acc[qa * TILE + qb], P.metric);
-                    bool ea = r < thr_s[uo + a], eb = (b != a) && r < thr_s[uo + b];
-                    if (hk && (ea || eb)) {
-                        const int32_t pa = ids[uo + a], pb = ids[uo + b];
-                        const int32_t *ra = hrow + (uo + a) * hk, *rb = hrow + (uo + b) * hk;
-                        bool ina = false, inb = false;
-                        for (int j = 0; j < hk; ++j) { ina |= (ra[j] == pb); inb |= (rb[j] == pa); }
-                        ea = ea && !ina; eb = eb && !inb;
-                    }
-                    if (ea) pm |= 1u << (2 * (qa * TILE + qb));
-                    if (eb) pm |= 2u << (2 * (qa * TILE + qb));
+                    if (r < thr_s[uo + a]) pm |= 1u << (2 * (qa * TILE + qb));
+                    if (b != a && r < thr_s[uo + b]) pm |= 2u << (2 * (qa * TILE + qb));
                 }
                 acc[qa * TILE + qb] = r;
             }
@@ -781,170 +748,6 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) k_apply(int32_t *heap_idx, f
 }
 
 
-// ---- NND_APPLY_HALF (default off): k_apply for rows with at most APPLY_SMALL records, TWO ROWS PER WARP.  A heap row has k <= 16
-// useful lanes in the duplicate test and one in the sift, and a touched row rarely keeps more than 16 records, so a whole warp
-// per row spends half of its issue slots on idle lanes (ncu: k_apply is issue-bound, 75 % busy).  Each half-warp runs exactly
-// the same algorithm (filter by the initial root, order by emission sequence, replay checked_flagged_heap_push); rows with
-// more records stay with k_apply (skip_small).
-#define APPLY_SMALL 48
-#define AH_ROWS 16   // half-warps (rows) per CTA
-__device__ __forceinline__ int half_heap_push(float *pri, int32_t *ind, uint8_t *flg, int size, float p, int32_t n, uint8_t f, int hl,
-                                              unsigned mask) {
-    if (p >= pri[0]) return 0;
-    bool dup = false;
-    for (int i = hl; i < size; i += 16) dup |= (ind[i] == n);
-    if (__ballot_sync(mask, dup) != 0) return 0;
-    if (hl == 0) {
-        int i = 0, i_swap;
-        for (;;) {
-            int ic1 = 2 * i + 1, ic2 = ic1 + 1;
-            if (ic1 >= size) break;
-            else if (ic2 >= size) { if (pri[ic1] > p) i_swap = ic1; else break; }
-            else if (pri[ic1] >= pri[ic2]) { if (p < pri[ic1]) i_swap = ic1; else break; }
-            else { if (p < pri[ic2]) i_swap = ic2; else break; }
-            pri[i] = pri[i_swap]; ind[i] = ind[i_swap]; flg[i] = flg[i_swap];
-            i = i_swap;
-        }
-        pri[i] = p; ind[i] = n; flg[i] = f;
-    }
-    __syncwarp(mask);
-    return 1;
-}
-__global__ void __launch_bounds__(AH_ROWS * 16) k_apply_half(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int k, int64_t N,
-                                                            const uint32_t *cnt, const uint32_t *off, const Rec16 *rec,
-                                                            unsigned long long *c_total) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
-    const unsigned mask = 0xFFFFu << (16 * (hw & 1));                 // my half of the warp
-    const int sh = 16 * (hw & 1);
-    const int64_t row = (int64_t)blockIdx.x * AH_ROWS + hw;
-    if (row >= N) return;
-    const uint32_t n = cnt[row];
-    if (n == 0 || n > APPLY_SMALL) return;
-    Rec16 *buf = (Rec16 *)smem_raw + (size_t)hw * 64;                  // up to 48 kept records, padded to 64 for the in-memory sort
-    unsigned char *hp = smem_raw + (size_t)AH_ROWS * 64 * sizeof(Rec16) + (size_t)hw * (((size_t)k * 9 + 15) & ~size_t(15));
-    float *pri = (float *)hp; int32_t *ind = (int32_t *)(pri + k); uint8_t *flg = (uint8_t *)(ind + k);
-    for (int j = hl; j < k; j += 16) { pri[j] = heap_dist[row * k + j]; ind[j] = heap_idx[row * k + j]; flg[j] = heap_flag[row * k + j]; }
-    __syncwarp(mask);
-    const float root0 = pri[0];
-    const Rec16 *seg = rec + off[row];
-    int kept = 0;
-    for (uint32_t b0 = 0; b0 < n; b0 += 16) {      // keep only what can still be accepted (the root only decreases)
-        const uint32_t j = b0 + hl;
-        Rec16 r; r.key = ~0ULL; r.oth = -1; r.d = 0.f;
-        bool keep = false;
-        if (j < n) { r = seg[j]; keep = r.d < root0; }
-        const unsigned mk = (__ballot_sync(mask, keep) >> sh) & 0xFFFFu;
-        if (keep) buf[kept + __popc(mk & ((1u << hl) - 1))] = r;
-        kept += __popc(mk);
-    }
-    if (kept == 0) return;
-    __syncwarp(mask);
-    int c = 0;
-    if (kept <= 16) {
-        unsigned long long key = hl < kept ? buf[hl].key : ~0ULL;
-        int slot = hl;
-        const int top = (int)next_pow2_u32((uint32_t)(kept > 2 ? kept : 2));
-#pragma unroll
-        for (int k2 = 2; k2 <= 16; k2 <<= 1) {
-            if (k2 > top) break;
-#pragma unroll
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
-                const unsigned long long ok = __shfl_xor_sync(mask, key, j);
-                const int os = __shfl_xor_sync(mask, slot, j);
-                const bool up = ((hl & k2) == 0), lower = ((hl & j) == 0);
-                const bool take = (lower == up) ? (ok < key) : (ok > key);
-                if (take) { key = ok; slot = os; }
-            }
-        }
-        for (int s2 = 0; s2 < kept; ++s2) {
-            const int sl = __shfl_sync(mask, slot, sh + s2);
-            const Rec16 r = buf[sl];
-            c += half_heap_push(pri, ind, flg, k, r.d, r.oth, (uint8_t)1, hl, mask);
-        }
-    } else {
-        const int p2 = (int)next_pow2_u32((uint32_t)kept);             // <= 64
-        for (int j = kept + hl; j < p2; j += 16) { buf[j].key = ~0ULL; buf[j].oth = -1; buf[j].d = CUDART_INF_F; }
-        __syncwarp(mask);
-        for (int k2 = 2; k2 <= p2; k2 <<= 1)
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
-                for (int i = hl; i < p2; i += 16) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const Rec16 x = buf[i], y = buf[l];
-                        const bool up = ((i & k2) == 0);
-                        if ((x.key > y.key) == up) { buf[i] = y; buf[l] = x; }
-                    }
-                }
-                __syncwarp(mask);
-            }
-        for (int s = 0; s < kept; ++s) {
-            const Rec16 r = buf[s];
-            c += half_heap_push(pri, ind, flg, k, r.d, r.oth, (uint8_t)1, hl, mask);
-        }
-    }
-    if (c > 0) {
-        for (int j = hl; j < k; j += 16) { heap_dist[row * k + j] = pri[j]; heap_idx[row * k + j] = ind[j]; heap_flag[row * k + j] = flg[j]; }
-        if (hl == 0) atomicAdd(c_total, (unsigned long long)c);
-    }
-}
-
-// ---- thread-per-row apply for rows with few records (the common case): column-layout heap in smem, the
-// next record in emission order is found by selection among the records that can still be accepted
-// (d < current root), so no sort is needed.  Rows with more than APPLY_SMALL records go to k_apply.
-#define APPLY_T 128
-__global__ void __launch_bounds__(APPLY_T) k_apply_small(int32_t *heap_idx, float *heap_dist, uint8_t *heap_flag, int k,
-                                                         int64_t N, const uint32_t *cnt, const uint32_t *off,
-                                                         const Rec16 *rec, unsigned long long *c_total) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t row = (int64_t)blockIdx.x * APPLY_T + tid;
-    float *pri = (float *)smem_raw + tid;                                    // [k][APPLY_T]
-    int32_t *ind = (int32_t *)(smem_raw + (size_t)k * APPLY_T * 4) + tid;
-    uint8_t *flg = smem_raw + (size_t)k * APPLY_T * 8 + tid;
-    int c = 0;
-    uint32_t n = 0;
-    if (row < N) n = cnt[row];
-    if (n > 0 && n <= APPLY_SMALL) {
-        for (int j = 0; j < k; ++j) { pri[j * APPLY_T] = heap_dist[row * k + j]; ind[j * APPLY_T] = heap_idx[row * k + j]; flg[j * APPLY_T] = heap_flag[row * k + j]; }
-        const Rec16 *seg = rec + off[row];
-        unsigned long long last = 0; bool first = true;
-        for (;;) {
-            const float root = pri[0];
-            unsigned long long best = ~0ULL; int bj = -1;
-            for (uint32_t j = 0; j < n; ++j) {
-                Rec16 r = seg[j];
-                if (r.d < root && (first || r.key > last) && r.key < best) { best = r.key; bj = (int)j; }
-            }
-            if (bj < 0) break;
-            first = false; last = best;
-            const Rec16 r = seg[bj];
-            const float p = r.d; const int32_t nb = r.oth;
-            bool dup = false;
-            for (int j = 0; j < k; ++j) dup |= (ind[j * APPLY_T] == nb);
-            if (dup) continue;
-            int i = 0, i_swap;
-            for (;;) {
-                int ic1 = 2 * i + 1, ic2 = ic1 + 1;
-                if (ic1 >= k) break;
-                else if (ic2 >= k) { if (pri[ic1 * APPLY_T] > p) i_swap = ic1; else break; }
-                else if (pri[ic1 * APPLY_T] >= pri[ic2 * APPLY_T]) { if (p < pri[ic1 * APPLY_T]) i_swap = ic1; else break; }
-                else { if (p < pri[ic2 * APPLY_T]) i_swap = ic2; else break; }
-                pri[i * APPLY_T] = pri[i_swap * APPLY_T]; ind[i * APPLY_T] = ind[i_swap * APPLY_T]; flg[i * APPLY_T] = flg[i_swap * APPLY_T];
-                i = i_swap;
-            }
-            pri[i * APPLY_T] = p; ind[i * APPLY_T] = nb; flg[i * APPLY_T] = 1;
-            ++c;
-        }
-        if (c > 0)
-            for (int j = 0; j < k; ++j) { heap_dist[row * k + j] = pri[j * APPLY_T]; heap_idx[row * k + j] = ind[j * APPLY_T]; heap_flag[row * k + j] = flg[j * APPLY_T]; }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0 && c > 0) atomicAdd(c_total, (unsigned long long)c);
-}
-
-// ------------------------------------------------------------------ per-row worst-case push bound (for blocking)
 __global__ void k_row_bound(const int32_t *newc, const int32_t *oldc, int C, int64_t N, uint32_t *bound, int64_t lo, int64_t hi) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -1164,7 +967,8 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     const bool rank_scatter = JB && do_apply && ctx->opt_rank_scatter;
     if (JB) {
         JB->thr = thr; JB->batch_begin = u0; JB->batch_end = u1;
-        JB->out_tgt = W.l_tgt; JB->out_oth = W.l_oth; JB->out_d = W.l_d; JB->out_pos = rank_scatter ? nullptr : W.l_pos; JB->out_seq = W.l_seq;
+        // (records that are exported to their owner process -- do_apply false -- are ranked there: fire-and-forget counting here too)
+        JB->out_tgt = W.l_tgt; JB->out_oth = W.l_oth; JB->out_d = W.l_d; JB->out_pos = (rank_scatter || !do_apply) ? nullptr : W.l_pos; JB->out_seq = W.l_seq;
         JB->tgt_count = W.cnt; JB->cursor = W.dev_scalars; JB->capacity = (unsigned long long)cap;
         JB->overflow = (int *)(W.dev_scalars + 4); JB->stats = W.dev_scalars + 5;
         NND_TRY(launch_join_batch(ctx, *JB, st));
@@ -1204,25 +1008,7 @@ static int route_round(nnd_ctx *ctx, const nnd_problem *P, JoinParams &J, int64_
     NND_CHECK(smem <= 200 * 1024, NND_ERR_UNSUPPORTED, "apply: k=%d too large", P->k);
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ctx->opt_carveout) cudaFuncSetAttribute(k_apply, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    size_t smem_s = (size_t)P->k * APPLY_T * 9 + 16;
-    const char *e_small = getenv("NND_APPLY_SMALL");   // experimental: thread-per-row apply (slower on B200 as measured)
-    int use_small = (e_small && e_small[0] == '1') && smem_s <= 64 * 1024;
-    if (ctx->opt_apply_half && !use_small) {            // NND_APPLY_HALF: rows with <= APPLY_SMALL records, two per warp
-        const size_t smem_h = (size_t)AH_ROWS * 64 * sizeof(Rec16) + (size_t)AH_ROWS * (((size_t)P->k * 9 + 15) & ~size_t(15));
-        if (smem_h <= 200 * 1024) {
-            NND_CUDA(cudaFuncSetAttribute(k_apply_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
-            k_apply_half<<<(unsigned)cdiv(N, AH_ROWS), AH_ROWS * 16, smem_h, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N, W.cnt, W.off,
-                                                                              W.rec, W.dev_scalars + 1);
-            NND_LAUNCH(ctx);
-            use_small = 2;                              // k_apply below skips the rows handled here
-        }
-    }
-    if (use_small == 1) {
-        NND_CUDA(cudaFuncSetAttribute(k_apply_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-        k_apply_small<<<(unsigned)cdiv(N, APPLY_T), APPLY_T, smem_s, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N, W.cnt,
-                                                                        W.off, W.rec, W.dev_scalars + 1);
-        NND_LAUNCH(ctx);
-    }
+    const int use_small = 0;
     k_apply<<<(unsigned)cdiv(N, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx, P->heap_dist, P->heap_flag, P->k, N,
                                                                            W.cnt, W.off, W.rec, W.dev_scalars + 1, use_small, (ctx->opt_apply_short ? 1 : 0) | (ctx->heap_trusted ? 2 : 0));
     NND_LAUNCH(ctx);
@@ -1456,8 +1242,6 @@ static int build_join_plan(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const 
             JB.X = P->X; JB.N = N; JB.ld = P->ld; JB.metric = P->metric; JB.aux = P->aux;
             JB.act_unit = W.act_unit; JB.act_info = W.act_info; JB.act_poff = W.act_poff; JB.members = W.members;
             JB.batch_first = W.batch_first; JB.n_active = n_active; JB.n_batches = n_batches; JB.slot_stride = 2 * C;
-            // presence filter: k heap indices per member must fit the (single-chunk: one) row buffer of JB_SCAP x (32 + 4) floats
-            if (ctx->opt_presence && ctx->heap_trusted && P->k <= 16) { JB.heap_idx = P->heap_idx; JB.k = P->k; }
             // rounds are planned optimistically (16 half-updates per tile slot; the worst case is 32 and the measured
             // average 7); a round that overflows is detected (never silent) and split by the caller
             // ... and from the second iteration of a build on by the measured emission of the previous iteration's rounds
@@ -1670,16 +1454,7 @@ extern "C" int nnd_apply_records(nnd_ctx *ctx, const nnd_problem *P, int32_t C, 
     k_rec_scatter<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const Rec24 *)records, W.l_pos, (unsigned long long)n, W.off, W.rec, lo); NND_LAUNCH(ctx);
     size_t smem = (size_t)APPLY_WARPS * NND_SEG_SMEM * sizeof(Rec16) + (size_t)APPLY_WARPS * (((size_t)P->k * 9 + 15) & ~size_t(15));
     NND_CUDA(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int skip_small = 0;
-    const size_t smem_h = (size_t)AH_ROWS * 64 * sizeof(Rec16) + (size_t)AH_ROWS * (((size_t)P->k * 9 + 15) & ~size_t(15));
-    if (ctx->opt_apply_half && smem_h <= 200 * 1024) {   // NND_APPLY_HALF: rows with <= APPLY_SMALL records, two per warp
-        NND_CUDA(cudaFuncSetAttribute(k_apply_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
-        k_apply_half<<<(unsigned)cdiv(Nr, AH_ROWS), AH_ROWS * 16, smem_h, st>>>(P->heap_idx + lo * P->k, P->heap_dist + lo * P->k,
-                                                                           P->heap_flag + lo * P->k, P->k, Nr, W.cnt, W.off, W.rec,
-                                                                           W.dev_scalars + 1);
-        NND_LAUNCH(ctx);
-        skip_small = 2;
-    }
+    const int skip_small = 0;
     k_apply<<<(unsigned)cdiv(Nr, APPLY_WARPS), APPLY_WARPS * 32, smem, st>>>(P->heap_idx + lo * P->k, P->heap_dist + lo * P->k,
                                                                             P->heap_flag + lo * P->k, P->k, Nr, W.cnt, W.off, W.rec,
                                                                             W.dev_scalars + 1, skip_small, (ctx->opt_apply_short ? 1 : 0) | (ctx->heap_trusted ? 2 : 0));

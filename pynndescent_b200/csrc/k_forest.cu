@@ -361,67 +361,6 @@ __global__ void __launch_bounds__(256) k_forest_side_pm(const float *X, int ld, 
     }
 }
 
-// ---- rows of at most 128 floats: FOUR lanes per point, eight points per warp.  The one-warp-per-point pass above is issue-bound
-// (ncu: 80 % of the issue slots, 63 warp instructions per (point, tree), a five-step shuffle butterfly for four fma per lane).
-// Here sub-lane r of a quad owns the eight "virtual lanes" v = r + 4m of the canonical reduction (element e -> lane (e/4) mod 32,
-// xor butterfly 16, 8, 4, 2, 1): the xor-16/8/4 stages pair virtual lanes of the SAME sub-lane (they differ in the bits of m), so
-// they are seven in-register additions, and only the xor-2 / xor-1 stages are shuffles inside the quad.  Same partial sums, same
-// pairing tree => the same margin bits as k_forest_side / k_forest_side_pm<1> / the oracle; about 8 warp instructions per (point, tree).
-#define PM4_RUN 4
-__global__ void __launch_bounds__(256) k_forest_side_pm4(const float *X, int ld, int64_t N, int n_trees, int level,
-                                                         const int32_t *invp, const int32_t *seg, const int32_t *nstart,
-                                                         const int32_t *tree_first, const uint64_t *tree_seed, const float *hyper,
-                                                         const float *noff, uint8_t *side, uint32_t *flag32) {
-    const int lane = threadIdx.x & 31, r = lane & 3, q = lane >> 2;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int it = 0; it < PM4_RUN; ++it) {
-        const int64_t p = (w * PM4_RUN + it) * 8 + q;
-        if ((w * PM4_RUN + it) * 8 >= N) break;                    // warp-uniform
-        const bool pv = p < N;
-        float4 x[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) { const int c = (r + 4 * m) * 4; x[m] = (pv && c < ld) ? *(const float4 *)(X + p * ld + c) : zero4; }
-        for (int t = 0; t < n_trees; ++t) {
-            int32_t pos = -1, o = 0;
-            if (pv) { pos = invp[(int64_t)t * N + p]; if (pos >= 0) o = seg[pos]; }
-            const bool live = pos >= 0;
-            if (!__any_sync(0xffffffffu, live)) continue;            // warp-uniform
-            const float *hrow = hyper + (size_t)o * ld;
-            float part[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int c = (r + 4 * m) * 4;
-                float acc = 0.0f;
-                if (live && c < ld) {
-                    const float4 h4 = *(const float4 *)(hrow + c);
-                    acc = __fmaf_rn(h4.x, x[m].x, acc); acc = __fmaf_rn(h4.y, x[m].y, acc);
-                    acc = __fmaf_rn(h4.z, x[m].z, acc); acc = __fmaf_rn(h4.w, x[m].w, acc);
-                }
-                part[m] = acc;
-            }
-            // xor 16 (m ^ 4), xor 8 (m ^ 2), xor 4 (m ^ 1): inside the sub-lane; xor 2, xor 1: inside the quad
-            const float a0 = __fadd_rn(part[0], part[4]), a1 = __fadd_rn(part[1], part[5]), a2 = __fadd_rn(part[2], part[6]), a3 = __fadd_rn(part[3], part[7]);
-            const float b0 = __fadd_rn(a0, a2), b1 = __fadd_rn(a1, a3);
-            float acc = __fadd_rn(b0, b1);
-            acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
-            acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
-            if (live && r == 0) {
-                const float margin = __fadd_rn(noff[o], acc);
-                uint32_t sd;
-                if (fabs((double)margin) < 1e-8) {
-                    const int start = nstart[o];
-                    const int tree = (int)(start / N);
-                    const uint64_t key = node_key(tree_seed[tree], level, (int64_t)(o - tree_first[tree]));
-                    sd = (uint32_t)(mix64(key ^ (0x100ULL + (uint64_t)(pos - start))) & 1ULL);
-                } else sd = margin > 0 ? 0u : 1u;
-                side[pos] = (uint8_t)sd;
-                flag32[pos] = (sd == 0);
-            }
-        }
-    }
-}
-
 // degenerate nodes (all points on one side): random split (rp_trees.py:395-403)
 __global__ void k_forest_fix_side(int64_t n_act, const int32_t *act, int64_t N, int level, const int32_t *seg,
                                   const int32_t *nstart, const uint8_t *ndegen, const int32_t *tree_first,
@@ -589,13 +528,7 @@ extern "C" int nnd_forest_build(nnd_ctx *ctx, const float *X, int64_t N, int32_t
             const unsigned g = (unsigned)cdiv(cdiv(N, PM_RUN) * 32, 256);
 #define PMK(NCH_) k_forest_side_pm<NCH_><<<g, 256, 0, st>>>(X, ld, N, n_trees, level, invp, W.seg[cur], W.nstart[ncur], W.tree_first, \
                                                           W.tree_seed, W.hyper, W.noff, W.side, W.flag32)
-            static int pm4 = -1;
-            if (pm4 < 0) { const char *e = getenv("NND_FOREST_PM4"); pm4 = (e && e[0] == '0') ? 0 : 1; }   // A/B switch of the round-2 kernel
-            if (ld <= 128 && !pm4) PMK(1);
-            else if (ld <= 128) {
-                k_forest_side_pm4<<<(unsigned)cdiv(cdiv(N, 8 * PM4_RUN) * 32, 256), 256, 0, st>>>(X, ld, N, n_trees, level, invp, W.seg[cur], W.nstart[ncur],
-                                                                                             W.tree_first, W.tree_seed, W.hyper, W.noff, W.side, W.flag32);
-            } else if (ld <= 256) PMK(2); else if (ld <= 512) PMK(4); else PMK(8);
+            if (ld <= 128) PMK(1); else if (ld <= 256) PMK(2); else if (ld <= 512) PMK(4); else PMK(8);
 #undef PMK
         } else if (ld <= 128)
             k_forest_side128<<<(unsigned)cdiv(cdiv(n_act, SIDE_RUN) * 32, 256), 256, 0, st>>>(X, ld, n_act, W.act[cur], N, level,

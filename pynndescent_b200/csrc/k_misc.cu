@@ -56,13 +56,10 @@ extern "C" int nnd_create(nnd_ctx **out, int device) {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
         c->opt_rank_scatter = env_int("NND_RANK_SCATTER", 1);
         c->opt_cand_skip = env_int("NND_CAND_SKIP", 1);
-        c->opt_presence = env_int("NND_PRESENCE", 1);
-        c->opt_cand_partition = env_int("NND_CAND_PARTITION", 1);
-        c->opt_cand_keys = env_int("NND_CAND_KEYS", 0);
+        c->opt_cand_partition = env_int("NND_CAND_PARTITION", 0);
         c->opt_leaf_split = env_int("NND_LEAF_SPLIT", 1);
         c->opt_carveout = env_int("NND_SMEM_CARVEOUT", 1);
         c->opt_apply_short = env_int("NND_APPLY_SHORT_SORT", 1);
-        c->opt_apply_half = env_int("NND_APPLY_HALF", 0);
         c->opt_forest_pm = env_int("NND_FOREST_PM", 1);
         c->opt_forest_pm_mb = env_int("NND_FOREST_PM_MB", 4096);   // 10M: 48/96 MB 250 ms, 200+ MB 241 ms (A/B): point-major on every level
     }

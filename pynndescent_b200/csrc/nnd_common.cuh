@@ -53,13 +53,11 @@ struct nnd_ctx {
     cudaEvent_t *sp_ev; int *sp_id;
     double sp_ms[NND_STAGE_COUNT];
     // ---- schedule options (read from the environment by nnd_create; none of them changes any result)
-    int opt_apply_half;       // NND_APPLY_HALF=1: rows with <= 48 records are applied two per warp (k_apply_half)
     int opt_apply_short;      // NND_APPLY_SHORT_SORT=1: k_apply sorts only next_pow2(kept) lanes
     int opt_carveout;         // NND_SMEM_CARVEOUT=1: prefer the maximum shared-memory carveout for the occupancy-by-smem kernels
     int opt_leaf_split;       // NND_LEAF_SPLIT=1: leaf init = distance-matrix kernel + thread-per-member push kernel (k_descent.cu)
-    int opt_cand_keys;        // NND_CAND_KEYS=1: k_cand_select_small stages the reverse-edge key words in shared memory
-    int opt_presence;         // NND_PRESENCE=1 (default): the batched join drops half-updates whose source already sits in the target's heap row
-    int opt_cand_partition;   // NND_CAND_PARTITION=1 (default): reverse edges go through range buckets (sequential appends + L2-local import)
+    int opt_cand_partition;   // NND_CAND_PARTITION=1: one process routes its reverse edges through range buckets like the sharded build does
+                              // (default 0: the direct scatter is faster on one GPU -- cand_fill 120 vs 196 ms at 10M, profiles/ab_r02_10m_call6.json)
     int opt_cand_skip;        // NND_CAND_SKIP=1: candidates are sampled only for vertices that will have NEW candidates (k_cand.cu)
     int opt_forest_pm;        // NND_FOREST_PM=1: point-major hyperplane pass of the RP forest (k_forest_side_pm<NCH>, k_forest.cu)
     int opt_forest_pm_mb;     // NND_FOREST_PM_MB: ... while the level's hyperplane table is at most this many MB (default 48)

@@ -5,7 +5,8 @@ rows and the local-join rows of the contiguous range [r*B, (r+1)*B), B = N // wo
 gathers arbitrary vertices); heap tensors keep global row indexing on every process, but only the owner's copy of a row is
 authoritative -- the heap is never all-gathered inside the iteration loop.  What crosses NVLink:
 
-  forest      trees t = rank, rank+world, ... are built locally, every tree's leaves (CSR, 4 B per point) are broadcast
+  forest      trees t = rank, rank+world, ... are built locally, every tree's leaves (CSR, 4 B per point + 1 B per point for
+              "which rank's share holds it") are broadcast
   leaf init   per tree the leaves are split by position among the ranks; the heap rows of a rank's share travel to it from
               the rank that processed them in the previous tree (one all-to-all-v of 9k B per row), and home to their owners
               after the last tree
@@ -86,23 +87,20 @@ class ShardedBuilder:
         if nr:
             e.heap_pack_rows(recv_rows, nr, bufs[0][1], bufs[1][1], bufs[2][1], True)
 
-    def _move_rows(self, holder, my_next, next_rank_of):
-        """Bring the heap rows of the points `my_next` (int32 device tensor: what this rank works on next) up to date.
+    def _move_rows(self, have, dest_of_have, want, src_of_want):
+        """Bring the heap rows of the points `want` (int32 device tensor: what this rank works on next) up to date.
 
-        holder[p] = rank that holds the current copy of row p (replicated plan data); next_rank_of(points) -> rank that works
-        on each of `points` next.  Rows already here stay; one host sync (the two count vectors)."""
+        `have` = the points whose current row copy is here, `dest_of_have` = the rank that works on each of them next,
+        `src_of_want` = the rank that holds the current copy of each wanted point (all derived from replicated plan data, so
+        the two sides of every (source, destination) pair list the same points: ascending point id).  Rows that stay are not
+        moved; one host sync (the two count vectors)."""
         W, me, N = self.world, self.rank, self.N
-        mine_now = torch.nonzero(holder == me).squeeze(1).to(torch.int32)            # rows whose current copy is here
-        dest = next_rank_of(mine_now)
-        go = dest != me
-        s_pts, s_dst = mine_now[go], dest[go]
-        s_order = torch.argsort(s_dst.to(torch.int64) * N + s_pts.to(torch.int64))
-        s_pts = s_pts[s_order].contiguous()
-        src = holder[my_next.long()]
-        come = src != me
-        r_pts, r_src = my_next[come], src[come]
-        r_order = torch.argsort(r_src.to(torch.int64) * N + r_pts.to(torch.int64))
-        r_pts = r_pts[r_order].contiguous()
+        go = dest_of_have != me
+        s_pts, s_dst = have[go], dest_of_have[go]
+        s_pts = s_pts[torch.argsort(s_dst.to(torch.int64) * N + s_pts.to(torch.int64))].contiguous()
+        come = src_of_want != me
+        r_pts, r_src = want[come], src_of_want[come]
+        r_pts = r_pts[torch.argsort(r_src.to(torch.int64) * N + r_pts.to(torch.int64))].contiguous()
         counts = torch.stack([torch.bincount(s_dst.long(), minlength=W), torch.bincount(r_src.long(), minlength=W)]).cpu().numpy()
         self._exchange_rows(s_pts, [int(c) for c in counts[0]], r_pts, [int(c) for c in counts[1]])
 
@@ -119,52 +117,56 @@ class ShardedBuilder:
             lo_h = lo.cpu().numpy()
             for j, t in enumerate(mine):                     # split the tree-major CSR back into trees
                 a = int(np.searchsorted(lo_h, j * N)); b = int(np.searchsorted(lo_h, (j + 1) * N))
-                local[t] = (lp[j * N: (j + 1) * N], lo[a: b + 1] - j * N)
+                local[t] = (lp[j * N: (j + 1) * N], lo[a: b + 1] - j * N, lo_h[a: b + 1] - j * N)
                 meta[t, 0] = b - a; meta[t, 1] = max_leaf
         dist.all_reduce(meta, op=dist.ReduceOp.SUM)
         meta_h = meta.cpu().numpy()
         max_leaf = int(meta_h[:, 1].max())
-        # every tree's leaves to every rank: one points buffer + one offsets buffer, filled by broadcasts
+
+        def cuts_of(oh, n_leaves_t):
+            """rank r takes the leaves whose first position lies in [r*N/world, (r+1)*N/world): (leaf cuts, position cuts)"""
+            cuts = [int(np.searchsorted(oh[:-1], (r * N) // W)) for r in range(W)] + [int(n_leaves_t)]
+            return cuts, [int(oh[c]) for c in cuts]
+        # every tree's leaves to every rank: one points buffer + one offsets buffer, filled by broadcasts; with them travels
+        # share_of[t][p] = the rank whose share of tree t contains point p (one N-sized scatter on the tree's owner only)
         pts_all = torch.empty((n_trees, N), dtype=torch.int32, device=dev)
+        share_of = torch.empty((n_trees, N), dtype=torch.uint8, device=dev)
         offs_all = torch.empty(int(meta_h[:, 0].sum()) + n_trees, dtype=torch.int64, device=dev)
         obase = np.concatenate([[0], np.cumsum(meta_h[:, 0] + 1)])
+        ar = None
         for t in range(n_trees):
             owner = t % W
             ov = offs_all[obase[t]: obase[t + 1]]
             if owner == me:
                 pts_all[t].copy_(local[t][0]); ov.copy_(local[t][1])
+                _, p0 = cuts_of(local[t][2], meta_h[t, 0])
+                if ar is None:
+                    ar = torch.arange(N, dtype=torch.int64, device=dev)
+                bounds = torch.tensor(p0[1:-1], dtype=torch.int64, device=dev)
+                share_of[t][local[t][0].long()] = torch.bucketize(ar, bounds, right=True).to(torch.uint8)
             dist.broadcast(pts_all[t], src=owner)
             dist.broadcast(ov, src=owner)
-        self.comm_bytes += pts_all.numel() * 4 + offs_all.numel() * 8
+            dist.broadcast(share_of[t], src=owner)
+        del ar
+        self.comm_bytes += pts_all.numel() * 5 + offs_all.numel() * 8
         offs_h = offs_all.cpu().numpy()
-        # rank r takes, in every tree, the leaves whose first position lies in [r*N/world, (r+1)*N/world)
-        plan = []
-        for t in range(n_trees):
-            oh = offs_h[obase[t]: obase[t + 1]]
-            cuts = [int(np.searchsorted(oh[:-1], (r * N) // W)) for r in range(W)] + [int(meta_h[t, 0])]
-            plan.append((cuts, [int(oh[c]) for c in cuts]))
-        # holder[p] = rank with the current copy of heap row p.  Before the first tree every rank holds the same fresh heap
-        # (make_heap), so nothing moves for tree 0; afterwards the holder of p is the rank whose share of the tree contains p.
-        holder = None
-        posn = torch.empty(N, dtype=torch.int64, device=dev)
-        ar = torch.arange(N, dtype=torch.int64, device=dev)
+        plan = [cuts_of(offs_h[obase[t]: obase[t + 1]], meta_h[t, 0]) for t in range(n_trees)]
+        # Before the first tree every rank holds the same fresh heap (make_heap), so nothing moves for tree 0; afterwards the
+        # current copy of row p sits on rank share_of[t][p] of the tree processed last.
         fused_ok = True
+        prev = None                                                               # (tree index, my share of it)
         for t in range(n_trees):
             cuts, p0 = plan[t]
             pts = pts_all[t]; offs = offs_all[obase[t]: obase[t + 1]]
-            bounds = torch.tensor(p0[1:-1], dtype=torch.int64, device=dev)
-            if holder is not None:
-                posn[pts.long()] = ar                                             # position of every point in this tree's order
-                self._move_rows(holder, pts[p0[me]: p0[me + 1]],
-                                lambda p: torch.bucketize(posn[p.long()], bounds, right=True).to(torch.int32))
+            share = pts[p0[me]: p0[me + 1]]
+            if prev is not None:
+                self._move_rows(prev[1], share_of[t][prev[1].long()].to(torch.int32), share, share_of[prev[0]][share.long()].to(torch.int32))
             try:
                 e.leaf_fused_range(pts, offs, cuts[me], cuts[me + 1], max_leaf, pos0=p0[me], npos=p0[me + 1] - p0[me], cap=cap)
             except NotImplementedError:
                 fused_ok = False
                 break
-            if holder is None:
-                holder = torch.empty(N, dtype=torch.int32, device=dev)
-            holder[pts.long()] = torch.bucketize(ar, bounds, right=True).to(torch.int32)
+            prev = (t, share)
         if not fused_ok:
             # leaves too large for the fused / split kernels: every rank runs the routed leaf init on all trees (replicated)
             e.make_heap()
@@ -172,11 +174,11 @@ class ShardedBuilder:
                            [torch.tensor([n_trees * N], dtype=torch.int64, device=dev)])
             e.leaf_init(pts_all.reshape(-1), lo, lo.numel() - 1, max_leaf, cap)
             return
-        if holder is not None:
+        if prev is not None:
             # rows go home: the owner of p is p // B
-            B = self.B
-            self._move_rows(holder, torch.arange(self.lo, self.hi, dtype=torch.int32, device=dev),
-                            lambda p: torch.clamp(p.to(torch.int64) // B, max=W - 1).to(torch.int32))
+            own = torch.arange(self.lo, self.hi, dtype=torch.int32, device=dev)
+            self._move_rows(prev[1], torch.clamp(prev[1].to(torch.int64) // self.B, max=W - 1).to(torch.int32), own,
+                            share_of[prev[0]][self.lo: self.hi].to(torch.int32))
 
     def init_random(self, rng_state):
         """pynndescent_.py:188-203 on the sharded heap: rows whose root is empty draw from ONE sequential stream in row order.

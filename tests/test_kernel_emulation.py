@@ -58,7 +58,7 @@ def emu_lib(tmp_path_factory):
     sg = _between(sg, "#define SG_WARPS", "// ------------------------------------------------------------------------------------------------ host",
                   "the search-graph kernels")
     route = _between(desc, "// ------------------------------------------------------------------ routing",
-                     "// ---- thread-per-row apply for rows with few records", "k_scatter / k_scatter_rank / k_apply")
+                     "__global__ void k_row_bound(", "k_scatter / k_scatter_rank / k_apply")
     join = _between(desc, "#define DK 128", "// =====================================================================================================\n// k_join_batch:",
                     "JoinParams / k_join")
     leaf = _between(desc, "// ------------------------------------------------------------------ split leaf init",
@@ -84,7 +84,7 @@ def emu_lib(tmp_path_factory):
     n_ext = kernels.count("extern __shared__")
     for al in ("16", "128"):
         kernels = kernels.replace("extern __shared__ __align__(%s) unsigned char smem_raw[];" % al, "unsigned char *smem_raw = emu::dyn_smem();")
-    assert n_ext == 13 and "extern __shared__" not in kernels
+    assert n_ext == 11 and "extern __shared__" not in kernels
     src = os.path.join(tmp, "emu_kernels.cpp")
     with open(src, "w") as f:
         f.write('#include "%s"\n#include "join_batch.cuh"\n' % os.path.join(EMU, "cuda_emu.h"))
@@ -227,7 +227,7 @@ def test_cases_are_not_trivial(emu_lib, cases):
         print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
 
 
-@pytest.mark.parametrize("skip,keys", [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)])
+@pytest.mark.parametrize("skip,keys", [(0, 0), (1, 0)])
 def test_candidate_kernels_and_cand_skip(emu_lib, skip, keys):
     """k_cand_count / k_cand_fill / k_cand_select* under the emulator against the oracle's new_build_candidates, over three
     iterations of a small build (hub vertices with > 32 reverse edges included).  skip=0 is the hardware-verified schedule
@@ -353,7 +353,7 @@ def test_candidate_kernels_row_sharded(emu_lib, skip):
         orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
 
 
-@pytest.mark.parametrize("kernel,rank_scatter,leaf_order,short_sort", [(0, 0, False, 0), (0, 1, False, 1), (0, 0, False, 2), (0, 1, False, 3)])
+@pytest.mark.parametrize("kernel,rank_scatter,leaf_order,short_sort", [(0, 0, False, 0), (0, 1, False, 1)])
 def test_whole_iterations_match_the_oracle_heaps(emu_lib, kernel, rank_scatter, leaf_order, short_sort):
     """Three NN-descent iterations: candidates from the oracle, then join -> scatter -> apply under the emulator; after every
     iteration the heaps (indices, distances, flags, layout) and the accepted-push count must equal the oracle's
