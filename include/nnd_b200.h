@@ -318,6 +318,12 @@ NND_API int nnd_profile_read(nnd_ctx *ctx, double *out10, int32_t reset);
 #define NND_STAGE_COUNT 16
 NND_API int nnd_stage_profile(nnd_ctx *ctx, int32_t enable);
 NND_API int nnd_stage_read(nnd_ctx *ctx, double *out_ms, int32_t reset);
+/* EXPERIMENT (scripts/leaf_tc_experiment.py only; no product path calls it): the leaf join's pair matrix of leaves [l0, l1) as a
+ * BF16 tensor-core Gram (mma.sync m16n8k16) used as a conservative lower bound of the squared distance.  counts_dev[3] (device,
+ * accumulated): pairs, pairs the bound cannot exclude (lb < max(thr_i, thr_j)), and -- exact != 0 -- pairs whose exact distance
+ * passes the reference's filter (pynndescent_.py:104).  Squared euclidean, d <= 128, leaves of at most 80 points.            */
+NND_API int nnd_x_leaf_gram_tc(nnd_ctx *ctx, const nnd_problem *P, const int32_t *leaf_points, const int64_t *leaf_offsets, int64_t l0,
+                       int64_t l1, int32_t max_leaf, int32_t exact, unsigned long long *counts_dev, void *stream);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 NND_API int64_t nnd_launch_count(nnd_ctx *ctx);
 

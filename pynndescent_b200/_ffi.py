@@ -89,6 +89,7 @@ SIGNATURES = {
     "nnd_rng_advance_host": (C.c_int, [_vp, _pi64, _i64]),
     "nnd_pair_distances": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _vp, _vp]),
     "nnd_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), _i32]),
+    "nnd_x_leaf_gram_tc": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "nnd_launch_count": (C.c_int64, [_vp]),
     "nnd_stage_profile": (C.c_int, [_vp, _i32]),
     "nnd_stage_read": (C.c_int, [_vp, C.POINTER(C.c_double), _i32]),

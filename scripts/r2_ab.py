@@ -19,27 +19,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CONFIGS = {
     "default": {},
-    "applyshort": {"NND_APPLY_SHORT_SORT": "1"},
-    "applyhalf": {"NND_APPLY_HALF": "1"},
-    "candskip": {"NND_CAND_SKIP": "1"},
-    "candkeys": {"NND_CAND_KEYS": "1"},
-    "candtile": {"NND_CAND_KEYS": "2"},
-    "candskip+tile": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "2"},
-    "candskip+keys": {"NND_CAND_SKIP": "1", "NND_CAND_KEYS": "1"},
-    "forestpm48": {"NND_FOREST_PM_MB": "48"},
-    "forestpm200": {"NND_FOREST_PM_MB": "200"},
-    "forestpm1000": {"NND_FOREST_PM_MB": "1000"},
+    "noapplyshort": {"NND_APPLY_SHORT_SORT": "0"},
+    "nocandskip": {"NND_CAND_SKIP": "0"},
+    "candpartition": {"NND_CAND_PARTITION": "1"},
+    "forestpm96": {"NND_FOREST_PM_MB": "96"},
     "noforestpm": {"NND_FOREST_PM": "0"},
     "norank": {"NND_RANK_SCATTER": "0"},
     "noleafsplit": {"NND_LEAF_SPLIT": "0"},
     "nocarveout": {"NND_SMEM_CARVEOUT": "0"},
     "round1-defaults": {"NND_RANK_SCATTER": "0", "NND_LEAF_SPLIT": "0", "NND_SMEM_CARVEOUT": "0", "NND_FOREST_PM": "0", "NND_CAND_SKIP": "0",
-                        "NND_APPLY_SHORT_SORT": "0", "NND_PRESENCE": "0"},
-    "nopresence": {"NND_PRESENCE": "0"},
-    "nocandskip": {"NND_CAND_SKIP": "0"},
-    "nocandpartition": {"NND_CAND_PARTITION": "0"},
-    "nopm4": {"NND_FOREST_PM4": "0"},
-    "nopresence+nocandpartition": {"NND_PRESENCE": "0", "NND_CAND_PARTITION": "0"},
+                        "NND_APPLY_SHORT_SORT": "0"},
 }
 
 
