@@ -427,8 +427,9 @@ def main():
     }
     if not args.no_e2e:
         out["e2e"] = {"value": n * k / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms,
-                      "h2d_bytes_per_step": int(n * d * 4) * world, "d2h_bytes_per_step": int(n * k * 8),
-                      "note": "NNDescent(X_pinned_host) + .neighbor_graph per step; X is copied to every GPU (replicated), the graph is read back once (rank 0)"}
+                      "h2d_bytes_per_step": int(n * d * 4), "d2h_bytes_per_step": int(n * k * 8),
+                      "note": "NNDescent(X_pinned_host) + .neighbor_graph per step; X is replicated on the GPUs: every rank uploads 1 / n_gpus of "
+                              "its rows over PCIe and an NVLink all-gather completes the copies; the graph is read back once (rank 0)"}
     if not args.no_cpu_baseline:
         cores = cpu_threads()
         n_s = min(n, args.cpu_sample)

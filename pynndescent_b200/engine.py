@@ -27,7 +27,7 @@ def _ptr(t):
 
 
 class Engine:
-    def __init__(self, data, metric_id, n_neighbors, device=None, metric_param=None):
+    def __init__(self, data, metric_id, n_neighbors, device=None, metric_param=None, distributed_upload=False):
         if not torch.cuda.is_available():
             raise RuntimeError("pynndescent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -41,12 +41,29 @@ class Engine:
         self.metric_id = int(metric_id)
         self.stream = torch.cuda.current_stream(self.device)
         host = torch.from_numpy(data)
-        if self.ld == self.d:
-            self.X = torch.empty((self.N, self.ld), dtype=torch.float32, device=self.device)
-            self.X.copy_(host, non_blocking=host.is_pinned())
-        else:  # pad rows to a multiple of 4 floats (16-byte vector loads / bulk copies); pad columns are zero
-            self.X = torch.zeros((self.N, self.ld), dtype=torch.float32, device=self.device)
-            self.X[:, : self.d].copy_(host, non_blocking=host.is_pinned())
+        world = rank = None
+        if distributed_upload:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                world, rank = dist.get_world_size(), dist.get_rank()
+        if world is None:
+            if self.ld == self.d:
+                self.X = torch.empty((self.N, self.ld), dtype=torch.float32, device=self.device)
+                self.X.copy_(host, non_blocking=host.is_pinned())
+            else:  # pad rows to a multiple of 4 floats (16-byte vector loads / bulk copies); pad columns are zero
+                self.X = torch.zeros((self.N, self.ld), dtype=torch.float32, device=self.device)
+                self.X[:, : self.d].copy_(host, non_blocking=host.is_pinned())
+        else:
+            # sharded build: X is replicated on every GPU, but every process holds the same host matrix -- each uploads 1 / world of
+            # the rows over PCIe and the GPUs complete their copies over NVLink (one all-gather) instead of world full uploads
+            import torch.distributed as dist
+            rows = (self.N + world - 1) // world
+            buf = torch.zeros((world * rows, self.ld), dtype=torch.float32, device=self.device)
+            lo, hi = min(rank * rows, self.N), min((rank + 1) * rows, self.N)
+            if hi > lo:
+                buf[lo:hi, : self.d].copy_(host[lo:hi], non_blocking=host.is_pinned())
+            dist.all_gather_into_tensor(buf, buf[rank * rows: (rank + 1) * rows].clone())
+            self.X = buf[: self.N]
         nb = C.c_size_t()
         check(lib.nnd_metric_aux_bytes(self.metric_id, self.N, C.byref(nb)))
         self.aux = torch.empty(nb.value, dtype=torch.uint8, device=self.device)

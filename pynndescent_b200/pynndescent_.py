@@ -141,7 +141,7 @@ class NNDescent:
                                 push_capacity=push_capacity, sharded=bool(sharded))
 
         t0 = time.perf_counter()
-        eng = Engine(data, metric_id, n_neighbors, device=device, metric_param=metric_param)
+        eng = Engine(data, metric_id, n_neighbors, device=device, metric_param=metric_param, distributed_upload=bool(sharded))
         self._engine = eng
         if not eng.all_finite():
             raise ValueError("Input contains NaN, infinity or a value too large for dtype('float32').")
