@@ -32,3 +32,15 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_other_ranks_print_nothing():
     assert _run({"RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_both_arms_describe_the_same_config():
+    """The driver compares the two arms' lines: `config` must be the workload's description, identical in both (bench.config_of)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    j = json.loads(_run()[0])
+    assert j["config"] == bench.config_of(bench.WORKLOADS["cfg1"]) and j["scaling"] == "strong"
+    assert bench.DEFAULT_WORKLOAD == "cfg4" and bench.WORKLOADS["cfg4"]["n"] == 10_000_000      # the metric's own configuration
+    for wl in bench.WORKLOADS.values():
+        assert set(bench.config_of(wl)) >= {"workload", "n", "d", "k", "metric"}
