@@ -98,6 +98,12 @@ class SearchIndexGPU:
                             C.c_void_p(out_i.data_ptr()), C.c_void_p(out_d.data_ptr()), C.c_void_p(ws.data_ptr()), nb.value,
                             stats, st))
         self.last_stats = {"distance_evals": int(stats[0]), "pops": int(stats[1]), "sequential_queries": int(stats[2])}
+        if nq >= 64 and self.last_stats["sequential_queries"] > 0.05 * nq:
+            # queries that overflow the on-chip state (visited table / seed heap) or need the shared rng are replayed one after the
+            # other by ONE warp (k_query_seq): correct, but throughput collapses when many of a batch take that path (large k / epsilon)
+            from warnings import warn
+            warn("%d of %d queries were replayed sequentially on the GPU (on-chip search state overflow or rng draws); expect low "
+                 "throughput for this k / epsilon" % (self.last_stats["sequential_queries"], nq))
         sorted_d = torch.empty_like(out_d)
         check(lib.nnd_deheap_sort(self._ctx, C.c_void_p(out_i.data_ptr()), C.c_void_p(out_d.data_ptr()), nq, int(k),
                                   int(self.dev_correction), C.c_void_p(sorted_d.data_ptr()), st))           # :2361
