@@ -171,7 +171,7 @@ NND_API int nnd_descent(nnd_ctx *ctx, const nnd_problem *P, int32_t C, const int
 
 /* Schedule switches read from the environment by nnd_create (none changes a result; csrc/nnd_common.cuh, DESIGN.md section 10a;
  * defaults = the winners of the round-2 hardware A/B, profiles/ab_r02_1m_switches.json): NND_RANK_SCATTER, NND_LEAF_SPLIT,
- * NND_SMEM_CARVEOUT, NND_FOREST_PM (+ NND_FOREST_PM_MB), NND_CAND_SKIP, NND_CAND_KEYS.                                  */
+ * NND_SMEM_CARVEOUT, NND_FOREST_PM (+ NND_FOREST_PM_MB), NND_CAND_SKIP, NND_APPLY_SHORT_SORT, NND_CAND_PARTITION.           */
 
 /* ---- sharded build (one process per GPU) ----------------------------------------------
  * Every process holds X and the whole heap; it samples candidates and joins only rows [lo,hi), exchanges the

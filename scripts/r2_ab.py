@@ -1,14 +1,12 @@
-"""A/B harness for the schedule switches of libnnd_b200 (all default OFF, none may change a result).
+"""A/B harness for the schedule switches of libnnd_b200 (none may change a result).
 
     python scripts/r2_ab.py [N] [d] [k] [metric] [--configs name,name,...] [--reps R]
 
 Builds the same graph once per configuration in a FRESH subprocess (the switches are read by nnd_create / the engine from
 the environment), with a hard per-configuration timeout so that a hung experimental kernel cannot take the GPU box down
 with it, and prints for each: bit-equality of (indices, distances, per-iteration accepted pushes) against the default
-schedule, build ms, the local-join kernel ms (CUDA events inside the library) and stage timings.
-
-This is the first thing to run in a round that has GPU time: the kernels behind NND_JOIN_PIPE / NND_RANK_SCATTER /
-NND_JOIN_ORDER / NND_CAND_SKIP / NND_CAND_KEYS / NND_LEAF_SPLIT were written after round 1's GPU budget was spent and have only been compiled (see k_join_pipe.cu).
+schedule, build ms, the local-join kernel ms (CUDA events inside the library), host stage laps and the in-library stage timers.
+Round 2's outcomes: DESIGN.md section 6 (ledger), profiles/ab_r02_*.json.
 """
 import json
 import os

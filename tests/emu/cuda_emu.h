@@ -8,7 +8,7 @@
 // sequential), mbarriers follow the PTX semantics (phase completes when pending arrivals and pending transaction bytes
 // are both zero; try_wait.parity succeeds when the phase of that parity has completed) and cp.async.bulk is served by an
 // asynchronous "TMA" thread per block that copies and then signals complete_tx -- so the producer/consumer protocol of
-// k_join_pipe runs with genuine concurrency.  Arithmetic intrinsics map to IEEE operations (compile with
+// a warp-specialised kernel runs with genuine concurrency.  Arithmetic intrinsics map to IEEE operations (compile with
 // -ffp-contract=off), so results are bit-comparable with the oracle.
 #pragma once
 #include <atomic>
@@ -79,7 +79,7 @@ struct MBar {
 };
 struct Warp {
     std::barrier<> bar{32}; std::barrier<> hbar0{16}, hbar1{16}; uint64_t slot[32];
-    // full-warp masks and the two half-warp masks are supported (k_apply_half runs two heap rows per warp)
+    // full-warp masks and the two half-warp masks are supported (half-warp collectives)
     std::barrier<> &group(unsigned mask) {
         if (mask == 0xffffffffu) return bar;
         if (mask == 0x0000ffffu) return hbar0;
@@ -218,7 +218,7 @@ static inline unsigned __match_any_sync(unsigned mask, int v) {
     return r;
 }
 
-// ---- mbarrier + bulk copy (nnd_common.cuh's PTX wrappers, k_join_pipe.cu's mbar_arrive)
+// ---- mbarrier + bulk copy (nnd_common.cuh's PTX wrappers, mbar_arrive)
 static inline void mbar_init(uint64_t *bar, uint32_t count) {
     std::lock_guard<std::mutex> g(emu::g_block->bm);
     auto &p = emu::g_block->bars[bar];

@@ -1,17 +1,16 @@
-"""CPU emulation of the SOURCE of the batched local-join kernels (tests/emu/cuda_emu.h).
+"""CPU emulation of the SOURCE of the CUDA kernels (tests/emu/cuda_emu.h).
 
-The schedule experiments of DESIGN.md 10a were written when no GPU time was left, so this test runs their actual source on
-the CPU: the kernels are cut out of pynndescent_b200/csrc/*.cu by their section markers (the test fails loudly if a marker
-disappears), compiled with g++ against a small emulation of the CUDA execution model (one OS thread per CUDA thread, real
-barriers, PTX-semantics mbarriers, an asynchronous "TMA" thread serving the bulk copies) and driven through the same
-prepass as build_join_plan.  Checked against the oracle, half-update by half-update in emission order:
+The kernels are cut out of pynndescent_b200/csrc/*.cu by their section markers (the test fails loudly if a marker disappears),
+compiled with g++ against a small emulation of the CUDA execution model (one OS thread per CUDA thread, real barriers and
+shuffles, PTX-semantics mbarriers, an asynchronous "TMA" thread serving the bulk copies) and driven through the same host
+sequences as the library.  Checked against the oracle bit for bit: the batched local join half-update by half-update in emission
+order, whole iterations (join -> counting sort -> ordered replay with its filters), the candidate kernels, leaf init (fused and
+split), the forest (position- and point-major passes), the query walk, init_random / deheap_sort / diversification, the
+search-graph kernels and the hub tree.
 
-* k_join_batch (the kernel that IS verified on hardware) -- validates the emulator itself;
-* k_jp_meta + k_join_pipe for several (chunk, stage-ring, grid) shapes, with and without NND_RANK_SCATTER's RED path, with
-  a permuted row order (nnd_set_join_order) and with a push list that overflows.
-
-This is an emulation of the programming model, not of the hardware: it proves indexing, tiling, descriptor packing, the
-producer/consumer protocol and the arithmetic order, not performance and not memory-model subtleties of the async proxy.
+It started in round 1 as a stand-in for GPU time; every kernel it covers has since run on hardware (`-m gpu` suite), and it stays
+as the CPU-side regression net for the kernel sources.  This is an emulation of the programming model, not of the hardware: it
+proves indexing, tiling, protocols and the arithmetic order, not performance and not memory-model subtleties of the async proxy.
 """
 import ctypes as C
 import os
@@ -53,6 +52,7 @@ def emu_lib(tmp_path_factory):
     batch = _between(desc, "// prepass 1: per row -> active flag", "// ------------------------------------------------------------------ routing",
                      "k_jb_* / k_join_batch")
     cand = open(os.path.join(CSRC, "k_cand.cu")).read()
+    cand_sh = _between(cand, "struct __align__(4) CandRec", "static int cand_range(", "the partitioned / row-sharded candidate kernels")
     cand = _between(cand, "__global__ void k_cand_count", "__global__ void k_rng_table", "the candidate kernels")
     sg = open(os.path.join(CSRC, "k_search_graph.cu")).read()
     sg = _between(sg, "#define SG_WARPS", "// ------------------------------------------------------------------------------------------------ host",
@@ -77,7 +77,7 @@ def emu_lib(tmp_path_factory):
     hub = _between(prep, "// ------------------------------------------------------------------ canonical warp reductions (as in k_forest.cu)",
                    'extern "C" int nnd_hub_tree_workspace_bytes', "the hub-tree kernels")
     hub = hub.replace("extern __shared__ float s_t[];", "float *s_t = (float *)emu::dyn_smem();")
-    kernels = (join + "\n" + batch + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_SG 1\n" + sg +
+    kernels = (join + "\n" + batch + "\n#define EMU_WITH_CAND 1\n" + cand + "\n#define EMU_WITH_CANDSH 1\n" + cand_sh + "\n#define EMU_WITH_SG 1\n" + sg +
                "\n#define EMU_WITH_APPLY 1\n" + route + "\n#define EMU_WITH_LEAF 1\n" + leaf + "\n#define EMU_WITH_FOREST 1\n" + forest +
                "\n#define EMU_WITH_QUERY 1\n" + query + "\n#define EMU_WITH_MISC 1\n" + misc +
                "\n#define EMU_WITH_HUB 1\n" + hub)
@@ -102,6 +102,7 @@ def emu_lib(tmp_path_factory):
     lib.emu_norms.argtypes = [f32, C.c_long, C.c_int, f32]
     u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
     lib.emu_cand.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, i32, i32, C.c_long, C.c_long, C.c_int]
+    lib.emu_cand_sharded.argtypes = [i32, u8, C.c_long, C.c_int, C.c_int, C.c_int, i64, C.c_int, C.c_int, i32, i32]
     lib.emu_search_graph.argtypes = [i32, f32, i32, f32, C.c_long, C.c_int, i32, C.c_int, i32, i32, f32]
     lib.emu_search_graph.restype = C.c_long
     lib.emu_process_candidates.argtypes = [f32, C.c_long, C.c_int, C.c_int, C.c_void_p, i32, f32, u8, C.c_int, i32, i32, C.c_int, C.c_void_p,
@@ -227,11 +228,39 @@ def test_cases_are_not_trivial(emu_lib, cases):
         print(name, "batches", r["n_batches"], "active rows", r["n_active"], "half-updates", r["n_out"], "pairs", r["pairs"])
 
 
+@pytest.mark.parametrize("world,skip", [(1, 0), (2, 1), (3, 0), (5, 1)])
+def test_partitioned_candidate_kernels_for_simulated_processes(emu_lib, world, skip):
+    """The row-sharded candidate build's kernels (k_cand_count_sh / k_cand_bucket_scan / k_cand_locals / k_cand_export /
+    k_cand_import_* + the selection kernels) under the emulator, `world` processes simulated on one heap with the host sequence of
+    sharded.py (count tables summed and offset, records routed by owner): identical lists and flag clearing to the oracle's
+    new_build_candidates over three iterations of a small build."""
+    from sklearn.utils import check_random_state
+    from oracle import nnd_oracle as orc
+    n, d, k = 700, 16, 8
+    X = latent(n, d, 12)
+    rs = check_random_state(4)
+    rng_state = rs.randint(orc.INT32_MIN, orc.INT32_MAX, 3).astype(np.int64)
+    la, _ = orc.make_forest(X, k, 3, None, rs, False, 200, "level")
+    heap = orc.make_heap(n, k)
+    orc.init_rp_tree(X, "euclidean", heap, la); orc.init_random(X, "euclidean", heap, rng_state)
+    for it in range(3):
+        ind = heap[0].copy(); flags_emu = heap[2].copy()
+        en = np.full((n, k), -7, np.int32); eo = np.full((n, k), -7, np.int32)
+        assert emu_lib.emu_cand_sharded(ind, flags_emu, n, k, k, 8, rng_state, world, skip, en, eo) == 0
+        newc, oldc = orc.new_build_candidates(heap, k, rng_state, 8)
+        assert np.array_equal(en, newc)
+        has_new = (newc >= 0).any(1)
+        assert np.array_equal(eo[has_new], oldc[has_new])
+        assert np.all(eo[~has_new] == -1) if skip else np.array_equal(eo, oldc)
+        assert np.array_equal(flags_emu, heap[2])
+        orc.process_candidates(X, "euclidean", heap, newc, oldc, 8)
+
+
 @pytest.mark.parametrize("skip,keys", [(0, 0), (1, 0)])
 def test_candidate_kernels_and_cand_skip(emu_lib, skip, keys):
     """k_cand_count / k_cand_fill / k_cand_select* under the emulator against the oracle's new_build_candidates, over three
     iterations of a small build (hub vertices with > 32 reverse edges included).  skip=0 is the hardware-verified schedule
-    (all rows must match); keys=1 / 2 = NND_CAND_KEYS (reverse-edge key words / the whole tile staged in shared memory); skip=1 = NND_CAND_SKIP: rows WITH new candidates must match exactly, the others must come out
+    (all rows must match); skip=1 = NND_CAND_SKIP: rows WITH new candidates must match exactly, the others must come out
     empty, and the sampled-flag clearing must be identical."""
     from sklearn.utils import check_random_state
     from oracle import nnd_oracle as orc
@@ -358,7 +387,7 @@ def test_whole_iterations_match_the_oracle_heaps(emu_lib, kernel, rank_scatter, 
     """Three NN-descent iterations: candidates from the oracle, then join -> scatter -> apply under the emulator; after every
     iteration the heaps (indices, distances, flags, layout) and the accepted-push count must equal the oracle's
     process_candidates.  (0, 0) is the hardware-verified schedule = emulator check; the others are the switches of DESIGN 10a
-    (k_join_pipe, NND_RANK_SCATTER, a permuted join order; short_sort bit 0 = NND_APPLY_SHORT_SORT, bit 1 = NND_APPLY_HALF)."""
+    (NND_RANK_SCATTER; short_sort bit 0 = NND_APPLY_SHORT_SORT; the replay filters of k_apply are always on)."""
     from sklearn.utils import check_random_state
     from oracle import nnd_oracle as orc
     n, d, k = 450, 24, 10
