@@ -15,7 +15,7 @@ ID_TO_NAME = {0: "sqeuclidean", 1: "cosine", 2: "dot", 3: "correlation", 4: "man
 
 
 class OracleEngine:
-    def __init__(self, data, metric_id, n_neighbors, device=None, metric_param=None):
+    def __init__(self, data, metric_id, n_neighbors, device=None, metric_param=None, distributed_upload=False):
         if metric_param is not None:
             orc.lib().orc_set_metric_param(float(metric_param))
         self.X = np.ascontiguousarray(data, np.float32)
