@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W              # this repo's sm_100a path
     python bench.py --impl reference --gpus N --steps K ...     # CPU port of the reference path (rank 0 only)
     python bench.py --workload cfg2|cfg3|cfg5 ...               # the other BASELINE.json configurations
+    python bench.py --impl reference --thread-sweep | --full-size  # CPU-side evidence for the baseline (thread count; one whole build)
 
 Default workload = the configuration BASELINE.json quotes the metric on: ONE graph over 10M x 128 float32 points,
 k = 15, euclidean ("cfg4").  It fits one B200 (X 5.1 GB + heaps 1.35 GB + scratch), so `--gpus 1` builds it on one GPU and
@@ -221,6 +222,37 @@ def reference_arm(args, wl):
     print(json.dumps(out), flush=True)
 
 
+def reference_thread_sweep(args, wl):
+    """`--impl reference --thread-sweep`: the CPU port's build time against its OpenMP thread count on the first --ref-sample points
+    (what justifies cpu_threads(); profiles/cpu_thread_sweep_r02.json)."""
+    n_s = min(wl["n"], args.ref_sample)
+    X = latent_prefix(wl, n_s)
+    rows = []
+    for T in (4, 8, 16, 32, 64, 128):
+        if T > (os.cpu_count() or 1):
+            break
+        dt, o = run_cpu_port(X, wl["metric"], wl["k"], 42, T)
+        rows.append({"threads": T, "seconds": round(dt, 3), "edges_per_s": n_s * wl["k"] / dt, "iterations": int(o.n_iters_run)})
+        print(json.dumps(rows[-1]), file=sys.stderr, flush=True)
+    print(json.dumps({"impl": "reference", "mode": "thread-sweep", "n": n_s, "d": wl["d"], "k": wl["k"], "host_cores": os.cpu_count(), "rows": rows}), flush=True)
+
+
+def reference_full_size(args, wl):
+    """`--impl reference --full-size`: ONE build of the whole workload by the CPU port (minutes at 10M points;
+    profiles/cpu_full_cfg4_r02.json), with its recall on the fixture's rows."""
+    cores = cpu_threads()
+    X = latent(wl["n"], wl["d"], 0)
+    dt, o = run_cpu_port(X, wl["metric"], wl["k"], 42, cores)
+    gi, _ = o.neighbor_graph
+    out = {"impl": "reference", "mode": "full-size", "workload": wl["name"], "n": wl["n"], "seconds": round(dt, 1), "edges_per_s": wl["n"] * wl["k"] / dt,
+           "threads": cores, "host_cores": os.cpu_count(), "iterations": int(o.n_iters_run), "kind": "port (oracle/nnd_oracle.c, dfs forest)"}
+    fx = load_fixture(args.workload)
+    if fx and "exact_knn_of_sample" in fx:
+        true = np.asarray(fx["exact_knn_of_sample"]); rr = recall_rows(wl["n"])
+        out["recall_at_k"] = float(np.mean([len(np.intersect1d(true[i], gi[r])) for i, r in enumerate(rr)]) / wl["k"])
+    print(json.dumps(out), flush=True)
+
+
 def latent_prefix(wl, n_s):
     """The first n_s rows of latent(n, d) without materialising all n rows twice: the generator draws Z (n x 16) first, then A,
     then the noise row by row, so the prefix of the noise stream is the prefix of the matrix."""
@@ -244,9 +276,15 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--thread-sweep", action="store_true", help="with --impl reference: CPU port build time vs thread count")
+    ap.add_argument("--full-size", action="store_true", help="with --impl reference: one full-size CPU build of the workload")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0 and args.thread_sweep:
+            return reference_thread_sweep(args, wl)
+        if int(os.environ.get("RANK", "0")) == 0 and args.full_size:
+            return reference_full_size(args, wl)
         return reference_arm(args, wl)
 
     import torch
