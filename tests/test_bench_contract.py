@@ -44,3 +44,13 @@ def test_both_arms_describe_the_same_config():
     assert bench.DEFAULT_WORKLOAD == "cfg4" and bench.WORKLOADS["cfg4"]["n"] == 10_000_000      # the metric's own configuration
     for wl in bench.WORKLOADS.values():
         assert set(bench.config_of(wl)) >= {"workload", "n", "d", "k", "metric"}
+
+
+def test_reference_sample_is_a_prefix_of_the_workload_matrix():
+    """The reference arm builds the FIRST rows of the GPU arm's matrix without generating all of it (bench.latent_prefix)."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    wl = dict(n=5000, d=24)
+    assert np.array_equal(bench.latent(5000, 24, 0)[:1234], bench.latent_prefix(wl, 1234))
