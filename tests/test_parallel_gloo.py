@@ -381,15 +381,19 @@ class OracleShardEngine:
         return self.heap_idx, torch.from_numpy(np.sqrt(b) if correction == 1 else b.copy())
 
 
+NO_TREES = os.environ.get("NND_TEST_NO_TREES") == "1"      # tree_init=False: every row is filled by init_random (the all-gather branch)
 e = OracleShardEngine()
 sb = ShardedBuilder(e)
-idx_t, dist_t, iters, c_hist = sb.build(rng_state.copy(), states, LEAF, False, K, T, 8, 0.001, 1)
+rng_run = rng_state.copy()
+idx_t, dist_t, iters, c_hist = sb.build(rng_run, None if NO_TREES else states, LEAF, False, K, T, 8, 0.001, 1)
 # single-process oracle with the same seeds (forest scheme "level" from the same tree states)
-la = orc.forest_leaf_array(X, states, LEAF, False, 200, "level")
 ref = orc.make_heap(N, K)
-orc.init_rp_tree(X, "euclidean", ref, la)
+if not NO_TREES:
+    la = orc.forest_leaf_array(X, states, LEAF, False, 200, "level")
+    orc.init_rp_tree(X, "euclidean", ref, la)
 rng2 = rng_state.copy()
 orc.init_random(X, "euclidean", ref, rng2)
+assert np.array_equal(rng_run, rng2), "init_random must advance the rng identically on every rank"
 ch = np.zeros(8, np.int64)
 it2 = orc.lib().orc_nn_descent_internal(X, N, D, 0, ref[0], ref[1], ref[2], K, K, rng2, T, 8, 0.001, 16384, ch)
 orc.deheap_sort(ref[0], ref[1])
@@ -403,11 +407,11 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_whole_sharded_build_equals_single_process_oracle_gloo(tmp_path, world):
+@pytest.mark.parametrize("world,no_trees", [(2, False), (3, False), (2, True)])
+def test_whole_sharded_build_equals_single_process_oracle_gloo(tmp_path, world, no_trees):
     script = tmp_path / "build_worker.py"
     script.write_text(BUILD_WORKER)
-    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1", NND_TEST_NO_TREES="1" if no_trees else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
