@@ -53,26 +53,46 @@ def _fake_prepared_index(G):
     return o
 
 
-@pytest.mark.parametrize("name", ["query_euclid_3k32", "query_cosine_2k24", "query_manhattan_2k20"])   # the last has no fast alternative
-def test_reference_loads_and_queries_our_pickle(tmp_path, name):
+REF_CASES = ["query_euclid_3k32", "query_cosine_2k24", "query_manhattan_2k20"]          # the last has no fast alternative
+
+
+@pytest.fixture(scope="module")
+def reference_loader_runs(tmp_path_factory):
+    """One stock-reference process per case, all started together (each spends most of its time in numba's JIT for its own
+    metric, so running them side by side keeps the CPU suite short); the test of a case waits for its process."""
     from oracle import ref_shim
     if not ref_shim.available():
+        return None
+    runs = {}
+    for name in REF_CASES:
+        tmp = tmp_path_factory.mktemp(name)
+        G = load_golden(name)
+        idx = _fake_prepared_index(G)
+        state = idx.reference_state()
+        assert np.array_equal(state["_raw_data"], G["data"])                 # leaf-order data (pynndescent_.py:1639-1641)
+        assert state["_search_graph"].dtype == np.uint8 and state["_search_graph"].nnz == G["indices"].shape[0]
+        assert "pynndescent" not in sys.modules                              # written WITHOUT the reference importable
+        pk = tmp / "index.pkl"
+        idx.save_for_reference(str(pk))
+        assert "pynndescent" not in sys.modules and "pynndescent.pynndescent_" not in sys.modules
+        script = tmp / "loader.py"; script.write_text(LOADER)
+        out = tmp / "out.npz"
+        proc = subprocess.Popen([sys.executable, str(script), ROOT, str(pk), os.path.join(ROOT, "tests", "golden", name + ".npz"), str(out)],
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        runs[name] = (proc, out, G)
+    yield runs
+    for proc, _, _ in runs.values():
+        if proc.poll() is None:
+            proc.kill()
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_reference_loads_and_queries_our_pickle(reference_loader_runs, name):
+    if reference_loader_runs is None:
         pytest.skip("reference tree not present on this machine")
-    G = load_golden(name)
-    idx = _fake_prepared_index(G)
-    state = idx.reference_state()
-    assert np.array_equal(state["_raw_data"], G["data"])                 # leaf-order data (pynndescent_.py:1639-1641)
-    assert state["_search_graph"].dtype == np.uint8 and state["_search_graph"].nnz == G["indices"].shape[0]
-    assert "pynndescent" not in sys.modules                              # written WITHOUT the reference importable
-    pk = tmp_path / "index.pkl"
-    idx.save_for_reference(str(pk))
-    assert "pynndescent" not in sys.modules and "pynndescent.pynndescent_" not in sys.modules
-    raw = pickle.dumps(0)  # noqa: F841  (pickle module still healthy)
-    script = tmp_path / "loader.py"; script.write_text(LOADER)
-    out = tmp_path / "out.npz"
-    r = subprocess.run([sys.executable, str(script), ROOT, str(pk), os.path.join(ROOT, "tests", "golden", name + ".npz"), str(out)],
-                       capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stderr[-3000:]
+    proc, out, G = reference_loader_runs[name]
+    _, err = proc.communicate(timeout=900)
+    assert proc.returncode == 0, err[-3000:]
     R = np.load(out)
     # the stock reference, running ITS OWN numba search on the unpickled structures, returns its golden answers
     assert np.array_equal(R["qi"], G["out_idx"]) and np.array_equal(R["qd"], G["out_dist"])
